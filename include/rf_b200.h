@@ -1,0 +1,137 @@
+/* rf_b200.h -- C-ABI of the B200-native store-scoped chunk retriever (librf_b200.so).
+ *
+ * This is the drop-in boundary UNDER the Python adapter (rag_foundation_b200/adapter.py:B200Rag),
+ * which itself duck-types the reference's adapter object:
+ *   backend/app/services/gemini_rag.py:242-599 (GeminiRag), :602-718 (MockGeminiRag),
+ *   :721-725 (get_rag_client).
+ * The reference has no FFI for this path (it is pure Python calling a remote service), so each
+ * entry point below cites the reference METHOD whose work it carries out on the GPU.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; 0 = RF_OK, negative = error
+ * (rf_strerror); no exceptions cross the ABI; the caller owns every output buffer; all entry
+ * points are thread-safe except rf_engine_create/destroy.  There is NO CPU fallback: every compute
+ * entry point launches sm_100a kernels and fails with RF_ECUDA/RF_ENODEVICE when it cannot.
+ *
+ * Arithmetic is the frozen RF-1 spec (oracle/SPEC.md): D = 256 int8 hashed term counts per chunk,
+ * int32 dot-product scores, rank by (score desc, global chunk id asc), float32 cosine reported.
+ */
+#ifndef RF_B200_H
+#define RF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_DIM 256u           /* feature dimension (int8 per chunk row)               */
+#define RF_TOPK_MAX 32u       /* largest k a search may ask for (reference default 10) */
+#define RF_SCOPE_MAX 16u      /* store segments per query scope (reference: <= 10 stores/user, config.py:127) */
+#define RF_TOMBSTONE 0xFFFFFFFFu
+
+enum {
+    RF_OK = 0,
+    RF_EINVAL = -1,     /* bad argument                                   -> RuntimeError   */
+    RF_ENOMEM = -2,     /* HBM arena / host allocation exhausted          -> RuntimeError   */
+    RF_ECUDA = -3,      /* a CUDA call or kernel failed                   -> RuntimeError   */
+    RF_ENODEVICE = -4,  /* no sm_100 device visible                       -> RuntimeError   */
+    RF_ENOTFOUND = -5,  /* unknown store / document                       -> RuntimeError   */
+    RF_EBUSY = -6,      /* no free search context within the wait budget  -> TimeoutError (retryable, gemini_rag.py:22-27) */
+    RF_ECAPACITY = -7   /* more rows than capacity_rows                   -> RuntimeError   */
+};
+
+typedef struct rf_engine rf_engine;
+
+typedef struct rf_config {
+    uint32_t struct_size;    /* sizeof(rf_config), for forward compatibility            */
+    int32_t device;          /* CUDA ordinal                                            */
+    uint32_t dim;            /* must be RF_DIM                                          */
+    uint32_t n_contexts;     /* concurrent searches (reference: 50 streams/process, routes/chat.py:40); 0 -> 8 */
+    uint64_t capacity_rows;  /* chunk rows reserved in HBM (260 B + 12 B sidecar each)  */
+    uint64_t id_base;        /* global chunk id of row 0 (shard offset in sharded mode) */
+} rf_config;
+
+typedef struct rf_stats {
+    uint64_t n_rows;          /* rows appended so far (including tombstoned)  */
+    uint64_t capacity_rows;
+    uint64_t n_stores;
+    uint64_t n_docs;
+    uint64_t hbm_bytes;       /* device bytes held by the engine              */
+    uint64_t searches;        /* queries answered                             */
+    uint64_t kernel_launches; /* kernels launched by this engine since create */
+} rf_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int rf_engine_create(const rf_config *cfg, rf_engine **out);
+int rf_engine_destroy(rf_engine *e);
+int rf_engine_stats(rf_engine *e, rf_stats *out);
+const char *rf_strerror(int code);
+const char *rf_last_error(void);           /* thread-local detail of the last failure */
+int rf_build_info(char *buf, size_t n);    /* "sm_100a nvcc 12.9 ..." */
+
+/* ---- stores: GeminiRag.create_store / delete_store (gemini_rag.py:271-304, 610-612, 696-697) -- */
+int rf_store_open(rf_engine *e, const char *fs_name, uint32_t *store_seg);   /* idempotent */
+int rf_store_lookup(rf_engine *e, const char *fs_name, uint32_t *store_seg); /* RF_ENOTFOUND if absent */
+int rf_store_drop(rf_engine *e, uint32_t store_seg);                         /* tombstones its rows */
+
+/* ---- ingest: GeminiRag.upload_file (gemini_rag.py:307-352, 614-629), called by the ARQ worker at
+ * services/ingestion.py:45-52.  Featurises on the GPU (tokenise, chunk, FNV-1a, int8 histogram)
+ * and appends the rows to the store.  spans[2*i], spans[2*i+1] = byte span of chunk i in utf8
+ * (first max_spans chunks).  Synchronous: rows are searchable when it returns (op_status done,
+ * gemini_rag.py:631-638). */
+int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint8_t *utf8, size_t n,
+                   uint64_t *first_chunk, uint32_t *n_chunks, int64_t *spans, uint32_t max_spans);
+
+/* Append pre-computed int8 rows (host or device pointer, n_rows x RF_DIM). */
+int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const int8_t *rows,
+                       uint64_t n_rows, int rows_on_device, uint64_t *first_chunk);
+
+/* Append n_rows rows of the RF-1 synthetic corpus `seed`, counters start_counter.. (oracle/SPEC.md),
+ * generated on the GPU.  Row i goes to store segment first_seg + i / rows_per_store (all of which
+ * must be open); rows_per_store = 0 puts every row in first_seg.  zipf_vocab: uint16[65536] host. */
+int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_store, uint64_t seed,
+                        uint64_t start_counter, uint64_t n_rows, const uint16_t *zipf_vocab,
+                        uint64_t *first_chunk);
+
+/* GeminiRag.delete_document_from_store (gemini_rag.py:354-424, 699-702). */
+int rf_doc_tombstone(rf_engine *e, uint64_t doc_id);
+
+/* Copy rows [first, first+n) back to the host (tests / snapshots): any of the outputs may be NULL. */
+int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uint32_t *store_seg,
+                 int32_t *ff);
+
+/* ---- query: GeminiRag.ask_stream / ask retrieval step (gemini_rag.py:472-551, 656-694) --------
+ * q: nq x RF_DIM int8 query vectors (HOST).  Scope of query i = store_segs[seg_off[i] .. seg_off[i+1])
+ * (CSR, at most RF_SCOPE_MAX each).  Outputs are HOST buffers, nq x k, rows padded with id
+ * UINT64_MAX / score 0 / cos 0 beyond out_counts[i].  out_cos / out_counts may be NULL.
+ * Blocks until the results are in the caller's buffers. */
+int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs,
+              const uint32_t *seg_off, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
+              float *out_cos, uint32_t *out_counts);
+
+/* Same, from query text: tokenise + hash on the GPU, then search, no host round trip between.
+ * (MockGeminiRag._contents_to_text picks the text, gemini_rag.py:640-654.) */
+int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs,
+                   uint32_t n_segs, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
+                   float *out_cos, uint32_t *out_count, int8_t *out_q /* RF_DIM, may be NULL */);
+
+/* Device-resident variant for pipelines and the sharded (multi-GPU) path: q_dev and out_keys_dev
+ * are DEVICE pointers, the work is enqueued on `stream` (a cudaStream_t; NULL = legacy default
+ * stream) and the call returns without synchronising.  out_keys_dev: nq x k packed RF-1 keys
+ * ((uint64(score) << 32) | (0xFFFFFFFF - global_id)), 0 = no result.  All queries share one scope. */
+int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                          uint32_t n_segs, uint32_t k, uint64_t *out_keys_dev, void *stream);
+
+/* k-way merge after the all-gather of the sharded path: keys_dev is n_lists x nq x k packed keys
+ * (device), out_keys_dev nq x k.  Enqueued on `stream`, no synchronisation. */
+int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq,
+                         uint32_t k, uint64_t *out_keys_dev, void *stream);
+
+/* Query featurisation alone (text -> int8[RF_DIM] on the GPU), host buffers. */
+int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H */

@@ -1,0 +1,290 @@
+"""B200Rag -- drop-in for the object `get_rag_client()` returns in the reference.
+
+Mirrors the duck-typed adapter protocol of backend/app/services/gemini_rag.py (paths relative to
+/root/reference): GeminiRag :242-599, MockGeminiRag :602-718, get_rag_client :721-725.  Same method
+names, argument meaning, return shapes and error behaviour, so the SSE chat route
+(routes/chat.py:499-505, 576-586) and the ARQ ingest worker (services/ingestion.py:45-52,106-139)
+need no change.  Where the reference calls a remote service (or, in mock mode, returns one canned
+citation), this adapter featurises on the GPU at upload and runs the score/top-k kernels at query
+time; see include/rf_b200.h for the C-ABI underneath.
+
+The adapter object is re-created on every request (gemini_rag.py:721-725), so it is a stateless
+facade over one process-global Registry (engine handle + chunk-text sidecar).
+"""
+from __future__ import annotations
+
+import bisect
+import os
+import threading
+import time
+import uuid
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Any, Dict, Generator, List, Optional, Sequence, Union
+
+import numpy as np
+
+from .engine import Engine
+
+TOPK_DEFAULT = int(os.environ.get("RAG_TOPK", "10"))
+SNIPPET_MAX_BYTES = 1024
+
+
+@dataclass
+class UploadResult:  # gemini_rag.py:30-33
+    operation_name: str
+    file_id: str | None = None
+
+
+@dataclass
+class _Doc:
+    doc_id: int
+    store_name: str
+    display_name: str
+    file_id: str
+    first_chunk: int
+    n_chunks: int
+    spans: np.ndarray
+    data: bytes
+    custom_metadata: Any = None
+    deleted: bool = False
+
+
+class Registry:
+    """Process-global state behind every B200Rag facade: the engine and the chunk sidecar."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.lock = threading.RLock()
+        self.docs: Dict[int, _Doc] = {}
+        self.doc_by_file: Dict[str, int] = {}
+        self.first_chunks: List[int] = []   # sorted, parallel to first_chunk_doc
+        self.first_chunk_doc: List[int] = []
+        self.ops: Dict[str, dict] = {}
+        self.next_doc = 1
+
+    def chunk_to_doc(self, chunk_id: int) -> Optional[tuple]:
+        with self.lock:
+            i = bisect.bisect_right(self.first_chunks, chunk_id) - 1
+            if i < 0:
+                return None
+            d = self.docs.get(self.first_chunk_doc[i])
+            if d is None or not (d.first_chunk <= chunk_id < d.first_chunk + d.n_chunks):
+                return None
+            return d, chunk_id - d.first_chunk
+
+
+_registry: Optional[Registry] = None
+_registry_lock = threading.Lock()
+
+
+def get_registry() -> Registry:
+    """Lazily create the process-global engine from env flags (kept beside, not inside, the
+    reference's Settings -- SURVEY.md §5): RAG_B200_CAPACITY_ROWS, RAG_B200_DEVICE."""
+    global _registry
+    with _registry_lock:
+        if _registry is None:
+            cap = int(os.environ.get("RAG_B200_CAPACITY_ROWS", str(4_000_000)))
+            dev = int(os.environ.get("RAG_B200_DEVICE", "0"))
+            _registry = Registry(Engine(capacity_rows=cap, device=dev, n_contexts=int(os.environ.get("RAG_B200_CONTEXTS", "16"))))
+        return _registry
+
+
+def set_registry(reg: Optional[Registry]) -> None:
+    global _registry
+    with _registry_lock:
+        _registry = reg
+
+
+def contents_to_text(contents: Any) -> str:
+    """Last non-empty user turn; same rule as MockGeminiRag._contents_to_text (gemini_rag.py:640-654)."""
+    if isinstance(contents, str):
+        return contents
+    if isinstance(contents, list):
+        for item in reversed(contents):
+            if isinstance(item, str) and item.strip():
+                return item.strip()
+            if isinstance(item, dict):
+                parts = item.get("parts")
+                if isinstance(parts, list) and parts and isinstance(parts[0], dict):
+                    text = parts[0].get("text")
+                    if isinstance(text, str) and text.strip():
+                        return text.strip()
+    return str(contents)
+
+
+def _get_response_name(response: Any, *, context: str) -> str:  # gemini_rag.py:96-102
+    if isinstance(response, str):
+        return response
+    name = response.get("name") if isinstance(response, dict) else getattr(response, "name", None)
+    if not name:
+        raise ValueError(f"Missing name in {context} response")
+    return name
+
+
+def build_final_response(grounding: Sequence[dict]) -> Any:
+    """Final stream chunk, shaped like MockGeminiRag._mock_response (gemini_rag.py:704-718) but
+    with one grounding chunk per retrieved citation, in rank order."""
+    usage = SimpleNamespace(prompt_token_count=0, candidates_token_count=0)
+    chunks = [SimpleNamespace(retrieved_context=SimpleNamespace(uri=g["uri"], title=g["title"], text=g["text"],
+                                                                file_search_store=g["file_search_store"],
+                                                                score=g.get("score"), cosine=g.get("cosine"),
+                                                                chunk_id=g.get("chunk_id")), web=None)
+              for g in grounding]
+    candidate = SimpleNamespace(grounding_metadata=SimpleNamespace(grounding_chunks=chunks), usage_metadata=usage)
+    return SimpleNamespace(text=None, candidates=[candidate], usage_metadata=usage)
+
+
+class B200Rag:
+    """GeminiRag-shaped retriever backed by the B200 engine."""
+
+    def __init__(self, registry: Optional[Registry] = None, top_k: int = TOPK_DEFAULT) -> None:
+        self._reg = registry or get_registry()
+        self.is_mock = True          # main.py:385 skips the remote health probe when truthy
+        self.is_b200 = True
+        self.top_k = top_k
+
+    # -------- Stores (gemini_rag.py:268-304, 607-612, 696-697) --------
+    def list_stores(self) -> List[Any]:
+        return []
+
+    def create_store(self, display_name: str) -> str:
+        name = f"fileSearchStores/b200-{uuid.uuid4().hex}"   # routes/stores.py:46 requires this prefix
+        self._reg.engine.open_store(name)
+        return name
+
+    def delete_store(self, store_name: str) -> None:
+        reg = self._reg
+        seg = reg.engine.lookup_store(store_name)
+        if seg is None:
+            return
+        reg.engine.drop_store(seg)
+        with reg.lock:
+            for d in reg.docs.values():
+                if d.store_name == store_name:
+                    d.deleted = True
+
+    # -------- Upload & operations (gemini_rag.py:307-352, 426-460, 614-638) --------
+    def upload_file(self, store_name: str, file_path: str, *, display_name: Optional[str] = None,
+                    custom_metadata: Optional[List[Dict[str, Union[str, float, int]]]] = None,
+                    chunking_config: Optional[Dict] = None) -> UploadResult:
+        reg = self._reg
+        with open(file_path, "rb") as f:
+            data = f.read()
+        seg = reg.engine.lookup_store(store_name)
+        if seg is None:
+            seg = reg.engine.open_store(store_name)   # stores created before this process started
+        with reg.lock:
+            doc_id = reg.next_doc
+            reg.next_doc += 1
+        op_name = f"operations/b200-{uuid.uuid4().hex}"
+        file_id = f"files/b200-{doc_id:016x}"
+        try:
+            first, n_chunks, spans = reg.engine.ingest_text(seg, doc_id, data)
+        except Exception as exc:
+            with reg.lock:
+                reg.ops[op_name] = {"done": True, "error": str(exc)}
+            raise
+        doc = _Doc(doc_id, store_name, display_name or os.path.basename(file_path), file_id, first, n_chunks, spans,
+                   data, custom_metadata)
+        with reg.lock:
+            reg.docs[doc_id] = doc
+            reg.doc_by_file[file_id] = doc_id
+            if n_chunks:
+                i = bisect.bisect_right(reg.first_chunks, first)
+                reg.first_chunks.insert(i, first)
+                reg.first_chunk_doc.insert(i, doc_id)
+            reg.ops[op_name] = {"done": True, "error": None, "n_chunks": n_chunks, "file_id": file_id}
+        return UploadResult(operation_name=op_name, file_id=file_id)
+
+    def op_status(self, op_name: str | dict) -> dict[str, Any]:
+        name = _get_response_name(op_name, context="operation status request")
+        with self._reg.lock:
+            op = self._reg.ops.get(name)
+        if op is None:   # unknown operations read as finished, like the mock (gemini_rag.py:631-638)
+            return {"name": name, "done": True, "metadata": {}, "error": None}
+        return {"name": name, "done": bool(op["done"]), "metadata": {k: v for k, v in op.items() if k in ("n_chunks", "file_id")},
+                "error": op["error"]}
+
+    def delete_document_from_store(self, store_name: str, document_id: int, filename: str | None = None,
+                                   file_id: str | None = None) -> None:
+        reg = self._reg
+        with reg.lock:
+            doc_id = reg.doc_by_file.get(file_id or "")
+            doc = reg.docs.get(doc_id) if doc_id is not None else None
+            if doc is None or doc.deleted:
+                return
+            doc.deleted = True
+        if doc.n_chunks:
+            reg.engine.tombstone_doc(doc.doc_id)
+
+    # -------- Query (gemini_rag.py:472-551, 656-694) --------
+    def retrieve(self, text: str, store_names: Sequence[str], k: Optional[int] = None) -> List[dict]:
+        """Top-k grounding contexts for `text` within `store_names`, rank order."""
+        reg = self._reg
+        segs = []
+        for s in store_names:
+            seg = reg.engine.lookup_store(s)
+            if seg is not None and seg not in segs:
+                segs.append(seg)
+        if not segs:
+            return []
+        ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k)
+        out = []
+        for gid, sc, c in zip(ids.tolist(), scores.tolist(), cos.tolist()):
+            hit = reg.chunk_to_doc(int(gid))
+            if hit is None:
+                continue
+            doc, chunk_no = hit
+            b0, b1 = int(doc.spans[chunk_no, 0]), int(doc.spans[chunk_no, 1])
+            snippet = doc.data[b0:min(b1, b0 + SNIPPET_MAX_BYTES)].decode("utf-8", "replace")
+            out.append({"uri": f"chunk://{doc.store_name}/{doc.doc_id}/{chunk_no}#{gid}", "title": doc.display_name,
+                        "text": snippet, "file_search_store": doc.store_name, "score": int(sc), "cosine": float(c),
+                        "chunk_id": int(gid)})
+        return out
+
+    def ask(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
+            system: str | None = None) -> Any:
+        return build_final_response(self.retrieve(contents_to_text(contents), store_names))
+
+    def ask_stream(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
+                   system: str | None = None) -> Generator:
+        text = contents_to_text(contents)
+        grounding = self.retrieve(text, store_names)   # the GPU work; no lock is held across the yields
+        lead = grounding[0]["text"].strip().splitlines()[0][:200] if grounding else "no matching passages"
+        yield SimpleNamespace(text=f"[b200-retrieval] {lead}", candidates=None,
+                              usage_metadata=SimpleNamespace(prompt_token_count=0, candidates_token_count=0))
+        yield build_final_response(grounding)
+
+    # -------- Citations (gemini_rag.py:554-599) --------
+    @staticmethod
+    def extract_citations_from_response(response: Any) -> List[dict[str, Any]]:
+        out: List[dict[str, Any]] = []
+        try:
+            cand = response.candidates[0]
+            gm = getattr(cand, "grounding_metadata", None)
+            if not gm:
+                return out
+            for i, ch in enumerate(list(getattr(gm, "grounding_chunks", []) or [])):
+                rc = getattr(ch, "retrieved_context", None)
+                if rc:
+                    out.append({"index": i, "source_type": "retrieved_context", "uri": getattr(rc, "uri", None),
+                                "title": getattr(rc, "title", None), "snippet": getattr(rc, "text", None),
+                                "store": getattr(rc, "file_search_store", None)})
+                    continue
+                web = getattr(ch, "web", None)
+                if web:
+                    out.append({"index": i, "source_type": "web", "uri": getattr(web, "uri", None),
+                                "title": getattr(web, "title", None), "snippet": None, "store": None})
+            return out
+        except (AttributeError, KeyError, IndexError, TypeError):
+            return out
+
+    @staticmethod
+    def new_stream_ids() -> tuple[str, str]:
+        return str(uuid.uuid4()), str(uuid.uuid4())
+
+
+def get_rag_client() -> B200Rag:
+    """What gemini_rag.get_rag_client() (:721-725) returns when RAG_BACKEND=b200."""
+    return B200Rag()

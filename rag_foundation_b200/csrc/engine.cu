@@ -1,0 +1,859 @@
+// librf_b200.so -- engine and C-ABI (include/rf_b200.h).
+//
+// One engine owns one GPU's share of the chunk index: a feature arena F[capacity, 256] int8 in HBM
+// with three sidecar arrays (store-segment word, sum of squares, nothing else is per-row), rows in
+// append order (row index + id_base = global chunk id).  Host-side it keeps, per store, the list of
+// row extents that hold the store's rows, so a store-scoped query scans only those rows; the
+// per-row segment word is still checked in the kernel, so extents are a performance hint only.
+//
+// The engine stands where the reference's remote File Search service stands behind
+// backend/app/services/gemini_rag.py (GeminiRag :242-599 / MockGeminiRag :602-718); the adapter
+// object itself is re-created per request (get_rag_client, :721-725), so all state lives here.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "rf_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RF_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(RF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct Extent {
+    uint32_t lo, hi;
+};
+
+void extents_append(std::vector<Extent> &v, uint32_t lo, uint32_t hi) {
+    if (lo >= hi) return;
+    if (!v.empty() && v.back().hi == lo) v.back().hi = hi;
+    else v.push_back({lo, hi});
+}
+
+struct Store {
+    std::string name;
+    std::vector<Extent> ext;
+    bool dropped = false;
+};
+
+struct Doc {
+    uint32_t store;
+    std::vector<Extent> ext;
+};
+
+constexpr uint32_t kMaxExtPerQuery = 64;   // more are coalesced (the row mask keeps it exact)
+constexpr uint32_t kTilesPerBlockTarget = 48;
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(n, 4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(n, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    PinnedBuf h_in, h_out;
+    DeviceBuf d_in, d_out, d_partial, d_tickets;
+};
+
+// A scan plan resident on the device for rf_search_keys_device (cached per scope + stream).
+struct DevicePlan {
+    uint64_t epoch = ~0ull;
+    DeviceBuf blob, partial, tickets;
+    uint32_t n_ext = 0, max_tiles = 0;
+};
+
+struct PlanBlob {  // host staging of everything one launch needs besides F/seg/ff
+    std::vector<uint8_t> bytes;
+    size_t off_q = 0, off_plans = 0, off_lo = 0, off_hi = 0, off_tile0 = 0;
+    uint32_t max_tiles = 0;
+};
+
+}  // namespace
+
+struct rf_engine {
+    rf_config cfg{};
+    int sm_count = 148;
+    int8_t *F = nullptr;
+    uint32_t *seg = nullptr;
+    int32_t *ff = nullptr;
+    uint8_t *zipf_bucket = nullptr;  // device, 65536 B, built on first synthetic ingest
+    uint64_t hbm_bytes = 0;
+
+    std::shared_mutex meta_mu;       // stores / docs / n_rows
+    std::vector<Store> stores;
+    std::unordered_map<std::string, uint32_t> store_by_name;
+    std::unordered_map<uint64_t, Doc> docs;
+    uint64_t n_rows = 0;             // published rows
+    std::atomic<uint64_t> epoch{0};  // bumps whenever extents change
+
+    std::mutex ingest_mu;            // one ingest at a time (shared scratch + append cursor)
+    cudaStream_t ingest_stream = nullptr;
+    DeviceBuf sc_text, sc_counts, sc_bucket, sc_start, sc_end, sc_ntok, sc_spans;
+
+    std::mutex ctx_mu;
+    std::condition_variable ctx_cv;
+    std::vector<SearchCtx *> free_ctx;
+    std::vector<SearchCtx *> all_ctx;
+
+    std::mutex plan_mu;
+    std::map<std::pair<std::vector<uint32_t>, void *>, DevicePlan *> dev_plans;
+
+    std::atomic<uint64_t> searches{0};
+    std::atomic<uint64_t> launches{0};
+    uint32_t blocks_override = 0;
+};
+
+namespace {
+
+using rf::ScanArgs;
+using rf::ScanPlan;
+
+// Collect the extents to scan for one scope (under a shared lock on meta_mu).
+void gather_extents(rf_engine *e, const uint32_t *segs, uint32_t n_segs, std::vector<Extent> &out) {
+    out.clear();
+    for (uint32_t i = 0; i < n_segs; ++i) {
+        const uint32_t s = segs[i];
+        if (s >= e->stores.size() || e->stores[s].dropped) continue;
+        bool seen = false;
+        for (uint32_t j = 0; j < i; ++j) seen |= (segs[j] == s);
+        if (seen) continue;
+        out.insert(out.end(), e->stores[s].ext.begin(), e->stores[s].ext.end());
+    }
+    if (out.size() > 1) {
+        std::sort(out.begin(), out.end(), [](const Extent &a, const Extent &b) { return a.lo < b.lo; });
+        std::vector<Extent> merged;
+        for (const Extent &x : out) {
+            if (!merged.empty() && merged.back().hi >= x.lo) merged.back().hi = std::max(merged.back().hi, x.hi);
+            else merged.push_back(x);
+        }
+        out.swap(merged);
+    }
+    if (out.size() > kMaxExtPerQuery) {  // keep the kMaxExtPerQuery-1 widest gaps as split points
+        std::vector<std::pair<uint32_t, size_t>> gaps;
+        for (size_t i = 1; i < out.size(); ++i) gaps.push_back({out[i].lo - out[i - 1].hi, i});
+        std::nth_element(gaps.begin(), gaps.begin() + (kMaxExtPerQuery - 1), gaps.end(),
+                         [](const auto &a, const auto &b) { return a.first > b.first; });
+        std::vector<char> split(out.size(), 0);
+        for (size_t i = 0; i < kMaxExtPerQuery - 1; ++i) split[gaps[i].second] = 1;
+        std::vector<Extent> merged;
+        for (size_t i = 0; i < out.size(); ++i) {
+            if (i == 0 || split[i]) merged.push_back(out[i]);
+            else merged.back().hi = out[i].hi;
+        }
+        out.swap(merged);
+    }
+}
+
+// Build the launch blob for nq queries with CSR scopes.  q may be null (device-resident queries).
+int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off,
+               bool shared_scope, PlanBlob &b) {
+    std::vector<ScanPlan> plans(shared_scope ? 1 : nq);
+    std::vector<uint32_t> lo, hi, tile0;
+    std::vector<Extent> ext;
+    b.max_tiles = 0;
+    {
+        std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+        for (size_t i = 0; i < plans.size(); ++i) {
+            const uint32_t s0 = seg_off[i], s1 = seg_off[i + 1];
+            if (s1 < s0 || s1 - s0 > RF_SCOPE_MAX) return fail(RF_EINVAL, "scope of query %zu has %u segments (max %u)", i, s1 - s0, RF_SCOPE_MAX);
+            ScanPlan &p = plans[i];
+            memset(&p, 0, sizeof p);
+            p.n_scope = s1 - s0;
+            for (uint32_t j = 0; j < RF_SCOPE_MAX; ++j) p.scope[j] = j < p.n_scope ? store_segs[s0 + j] : RF_TOMBSTONE;
+            gather_extents(e, store_segs + s0, p.n_scope, ext);
+            p.ext_off = static_cast<uint32_t>(lo.size());
+            p.n_ext = static_cast<uint32_t>(ext.size());
+            uint32_t tiles = 0;
+            for (const Extent &x : ext) {
+                lo.push_back(x.lo);
+                hi.push_back(x.hi);
+                tile0.push_back(tiles);
+                tiles += (x.hi - x.lo + rf::kScanTileRows - 1) / rf::kScanTileRows;
+            }
+            tile0.push_back(tiles);
+            p.total_tiles = tiles;
+            b.max_tiles = std::max(b.max_tiles, tiles);
+        }
+    }
+    if (lo.empty()) { lo.push_back(0); hi.push_back(0); }
+    auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
+    b.off_q = 0;
+    b.off_plans = align(q ? static_cast<size_t>(nq) * RF_DIM : 0);
+    b.off_lo = align(b.off_plans + plans.size() * sizeof(ScanPlan));
+    b.off_hi = align(b.off_lo + lo.size() * 4);
+    b.off_tile0 = align(b.off_hi + hi.size() * 4);
+    const size_t total = align(b.off_tile0 + tile0.size() * 4);
+    b.bytes.assign(total, 0);
+    if (q) memcpy(b.bytes.data() + b.off_q, q, static_cast<size_t>(nq) * RF_DIM);
+    memcpy(b.bytes.data() + b.off_plans, plans.data(), plans.size() * sizeof(ScanPlan));
+    memcpy(b.bytes.data() + b.off_lo, lo.data(), lo.size() * 4);
+    memcpy(b.bytes.data() + b.off_hi, hi.data(), hi.size() * 4);
+    memcpy(b.bytes.data() + b.off_tile0, tile0.data(), tile0.size() * 4);
+    return RF_OK;
+}
+
+uint32_t pick_blocks(rf_engine *e, uint32_t nq, uint32_t max_tiles) {
+    if (e->blocks_override) return std::max(1u, std::min(e->blocks_override, std::max(max_tiles, 1u)));
+    const uint32_t wave = rf::scan_default_blocks_per_query(e->sm_count);
+    uint32_t x = (max_tiles + kTilesPerBlockTarget - 1) / kTilesPerBlockTarget;
+    const uint32_t fill = (wave + nq - 1) / nq;  // at least one full wave over all queries
+    x = std::max(x, fill);
+    if (nq == 1) x = wave;                       // single query: exactly one resident wave
+    x = std::min(x, std::max(max_tiles, 1u));
+    return std::max(x, 1u);
+}
+
+SearchCtx *ctx_acquire(rf_engine *e) {
+    std::unique_lock<std::mutex> lk(e->ctx_mu);
+    if (!e->ctx_cv.wait_for(lk, std::chrono::seconds(5), [&] { return !e->free_ctx.empty(); })) return nullptr;
+    SearchCtx *c = e->free_ctx.back();
+    e->free_ctx.pop_back();
+    return c;
+}
+void ctx_release(rf_engine *e, SearchCtx *c) {
+    {
+        std::lock_guard<std::mutex> lk(e->ctx_mu);
+        e->free_ctx.push_back(c);
+    }
+    e->ctx_cv.notify_one();
+}
+struct CtxGuard {
+    rf_engine *e;
+    SearchCtx *c;
+    ~CtxGuard() { if (c) ctx_release(e, c); }
+};
+
+void fill_args(rf_engine *e, ScanArgs &a, const uint8_t *d_blob, const PlanBlob &b, const int8_t *q_dev, uint32_t k,
+               bool shared) {
+    a.F = e->F;
+    a.seg = e->seg;
+    a.ff = e->ff;
+    a.q = q_dev ? q_dev : reinterpret_cast<const int8_t *>(d_blob + b.off_q);
+    a.plans = reinterpret_cast<const ScanPlan *>(d_blob + b.off_plans);
+    a.ext_lo = reinterpret_cast<const uint32_t *>(d_blob + b.off_lo);
+    a.ext_hi = reinterpret_cast<const uint32_t *>(d_blob + b.off_hi);
+    a.ext_tile0 = reinterpret_cast<const uint32_t *>(d_blob + b.off_tile0);
+    a.id_base = static_cast<uint32_t>(e->cfg.id_base);
+    a.k = k;
+    a.shared_plan = shared ? 1u : 0u;
+}
+
+struct OutLayout {
+    size_t off_keys, off_ids, off_scores, off_cos, off_counts, total;
+    OutLayout(uint32_t nq, uint32_t k) {
+        const size_t n = static_cast<size_t>(nq) * k;
+        off_keys = 0;
+        off_ids = n * 8;
+        off_scores = off_ids + n * 8;
+        off_cos = off_scores + n * 4;
+        off_counts = off_cos + n * 4;
+        total = off_counts + static_cast<size_t>(nq) * 4;
+    }
+};
+
+// Enqueue blob upload + scan + result download on the context's stream, then wait.
+int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_dev, uint32_t nq, uint32_t k, bool shared,
+               uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
+    const OutLayout L(nq, k);
+    const uint32_t X = pick_blocks(e, nq, b.max_tiles);
+    RF_CUDA(c->h_in.reserve(b.bytes.size()));
+    RF_CUDA(c->d_in.reserve(b.bytes.size()));
+    RF_CUDA(c->h_out.reserve(L.total));
+    RF_CUDA(c->d_out.reserve(L.total));
+    RF_CUDA(c->d_partial.reserve(static_cast<size_t>(nq) * X * k * 8));
+    if (static_cast<size_t>(nq) * 4 > c->d_tickets.cap) {
+        RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * 4));
+        RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
+    }
+    memcpy(c->h_in.p, b.bytes.data(), b.bytes.size());
+    RF_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, b.bytes.size(), cudaMemcpyHostToDevice, c->stream));
+    ScanArgs a{};
+    fill_args(e, a, static_cast<const uint8_t *>(c->d_in.p), b, q_dev, k, shared);
+    uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
+    a.partial = static_cast<uint64_t *>(c->d_partial.p);
+    a.tickets = static_cast<uint32_t *>(c->d_tickets.p);
+    a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
+    a.out_ids = reinterpret_cast<uint64_t *>(d_out + L.off_ids);
+    a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
+    a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
+    a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, c->stream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    // keys are not needed on the host: copy ids..counts only
+    RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
+                            cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaStreamSynchronize(c->stream));
+    const uint8_t *h = static_cast<const uint8_t *>(c->h_out.p);
+    const size_t n = static_cast<size_t>(nq) * k;
+    memcpy(out_ids, h + L.off_ids, n * 8);
+    memcpy(out_scores, h + L.off_scores, n * 4);
+    if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
+    if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(nq) * 4);
+    e->searches.fetch_add(nq, std::memory_order_relaxed);
+    return RF_OK;
+}
+
+// Reserve the next `n` rows (caller holds ingest_mu).  Published later by publish_rows.
+int reserve_rows(rf_engine *e, uint64_t n, uint64_t *first) {
+    if (e->n_rows + n > e->cfg.capacity_rows)
+        return fail(RF_ECAPACITY, "arena full: %llu + %llu rows > capacity %llu", (unsigned long long)e->n_rows,
+                    (unsigned long long)n, (unsigned long long)e->cfg.capacity_rows);
+    *first = e->n_rows;
+    return RF_OK;
+}
+
+void publish_rows(rf_engine *e, uint32_t store_seg, uint64_t doc_id, bool track_doc, uint64_t first, uint64_t n) {
+    std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+    extents_append(e->stores[store_seg].ext, static_cast<uint32_t>(first), static_cast<uint32_t>(first + n));
+    if (track_doc) {
+        Doc &d = e->docs[doc_id];
+        d.store = store_seg;
+        extents_append(d.ext, static_cast<uint32_t>(first), static_cast<uint32_t>(first + n));
+    }
+    e->n_rows = first + n;
+    e->epoch.fetch_add(1);
+}
+
+int check_store(rf_engine *e, uint32_t seg) {
+    std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+    if (seg >= e->stores.size() || e->stores[seg].dropped) return fail(RF_ENOTFOUND, "unknown store segment %u", seg);
+    return RF_OK;
+}
+
+uint32_t fnv1a32(const char *s, size_t n) {
+    uint32_t h = 0x811C9DC5u;
+    for (size_t i = 0; i < n; ++i) { h ^= static_cast<uint8_t>(s[i]); h *= 0x01000193u; }
+    return h;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rf_strerror(int code) {
+    switch (code) {
+        case RF_OK: return "ok";
+        case RF_EINVAL: return "invalid argument";
+        case RF_ENOMEM: return "out of memory";
+        case RF_ECUDA: return "CUDA error";
+        case RF_ENODEVICE: return "no sm_100 CUDA device";
+        case RF_ENOTFOUND: return "not found";
+        case RF_EBUSY: return "busy: no search context became free";
+        case RF_ECAPACITY: return "arena capacity exceeded";
+        default: return "unknown error";
+    }
+}
+
+const char *rf_last_error(void) { return g_err; }
+
+int rf_build_info(char *buf, size_t n) {
+    if (!buf || !n) return RF_EINVAL;
+    snprintf(buf, n, "librf_b200 sm_100a cuda-runtime %d dim %u topk_max %u scope_max %u", CUDART_VERSION, RF_DIM,
+             RF_TOPK_MAX, RF_SCOPE_MAX);
+    return RF_OK;
+}
+
+int rf_engine_create(const rf_config *cfg, rf_engine **out) {
+    if (!cfg || !out) return fail(RF_EINVAL, "null argument");
+    if (cfg->struct_size != sizeof(rf_config)) return fail(RF_EINVAL, "rf_config.struct_size %u != %zu", cfg->struct_size, sizeof(rf_config));
+    if (cfg->dim != RF_DIM) return fail(RF_EINVAL, "dim must be %u", RF_DIM);
+    if (cfg->capacity_rows == 0 || cfg->id_base + cfg->capacity_rows > 0xFFFFFFFEull)
+        return fail(RF_EINVAL, "id_base + capacity_rows must be in (0, 2^32 - 2]");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(RF_ENODEVICE, "no CUDA device visible");
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(RF_EINVAL, "device %d out of range (%d visible)", cfg->device, n_dev);
+    cudaDeviceProp prop{};
+    RF_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(RF_ENODEVICE, "device %d is sm_%d%d; this library holds sm_100a code only", cfg->device, prop.major, prop.minor);
+    RF_CUDA(cudaSetDevice(cfg->device));
+
+    rf_engine *e = new (std::nothrow) rf_engine();
+    if (!e) return fail(RF_ENOMEM, "host allocation failed");
+    e->cfg = *cfg;
+    if (e->cfg.n_contexts == 0) e->cfg.n_contexts = 8;
+    e->sm_count = prop.multiProcessorCount;
+    if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
+
+    const uint64_t cap = cfg->capacity_rows;
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&e->F, cap * RF_DIM)) != cudaSuccess || (ce = cudaMalloc(&e->seg, cap * 4)) != cudaSuccess ||
+        (ce = cudaMalloc(&e->ff, cap * 4)) != cudaSuccess) {
+        const int rc = fail(RF_ENOMEM, "cudaMalloc of %llu rows failed: %s", (unsigned long long)cap, cudaGetErrorString(ce));
+        cudaGetLastError();
+        rf_engine_destroy(e);
+        return rc;
+    }
+    e->hbm_bytes = cap * (RF_DIM + 8);
+    // unwritten rows read as tombstones
+    if ((ce = cudaMemset(e->seg, 0xFF, cap * 4)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        const int rc = fail(RF_ECUDA, "engine init failed: %s", cudaGetErrorString(ce));
+        rf_engine_destroy(e);
+        return rc;
+    }
+    for (uint32_t i = 0; i < e->cfg.n_contexts; ++i) {
+        SearchCtx *c = new (std::nothrow) SearchCtx();
+        if (!c || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            rf_engine_destroy(e);
+            return fail(RF_ECUDA, "search context creation failed");
+        }
+        e->all_ctx.push_back(c);
+        e->free_ctx.push_back(c);
+    }
+    *out = e;
+    return RF_OK;
+}
+
+int rf_engine_destroy(rf_engine *e) {
+    if (!e) return RF_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (SearchCtx *c : e->all_ctx) {
+        if (c->stream) cudaStreamDestroy(c->stream);
+        c->h_in.release(); c->h_out.release();
+        c->d_in.release(); c->d_out.release(); c->d_partial.release(); c->d_tickets.release();
+        delete c;
+    }
+    for (auto &kv : e->dev_plans) {
+        kv.second->blob.release(); kv.second->partial.release(); kv.second->tickets.release();
+        delete kv.second;
+    }
+    if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
+    e->sc_text.release(); e->sc_counts.release(); e->sc_bucket.release(); e->sc_start.release();
+    e->sc_end.release(); e->sc_ntok.release(); e->sc_spans.release();
+    if (e->zipf_bucket) cudaFree(e->zipf_bucket);
+    if (e->F) cudaFree(e->F);
+    if (e->seg) cudaFree(e->seg);
+    if (e->ff) cudaFree(e->ff);
+    delete e;
+    return RF_OK;
+}
+
+int rf_engine_stats(rf_engine *e, rf_stats *out) {
+    if (!e || !out) return fail(RF_EINVAL, "null argument");
+    std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+    out->n_rows = e->n_rows;
+    out->capacity_rows = e->cfg.capacity_rows;
+    uint64_t live = 0;
+    for (const Store &s : e->stores) live += s.dropped ? 0 : 1;
+    out->n_stores = live;
+    out->n_docs = e->docs.size();
+    out->hbm_bytes = e->hbm_bytes;
+    out->searches = e->searches.load();
+    out->kernel_launches = e->launches.load();
+    return RF_OK;
+}
+
+int rf_store_open(rf_engine *e, const char *fs_name, uint32_t *store_seg) {
+    if (!e || !fs_name || !store_seg) return fail(RF_EINVAL, "null argument");
+    std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+    auto it = e->store_by_name.find(fs_name);
+    if (it != e->store_by_name.end()) { *store_seg = it->second; return RF_OK; }
+    if (e->stores.size() >= 0xFFFFFFFEull) return fail(RF_ENOMEM, "store segment space exhausted");
+    const uint32_t seg = static_cast<uint32_t>(e->stores.size());
+    e->stores.emplace_back();
+    e->stores.back().name = fs_name;
+    e->store_by_name.emplace(fs_name, seg);
+    *store_seg = seg;
+    return RF_OK;
+}
+
+int rf_store_lookup(rf_engine *e, const char *fs_name, uint32_t *store_seg) {
+    if (!e || !fs_name || !store_seg) return fail(RF_EINVAL, "null argument");
+    std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+    auto it = e->store_by_name.find(fs_name);
+    if (it == e->store_by_name.end()) return fail(RF_ENOTFOUND, "unknown store '%s'", fs_name);
+    *store_seg = it->second;
+    return RF_OK;
+}
+
+static int tombstone_extents(rf_engine *e, const std::vector<Extent> &ext) {
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    for (const Extent &x : ext)
+        RF_CUDA(cudaMemsetAsync(e->seg + x.lo, 0xFF, static_cast<size_t>(x.hi - x.lo) * 4, e->ingest_stream));
+    RF_CUDA(cudaStreamSynchronize(e->ingest_stream));
+    return RF_OK;
+}
+
+int rf_store_drop(rf_engine *e, uint32_t store_seg) {
+    if (!e) return fail(RF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    std::vector<Extent> ext;
+    {
+        std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+        if (store_seg >= e->stores.size() || e->stores[store_seg].dropped) return fail(RF_ENOTFOUND, "unknown store segment %u", store_seg);
+        Store &s = e->stores[store_seg];
+        ext.swap(s.ext);
+        s.dropped = true;
+        e->store_by_name.erase(s.name);
+        for (auto it = e->docs.begin(); it != e->docs.end();) it = (it->second.store == store_seg) ? e->docs.erase(it) : std::next(it);
+        e->epoch.fetch_add(1);
+    }
+    return tombstone_extents(e, ext);
+}
+
+int rf_doc_tombstone(rf_engine *e, uint64_t doc_id) {
+    if (!e) return fail(RF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    std::vector<Extent> ext;
+    {
+        std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+        auto it = e->docs.find(doc_id);
+        if (it == e->docs.end()) return fail(RF_ENOTFOUND, "unknown document %llu", (unsigned long long)doc_id);
+        ext.swap(it->second.ext);
+        e->docs.erase(it);
+    }
+    return tombstone_extents(e, ext);
+}
+
+int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint8_t *utf8, size_t n, uint64_t *first_chunk,
+                   uint32_t *n_chunks, int64_t *spans, uint32_t max_spans) {
+    if (!e || (!utf8 && n)) return fail(RF_EINVAL, "null argument");
+    if (n > 0xFFFFFFF0ull) return fail(RF_EINVAL, "document larger than 4 GiB");
+    int rc = check_store(e, store_seg);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->ingest_stream;
+    const uint32_t n_blocks = static_cast<uint32_t>((n + rf::kFeatBlockBytes - 1) / rf::kFeatBlockBytes);
+    const size_t max_tokens = n / 2 + 1;
+    RF_CUDA(e->sc_text.reserve(n + 64));
+    RF_CUDA(e->sc_counts.reserve((static_cast<size_t>(n_blocks) + 1) * 4));
+    RF_CUDA(e->sc_bucket.reserve(max_tokens));
+    RF_CUDA(e->sc_start.reserve(max_tokens * 4));
+    RF_CUDA(e->sc_end.reserve(max_tokens * 4));
+    RF_CUDA(e->sc_ntok.reserve(4));
+    rf::FeaturizeWork w{static_cast<uint8_t *>(e->sc_text.p), static_cast<uint32_t *>(e->sc_counts.p),
+                        static_cast<uint8_t *>(e->sc_bucket.p), static_cast<uint32_t *>(e->sc_start.p),
+                        static_cast<uint32_t *>(e->sc_end.p), static_cast<uint32_t *>(e->sc_ntok.p)};
+    if (n) RF_CUDA(cudaMemcpyAsync(w.text, utf8, n, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+    RF_CUDA(rf::launch_tokenize(w, n, s, &launches));
+    uint32_t n_tokens = 0;
+    RF_CUDA(cudaMemcpyAsync(&n_tokens, w.n_tokens, 4, cudaMemcpyDeviceToHost, s));
+    RF_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nc = n_tokens == 0 ? 0 : 1 + ((n_tokens > 128 ? n_tokens - 128 : 0) + 111) / 112;
+    uint64_t first = 0;
+    if ((rc = reserve_rows(e, nc, &first))) return rc;
+    if (nc) {
+        RF_CUDA(e->sc_spans.reserve(static_cast<size_t>(nc) * 16));
+        int64_t *d_spans = static_cast<int64_t *>(e->sc_spans.p);
+        RF_CUDA(rf::launch_rows_from_tokens(w, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, e->seg + first, store_seg,
+                                            d_spans, s));
+        ++launches;
+        const uint32_t ns = spans ? std::min(nc, max_spans) : 0;
+        if (ns) RF_CUDA(cudaMemcpyAsync(spans, d_spans, static_cast<size_t>(ns) * 16, cudaMemcpyDeviceToHost, s));
+        RF_CUDA(cudaStreamSynchronize(s));
+    }
+    e->launches.fetch_add(launches);
+    publish_rows(e, store_seg, doc_id, true, first, nc);
+    if (first_chunk) *first_chunk = e->cfg.id_base + first;
+    if (n_chunks) *n_chunks = nc;
+    return RF_OK;
+}
+
+int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const int8_t *rows, uint64_t n_rows,
+                       int rows_on_device, uint64_t *first_chunk) {
+    if (!e || (!rows && n_rows)) return fail(RF_EINVAL, "null argument");
+    int rc = check_store(e, store_seg);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    uint64_t first = 0;
+    if ((rc = reserve_rows(e, n_rows, &first))) return rc;
+    cudaStream_t s = e->ingest_stream;
+    if (n_rows) {
+        RF_CUDA(cudaMemcpyAsync(e->F + first * RF_DIM, rows, n_rows * RF_DIM,
+                                rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        RF_CUDA(rf::launch_row_meta(e->F + first * RF_DIM, n_rows, e->ff + first, e->seg + first, store_seg, s));
+        e->launches.fetch_add(1);
+        RF_CUDA(cudaStreamSynchronize(s));
+    }
+    publish_rows(e, store_seg, doc_id, true, first, n_rows);
+    if (first_chunk) *first_chunk = e->cfg.id_base + first;
+    return RF_OK;
+}
+
+int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_store, uint64_t seed, uint64_t start_counter,
+                        uint64_t n_rows, const uint16_t *zipf_vocab, uint64_t *first_chunk) {
+    if (!e || !zipf_vocab) return fail(RF_EINVAL, "null argument");
+    const uint64_t n_stores = rows_per_store ? (n_rows + rows_per_store - 1) / rows_per_store : 1;
+    {
+        std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+        if (first_seg + n_stores > e->stores.size()) return fail(RF_ENOTFOUND, "store segments %u..%llu are not all open", first_seg, (unsigned long long)(first_seg + n_stores - 1));
+    }
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->ingest_stream;
+    if (!e->zipf_bucket) {  // bucket of the decimal-ASCII token of each table entry (table prep, 64 KB)
+        std::vector<uint8_t> zb(65536);
+        char tmp[8];
+        for (int r = 0; r < 65536; ++r) {
+            const int len = snprintf(tmp, sizeof tmp, "%u", static_cast<unsigned>(zipf_vocab[r]));
+            zb[r] = static_cast<uint8_t>(fnv1a32(tmp, static_cast<size_t>(len)) & (RF_DIM - 1));
+        }
+        RF_CUDA(cudaMalloc(&e->zipf_bucket, 65536));
+        RF_CUDA(cudaMemcpy(e->zipf_bucket, zb.data(), 65536, cudaMemcpyHostToDevice));
+    }
+    uint64_t first = 0;
+    int rc = reserve_rows(e, n_rows, &first);
+    if (rc) return rc;
+    RF_CUDA(rf::launch_synth_rows(seed, start_counter, n_rows, e->zipf_bucket, e->F + first * RF_DIM, e->ff + first,
+                                  e->seg + first, first_seg, rows_per_store, s));
+    e->launches.fetch_add(1);
+    RF_CUDA(cudaStreamSynchronize(s));
+    {
+        std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+        for (uint64_t i = 0; i < n_stores; ++i) {
+            const uint64_t lo = first + i * (rows_per_store ? rows_per_store : n_rows);
+            const uint64_t hi = std::min(first + n_rows, lo + (rows_per_store ? rows_per_store : n_rows));
+            extents_append(e->stores[first_seg + i].ext, static_cast<uint32_t>(lo), static_cast<uint32_t>(hi));
+        }
+        e->n_rows = first + n_rows;
+        e->epoch.fetch_add(1);
+    }
+    if (first_chunk) *first_chunk = e->cfg.id_base + first;
+    return RF_OK;
+}
+
+int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uint32_t *store_seg, int32_t *ff) {
+    if (!e) return fail(RF_EINVAL, "null argument");
+    {
+        std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+        if (first_row + n > e->n_rows) return fail(RF_EINVAL, "rows %llu..%llu beyond n_rows %llu", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)e->n_rows);
+    }
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    if (rows) RF_CUDA(cudaMemcpy(rows, e->F + first_row * RF_DIM, n * RF_DIM, cudaMemcpyDeviceToHost));
+    if (store_seg) RF_CUDA(cudaMemcpy(store_seg, e->seg + first_row, n * 4, cudaMemcpyDeviceToHost));
+    if (ff) RF_CUDA(cudaMemcpy(ff, e->ff + first_row, n * 4, cudaMemcpyDeviceToHost));
+    return RF_OK;
+}
+
+int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off, uint32_t k,
+              uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
+    if (!e || !q || !seg_off || !out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+    if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
+    if (nq == 0) return RF_OK;
+    if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    PlanBlob b;
+    int rc = build_blob(e, q, nq, store_segs, seg_off, false, b);
+    if (rc) return rc;
+    SearchCtx *c = ctx_acquire(e);
+    if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
+    CtxGuard g{e, c};
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    return run_search(e, c, b, nullptr, nq, k, false, out_ids, out_scores, out_cos, out_counts);
+}
+
+int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_q) {
+    if (!e || (!utf8 && n) || !out_q) return fail(RF_EINVAL, "null argument");
+    if (n > (1u << 26)) return fail(RF_EINVAL, "query text too long");
+    SearchCtx *c = ctx_acquire(e);
+    if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
+    CtxGuard g{e, c};
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
+    RF_CUDA(c->h_in.reserve(n + RF_DIM));
+    RF_CUDA(c->d_in.reserve(text_pad + RF_DIM));
+    if (n) memcpy(c->h_in.p, utf8, n);
+    uint8_t *d_text = static_cast<uint8_t *>(c->d_in.p);
+    int8_t *d_q = reinterpret_cast<int8_t *>(d_text + text_pad);
+    if (n) RF_CUDA(cudaMemcpyAsync(d_text, c->h_in.p, n, cudaMemcpyHostToDevice, c->stream));
+    RF_CUDA(rf::launch_featurize_query(d_text, static_cast<uint32_t>(n), d_q, c->stream));
+    e->launches.fetch_add(1);
+    RF_CUDA(cudaMemcpyAsync(c->h_in.p, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out_q, c->h_in.p, RF_DIM);
+    return RF_OK;
+}
+
+int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs, uint32_t k,
+                   uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_count, int8_t *out_q) {
+    if (!e || (!utf8 && n) || !out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+    if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
+    if (n > (1u << 26)) return fail(RF_EINVAL, "query text too long");
+    const uint32_t seg_off[2] = {0, n_segs};
+    PlanBlob b;
+    int rc = build_blob(e, nullptr, 1, store_segs, seg_off, false, b);
+    if (rc) return rc;
+    SearchCtx *c = ctx_acquire(e);
+    if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
+    CtxGuard g{e, c};
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    // blob, query text and the query vector share the context's input buffer: one H2D copy
+    const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
+    const size_t blob_pad = (b.bytes.size() + 255) & ~static_cast<size_t>(255);
+    const size_t need = blob_pad + text_pad + RF_DIM;
+    RF_CUDA(c->h_in.reserve(need));
+    RF_CUDA(c->d_in.reserve(need));
+    uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
+    uint8_t *d = static_cast<uint8_t *>(c->d_in.p);
+    memcpy(h, b.bytes.data(), b.bytes.size());
+    if (n) memcpy(h + blob_pad, utf8, n);
+    RF_CUDA(cudaMemcpyAsync(d, h, blob_pad + n, cudaMemcpyHostToDevice, c->stream));
+    int8_t *d_q = reinterpret_cast<int8_t *>(d + blob_pad + text_pad);
+    RF_CUDA(rf::launch_featurize_query(d + blob_pad, static_cast<uint32_t>(n), d_q, c->stream));
+    e->launches.fetch_add(1);
+
+    const OutLayout L(1, k);
+    const uint32_t X = pick_blocks(e, 1, b.max_tiles);
+    RF_CUDA(c->h_out.reserve(L.total + RF_DIM));
+    RF_CUDA(c->d_out.reserve(L.total));
+    RF_CUDA(c->d_partial.reserve(static_cast<size_t>(X) * k * 8));
+    if (c->d_tickets.cap < 4) {
+        RF_CUDA(c->d_tickets.reserve(4));
+        RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
+    }
+    ScanArgs a{};
+    fill_args(e, a, d, b, d_q, k, false);
+    uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
+    a.partial = static_cast<uint64_t *>(c->d_partial.p);
+    a.tickets = static_cast<uint32_t *>(c->d_tickets.p);
+    a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
+    a.out_ids = reinterpret_cast<uint64_t *>(d_out + L.off_ids);
+    a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
+    a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
+    a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
+    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, c->stream));
+    e->launches.fetch_add(1);
+    uint8_t *ho = static_cast<uint8_t *>(c->h_out.p);
+    RF_CUDA(cudaMemcpyAsync(ho + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
+    if (out_q) RF_CUDA(cudaMemcpyAsync(ho + L.total, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out_ids, ho + L.off_ids, static_cast<size_t>(k) * 8);
+    memcpy(out_scores, ho + L.off_scores, static_cast<size_t>(k) * 4);
+    if (out_cos) memcpy(out_cos, ho + L.off_cos, static_cast<size_t>(k) * 4);
+    if (out_count) memcpy(out_count, ho + L.off_counts, 4);
+    if (out_q) memcpy(out_q, ho + L.total, RF_DIM);
+    e->searches.fetch_add(1);
+    return RF_OK;
+}
+
+int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
+                          uint32_t k, uint64_t *out_keys_dev, void *stream) {
+    if (!e || !q_dev || !out_keys_dev) return fail(RF_EINVAL, "null argument");
+    if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
+    if (nq == 0) return RF_OK;
+    if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    if (n_segs > RF_SCOPE_MAX) return fail(RF_EINVAL, "scope has %u segments (max %u)", n_segs, RF_SCOPE_MAX);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::vector<uint32_t> key(store_segs, store_segs + n_segs);
+    DevicePlan *dp = nullptr;
+    PlanBlob b;
+    {
+        std::lock_guard<std::mutex> lk(e->plan_mu);
+        DevicePlan *&slot = e->dev_plans[{key, stream}];
+        if (!slot) slot = new DevicePlan();
+        dp = slot;
+        const uint64_t now = e->epoch.load();
+        const uint32_t seg_off[2] = {0, n_segs};
+        int rc = build_blob(e, nullptr, 1, store_segs, seg_off, true, b);  // offsets are deterministic for a scope
+        if (rc) return rc;
+        if (dp->epoch != now) {
+            // synchronous (rare: only when the scope's extents changed since the last call)
+            RF_CUDA(cudaStreamSynchronize(s));
+            RF_CUDA(dp->blob.reserve(b.bytes.size()));
+            RF_CUDA(cudaMemcpy(dp->blob.p, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice));
+            dp->epoch = now;
+            dp->max_tiles = b.max_tiles;
+        }
+        const uint32_t X = pick_blocks(e, nq, dp->max_tiles);
+        const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
+        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * 4 > dp->tickets.cap) {
+            RF_CUDA(cudaStreamSynchronize(s));
+            RF_CUDA(dp->partial.reserve(need_partial));
+            if (static_cast<size_t>(nq) * 4 > dp->tickets.cap) {
+                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * 4));
+                RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
+            }
+        }
+        ScanArgs a{};
+        fill_args(e, a, static_cast<const uint8_t *>(dp->blob.p), b, q_dev, k, true);
+        a.partial = static_cast<uint64_t *>(dp->partial.p);
+        a.tickets = static_cast<uint32_t *>(dp->tickets.p);
+        a.out_keys = out_keys_dev;
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, s));
+    }
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    e->searches.fetch_add(nq, std::memory_order_relaxed);
+    return RF_OK;
+}
+
+int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k,
+                         uint64_t *out_keys_dev, void *stream) {
+    if (!e || !keys_dev || !out_keys_dev) return fail(RF_EINVAL, "null argument");
+    if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
+    if (nq == 0 || n_lists == 0) return RF_OK;
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    RF_CUDA(rf::launch_merge_topk(keys_dev, n_lists, nq, k, out_keys_dev, static_cast<cudaStream_t>(stream)));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    return RF_OK;
+}
+
+}  // extern "C"

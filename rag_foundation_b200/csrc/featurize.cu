@@ -1,0 +1,296 @@
+// Ingest-side chunk featurisation on the GPU (sm_100a): RF-1 steps 1-5 (oracle/SPEC.md).
+//
+// Replaces the work GeminiRag.upload_file hands to the remote service (reference
+// backend/app/services/gemini_rag.py:307-352; the mock, :614-629, reads nothing), reached from the
+// ARQ worker at backend/app/services/ingestion.py:45-52.  The tokeniser rule restates
+// scripts/benchmark/metrics.py:6,13-19 at byte level.
+//
+// Byte/integer work, bound by the H2D copy of the text (PCIe) and then HBM:
+//   pass A  count kept-token starts per 4 KB block          (reads text once)
+//   pass B  exclusive scan of the block counts               (one block, <= 6400 entries for 25 MB)
+//   pass C  recompute flags, in-block scan, hash each kept token (FNV-1a 32) and emit
+//           (bucket, byte start, byte end) at its global token ordinal
+//   rows    one warp per chunk window [112 w, 112 w + 128): shared-memory histogram of the
+//           window's buckets -> one 256-byte int8 row, its sum of squares, store word, byte span
+// A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
+// look-ahead, so stop-word removal needs no second compaction.
+#include "rf_device.cuh"
+#include "rf_internal.h"
+
+namespace rf {
+
+namespace {
+
+constexpr int kFeatThreads = 256;
+constexpr int kBytesPerThread = kFeatBlockBytes / kFeatThreads;  // 16
+constexpr int kChunkTokens = 128;
+constexpr int kChunkStride = 112;
+
+__device__ __forceinline__ uint8_t lower_byte(uint8_t b) { return (b >= 'A' && b <= 'Z') ? b + 32 : b; }
+__device__ __forceinline__ bool token_byte(uint8_t lowered) {
+    return (lowered >= 'a' && lowered <= 'z') || (lowered >= '0' && lowered <= '9');
+}
+
+// s points at lowered bytes with s[-1] .. s[+3] readable.  True when a kept token starts at s[0].
+__device__ __forceinline__ bool kept_start(const uint8_t *s) {
+    const uint8_t c0 = s[0];
+    if (!token_byte(c0) || token_byte(s[-1])) return false;
+    const uint8_t c1 = s[1], c2 = s[2], c3 = s[3];
+    const bool t1 = token_byte(c1), t2 = token_byte(c2), t3 = token_byte(c3);
+    const bool stop = (c0 == 'a' && !t1) || (c0 == 'a' && c1 == 'n' && !t2) ||
+                      (c0 == 't' && c1 == 'h' && c2 == 'e' && !t3);
+    return !stop;
+}
+
+// Stage one 4 KB block of lowered text (+1 byte before, +4 after; zero = separator outside).
+__device__ __forceinline__ void stage_block(const uint8_t *__restrict__ text, size_t n, size_t base, uint8_t *s_txt) {
+    for (int i = threadIdx.x; i < static_cast<int>(kFeatBlockBytes) + 5; i += kFeatThreads) {
+        const long long g = static_cast<long long>(base) + i - 1;
+        const uint8_t b = (g >= 0 && static_cast<size_t>(g) < n) ? text[g] : 0;
+        s_txt[i] = lower_byte(b);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_txt) {
+    const uint8_t *s = s_txt + 1 + threadIdx.x * kBytesPerThread;
+    uint32_t flags = 0;
+#pragma unroll
+    for (int j = 0; j < kBytesPerThread; ++j) flags |= (kept_start(s + j) ? 1u : 0u) << j;
+    return flags;
+}
+
+__global__ void __launch_bounds__(kFeatThreads) count_tokens_kernel(const uint8_t *__restrict__ text, size_t n,
+                                                                    uint32_t *__restrict__ block_counts) {
+    __shared__ uint8_t s_txt[kFeatBlockBytes + 8];
+    __shared__ uint32_t s_warp[kFeatThreads / 32];
+    stage_block(text, n, static_cast<size_t>(blockIdx.x) * kFeatBlockBytes, s_txt);
+    uint32_t c = __popc(thread_flags(s_txt));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kFeatThreads / 32; ++w) t += s_warp[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// In-place exclusive scan of counts[0..n), total to counts[n] and *n_tokens.  One block.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t *__restrict__ counts, uint32_t n,
+                                                           uint32_t *__restrict__ n_tokens) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? counts[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t warp_off = warp ? s_warp[warp - 1] : 0;
+        const uint32_t carry = s_carry;
+        if (i < n) counts[i] = carry + warp_off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counts[n] = s_carry;
+        *n_tokens = s_carry;
+    }
+}
+
+__global__ void __launch_bounds__(kFeatThreads) emit_tokens_kernel(const uint8_t *__restrict__ text, size_t n,
+                                                                   const uint32_t *__restrict__ block_off,
+                                                                   uint8_t *__restrict__ tok_bucket,
+                                                                   uint32_t *__restrict__ tok_start,
+                                                                   uint32_t *__restrict__ tok_end) {
+    __shared__ uint8_t s_txt[kFeatBlockBytes + 8];
+    __shared__ uint32_t s_warp[kFeatThreads / 32];
+    const size_t base = static_cast<size_t>(blockIdx.x) * kFeatBlockBytes;
+    stage_block(text, n, base, s_txt);
+    const uint32_t flags = thread_flags(s_txt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = __popc(flags);
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += s_warp[w];
+    uint32_t ord = block_off[blockIdx.x] + warp_off + inc - c;
+
+    uint32_t f = flags;
+    while (f) {
+        const int j = __ffs(f) - 1;
+        f &= f - 1;
+        const size_t start = base + static_cast<size_t>(threadIdx.x) * kBytesPerThread + j;
+        uint32_t h = 0x811C9DC5u;
+        size_t p = start;
+        // tokens are short; bytes past this block come from L2 (the block just streamed them in)
+        while (p < n) {
+            const uint8_t cb = (p - base) < static_cast<size_t>(kFeatBlockBytes) + 4 ? s_txt[p - base + 1]
+                                                                                    : lower_byte(text[p]);
+            if (!token_byte(cb)) break;
+            h ^= cb;
+            h *= 0x01000193u;
+            ++p;
+        }
+        tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
+        tok_start[ord] = static_cast<uint32_t>(start);
+        tok_end[ord] = static_cast<uint32_t>(p);
+        ++ord;
+    }
+}
+
+constexpr int kRowWarps = 8;
+
+__global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
+    const uint8_t *__restrict__ tok_bucket, const uint32_t *__restrict__ tok_start,
+    const uint32_t *__restrict__ tok_end, uint32_t n_tokens, uint32_t n_chunks, int8_t *__restrict__ F,
+    int32_t *__restrict__ ff, uint32_t *__restrict__ seg, uint32_t store_seg, int64_t *__restrict__ spans) {
+    __shared__ uint32_t hist[kRowWarps][kDim];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *h = hist[warp];
+    for (uint32_t w = blockIdx.x * kRowWarps + warp; w < n_chunks; w += gridDim.x * kRowWarps) {
+#pragma unroll
+        for (int j = 0; j < kDim / 32; ++j) h[lane + 32 * j] = 0;
+        __syncwarp();
+        const uint32_t lo = w * kChunkStride;
+        const uint32_t hi = min(lo + kChunkTokens, n_tokens);
+        for (uint32_t t = lo + lane; t < hi; t += 32) atomicAdd(&h[tok_bucket[t]], 1u);
+        __syncwarp();
+        uint32_t packed[2];
+        int sq = 0;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t t = min(h[lane * 8 + x * 4 + b], 127u);
+                v |= t << (8 * b);
+                sq += static_cast<int>(t * t);
+            }
+            packed[x] = v;
+        }
+        *reinterpret_cast<uint2 *>(F + static_cast<size_t>(w) * kRowBytes + lane * 8) = make_uint2(packed[0], packed[1]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
+        if (lane == 0) {
+            ff[w] = sq;
+            seg[w] = store_seg;
+            if (spans) {
+                spans[2 * static_cast<size_t>(w)] = tok_start[lo];
+                spans[2 * static_cast<size_t>(w) + 1] = tok_end[hi - 1];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Query featurisation (RF-1 step 5): no chunking, so no token ordinals are needed -- one block
+// histograms every kept token of the (<= 32 KB, routes/chat.py:48) query text.
+__global__ void __launch_bounds__(256) featurize_query_kernel(const uint8_t *__restrict__ text, uint32_t n,
+                                                              int8_t *__restrict__ q_out) {
+    __shared__ uint32_t hist[kDim];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    auto at = [&](long long i) -> uint8_t { return (i >= 0 && i < static_cast<long long>(n)) ? lower_byte(text[i]) : 0; };
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint8_t w[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) w[j] = at(static_cast<long long>(i) + j - 1);
+        if (!kept_start(w + 1)) continue;
+        uint32_t h = 0x811C9DC5u;
+        for (uint32_t p = i; p < n; ++p) {
+            const uint8_t cb = lower_byte(text[p]);
+            if (!token_byte(cb)) break;
+            h ^= cb;
+            h *= 0x01000193u;
+        }
+        atomicAdd(&hist[h & (kDim - 1)], 1u);
+    }
+    __syncthreads();
+    q_out[threadIdx.x] = static_cast<int8_t>(min(hist[threadIdx.x], 127u));
+}
+
+__global__ void __launch_bounds__(256) row_meta_kernel(const int8_t *__restrict__ F, uint64_t n_rows,
+                                                       int32_t *__restrict__ ff, uint32_t *__restrict__ seg,
+                                                       uint32_t store_seg) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
+    for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
+         r += warps_total) {
+        const int2 v = *reinterpret_cast<const int2 *>(F + r * kRowBytes + lane * 8);
+        int sq = __dp4a(v.x, v.x, 0);
+        sq = __dp4a(v.y, v.y, sq);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
+        if (lane == 0) {
+            ff[r] = sq;
+            seg[r] = store_seg;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
+                            cudaStream_t s) {
+    if (n_rows == 0) return cudaSuccess;
+    uint64_t blocks = (n_rows + 7) / 8;
+    if (blocks > 148ull * 8ull) blocks = 148ull * 8ull;
+    row_meta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(F, n_rows, ff, seg, store_seg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tokenize(const FeaturizeWork &w, size_t n_bytes, cudaStream_t s, int *launches) {
+    const uint32_t n_blocks = static_cast<uint32_t>((n_bytes + kFeatBlockBytes - 1) / kFeatBlockBytes);
+    if (n_blocks) count_tokens_kernel<<<n_blocks, kFeatThreads, 0, s>>>(w.text, n_bytes, w.block_counts);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(w.block_counts, n_blocks, w.n_tokens);
+    if (n_blocks)
+        emit_tokens_kernel<<<n_blocks, kFeatThreads, 0, s>>>(w.text, n_bytes, w.block_counts, w.tok_bucket, w.tok_start,
+                                                          w.tok_end);
+    if (launches) *launches += n_blocks ? 3 : 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F, int32_t *ff,
+                                    uint32_t *seg, uint32_t store_seg, int64_t *spans_dev, cudaStream_t s) {
+    if (n_chunks == 0) return cudaSuccess;
+    uint32_t blocks = (n_chunks + kRowWarps - 1) / kRowWarps;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    rows_from_tokens_kernel<<<blocks, kRowWarps * 32, 0, s>>>(w.tok_bucket, w.tok_start, w.tok_end, n_tokens, n_chunks, F, ff,
+                                                             seg, store_seg, spans_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, int8_t *q_out, cudaStream_t s) {
+    featurize_query_kernel<<<1, 256, 0, s>>>(text_dev, n_bytes, q_out);
+    return cudaGetLastError();
+}
+
+}  // namespace rf

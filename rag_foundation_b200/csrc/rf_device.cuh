@@ -1,0 +1,76 @@
+// Device-side helpers shared by the RF-1 kernels (sm_100a).
+//
+// Key order (oracle/SPEC.md step 7): one unsigned 64-bit key per chunk,
+//   (uint64(score) << 32) | (0xFFFFFFFF - global_chunk_id),
+// so "score desc, chunk id asc" is a plain unsigned max and the selection is independent of how
+// rows are spread over lanes, warps, blocks or GPUs.  Key 0 means "no result".
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rf {
+
+constexpr int kDim = 256;          // int8 features per chunk row
+constexpr int kRowBytes = 256;
+constexpr int kTileRows = 32;      // rows one warp scores per step (8 KB)
+constexpr uint32_t kTombstone = 0xFFFFFFFFu;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint64_t pack_key(int32_t score, uint32_t gid) {
+    return (static_cast<uint64_t>(static_cast<uint32_t>(score)) << 32) |
+           static_cast<uint64_t>(0xFFFFFFFFu - gid);
+}
+__device__ __forceinline__ int32_t key_score(uint64_t key) { return static_cast<int32_t>(key >> 32); }
+__device__ __forceinline__ uint32_t key_gid(uint64_t key) {
+    return 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu);
+}
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (each feature byte is used once).
+__device__ __forceinline__ int4 ld_stream_v4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(kFull, static_cast<uint32_t>(v), src);
+    uint32_t hi = __shfl_sync(kFull, static_cast<uint32_t>(v >> 32), src);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int delta) {
+    uint32_t lo = __shfl_up_sync(kFull, static_cast<uint32_t>(v), delta);
+    uint32_t hi = __shfl_up_sync(kFull, static_cast<uint32_t>(v >> 32), delta);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// A warp keeps its running top-32 as one key per lane, sorted descending by lane index.  `thr` is
+// the key at lane k-1 (0 until k keys have been seen): only keys above it can enter the top-k.
+struct WarpTopK {
+    uint64_t mine;   // this lane's entry of the sorted list
+    uint64_t thr;    // warp-uniform admission threshold
+
+    __device__ __forceinline__ void reset() { mine = 0; thr = 0; }
+
+    // Every lane offers one key (0 = nothing).  Rare path: scanned data is mostly below thr.
+    __device__ __forceinline__ void consume(uint64_t key, int k, int lane) {
+        unsigned pending = __ballot_sync(kFull, key > thr);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            const uint64_t cand = shfl_u64(key, src);
+            pending &= pending - 1;
+            const unsigned dup = __ballot_sync(kFull, mine == cand);
+            if (cand > thr && dup == 0) {
+                const int pos = __popc(__ballot_sync(kFull, mine > cand));  // sorted => a lane prefix
+                const uint64_t up = shfl_up_u64(mine, 1);
+                if (lane == pos) mine = cand;
+                else if (lane > pos) mine = up;
+                thr = shfl_u64(mine, k - 1);
+                pending &= __ballot_sync(kFull, key > thr);
+            }
+        }
+    }
+};
+
+}  // namespace rf

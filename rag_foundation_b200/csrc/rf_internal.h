@@ -1,0 +1,74 @@
+// Host-visible declarations shared between the engine (engine.cu) and the kernel translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/rf_b200.h"
+
+namespace rf {
+
+constexpr uint32_t kScanTileRows = 32;  // rows per warp step of the scan kernel (== rf::kTileRows)
+
+// One query's scan plan (device memory).  The rows to scan are the union of `n_ext` extents
+// [ext_lo, ext_hi); extents are a SUPERSET hint of the scoped stores' rows -- the per-row store
+// segment word is always checked against `scope`, so correctness never depends on the extents.
+struct ScanPlan {
+    uint32_t ext_off;      // first extent of this query in the flat extent arrays
+    uint32_t n_ext;
+    uint32_t total_tiles;  // sum over extents of ceil(rows / 32)
+    uint32_t n_scope;
+    uint32_t scope[RF_SCOPE_MAX];
+};
+
+struct ScanArgs {
+    const int8_t *F;            // [rows, 256] int8, row-major, 256-byte rows
+    const uint32_t *seg;        // [rows] store segment word (0xFFFFFFFF = tombstone)
+    const int32_t *ff;          // [rows] sum of squares (read for the k winners only); may be null
+    const int8_t *q;            // [nq, 256] query vectors (device)
+    const ScanPlan *plans;      // [nq]
+    const uint32_t *ext_lo;     // flat extents
+    const uint32_t *ext_hi;
+    const uint32_t *ext_tile0;  // exclusive prefix of tile counts within the query, n_ext + 1 entries per query (offset ext_off + qi)
+    uint64_t *partial;          // [nq, gridDim.x, k] per-block top-k keys
+    uint32_t *tickets;          // [nq] zero-initialised; reset to zero by the finishing block
+    uint64_t *out_keys;         // [nq, k]
+    uint64_t *out_ids;          // [nq, k] or null
+    int32_t *out_scores;        // [nq, k] or null
+    float *out_cos;             // [nq, k] or null
+    uint32_t *out_counts;       // [nq] or null
+    uint32_t id_base;           // global id of row 0
+    uint32_t k;
+    uint32_t shared_plan;       // 1: every query uses plans[0] (one scope for the whole batch)
+};
+
+// launchers (each returns the cudaError_t of the launch)
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, cudaStream_t s);
+cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,
+                              uint64_t *out_keys, cudaStream_t s);
+uint32_t scan_default_blocks_per_query(int sm_count);
+
+cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint8_t *zipf_bucket_dev,
+                              int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,
+                              cudaStream_t s);
+
+// featurisation (featurize.cu)
+struct FeaturizeWork {       // device scratch for one document
+    uint8_t *text;           // [cap_bytes + 64] padded copy of the document
+    uint32_t *block_counts;  // [n_blocks + 1]
+    uint8_t *tok_bucket;     // [cap_tokens]
+    uint32_t *tok_start;     // [cap_tokens]
+    uint32_t *tok_end;       // [cap_tokens]
+    uint32_t *n_tokens;      // [1]
+};
+constexpr uint32_t kFeatBlockBytes = 4096;
+cudaError_t launch_tokenize(const FeaturizeWork &w, size_t n_bytes, cudaStream_t s, int *launches);
+cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
+                                    int32_t *ff, uint32_t *seg, uint32_t store_seg, int64_t *spans_dev,
+                                    cudaStream_t s);
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, int8_t *q_out, cudaStream_t s);
+// ff[r] = sum of squares of row r, seg[r] = store_seg, for rows appended as raw features
+cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
+                            cudaStream_t s);
+
+}  // namespace rf

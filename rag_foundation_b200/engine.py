@@ -1,0 +1,208 @@
+"""Python host wrapper over the C-ABI engine (include/rf_b200.h).
+
+numpy in / numpy out for host buffers, raw device pointers + stream handles for the device-resident
+entry points (PyTorch supplies those: `tensor.data_ptr()`, `torch.cuda.current_stream().cuda_stream`).
+All compute happens in librf_b200.so's sm_100a kernels; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import RF_DIM, RF_SCOPE_MAX, RF_TOPK_MAX, check, lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ZIPF_VOCAB_PATH = os.path.join(_HERE, "data", "zipf_vocab_u16.bin")
+NO_ID = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def load_zipf_vocab() -> np.ndarray:
+    t = np.fromfile(ZIPF_VOCAB_PATH, dtype="<u2")
+    if t.shape != (65536,):
+        raise RuntimeError("zipf_vocab_u16.bin is corrupt")
+    return np.ascontiguousarray(t)
+
+
+def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+def scopes_to_csr(scopes: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    off = np.zeros(len(scopes) + 1, np.uint32)
+    flat: List[int] = []
+    for i, s in enumerate(scopes):
+        s = list(s)
+        if len(s) > RF_SCOPE_MAX:
+            raise ValueError(f"scope of query {i} has {len(s)} store segments (max {RF_SCOPE_MAX})")
+        flat.extend(int(x) for x in s)
+        off[i + 1] = len(flat)
+    segs = np.asarray(flat if flat else [0], dtype=np.uint32)
+    return segs, off
+
+
+class Engine:
+    """One GPU's share of the chunk index (feature arena in HBM + store extents)."""
+
+    def __init__(self, capacity_rows: int, device: int = 0, id_base: int = 0, n_contexts: int = 8):
+        self._L = lib()
+        cfg = _capi.rf_config(C.sizeof(_capi.rf_config), int(device), RF_DIM, int(n_contexts), int(capacity_rows),
+                              int(id_base))
+        h = C.c_void_p()
+        check(self._L.rf_engine_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.id_base = int(id_base)
+        self.capacity_rows = int(capacity_rows)
+        self._zipf = None
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.rf_engine_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise RuntimeError("engine is closed")
+        return self._h
+
+    def stats(self) -> dict:
+        st = _capi.rf_stats()
+        check(self._L.rf_engine_stats(self.handle, C.byref(st)))
+        return {f: int(getattr(st, f)) for f, _ in st._fields_}
+
+    # ------------------------------------------------------------------ stores
+    def open_store(self, fs_name: str) -> int:
+        seg = C.c_uint32()
+        check(self._L.rf_store_open(self.handle, fs_name.encode("utf-8"), C.byref(seg)))
+        return int(seg.value)
+
+    def lookup_store(self, fs_name: str) -> Optional[int]:
+        seg = C.c_uint32()
+        rc = self._L.rf_store_lookup(self.handle, fs_name.encode("utf-8"), C.byref(seg))
+        if rc == _capi.RF_ENOTFOUND:
+            return None
+        check(rc)
+        return int(seg.value)
+
+    def drop_store(self, seg: int) -> None:
+        check(self._L.rf_store_drop(self.handle, int(seg)))
+
+    # ------------------------------------------------------------------ ingest
+    def ingest_text(self, seg: int, doc_id: int, data: bytes, want_spans: bool = True):
+        """-> (first_chunk_id, n_chunks, spans int64 [n_chunks, 2])."""
+        data = bytes(data)
+        first = C.c_uint64()
+        nch = C.c_uint32()
+        # a kept token needs >= 1 byte + 1 separator; a chunk past the first needs 112 new tokens
+        max_spans = (len(data) // 2 + 1 + 111) // 112 + 1 if want_spans else 0
+        spans = np.zeros((max(max_spans, 1), 2), np.int64)
+        buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        check(self._L.rf_ingest_text(self.handle, int(seg), int(doc_id), C.addressof(buf), len(data), C.byref(first),
+                                     C.byref(nch), _ptr(spans) if want_spans else None, max_spans))
+        n = int(nch.value)
+        return int(first.value), n, spans[:n].copy()
+
+    def ingest_features(self, seg: int, doc_id: int, rows, n_rows: Optional[int] = None, on_device: bool = False) -> int:
+        first = C.c_uint64()
+        if on_device:
+            check(self._L.rf_ingest_features(self.handle, int(seg), int(doc_id), int(rows), int(n_rows), 1, C.byref(first)))
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, RF_DIM)
+            check(self._L.rf_ingest_features(self.handle, int(seg), int(doc_id), _ptr(rows), rows.shape[0], 0,
+                                             C.byref(first)))
+        return int(first.value)
+
+    def ingest_synthetic(self, first_seg: int, rows_per_store: int, seed: int, start_counter: int, n_rows: int) -> int:
+        if self._zipf is None:
+            self._zipf = load_zipf_vocab()
+        first = C.c_uint64()
+        check(self._L.rf_ingest_synthetic(self.handle, int(first_seg), int(rows_per_store), int(seed), int(start_counter),
+                                          int(n_rows), _ptr(self._zipf), C.byref(first)))
+        return int(first.value)
+
+    def tombstone_doc(self, doc_id: int) -> None:
+        check(self._L.rf_doc_tombstone(self.handle, int(doc_id)))
+
+    def read_rows(self, first_row: int, n: int):
+        F = np.zeros((n, RF_DIM), np.int8)
+        seg = np.zeros(n, np.uint32)
+        ff = np.zeros(n, np.int32)
+        check(self._L.rf_rows_read(self.handle, int(first_row), int(n), _ptr(F), _ptr(seg), _ptr(ff)))
+        return F, seg, ff
+
+    # ------------------------------------------------------------------ query
+    def search(self, q, scopes: Sequence[Sequence[int]], k: int = 10):
+        """q int8 [nq, 256] (host). -> ids uint64 [nq,k], scores int32, cos float32, counts uint32."""
+        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, RF_DIM)
+        nq = q.shape[0]
+        if len(scopes) != nq:
+            raise ValueError("one scope per query")
+        segs, off = scopes_to_csr(scopes)
+        ids = np.zeros((nq, k), np.uint64)
+        sc = np.zeros((nq, k), np.int32)
+        cs = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        check(self._L.rf_search(self.handle, _ptr(q), nq, _ptr(segs), _ptr(off), int(k), _ptr(ids), _ptr(sc), _ptr(cs),
+                                _ptr(cnt)))
+        return ids, sc, cs, cnt
+
+    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10):
+        """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [256]   (m <= k results)."""
+        text = bytes(text)
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        ids = np.zeros(k, np.uint64)
+        sc = np.zeros(k, np.int32)
+        cs = np.zeros(k, np.float32)
+        cnt = C.c_uint32()
+        q = np.zeros(RF_DIM, np.int8)
+        buf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0")
+        check(self._L.rf_search_text(self.handle, C.addressof(buf), len(text), _ptr(segs), len(scope), int(k), _ptr(ids),
+                                     _ptr(sc), _ptr(cs), C.byref(cnt), _ptr(q)))
+        m = int(cnt.value)
+        return ids[:m], sc[:m], cs[:m], q
+
+    def featurize_query(self, text: bytes) -> np.ndarray:
+        text = bytes(text)
+        q = np.zeros(RF_DIM, np.int8)
+        buf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0")
+        check(self._L.rf_featurize_query(self.handle, C.addressof(buf), len(text), _ptr(q)))
+        return q
+
+    def search_keys_device(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int,
+                           stream: int = 0) -> None:
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        check(self._L.rf_search_keys_device(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k),
+                                            int(out_keys_ptr), int(stream) or None))
+
+    def merge_topk_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, out_keys_ptr: int, stream: int = 0) -> None:
+        check(self._L.rf_merge_topk_device(self.handle, int(keys_ptr), int(n_lists), int(nq), int(k), int(out_keys_ptr),
+                                           int(stream) or None))
+
+
+def unpack_keys(keys: np.ndarray):
+    """Packed RF-1 keys -> (ids uint64, scores int32, valid bool)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    valid = keys != 0
+    ids = np.where(valid, np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF)), NO_ID)
+    scores = (keys >> np.uint64(32)).astype(np.int64).astype(np.int32)
+    return ids, scores, valid

@@ -1,0 +1,80 @@
+"""Chunk-sharded search across the GPUs of one box (BASELINE.json configs[3]).
+
+Each rank (one process per GPU, torch.distributed) owns a contiguous range of global chunk ids in
+its own Engine (id_base = first id of the shard).  A search is: local fused score+top-k kernel ->
+ONE all-gather of the nq x k packed 64-bit keys (80 B per query per rank at k = 10) -> k-way merge
+kernel on every rank.  Because the packed key is a total order on (score desc, id asc), the merged
+result is bit-identical to a single-GPU scan of the whole corpus.
+
+The local search and the merge are injected callables so the same plumbing runs under gloo on CPU
+tensors in the test-suite (there the callables are test doubles); `for_engine` wires the real
+CUDA entry points.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of global chunk ids owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def unpack_keys_torch(keys: torch.Tensor):
+    """int64 tensor of packed RF-1 keys -> (ids int64, scores int32, valid bool)."""
+    valid = keys != 0
+    low = keys & 0xFFFFFFFF
+    ids = torch.where(valid, 0xFFFFFFFF - low, torch.full_like(keys, -1))
+    scores = (keys >> 32).to(torch.int32)   # scores < 2^31, so the arithmetic shift is exact
+    return ids, scores, valid
+
+
+class ShardedSearcher:
+    def __init__(self, local_search: Callable[[torch.Tensor, Sequence[int], int], torch.Tensor],
+                 merge: Callable[[torch.Tensor, int], torch.Tensor], group: Optional[dist.ProcessGroup] = None):
+        self.local_search = local_search
+        self.merge = merge
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._gather_buf: Optional[torch.Tensor] = None
+
+    @classmethod
+    def for_engine(cls, engine, group: Optional[dist.ProcessGroup] = None) -> "ShardedSearcher":
+        """Real path: CUDA kernels through the C-ABI on torch's current stream."""
+
+        def local_search(q: torch.Tensor, scope: Sequence[int], k: int) -> torch.Tensor:
+            assert q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
+            out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            engine.search_keys_device(q.data_ptr(), q.shape[0], scope, k, out.data_ptr(),
+                                      torch.cuda.current_stream(q.device).cuda_stream)
+            return out
+
+        def merge(gathered: torch.Tensor, k: int) -> torch.Tensor:
+            n_lists, nq, _ = gathered.shape
+            out = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+            engine.merge_topk_device(gathered.data_ptr(), n_lists, nq, k, out.data_ptr(),
+                                     torch.cuda.current_stream(gathered.device).cuda_stream)
+            return out
+
+        return cls(local_search, merge, group)
+
+    def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: int = 10) -> torch.Tensor:
+        """q int8 [nq, 256] (replicated on every rank) -> merged packed keys int64 [nq, k] on every rank."""
+        local = self.local_search(q, scope, k)
+        if self.world == 1:
+            return local
+        shape = (self.world, local.shape[0], k)
+        if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != local.device:
+            self._gather_buf = torch.empty(shape, dtype=torch.int64, device=local.device)
+        # rank-major concatenation along dim 0 (the form both NCCL and gloo accept)
+        dist.all_gather_into_tensor(self._gather_buf.view(shape[0] * shape[1], k), local.contiguous(), group=self.group)
+        return self.merge(self._gather_buf, k)
+
+    def search(self, q: torch.Tensor, scope: Sequence[int], k: int = 10):
+        return unpack_keys_torch(self.search_keys(q, scope, k))

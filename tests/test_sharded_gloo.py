@@ -1,0 +1,81 @@
+"""The chunk-sharded search plumbing (rag_foundation_b200/sharded.py) under world_size = 2 on the
+gloo backend: contiguous shards, one all-gather of packed keys, merge == single-index answer.
+The CUDA entry points are replaced by the oracle here (CPU container); the GPU suite runs the
+same class with the real kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rag_foundation_b200.sharded import ShardedSearcher, shard_range, unpack_keys_torch
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in [(0, 2), (1, 2), (7, 3), (100_000_000, 8), (10, 16)]:
+        prev = 0
+        for r in range(w):
+            lo, hi = shard_range(n, r, w)
+            assert lo == prev and hi >= lo
+            prev = hi
+        assert prev == n
+        sizes = [shard_range(n, r, w)[1] - shard_range(n, r, w)[0] for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_unpack_keys_torch():
+    keys = torch.tensor([[(26 << 32) | (0xFFFFFFFF - 755), 0]], dtype=torch.int64)
+    ids, sc, valid = unpack_keys_torch(keys)
+    assert ids.tolist() == [[755, -1]] and sc.tolist() == [[26, 0]] and valid.tolist() == [[True, False]]
+
+
+def _worker(rank, world, port, n_total, seed, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import c_oracle as co, rf1
+        zb = rf1.zipf_bucket_table()
+        lo, hi = shard_range(n_total, rank, world)
+        F = co.synth_rows(seed, lo, hi - lo, zb)
+        seg = np.zeros(hi - lo, np.uint32)
+
+        def local_search(q, scope, k):
+            keys = np.stack([co.score_topk_keys(F, seg, q[i].numpy(), scope, k=k, id_base=lo) for i in range(q.shape[0])])
+            return torch.from_numpy(keys.view(np.int64))
+
+        def merge(gathered, k):
+            g = gathered.numpy().view(np.uint64)
+            out = np.stack([co.merge_topk(g[:, i, :], k) for i in range(g.shape[1])])
+            return torch.from_numpy(out.view(np.int64))
+
+        s = ShardedSearcher(local_search, merge)
+        assert s.world == world and s.rank == rank
+        q = torch.from_numpy(np.stack([co.synth_query(seed, i, zb) for i in range(5)]))
+        keys = s.search_keys(q, [0], 10)
+        ids, sc, valid = unpack_keys_torch(keys)
+        np.save(os.path.join(out_dir, f"ids_{rank}.npy"), ids.numpy())
+        np.save(os.path.join(out_dir, f"sc_{rank}.npy"), sc.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_search_equals_single_index(tmp_path):
+    from oracle import c_oracle as co, rf1
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    n_total, seed, world = 30_001, 2, 2
+    mp.spawn(_worker, args=(world, port, n_total, seed, str(tmp_path)), nprocs=world, join=True)
+    zb = rf1.zipf_bucket_table()
+    F = co.synth_rows(seed, 0, n_total, zb)
+    seg = np.zeros(n_total, np.uint32)
+    for r in range(world):
+        ids = np.load(tmp_path / f"ids_{r}.npy")
+        sc = np.load(tmp_path / f"sc_{r}.npy")
+        for i in range(5):
+            w_ids, w_sc, _ = co.score_topk(F, seg, co.synth_query(seed, i, zb), [0])
+            assert ids[i].tolist() == w_ids.tolist() and sc[i].tolist() == w_sc.tolist()
