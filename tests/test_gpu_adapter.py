@@ -1,0 +1,65 @@
+"""BASELINE.json configs[0] through the real engine: ingest docs/demo/sample-report.md (text embedded
+in tests/golden/rf1_golden.json) + the README demo query, citations through the B200Rag adapter;
+wire shapes against the reference's MockGeminiRag golden, ranking against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_demo_flow(tmp_path, golden_dir):
+    from oracle import c_oracle as co
+    from rag_foundation_b200 import Engine
+    from rag_foundation_b200 import adapter as ad
+
+    wire = json.load(open(os.path.join(golden_dir, "config1_wire.json")))
+    g = json.load(open(os.path.join(golden_dir, "rf1_golden.json")))
+    reg = ad.Registry(Engine(capacity_rows=4096))
+    try:
+        rag = ad.B200Rag(registry=reg)
+        store = rag.create_store("demo")
+        other = rag.create_store("someone-else")
+        p = tmp_path / "sample-report.md"
+        p.write_bytes(g["sample_report"]["text"].encode("utf-8"))
+        long_p = tmp_path / "long.txt"
+        long_p.write_bytes(g["long_doc"]["text"].encode("utf-8"))
+        up = rag.upload_file(store, str(p), display_name="sample-report.md")
+        rag.upload_file(store, str(long_p), display_name="long.txt")
+        rag.upload_file(other, str(p), display_name="not-yours.md")          # another tenant's copy
+        assert rag.op_status(up.operation_name) == {"name": up.operation_name, "done": True,
+                                                    "metadata": {"n_chunks": 1, "file_id": up.file_id}, "error": None}
+        contents = [{"role": "user", "parts": [{"text": wire["demo_query"]}]}]
+        chunks = list(rag.ask_stream(contents=contents, store_names=[store], metadata_filter=None,
+                                     model="gemini-2.5-flash", system=None))
+        assert len(chunks) == wire["n_stream_chunks"] and chunks[0].candidates is None and chunks[1].text is None
+        cits = rag.extract_citations_from_response(chunks[1])
+        assert sorted(cits[0]) == wire["citation_keys"]
+        assert all(c["store"] == store for c in cits)                         # tenant mask held
+        assert [c["index"] for c in cits] == list(range(len(cits)))
+
+        # ranking == oracle over the same rows
+        n_rows = 1 + g["long_doc"]["n_chunks"] + 1
+        F, seg, ff = reg.engine.read_rows(0, n_rows)
+        q = co.query_vector(wire["demo_query"].encode())
+        w_ids, w_sc, _ = co.score_topk(F, seg, q, [reg.engine.lookup_store(store)], ff=ff)
+        got = [int(c["uri"].rsplit("#", 1)[1]) for c in cits]
+        assert got == w_ids.tolist()
+        assert cits[0]["title"] == "sample-report.md" and cits[0]["snippet"].startswith("Demo Source Document")
+        assert chunks[0].text.startswith("[b200-retrieval] Demo Source Document")
+
+        # delete the demo document: its chunk disappears from the answer
+        rag.delete_document_from_store(store, 1, file_id=up.file_id)
+        cits2 = rag.extract_citations_from_response(rag.ask(contents=contents, store_names=[store],
+                                                            metadata_filter=None, model="m"))
+        assert all(c["title"] == "long.txt" for c in cits2)
+        # the other tenant still sees theirs
+        cits3 = rag.extract_citations_from_response(rag.ask(contents=contents, store_names=[other],
+                                                            metadata_filter=None, model="m"))
+        assert [c["title"] for c in cits3] == ["not-yours.md"]
+        rag.delete_store(other)
+        assert rag.retrieve(wire["demo_query"], [other]) == []
+    finally:
+        reg.engine.close()

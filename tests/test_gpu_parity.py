@@ -1,0 +1,442 @@
+"""Parity of the CUDA path (through the C-ABI, include/rf_b200.h) with the CPU oracle.
+Bit-exact for chunk ids, int32 scores, int8 features and byte spans; cosine within 1e-5 relative
+(the tolerance BASELINE.json states).  Run on the GPU box: pytest -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COS_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def co():
+    from oracle import c_oracle
+    return c_oracle
+
+
+@pytest.fixture(scope="module")
+def rf1():
+    from oracle import rf1 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def zb(rf1):
+    return rf1.zipf_bucket_table()
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "rf1_golden.json")))
+
+
+def _dense(sparse, n=256):
+    row = np.zeros(n, np.int8)
+    for i, v in sparse:
+        row[i] = v
+    return row
+
+
+def _engine(cap, **kw):
+    from rag_foundation_b200 import Engine
+    return Engine(capacity_rows=cap, **kw)
+
+
+def _check(co, eng_out, F, seg, q, scope, k, id_base, ff):
+    ids, sc, cs, cnt = eng_out
+    w_ids, w_sc, w_cs = co.score_topk(F, seg, q, scope, k=k, id_base=id_base, ff=ff)
+    m = len(w_ids)
+    assert int(cnt) == m
+    assert ids[:m].tolist() == w_ids.tolist()
+    assert sc[:m].tolist() == w_sc.tolist()
+    np.testing.assert_allclose(cs[:m], w_cs, rtol=COS_RTOL, atol=0)
+    assert (ids[m:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and (sc[m:] == 0).all()
+
+
+# ------------------------------------------------------------------ synthetic corpus generator
+def test_synthetic_rows_bit_exact(co, zb):
+    with _engine(70_000) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=5, start_counter=123_456, n_rows=65_537)
+        F, seg, ff = e.read_rows(0, 65_537)
+        wF, wff = co.synth_rows(5, 123_456, 65_537, zb, with_ff=True)
+        assert (F == wF).all() and (ff == wff).all() and (seg == s).all()
+
+
+# ------------------------------------------------------------------ single query scans
+@pytest.mark.parametrize("n_rows", [1, 31, 32, 33, 1000, 20_000, 262_144 + 17])
+def test_single_query_parity_sizes(co, zb, n_rows):
+    with _engine(n_rows + 64, id_base=1000) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=1, start_counter=0, n_rows=n_rows)
+        F, ff = co.synth_rows(1, 0, n_rows, zb, with_ff=True)
+        seg = np.full(n_rows, s, np.uint32)
+        for qi in range(4):
+            q = co.synth_query(1, qi, zb)
+            for k in (1, 10, 32):
+                ids, sc, cs, cnt = e.search(q[None, :], [[s]], k=k)
+                _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, q, [s], k, 1000, ff)
+
+
+def test_golden_top10_through_cuda(golden):
+    for case in golden["synth_top10"]:
+        with _engine(case["n_rows"]) as e:
+            s = e.open_store("fileSearchStores/a")
+            e.ingest_synthetic(s, 0, seed=case["seed"], start_counter=0, n_rows=case["n_rows"])
+            from oracle import c_oracle, rf1
+            q = c_oracle.synth_query(case["seed"], case["qi"], rf1.zipf_bucket_table())
+            ids, sc, _, cnt = e.search(q[None, :], [[s]], k=10)
+            assert ids[0].tolist() == case["ids"] and sc[0].tolist() == case["scores"]
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_one_million_chunks_parity(co, zb, seed):
+    """BASELINE.json configs[1]: synthetic single store, 1M chunks, 1 query at a time, top-10."""
+    n = 1_000_000
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=seed, start_counter=0, n_rows=n)
+        F, ff = co.synth_rows(seed, 0, n, zb, with_ff=True)
+        seg = np.full(n, s, np.uint32)
+        for qi in range(3):
+            q = co.synth_query(seed, qi, zb)
+            ids, sc, cs, cnt = e.search(q[None, :], [[s]], k=10)
+            _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, q, [s], 10, 0, ff)
+
+
+def test_tiny_golden_cases_via_ingest_features(golden):
+    g = golden["tiny"]
+    F = np.stack([_dense(r) for r in g["F_sparse"]])
+    q = _dense(g["q_sparse"])
+    segs = g["store_seg"]
+    for case in g["cases"]:
+        with _engine(64, id_base=case["id_base"]) as e:
+            for i in range(3):
+                assert e.open_store(f"fileSearchStores/s{i}") == i
+            doc = 1
+            for r, sg in enumerate(segs):   # one document per row so the tombstoned row can be deleted
+                e.ingest_features(sg if sg != 0xFFFFFFFF else 0, doc + r, F[r:r + 1])
+            e.tombstone_doc(doc + segs.index(0xFFFFFFFF))
+            scope = [x for x in case["scope"] if x != 0xFFFFFFFF]
+            ids, sc, cs, cnt = e.search(q[None, :], [scope], k=case["k"])
+            m = len(case["ids"])
+            assert int(cnt[0]) == m, case["name"]
+            assert ids[0, :m].tolist() == case["ids"] and sc[0, :m].tolist() == case["scores"], case["name"]
+
+
+def test_adversarial_orderings(co):
+    """Ascending scores (every row beats the running threshold), all-equal scores (pure id
+    tie-break) and all-zero scores."""
+    n = 40_000
+    rng = np.random.default_rng(0)
+    q = np.zeros(256, np.int8); q[3] = 1; q[200] = 2
+    for name in ("ascending", "all_equal", "all_zero", "descending"):
+        F = np.zeros((n, 256), np.int8)
+        if name == "ascending":
+            F[:, 3] = (np.arange(n) * 127 // n).astype(np.int8); F[:, 200] = (np.arange(n) % 100).astype(np.int8)
+        elif name == "descending":
+            F[:, 3] = ((n - 1 - np.arange(n)) * 127 // n).astype(np.int8)
+        elif name == "all_equal":
+            F[:, 3] = 5
+        F[:, 17] = rng.integers(0, 127, n).astype(np.int8)   # does not touch the score
+        with _engine(n) as e:
+            s = e.open_store("fileSearchStores/a")
+            e.ingest_features(s, 1, F)
+            ff = (F.astype(np.int32) ** 2).sum(1).astype(np.int32)
+            seg = np.full(n, s, np.uint32)
+            ids, sc, cs, cnt = e.search(q[None, :], [[s]], k=10)
+            _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, q, [s], 10, 0, ff)
+            if name == "all_equal":
+                assert ids[0].tolist() == list(range(10))
+
+
+# ------------------------------------------------------------------ tenant mask, tombstones, extents
+def test_store_mask_interleaved_and_multi_store_scope(co, zb):
+    rng = np.random.default_rng(3)
+    with _engine(60_000) as e:
+        stores = [e.open_store(f"fileSearchStores/t{i}") for i in range(5)]
+        F_all, seg_all = [], []
+        doc = 0
+        start = 0
+        for _ in range(120):   # many small documents, stores interleaved -> many extents per store
+            s = int(rng.integers(0, 5))
+            n = int(rng.integers(1, 400))
+            rows = co.synth_rows(9, start, n, zb)
+            doc += 1
+            e.ingest_features(stores[s], doc, rows)
+            F_all.append(rows); seg_all.append(np.full(n, stores[s], np.uint32))
+            start += n
+        F = np.concatenate(F_all); seg = np.concatenate(seg_all)
+        ff = (F.astype(np.int32) ** 2).sum(1).astype(np.int32)
+        scopes = [[stores[0]], [stores[1], stores[3]], stores, [stores[4], stores[4]], [77], []]
+        for qi in range(3):
+            q = co.synth_query(9, qi, zb)
+            ids, sc, cs, cnt = e.search(np.stack([q] * len(scopes)), scopes, k=10)
+            for i, scope in enumerate(scopes):
+                _check(co, (ids[i], sc[i], cs[i], cnt[i]), F, seg, q, scope, 10, 0, ff)
+        # delete a few documents, then a whole store
+        for d in (3, 40, 77):
+            e.tombstone_doc(d)
+        lo = 0
+        for d, rows in enumerate(F_all, start=1):
+            if d in (3, 40, 77):
+                seg[lo:lo + len(rows)] = 0xFFFFFFFF
+            lo += len(rows)
+        e.drop_store(stores[1])
+        seg[seg == stores[1]] = 0xFFFFFFFF
+        q = co.synth_query(9, 0, zb)
+        for scope in ([stores[0]], [stores[1]], stores):
+            ids, sc, cs, cnt = e.search(q[None, :], [scope], k=10)
+            _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, q, scope, 10, 0, ff)
+        with pytest.raises(RuntimeError):
+            e.tombstone_doc(3)   # already gone
+
+
+def test_many_extents_are_coalesced_but_exact(co, zb):
+    """> 64 extents for one store: the engine widens the scan ranges, the row mask keeps it exact."""
+    with _engine(20_000) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        F_all, seg_all = [], []
+        start = 0
+        for d in range(300):
+            n = 7 + d % 13
+            rows = co.synth_rows(4, start, n, zb)
+            s = a if d % 2 == 0 else b
+            e.ingest_features(s, d + 1, rows)
+            F_all.append(rows); seg_all.append(np.full(n, s, np.uint32)); start += n
+        F = np.concatenate(F_all); seg = np.concatenate(seg_all)
+        ff = (F.astype(np.int32) ** 2).sum(1).astype(np.int32)
+        q = co.synth_query(4, 1, zb)
+        for scope in ([a], [b], [a, b]):
+            ids, sc, cs, cnt = e.search(q[None, :], [scope], k=10)
+            _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, q, scope, 10, 0, ff)
+
+
+def test_multi_tenant_batch_store_scoped(co, zb):
+    """BASELINE.json configs[4] in miniature: store-sorted corpus, each query scoped to one store."""
+    n_stores, per = 200, 1000
+    with _engine(n_stores * per) as e:
+        first = e.open_store("fileSearchStores/m0")
+        for i in range(1, n_stores):
+            e.open_store(f"fileSearchStores/m{i}")
+        e.ingest_synthetic(first, per, seed=6, start_counter=0, n_rows=n_stores * per)
+        F, ff = co.synth_rows(6, 0, n_stores * per, zb, with_ff=True)
+        seg = (np.arange(n_stores * per) // per).astype(np.uint32) + first
+        rng = np.random.default_rng(1)
+        nq = 64
+        scopes = [[int(first + rng.integers(0, n_stores))] for _ in range(nq)]
+        Q = np.stack([co.synth_query(6, i, zb) for i in range(nq)])
+        ids, sc, cs, cnt = e.search(Q, scopes, k=10)
+        for i in range(nq):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), F, seg, Q[i], scopes[i], 10, 0, ff)
+
+
+def test_batched_queries_shared_store(co, zb):
+    n = 50_000
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=2, start_counter=0, n_rows=n)
+        F, ff = co.synth_rows(2, 0, n, zb, with_ff=True)
+        seg = np.full(n, s, np.uint32)
+        Q = np.stack([co.synth_query(2, i, zb) for i in range(33)])
+        ids, sc, cs, cnt = e.search(Q, [[s]] * 33, k=10)
+        for i in range(33):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), F, seg, Q[i], [s], 10, 0, ff)
+
+
+# ------------------------------------------------------------------ device-resident path + merge
+def test_device_keys_path_and_merge(co, zb):
+    import torch
+    from rag_foundation_b200 import unpack_keys
+    n = 100_000
+    with _engine(n, id_base=500) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=3, start_counter=0, n_rows=n)
+        F = co.synth_rows(3, 0, n, zb)
+        seg = np.full(n, s, np.uint32)
+        Q = np.stack([co.synth_query(3, i, zb) for i in range(6)])
+        qd = torch.from_numpy(Q).cuda()
+        out = torch.zeros((6, 10), dtype=torch.int64, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):   # cached plan reuse
+            e.search_keys_device(qd.data_ptr(), 6, [s], 10, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        keys = out.cpu().numpy().view(np.uint64)
+        for i in range(6):
+            want = co.score_topk_keys(F, seg, Q[i], [s], k=10, id_base=500)
+            assert keys[i].tolist() == want.tolist()
+        # merge: split each list in 3 interleaved parts + a duplicate list, shuffle -> same answer
+        parts = np.zeros((4, 6, 10), np.uint64)
+        for i in range(6):
+            for j in range(10):
+                parts[j % 3, i, j // 3] = keys[i, j]
+            parts[3, i, :4] = keys[i, :4]
+        pd = torch.from_numpy(parts.view(np.int64)).cuda()
+        merged = torch.zeros((6, 10), dtype=torch.int64, device="cuda")
+        e.merge_topk_device(pd.data_ptr(), 4, 6, 10, merged.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert (merged.cpu().numpy().view(np.uint64) == keys).all()
+        ids, sc, valid = unpack_keys(keys)
+        assert valid.all() and (ids >= 500).all()
+
+
+def test_sharded_searcher_single_process_two_engines(co, zb):
+    """Two shards on one GPU, merged with the CUDA merge kernel, equals the unsharded scan."""
+    import torch
+    from rag_foundation_b200.sharded import ShardedSearcher, shard_range, unpack_keys_torch
+    n = 60_001
+    engines = []
+    try:
+        local = []
+        Q = np.stack([co.synth_query(8, i, zb) for i in range(4)])
+        qd = torch.from_numpy(Q).cuda()
+        for r in range(2):
+            lo, hi = shard_range(n, r, 2)
+            e = _engine(hi - lo, id_base=lo); engines.append(e)
+            s = e.open_store("fileSearchStores/a")
+            e.ingest_synthetic(s, 0, seed=8, start_counter=lo, n_rows=hi - lo)
+            srch = ShardedSearcher.for_engine(e)
+            local.append(srch.local_search(qd, [s], 10))
+        gathered = torch.stack(local).contiguous()
+        merged = ShardedSearcher.for_engine(engines[0]).merge(gathered, 10)
+        torch.cuda.synchronize()
+        ids, sc, valid = unpack_keys_torch(merged.cpu())
+        F = co.synth_rows(8, 0, n, zb)
+        for i in range(4):
+            w_ids, w_sc, _ = co.score_topk(F, np.zeros(n, np.uint32), Q[i], [0])
+            assert ids[i].tolist() == w_ids.tolist() and sc[i].tolist() == w_sc.tolist()
+    finally:
+        for e in engines:
+            e.close()
+
+
+# ------------------------------------------------------------------ featurisation (ingest + query)
+def _check_doc(e, seg, doc_id, data, oracle_mod, first_expected):
+    first, n, spans = e.ingest_text(seg, doc_id, data)
+    wF, wff, wsp, _ = oracle_mod.featurize_doc(data)
+    assert first == first_expected and n == len(wF)
+    if n:
+        F, sg, ff = e.read_rows(first - e.id_base, n)
+        assert (F == wF).all() and (ff == wff).all() and (sg == seg).all()
+        assert (spans == wsp).all()
+    return n
+
+
+def test_ingest_text_golden_documents(golden, co):
+    with _engine(4096) as e:
+        s = e.open_store("fileSearchStores/a")
+        nxt = 0
+        for name in ("sample_report", "long_doc"):
+            data = golden[name]["text"].encode("utf-8")
+            n = _check_doc(e, s, hash(name) & 0xFFFF, data, co, nxt)
+            assert n == golden[name]["n_chunks"]
+            nxt += n
+        sat = golden["saturation"]
+        assert (e.featurize_query(sat["text"].encode()) == _dense(sat["q_sparse"])).all()
+
+
+def test_ingest_text_edge_cases(co):
+    cases = [b"", b"   \n\t ", b"the a an The AN", b"x", b"a", b"the", b"thee", b"ana", b"a1 an2 3the",
+             b"The" * 2000, b"z" * 10_000, ("café naïve 中文 text " * 50).encode(),
+             b" ".join(b"w%d" % i for i in range(128)), b" ".join(b"w%d" % i for i in range(129)),
+             b" ".join(b"w%d" % i for i in range(144)), b" ".join(b"w%d" % i for i in range(145)),
+             b"A" + b" " * 4095 + b"the" + b" " * 4093 + b"an bc",       # tokens straddling 4 KB block edges
+             b"q" * 4095 + b" " + b"r" * 4097 + b" the", b"ab" * 2047 + b"the" + b" x"]
+    with _engine(8192) as e:
+        s = e.open_store("fileSearchStores/a")
+        nxt = 0
+        for i, data in enumerate(cases):
+            nxt += _check_doc(e, s, i + 1, data, co, nxt)
+            assert (e.featurize_query(data) == co.query_vector(data)).all(), i
+
+
+def test_ingest_text_fuzz(co):
+    rng = np.random.default_rng(11)
+    pieces = [b"the", b"a", b"an", b"The", b"AN", b" ", b"  ", b"\n", b",", b"-", b"_", b"x", b"9", b"ab", b"Zq7",
+              "é".encode(), "中".encode(), b"theory", b"anagram", b"a1"]
+    with _engine(40_000) as e:
+        s = e.open_store("fileSearchStores/a")
+        nxt = 0
+        for i in range(40):
+            n_p = int(rng.integers(0, 6000))
+            data = b"".join(pieces[j] for j in rng.integers(0, len(pieces), n_p))
+            nxt += _check_doc(e, s, i + 1, data, co, nxt)
+            assert (e.featurize_query(data) == co.query_vector(data)).all()
+
+
+def test_ingest_large_document(co, rf1):
+    data = rf1.synth_text(0, 700_000)   # ~2.6 MB, ~6200 chunks
+    assert len(data) > 2_000_000
+    with _engine(8192) as e:
+        s = e.open_store("fileSearchStores/a")
+        n = _check_doc(e, s, 1, data, co, 0)
+        assert n > 6000
+
+
+def test_search_text_equals_search_of_oracle_vector(co, golden):
+    g = golden["sample_report"]
+    with _engine(1024) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_text(s, 1, g["text"].encode())
+        e.ingest_text(s, 2, golden["long_doc"]["text"].encode())
+        ids, sc, cs, q = e.search_text(g["query"].encode(), [s], 10)
+        assert (q == _dense(g["q_sparse"])).all()
+        n = 1 + golden["long_doc"]["n_chunks"]
+        F, seg, ff = e.read_rows(0, n)
+        w_ids, w_sc, w_cs = co.score_topk(F, seg, q, [s], ff=ff)
+        assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist()
+        np.testing.assert_allclose(cs, w_cs, rtol=COS_RTOL)
+        assert ids[0] == 0 and sc[0] == g["scores"][0]
+        np.testing.assert_allclose(cs[0], g["cos"][0], rtol=COS_RTOL)
+
+
+# ------------------------------------------------------------------ errors and limits
+def test_errors_are_loud():
+    from rag_foundation_b200 import Engine
+    with _engine(100) as e:
+        s = e.open_store("fileSearchStores/a")
+        assert e.open_store("fileSearchStores/a") == s and e.lookup_store("nope") is None
+        with pytest.raises(RuntimeError):
+            e.ingest_features(s, 1, np.zeros((101, 256), np.int8))       # capacity
+        with pytest.raises(RuntimeError):
+            e.ingest_features(99, 1, np.zeros((1, 256), np.int8))        # unknown store
+        with pytest.raises(RuntimeError):
+            e.search(np.zeros((1, 256), np.int8), [[s]], k=33)           # k > RF_TOPK_MAX
+        with pytest.raises(ValueError):
+            e.search(np.zeros((1, 256), np.int8), [list(range(17))], k=10)
+        ids, sc, cs, cnt = e.search(np.zeros((1, 256), np.int8), [[s]], k=10)   # empty store
+        assert cnt[0] == 0
+    with pytest.raises(RuntimeError):
+        Engine(capacity_rows=0)
+    st_ok = _engine(10)
+    st = st_ok.stats(); st_ok.close()
+    assert st["capacity_rows"] == 10 and st["hbm_bytes"] >= 2640
+
+
+def test_concurrent_searches_from_threads(co, zb):
+    """routes/chat.py:520 runs ask_stream on one daemon thread per request (<= 50 per process)."""
+    import threading
+    n = 200_000
+    with _engine(n, n_contexts=4) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=12, start_counter=0, n_rows=n)
+        F = co.synth_rows(12, 0, n, zb)
+        seg = np.full(n, s, np.uint32)
+        Q = [co.synth_query(12, i, zb) for i in range(16)]
+        want = [co.score_topk(F, seg, q, [s])[0].tolist() for q in Q]
+        errs = []
+
+        def work(i):
+            try:
+                for _ in range(5):
+                    ids, _, _, _ = e.search(Q[i][None, :], [[s]], k=10)
+                    assert ids[0].tolist() == want[i]
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(16)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs[:1]
