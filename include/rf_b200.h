@@ -70,6 +70,10 @@ const char *rf_strerror(int code);
 const char *rf_last_error(void);           /* thread-local detail of the last failure */
 int rf_build_info(char *buf, size_t n);    /* "sm_100a nvcc 12.9 ..." */
 
+/* Diagnostics: with RF_SCAN_DEBUG=1 in the environment at rf_engine_create, the scan kernel stamps
+ * %globaltimer at 6 points per block ([block][8] words); this copies them out (and clears them). */
+int rf_debug_timestamps(rf_engine *e, uint64_t *out, uint64_t n_words, int clear);
+
 /* ---- stores: GeminiRag.create_store / delete_store (gemini_rag.py:271-304, 610-612, 696-697) -- */
 int rf_store_open(rf_engine *e, const char *fs_name, uint32_t *store_seg);   /* idempotent */
 int rf_store_lookup(rf_engine *e, const char *fs_name, uint32_t *store_seg); /* RF_ENOTFOUND if absent */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rf_strerror": (C.c_char_p, [_i32]),
     "rf_last_error": (C.c_char_p, []),
     "rf_build_info": (_i32, [C.c_char_p, _sz]),
+    "rf_debug_timestamps": (_i32, [_vp, _vp, _u64, _i32]),
     "rf_store_open": (_i32, [_vp, C.c_char_p, C.POINTER(_u32)]),
     "rf_store_lookup": (_i32, [_vp, C.c_char_p, C.POINTER(_u32)]),
     "rf_store_drop": (_i32, [_vp, _u32]),

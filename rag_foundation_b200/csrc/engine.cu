@@ -115,6 +115,7 @@ struct SearchCtx {
     cudaStream_t stream = nullptr;
     PinnedBuf h_in, h_out;
     DeviceBuf d_in, d_out, d_partial, d_tickets;
+    uint32_t launches = 0;   // parity selects the sync set
 };
 
 // A scan plan resident on the device for rf_search_keys_device (cached per scope + stream).
@@ -122,6 +123,7 @@ struct DevicePlan {
     uint64_t epoch = ~0ull;
     DeviceBuf blob, partial, tickets;
     uint32_t n_ext = 0, max_tiles = 0;
+    uint32_t launches = 0;
 };
 
 struct PlanBlob {  // host staging of everything one launch needs besides F/seg/ff
@@ -163,6 +165,9 @@ struct rf_engine {
     std::atomic<uint64_t> searches{0};
     std::atomic<uint64_t> launches{0};
     uint32_t blocks_override = 0;
+    int scan_variant = rf::kScanVariantTma8x24;
+    unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
+    size_t debug_cap = 0;
 };
 
 namespace {
@@ -255,13 +260,14 @@ int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store
 }
 
 uint32_t pick_blocks(rf_engine *e, uint32_t nq, uint32_t max_tiles) {
-    if (e->blocks_override) return std::max(1u, std::min(e->blocks_override, std::max(max_tiles, 1u)));
-    const uint32_t wave = rf::scan_default_blocks_per_query(e->sm_count);
+    if (e->blocks_override) return std::max(1u, std::min(std::min(e->blocks_override, 1024u), std::max(max_tiles, 1u)));
+    const uint32_t wave = rf::scan_default_blocks_per_query(e->sm_count, e->scan_variant);
     uint32_t x = (max_tiles + kTilesPerBlockTarget - 1) / kTilesPerBlockTarget;
     const uint32_t fill = (wave + nq - 1) / nq;  // at least one full wave over all queries
     x = std::max(x, fill);
     if (nq == 1) x = wave;                       // single query: exactly one resident wave
     x = std::min(x, std::max(max_tiles, 1u));
+    x = std::min(x, 1024u);                      // the final merge is two tournament levels of 32
     return std::max(x, 1u);
 }
 
@@ -298,6 +304,35 @@ void fill_args(rf_engine *e, ScanArgs &a, const uint8_t *d_blob, const PlanBlob 
     a.id_base = static_cast<uint32_t>(e->cfg.id_base);
     a.k = k;
     a.shared_plan = shared ? 1u : 0u;
+    a.inline_plan = 0;
+    a.debug_ts = e->debug_ts;
+}
+
+// Single plan with few extents: copy it into the kernel parameters (host copy of the blob).
+void maybe_inline_plan(ScanArgs &a, const PlanBlob &b, uint32_t nq, bool shared) {
+    if (!(shared || nq == 1)) return;
+    const ScanPlan *p = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
+    if (p->n_ext > rf::kInlineExt) return;
+    a.plan0 = *p;
+    const uint32_t *lo = reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo) + p->ext_off;
+    const uint32_t *hi = reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi) + p->ext_off;
+    const uint32_t *t0 = reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_tile0) + p->ext_off;
+    for (uint32_t i = 0; i < p->n_ext; ++i) { a.inl_lo[i] = lo[i]; a.inl_hi[i] = hi[i]; }
+    for (uint32_t i = 0; i <= p->n_ext; ++i) a.inl_tile0[i] = t0[i];
+    a.inline_plan = 1;
+}
+
+// The zero-initialised sync buffer holds TWO sets (consecutive launches alternate, so a query
+// that overlaps the previous one's tail under programmatic dependent launch never shares its
+// floor / tile counter); per set, for a capacity of n queries: n u64 floors, n u32 tickets,
+// n u32 tile counters.
+constexpr size_t kSyncBytesPerQuery = 2 * 16;
+void set_sync_bufs(ScanArgs &a, const DeviceBuf &buf, uint32_t parity) {
+    const size_t cap_q = buf.cap / kSyncBytesPerQuery;
+    uint8_t *base = static_cast<uint8_t *>(buf.p) + (parity & 1u) * cap_q * 16;
+    a.floors = reinterpret_cast<uint64_t *>(base);
+    a.tickets = reinterpret_cast<uint32_t *>(base + cap_q * 8);
+    a.tile_ctr = reinterpret_cast<uint32_t *>(base + cap_q * 12);
 }
 
 struct OutLayout {
@@ -323,23 +358,25 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_de
     RF_CUDA(c->h_out.reserve(L.total));
     RF_CUDA(c->d_out.reserve(L.total));
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(nq) * X * k * 8));
-    if (static_cast<size_t>(nq) * 4 > c->d_tickets.cap) {
-        RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * 4));
+    if (static_cast<size_t>(nq) * kSyncBytesPerQuery > c->d_tickets.cap) {
+        RF_CUDA(cudaStreamSynchronize(c->stream));
+        RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery));
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     memcpy(c->h_in.p, b.bytes.data(), b.bytes.size());
     RF_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, b.bytes.size(), cudaMemcpyHostToDevice, c->stream));
     ScanArgs a{};
     fill_args(e, a, static_cast<const uint8_t *>(c->d_in.p), b, q_dev, k, shared);
+    maybe_inline_plan(a, b, nq, shared);
     uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
     a.partial = static_cast<uint64_t *>(c->d_partial.p);
-    a.tickets = static_cast<uint32_t *>(c->d_tickets.p);
+    set_sync_bufs(a, c->d_tickets, c->launches++);
     a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
     a.out_ids = reinterpret_cast<uint64_t *>(d_out + L.off_ids);
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
-    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, c->stream));
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     // keys are not needed on the host: copy ids..counts only
     RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
@@ -438,9 +475,22 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     if (e->cfg.n_contexts == 0) e->cfg.n_contexts = 8;
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
+    if (const char *s = getenv("RF_SCAN_VARIANT")) {
+        const int v = atoi(s);
+        if (v < 0 || v >= rf::kScanVariantCount) {
+            delete e;
+            return fail(RF_EINVAL, "RF_SCAN_VARIANT=%d out of range", v);
+        }
+        e->scan_variant = v;
+    }
 
     const uint64_t cap = cfg->capacity_rows;
     cudaError_t ce;
+    if (getenv("RF_SCAN_DEBUG")) {
+        e->debug_cap = 4096 * 8;
+        if (cudaMalloc(&e->debug_ts, e->debug_cap * 8) != cudaSuccess) e->debug_ts = nullptr;
+        else cudaMemset(e->debug_ts, 0, e->debug_cap * 8);
+    }
     if ((ce = cudaMalloc(&e->F, cap * RF_DIM)) != cudaSuccess || (ce = cudaMalloc(&e->seg, cap * 4)) != cudaSuccess ||
         (ce = cudaMalloc(&e->ff, cap * 4)) != cudaSuccess) {
         const int rc = fail(RF_ENOMEM, "cudaMalloc of %llu rows failed: %s", (unsigned long long)cap, cudaGetErrorString(ce));
@@ -486,11 +536,23 @@ int rf_engine_destroy(rf_engine *e) {
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
     e->sc_text.release(); e->sc_counts.release(); e->sc_bucket.release(); e->sc_start.release();
     e->sc_end.release(); e->sc_ntok.release(); e->sc_spans.release();
+    if (e->debug_ts) cudaFree(e->debug_ts);
     if (e->zipf_bucket) cudaFree(e->zipf_bucket);
     if (e->F) cudaFree(e->F);
     if (e->seg) cudaFree(e->seg);
     if (e->ff) cudaFree(e->ff);
     delete e;
+    return RF_OK;
+}
+
+int rf_debug_timestamps(rf_engine *e, uint64_t *out, uint64_t n_words, int clear) {
+    if (!e || !out) return fail(RF_EINVAL, "null argument");
+    if (!e->debug_ts) return fail(RF_EINVAL, "engine was not created with RF_SCAN_DEBUG=1");
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    RF_CUDA(cudaDeviceSynchronize());
+    const size_t n = std::min<size_t>(n_words, e->debug_cap);
+    RF_CUDA(cudaMemcpy(out, e->debug_ts, n * 8, cudaMemcpyDeviceToHost));
+    if (clear) RF_CUDA(cudaMemset(e->debug_ts, 0, e->debug_cap * 8));
     return RF_OK;
 }
 
@@ -765,21 +827,22 @@ int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *
     RF_CUDA(c->h_out.reserve(L.total + RF_DIM));
     RF_CUDA(c->d_out.reserve(L.total));
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(X) * k * 8));
-    if (c->d_tickets.cap < 4) {
-        RF_CUDA(c->d_tickets.reserve(4));
+    if (c->d_tickets.cap < kSyncBytesPerQuery) {
+        RF_CUDA(c->d_tickets.reserve(kSyncBytesPerQuery));
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     ScanArgs a{};
     fill_args(e, a, d, b, d_q, k, false);
+    maybe_inline_plan(a, b, 1, false);
     uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
     a.partial = static_cast<uint64_t *>(c->d_partial.p);
-    a.tickets = static_cast<uint32_t *>(c->d_tickets.p);
+    set_sync_bufs(a, c->d_tickets, c->launches++);
     a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
     a.out_ids = reinterpret_cast<uint64_t *>(d_out + L.off_ids);
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
-    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, c->stream));
+    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, e->scan_variant, c->stream));
     e->launches.fetch_add(1);
     uint8_t *ho = static_cast<uint8_t *>(c->h_out.p);
     RF_CUDA(cudaMemcpyAsync(ho + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
@@ -825,20 +888,21 @@ int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const 
         }
         const uint32_t X = pick_blocks(e, nq, dp->max_tiles);
         const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
-        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * 4 > dp->tickets.cap) {
+        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * kSyncBytesPerQuery > dp->tickets.cap) {
             RF_CUDA(cudaStreamSynchronize(s));
             RF_CUDA(dp->partial.reserve(need_partial));
-            if (static_cast<size_t>(nq) * 4 > dp->tickets.cap) {
-                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * 4));
+            if (static_cast<size_t>(nq) * kSyncBytesPerQuery > dp->tickets.cap) {
+                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery));
                 RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
             }
         }
         ScanArgs a{};
         fill_args(e, a, static_cast<const uint8_t *>(dp->blob.p), b, q_dev, k, true);
+        maybe_inline_plan(a, b, nq, true);
         a.partial = static_cast<uint64_t *>(dp->partial.p);
-        a.tickets = static_cast<uint32_t *>(dp->tickets.p);
+        set_sync_bufs(a, dp->tickets, dp->launches++);
         a.out_keys = out_keys_dev;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, s));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
     }
     e->launches.fetch_add(1, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);

@@ -45,32 +45,99 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int delta) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+    uint32_t lo = __shfl_xor_sync(kFull, static_cast<uint32_t>(v), mask);
+    uint32_t hi = __shfl_xor_sync(kFull, static_cast<uint32_t>(v >> 32), mask);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // A warp keeps its running top-32 as one key per lane, sorted descending by lane index.  `thr` is
-// the key at lane k-1 (0 until k keys have been seen): only keys above it can enter the top-k.
+// the key at lane k-1 (0 until k keys have been seen); `floor` is a bound learnt from other warps
+// (a published k-th best key of some other list of the same query): a key below either cannot be
+// in the query's top-k, so it is dropped before it costs anything.
 struct WarpTopK {
     uint64_t mine;   // this lane's entry of the sorted list
-    uint64_t thr;    // warp-uniform admission threshold
+    uint64_t thr;    // warp-uniform: own k-th best key
+    uint64_t floor;  // warp-uniform: external lower bound (monotone)
 
-    __device__ __forceinline__ void reset() { mine = 0; thr = 0; }
+    __device__ __forceinline__ void reset() { mine = 0; thr = 0; floor = 0; }
+    __device__ __forceinline__ uint64_t bar() const { return thr > floor ? thr : floor; }
 
-    // Every lane offers one key (0 = nothing).  Rare path: scanned data is mostly below thr.
+    // First tile: take all 32 keys at once with a bitonic sort (descending) instead of 32 inserts.
+    __device__ __forceinline__ void init_sorted(uint64_t key, int k, int lane) {
+        uint64_t v = key;
+#pragma unroll
+        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                const uint64_t other = shfl_xor_u64(v, j);
+                const bool desc_block = (lane & k2) == 0;
+                const bool lower = (lane & j) == 0;
+                const bool keep_max = (lower == desc_block);
+                const uint64_t mx = v > other ? v : other;
+                const uint64_t mn = v > other ? other : v;
+                v = keep_max ? mx : mn;
+            }
+        }
+        mine = v;
+        thr = shfl_u64(mine, k - 1);
+    }
+
+    // Every lane offers one key (0 = nothing).  Rare path: scanned data is mostly below the bar.
     __device__ __forceinline__ void consume(uint64_t key, int k, int lane) {
-        unsigned pending = __ballot_sync(kFull, key > thr);
+        unsigned pending = __ballot_sync(kFull, key > bar());
         while (pending) {
             const int src = __ffs(pending) - 1;
             const uint64_t cand = shfl_u64(key, src);
             pending &= pending - 1;
             const unsigned dup = __ballot_sync(kFull, mine == cand);
-            if (cand > thr && dup == 0) {
+            if (cand > bar() && dup == 0) {
                 const int pos = __popc(__ballot_sync(kFull, mine > cand));  // sorted => a lane prefix
                 const uint64_t up = shfl_up_u64(mine, 1);
                 if (lane == pos) mine = cand;
                 else if (lane > pos) mine = up;
                 thr = shfl_u64(mine, k - 1);
-                pending &= __ballot_sync(kFull, key > thr);
+                pending &= __ballot_sync(kFull, key > bar());
             }
         }
     }
 };
+
+// ---- mbarrier / bulk-copy (TMA engine, 1-D) helpers -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (bytes).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 }  // namespace rf

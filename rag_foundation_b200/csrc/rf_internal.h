@@ -32,6 +32,8 @@ struct ScanArgs {
     const uint32_t *ext_tile0;  // exclusive prefix of tile counts within the query, n_ext + 1 entries per query (offset ext_off + qi)
     uint64_t *partial;          // [nq, gridDim.x, k] per-block top-k keys
     uint32_t *tickets;          // [nq] zero-initialised; reset to zero by the finishing block
+    uint64_t *floors;           // [nq] zero-initialised; per-query shared lower bound (atomicMax), reset likewise
+    uint32_t *tile_ctr;         // [nq] zero-initialised; per-query work-stealing tile counter, reset likewise
     uint64_t *out_keys;         // [nq, k]
     uint64_t *out_ids;          // [nq, k] or null
     int32_t *out_scores;        // [nq, k] or null
@@ -40,13 +42,32 @@ struct ScanArgs {
     uint32_t id_base;           // global id of row 0
     uint32_t k;
     uint32_t shared_plan;       // 1: every query uses plans[0] (one scope for the whole batch)
+    // Inline copy of plans[0] and its (<= kInlineExt) extents: used when inline_plan != 0, which
+    // requires shared_plan or nq == 1.  Kernel parameters live in the constant bank.
+    uint32_t inline_plan;
+    ScanPlan plan0;
+    uint32_t inl_lo[8];
+    uint32_t inl_hi[8];
+    uint32_t inl_tile0[9];
+    unsigned long long *debug_ts;  // diagnostics (RF_SCAN_DEBUG=1): [grid.x][8] globaltimer stamps, else null
 };
+constexpr uint32_t kInlineExt = 8;
 
 // launchers (each returns the cudaError_t of the launch)
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, cudaStream_t s);
+enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, default tma 8x24)
+    kScanVariantLdg = 0,        // direct 128-bit global loads, 8 warps, 2 blocks/SM
+    kScanVariantTma8x24 = 1,    // producer warp + 8 consumer warps, 24-stage (192 KB) bulk-copy ring
+    kScanVariantTma12x24 = 2,
+    kScanVariantTma8x16 = 3,
+    kScanVariantTma6x12 = 4,    // 96 KB ring: two blocks per SM
+    kScanVariantTma12x12 = 5,
+    kScanVariantTma4x12 = 6,
+    kScanVariantCount = 7
+};
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s);
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,
                               uint64_t *out_keys, cudaStream_t s);
-uint32_t scan_default_blocks_per_query(int sm_count);
+uint32_t scan_default_blocks_per_query(int sm_count, int variant);
 
 cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint8_t *zipf_bucket_dev,
                               int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,

@@ -2,18 +2,28 @@
 //
 // Carries out the retrieval step of GeminiRag.ask_stream (reference
 // backend/app/services/gemini_rag.py:517-551; the mock's canned citation is :704-718) as the
-// RF-1 spec, steps 6-7 (oracle/SPEC.md).  HBM-bound integer work: 260 algorithmic bytes per chunk
+// RF-1 spec, steps 6-8 (oracle/SPEC.md).  HBM-bound integer work: 260 algorithmic bytes per chunk
 // (256 B int8 features + 4 B store-segment word), one pass, scores never written back.
 //
-// Layout.  A warp scores a tile of 32 consecutive rows (8 KB) per step: 16 independent 128-bit
-// streaming loads per lane, issued back to back (512 contiguous bytes per warp-wide load, i.e.
-// perfectly coalesced), 4 dp4a per load against the lane's 16-byte slice of the query held in
+// Common to both variants.  A warp scores a tile of 32 consecutive rows (8 KB) per step: lane l
+// holds 16 bytes of each of 16 row pairs (load i covers rows 2i, 2i+1; 512 contiguous bytes per
+// warp-wide access), 4 dp4a per 16 bytes against the lane's 16-byte slice of the query held in
 // registers, then a 15-shuffle transposing butterfly that leaves lane l with the finished int32
 // score of row 2*(l&15) + (l>>4).  The lane checks its row's store-segment word against the
 // query scope (tenant mask + tombstones), packs (score, id) into one u64 key and offers it to the
-// warp's running top-k, which it enters only if it beats the warp's threshold (rare).  Warps merge
-// through shared memory, blocks through a per-query partial buffer, and the last block to finish
-// (ticket counter) merges the partials and writes ids / scores / cosines: one launch per search.
+// warp's running top-k, which it enters only above the warp's bar: the larger of the warp's own
+// k-th key and a per-query floor shared through global memory (atomicMax; any warp's k-th best key
+// is a valid lower bound for the query's top-k).  The first tile is taken with one bitonic sort.
+// Warps merge through shared memory, blocks through a per-query partial buffer, and the last
+// block to finish (ticket counter) merges the partials and writes ids / scores / cosines: one
+// launch per search.
+//
+// Variant "tma" (default): one producer warp streams tiles into a shared-memory ring with 1-D bulk
+// copies (cp.async.bulk, completion on an mbarrier per stage); consumer warps wait on the stage's
+// full barrier, read it with conflict-free 128-bit shared loads and release it on the empty
+// barrier.  Bytes in flight per SM = ring size, independent of registers and of how long a
+// consumer spends in the top-k path.
+// Variant "ldg": every warp issues its 16 128-bit streaming global loads itself (L1 no-allocate).
 #include "rf_device.cuh"
 #include "rf_internal.h"
 
@@ -21,9 +31,10 @@ namespace rf {
 
 namespace {
 
-constexpr int kScanWarps = 8;
-constexpr int kScanThreads = kScanWarps * 32;
 static_assert(kTileRows == static_cast<int>(kScanTileRows), "host and device disagree on the tile height");
+constexpr int kTileBytes = kTileRows * kRowBytes;  // 8192
+constexpr int kChunkTiles = 8;                     // tiles claimed per atomic by a producer lane (tma variant)
+constexpr int kMaxExtSmem = 64;                    // extents staged in shared memory (engine caps plans at 64)
 
 // Reduce 16 per-lane partial sums (one per load) across the 16 lanes of each half-warp, leaving
 // lane l with the total of partial index (l & 15).  8 + 4 + 2 + 1 shuffles.
@@ -64,95 +75,199 @@ __device__ __forceinline__ int transpose_reduce16(int (&p)[16], int lane) {
     return keep + __shfl_xor_sync(kFull, send, 1);
 }
 
-// Warps -> warp 0 through shared memory.  On return warp 0's `top` holds the block's top-k.
-__device__ __forceinline__ void block_merge(WarpTopK &top, uint64_t (*s_keys)[32], int k, int warp, int lane) {
-    __syncthreads();
-    s_keys[warp][lane] = lane < k ? top.mine : 0ull;
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < kScanWarps; ++w) top.consume(s_keys[w][lane], k, lane);
+__device__ __forceinline__ int score_tile(const int4 (&x)[16], const int4 &qv, int lane) {
+    int p[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int acc = __dp4a(x[i].x, qv.x, 0);
+        acc = __dp4a(x[i].y, qv.y, acc);
+        acc = __dp4a(x[i].z, qv.z, acc);
+        p[i] = __dp4a(x[i].w, qv.w, acc);
     }
+    return transpose_reduce16(p, lane);
 }
 
-__global__ void __launch_bounds__(kScanThreads, 2) score_topk_scan_kernel(const ScanArgs a) {
-    __shared__ uint64_t s_keys[kScanWarps][32];
-    __shared__ uint32_t s_scope[RF_SCOPE_MAX];
-    __shared__ uint32_t s_is_last;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// diagnostics: slot 0 entry, 1 plan staged, 2 first tile scored, 3 scan loop done (max over warps),
+// 4 block merged + partial published, 5 last block done
+__device__ __forceinline__ void stamp(const ScanArgs &a, int slot) {
+    if (a.debug_ts) a.debug_ts[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = gtime();
+}
+__device__ __forceinline__ void stamp_max(const ScanArgs &a, int slot) {
+    if (a.debug_ts) atomicMax(a.debug_ts + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot, gtime());
+}
 
-    const int qi = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int k = static_cast<int>(a.k);
+// Per-block view of one query's plan, staged in shared memory.
+struct BlockPlan {
+    uint32_t lo[kMaxExtSmem];
+    uint32_t hi[kMaxExtSmem];
+    uint32_t tile0[kMaxExtSmem + 1];
+    uint32_t scope[RF_SCOPE_MAX];
+    uint32_t n_ext, n_scope, t_lo, t_hi, total_tiles;
+};
+
+__device__ __forceinline__ void stage_plan(const ScanArgs &a, int qi, BlockPlan &bp) {
+    if (a.inline_plan) {
+        // single query / shared scope with few extents: the plan rides in the kernel parameters
+        // (constant bank), so no dependent global loads stand before the first feature load
+        const uint32_t n_ext = a.plan0.n_ext;
+        if (threadIdx.x < n_ext) {
+            bp.lo[threadIdx.x] = a.inl_lo[threadIdx.x];
+            bp.hi[threadIdx.x] = a.inl_hi[threadIdx.x];
+        }
+        if (threadIdx.x <= n_ext) bp.tile0[threadIdx.x] = a.inl_tile0[threadIdx.x];
+        if (threadIdx.x < RF_SCOPE_MAX) bp.scope[threadIdx.x] = threadIdx.x < a.plan0.n_scope ? a.plan0.scope[threadIdx.x] : kTombstone;
+        if (threadIdx.x == 0) {
+            const uint32_t total = a.plan0.total_tiles;
+            bp.n_ext = n_ext;
+            bp.total_tiles = total;
+            bp.n_scope = a.plan0.n_scope;
+            bp.t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total) * blockIdx.x / gridDim.x);
+            bp.t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total) * (blockIdx.x + 1) / gridDim.x);
+        }
+        __syncthreads();
+        return;
+    }
     const ScanPlan &plan = a.plans[a.shared_plan ? 0 : qi];
-    const uint32_t n_scope = plan.n_scope;
-    if (threadIdx.x < RF_SCOPE_MAX) s_scope[threadIdx.x] = threadIdx.x < n_scope ? plan.scope[threadIdx.x] : kTombstone;
+    const uint32_t n_ext = min(plan.n_ext, static_cast<uint32_t>(kMaxExtSmem));
+    const uint32_t *g_lo = a.ext_lo + plan.ext_off;
+    const uint32_t *g_hi = a.ext_hi + plan.ext_off;
+    const uint32_t *g_t0 = a.ext_tile0 + plan.ext_off + (a.shared_plan ? 0 : qi);
+    for (uint32_t i = threadIdx.x; i < n_ext; i += blockDim.x) {
+        bp.lo[i] = g_lo[i];
+        bp.hi[i] = g_hi[i];
+    }
+    for (uint32_t i = threadIdx.x; i <= n_ext; i += blockDim.x) bp.tile0[i] = g_t0[i];
+    if (threadIdx.x < RF_SCOPE_MAX) bp.scope[threadIdx.x] = threadIdx.x < plan.n_scope ? plan.scope[threadIdx.x] : kTombstone;
+    if (threadIdx.x == 0) {
+        const uint32_t total = plan.total_tiles;
+        bp.n_ext = n_ext;
+        bp.total_tiles = total;
+        bp.n_scope = plan.n_scope;
+        bp.t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total) * blockIdx.x / gridDim.x);
+        bp.t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total) * (blockIdx.x + 1) / gridDim.x);
+    }
     __syncthreads();
+}
 
-    // this lane's 16-byte slice of the query
-    const int4 qv = *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16);
-
-    const uint32_t total_tiles = plan.total_tiles;
-    const uint32_t t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * blockIdx.x / gridDim.x);
-    const uint32_t t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * (blockIdx.x + 1) / gridDim.x);
-    const uint32_t *ext_lo = a.ext_lo + plan.ext_off;
-    const uint32_t *ext_hi = a.ext_hi + plan.ext_off;
-    const uint32_t *ext_tile0 = a.ext_tile0 + plan.ext_off + (a.shared_plan ? 0 : qi);
-    const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
-
-    WarpTopK top;
-    top.reset();
-    uint32_t e = 0;
-    if (t_lo < t_hi && plan.n_ext > 1) {  // first extent holding tile t_lo (binary search)
-        uint32_t lo = 0, hi = plan.n_ext;
+// Extent cursor: tiles are visited in increasing order, so `e` only moves forward.
+struct TileCursor {
+    uint32_t e;
+    __device__ __forceinline__ void seek(const BlockPlan &bp, uint32_t t) {
+        uint32_t lo = 0, hi = bp.n_ext;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (ext_tile0[mid] <= t_lo) lo = mid; else hi = mid;
+            if (bp.tile0[mid] <= t) lo = mid; else hi = mid;
         }
         e = lo;
     }
+    __device__ __forceinline__ void locate(const BlockPlan &bp, uint32_t t, uint32_t &row0, uint32_t &row_end) {
+        while (t >= bp.tile0[e + 1]) ++e;
+        row0 = bp.lo[e] + (t - bp.tile0[e]) * kTileRows;
+        row_end = bp.hi[e];
+    }
+};
 
-    for (uint32_t t = t_lo + warp; t < t_hi; t += kScanWarps) {
-        while (t >= ext_tile0[e + 1]) ++e;
-        const uint32_t row0 = ext_lo[e] + (t - ext_tile0[e]) * kTileRows;
-        const uint32_t row_end = ext_hi[e];
-        const int4 *src = reinterpret_cast<const int4 *>(a.F + static_cast<size_t>(row0) * kRowBytes) + lane;
+// Random access (work-stealing order): binary search over the <= 64 extents.
+__device__ __forceinline__ void locate_tile(const BlockPlan &bp, uint32_t t, uint32_t &row0, uint32_t &row_end) {
+    uint32_t lo = 0, hi = bp.n_ext;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (bp.tile0[mid] <= t) lo = mid; else hi = mid;
+    }
+    row0 = bp.lo[lo] + (t - bp.tile0[lo]) * kTileRows;
+    row_end = bp.hi[lo];
+}
 
-        int4 x[16];
-        uint32_t seg;
-        const uint32_t my_row = row0 + my_row_in_tile;
-        if (row0 + kTileRows <= row_end) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = ld_stream_v4(src + i * 32);
-            seg = __ldg(a.seg + my_row);
-        } else {  // ragged last tile of an extent
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t r = row0 + 2 * i + (lane >> 4);
-                x[i] = r < row_end ? ld_stream_v4(src + i * 32) : make_int4(0, 0, 0, 0);
-            }
-            seg = my_row < row_end ? __ldg(a.seg + my_row) : kTombstone;
-        }
+__device__ __forceinline__ bool in_scope(const BlockPlan &bp, uint32_t seg) {
+    bool ok = false;
+    if (seg != kTombstone) {
+        for (uint32_t j = 0; j < bp.n_scope; ++j) ok |= (seg == bp.scope[j]);
+    }
+    return ok;
+}
 
-        int p[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            int acc = __dp4a(x[i].x, qv.x, 0);
-            acc = __dp4a(x[i].y, qv.y, acc);
-            acc = __dp4a(x[i].z, qv.z, acc);
-            p[i] = __dp4a(x[i].w, qv.w, acc);
-        }
-        const int score = transpose_reduce16(p, lane);
-
-        bool ok = false;
-        if (seg != kTombstone) {
-            for (uint32_t j = 0; j < n_scope; ++j) ok |= (seg == s_scope[j]);
-        }
-        const uint64_t key = ok ? pack_key(score, a.id_base + my_row) : 0ull;
+// Offer one tile's keys to the warp list; share / learn the per-query floor.
+__device__ __forceinline__ void offer_tile(WarpTopK &top, bool &first, uint64_t key, uint64_t floor_seen, uint64_t *g_floor,
+                                           int k, int lane) {
+    if (floor_seen > top.floor) top.floor = floor_seen;
+    const uint64_t before = top.thr;
+    if (first) {
+        top.init_sorted(key, k, lane);
+        first = false;
+    } else {
         top.consume(key, k, lane);
     }
+    if (top.thr > before && top.thr > top.floor) {  // warp-uniform
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(g_floor), static_cast<unsigned long long>(top.thr));
+    }
+}
 
-    // ---- block top-k -> partial buffer
-    block_merge(top, s_keys, k, warp, lane);
+// ---- merges -----------------------------------------------------------------------------------
+// Every list that is merged here is sorted descending and zero padded, so a merge is a tournament:
+// lane l holds the head of list l; k rounds of a two-step warp max (score word, then id word among
+// the lanes that tie on the score) pop the winners in rank order.  Cost is k rounds regardless of
+// ties, instead of one serial insertion per candidate.
+constexpr int kListCap = RF_TOPK_MAX;                      // keys per list slot
+constexpr int kWarpArea = 32 * kListCap;                   // one warp's staging area: 32 lists
+template <int kWarps>
+struct MergeScratch {                                      // lives in dynamic shared memory
+    static_assert(kWarps <= 32, "level 2 merges one list per lane");
+    static constexpr int kL1Warps = kWarps < 8 ? kWarps : 8;   // warps that run level-1 tournaments
+    uint64_t warp_area[kL1Warps][kWarpArea];               // level 1: 32 lists x k per warp
+    uint64_t level2[32 * kListCap];                        // level 2: up to 32 merged lists
+    uint32_t flag;
+};
+
+// lists[l * stride + j]: list l (l < n_lists <= 32), j < k.  Returns this lane's rank-th winner
+// (rank = lane, 0 beyond k or when the lists run dry).
+__device__ __forceinline__ uint64_t warp_tournament(const uint64_t *lists, int n_lists, int stride, int k, int lane) {
+    int pos = 0;
+    uint64_t head = lane < n_lists ? lists[lane * stride] : 0ull;
+    uint64_t result = 0ull;
+    for (int r = 0; r < k; ++r) {
+        const uint32_t hi = static_cast<uint32_t>(head >> 32);
+        const uint32_t lo = static_cast<uint32_t>(head);
+        const uint32_t mhi = __reduce_max_sync(kFull, hi);
+        const uint32_t mlo = __reduce_max_sync(kFull, hi == mhi ? lo : 0u);
+        const uint64_t win = (static_cast<uint64_t>(mhi) << 32) | mlo;
+        if (win == 0ull) break;                            // warp-uniform: nothing left anywhere
+        if (lane == r) result = win;
+        if (head == win) {                                 // duplicates across lists advance together
+            ++pos;
+            head = pos < k ? lists[lane * stride + pos] : 0ull;
+        }
+    }
+    return result;
+}
+
+__device__ __forceinline__ void set_list(WarpTopK &top, uint64_t mine, int k) {
+    top.mine = mine;
+    top.thr = shfl_u64(mine, k - 1);
+    top.floor = 0;
+}
+
+// Warps -> warp 0.  On return warp 0's `top` holds the block's top-k.
+template <int kWarps>
+__device__ __forceinline__ void block_merge(WarpTopK &top, MergeScratch<kWarps> &ms, int k, int warp, int lane) {
+    constexpr int n_warps = kWarps;
+    __syncthreads();
+    if (lane < k) ms.level2[warp * k + lane] = top.mine;
+    __syncthreads();
+    if (warp == 0) set_list(top, warp_tournament(ms.level2, n_warps, k, k, lane), k);
+}
+
+// Block top-k -> partial buffer; the last block of the query merges all partials and writes the
+// answer.  Called by every thread of the block.
+template <int kWarps>
+__device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK &top, const int4 &qv, MergeScratch<kWarps> &ms,
+                                             int k, int warp, int lane) {
+    constexpr int n_warps = kWarps;
+    block_merge(top, ms, k, warp, lane);
     uint64_t *part = a.partial + (static_cast<size_t>(qi) * gridDim.x) * k;
     if (warp == 0) {
         if (lane < k) __stcg(part + static_cast<size_t>(blockIdx.x) * k + lane, top.mine);
@@ -160,23 +275,32 @@ __global__ void __launch_bounds__(kScanThreads, 2) score_topk_scan_kernel(const 
         __syncwarp();
         if (lane == 0) {
             const uint32_t ticket = atomicAdd(a.tickets + qi, 1u);
-            s_is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+            ms.flag = (ticket == gridDim.x - 1) ? 1u : 0u;
+            stamp(a, 4);
         }
     }
     __syncthreads();
-    if (!s_is_last) return;
+    if (!ms.flag) return;
 
-    // ---- last block of this query: merge all partials, write the answer
+    // ---- last block of this query: two tournament levels over the gridDim.x partial lists
     __threadfence();
-    top.reset();
-    const uint32_t n_part = gridDim.x * k;
-    for (uint32_t base = 0; base < n_part; base += kScanThreads) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t key = i < n_part ? __ldcg(part + i) : 0ull;
-        top.consume(key, k, lane);
+    const int n_lists = static_cast<int>(gridDim.x);       // engine keeps this <= 1024
+    const int n_groups = (n_lists + 31) / 32;
+    constexpr int l1_warps = MergeScratch<kWarps>::kL1Warps;
+    for (int g = warp; g < n_groups && warp < l1_warps; g += l1_warps) {
+        const int lists_here = min(32, n_lists - g * 32);
+        const uint64_t *src = part + static_cast<size_t>(g) * 32 * k;
+        uint64_t *area = ms.warp_area[warp];
+        for (int i = lane; i < lists_here * k; i += 32) area[i] = __ldcg(src + i);
+        __syncwarp();
+        const uint64_t w = warp_tournament(area, lists_here, k, k, lane);
+        if (lane < k) ms.level2[g * k + lane] = w;
+        __syncwarp();
     }
-    block_merge(top, s_keys, k, warp, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) stamp(a, 6);
     if (warp != 0) return;
+    set_list(top, warp_tournament(ms.level2, n_groups, k, k, lane), k);
 
     // ||q||^2 for the reported cosine (lanes 0..15 cover the 256 query bytes once)
     int qq = __dp4a(qv.x, qv.x, 0);
@@ -209,8 +333,208 @@ __global__ void __launch_bounds__(kScanThreads, 2) score_topk_scan_kernel(const 
     }
     if (lane == 0) {
         if (a.out_counts) a.out_counts[qi] = __popc(found);
-        a.tickets[qi] = 0;  // ready for the next launch on this context
+        a.tickets[qi] = 0;  // ready for the next launch that uses this sync set
+        a.floors[qi] = 0;
+        a.tile_ctr[qi] = 0;
+        stamp(a, 5);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant "ldg": direct global loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLdgWarps = 8;
+
+__global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(const ScanArgs a) {
+    __shared__ BlockPlan bp;
+    extern __shared__ __align__(16) uint8_t ldg_dyn_smem[];
+    MergeScratch<kLdgWarps> &ms = *reinterpret_cast<MergeScratch<kLdgWarps> *>(ldg_dyn_smem);
+
+    const int qi = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int k = static_cast<int>(a.k);
+    if (threadIdx.x == 0) stamp(a, 0);
+    const int4 qv = *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16);
+    stage_plan(a, qi, bp);
+    if (threadIdx.x == 0) stamp(a, 1);
+    const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
+    uint64_t *g_floor = a.floors + qi;
+
+    WarpTopK top;
+    top.reset();
+    bool first = true;
+    TileCursor cur;
+    if (bp.t_lo + warp < bp.t_hi) cur.seek(bp, bp.t_lo + warp);
+
+    for (uint32_t t = bp.t_lo + warp; t < bp.t_hi; t += kLdgWarps) {
+        uint32_t row0, row_end;
+        cur.locate(bp, t, row0, row_end);
+        const int4 *src = reinterpret_cast<const int4 *>(a.F + static_cast<size_t>(row0) * kRowBytes) + lane;
+        int4 x[16];
+        uint32_t seg;
+        const uint32_t my_row = row0 + my_row_in_tile;
+        if (row0 + kTileRows <= row_end) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = ld_stream_v4(src + i * 32);
+            seg = __ldg(a.seg + my_row);
+        } else {  // ragged last tile of an extent
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t r = row0 + 2 * i + (lane >> 4);
+                x[i] = r < row_end ? ld_stream_v4(src + i * 32) : make_int4(0, 0, 0, 0);
+            }
+            seg = my_row < row_end ? __ldg(a.seg + my_row) : kTombstone;
+        }
+        const uint64_t floor_seen = __ldcg(g_floor);
+        const int score = score_tile(x, qv, lane);
+        const uint64_t key = in_scope(bp, seg) ? pack_key(score, a.id_base + my_row) : 0ull;
+        if (first && threadIdx.x == 0) stamp(a, 2);
+        offer_tile(top, first, key, floor_seen, g_floor, k, lane);
+    }
+    if (lane == 0) stamp_max(a, 3);
+    finish_query(a, qi, top, qv, ms, k, warp, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant "tma": producer warp + shared-memory ring filled by bulk copies.
+// ------------------------------------------------------------------------------------------------
+template <int kConsumers, int kStages>
+struct TmaSmem {
+    alignas(128) uint8_t stage[kStages][kTileBytes];
+    alignas(8) uint64_t full[kStages];
+    alignas(8) uint64_t empty[kStages];
+    alignas(16) uint32_t st_seg[kStages][kTileRows];   // store-segment words of the tile (when bulk-copied)
+    uint32_t st_row0[kStages];   // tile held by each stage (written by its producer lane)
+    uint32_t st_rows[kStages];   // rows | 0x100 if st_seg is valid; 0 = sentinel: no more tiles on this stage
+    BlockPlan bp;
+};
+
+template <int kConsumers, int kStages>
+__global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_kernel(const ScanArgs a) {
+    static_assert(kStages % kConsumers == 0, "a stage is always drained by the same consumer warp");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    using Smem = TmaSmem<kConsumers, kStages>;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int qi = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;  // 0 = producer, 1..kConsumers = consumers
+    const int k = static_cast<int>(a.k);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    if (threadIdx.x == 0) stamp(a, 0);
+    const int4 qv = *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16);
+    stage_plan(a, qi, sm.bp);  // ends with __syncthreads()
+    if (threadIdx.x == 0) stamp(a, 1);
+    const BlockPlan &bp = sm.bp;
+
+    WarpTopK top;
+    top.reset();
+
+    const uint32_t total_tiles = bp.total_tiles;
+    uint32_t *tile_ctr = a.tile_ctr + qi;
+
+    if (warp == 0) {
+        // ===== producer warp: lane s owns ring stage s and refills it as soon as it is released,
+        // so up to kStages bulk copies are in flight per SM.  Tiles are claimed kChunkTiles at a
+        // time from a per-query counter (work stealing): SMs that stream faster take more, every
+        // block finishes within a few tiles of the others, and a block that starts late (the next
+        // query overlapping this one's tail under programmatic dependent launch) just takes less.
+        static_assert(kStages <= 32, "one producer lane per stage");
+        if (lane < kStages) {
+            // The first round is static (tile = block * kStages + lane), so no atomic stands before
+            // the first copy; the counter hands out tiles from gridDim.x * kStages on.  Chunks
+            // shrink as the query runs out (guided self-scheduling) so the tail is one tile deep.
+            const uint32_t static_tiles = gridDim.x * kStages;
+            const uint32_t lanes_total = static_tiles;
+            uint32_t round = 0;
+            uint32_t next = blockIdx.x * kStages + lane, chunk_end = next + 1;
+            uint32_t seen = static_tiles;                       // last counter value this lane saw
+            while (true) {
+                if (round) mbar_wait(&sm.empty[lane], (round - 1) & 1);
+                if (next == chunk_end) {
+                    const uint32_t left = seen < total_tiles ? total_tiles - seen : 0u;
+                    const uint32_t want = max(1u, min(static_cast<uint32_t>(kChunkTiles), left / (2u * lanes_total)));
+                    seen = static_tiles + atomicAdd(tile_ctr, want);
+                    next = seen;
+                    chunk_end = min(next + want, total_tiles);
+                }
+                if (next >= total_tiles) {              // sentinel: this stage is done
+                    sm.st_rows[lane] = 0;
+                    mbar_arrive(&sm.full[lane]);
+                    break;
+                }
+                uint32_t row0, row_end;
+                locate_tile(bp, next, row0, row_end);
+                ++next;
+                const uint32_t rows = min(static_cast<uint32_t>(kTileRows), row_end - row0);
+                // the 32 store-segment words ride along when their 128 bytes are 16-byte aligned
+                const bool seg_copy = rows == kTileRows && (row0 & 3u) == 0u;
+                sm.st_row0[lane] = row0;
+                sm.st_rows[lane] = rows | (seg_copy ? 0x100u : 0u);
+                mbar_arrive_expect_tx(&sm.full[lane], rows * kRowBytes + (seg_copy ? 128u : 0u));   // release: publishes st_*
+                bulk_g2s(sm.stage[lane], a.F + static_cast<size_t>(row0) * kRowBytes, rows * kRowBytes, &sm.full[lane]);
+                if (seg_copy) bulk_g2s(sm.st_seg[lane], a.seg + row0, 128u, &sm.full[lane]);
+                ++round;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== consumers: warp c drains stages c, c + kConsumers, ... in ring order =====
+        const int cw = warp - 1;
+        const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
+        uint64_t *g_floor = a.floors + qi;
+        bool first = true;
+        constexpr int kMine = kStages / kConsumers;    // stages per consumer warp
+        uint32_t done_mask = 0;
+        for (uint32_t it = 0; done_mask != (1u << kMine) - 1u; ++it) {
+            const uint32_t slot = it % kMine;
+            if (done_mask & (1u << slot)) continue;
+            const uint32_t s = cw + slot * kConsumers;
+            const uint64_t floor_seen = __ldcg(g_floor);
+            mbar_wait(&sm.full[s], (it / kMine) & 1);
+            const uint32_t rows_word = sm.st_rows[s];
+            if (rows_word == 0) {                      // warp-uniform
+                done_mask |= 1u << slot;
+                continue;
+            }
+            const uint32_t rows = rows_word & 0xFFu;
+            const uint32_t row0 = sm.st_row0[s];
+            const uint32_t my_row = row0 + my_row_in_tile;
+            uint32_t seg;
+            if (rows_word & 0x100u) seg = sm.st_seg[s][my_row_in_tile];
+            else seg = my_row_in_tile < static_cast<int>(rows) ? __ldg(a.seg + my_row) : kTombstone;
+            const int4 *src = reinterpret_cast<const int4 *>(sm.stage[s]) + lane;
+            int4 x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = src[j * 32];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);   // stage may be refilled while we reduce
+            const int score = score_tile(x, qv, lane);
+            const uint64_t key = in_scope(bp, seg) ? pack_key(score, a.id_base + my_row) : 0ull;
+            if (first && threadIdx.x == 32) stamp(a, 2);
+            offer_tile(top, first, key, floor_seen, g_floor, k, lane);
+        }
+        if (lane == 0) stamp_max(a, 3);
+    }
+    // Programmatic dependent launch: wait until the previous kernel in the stream has completed
+    // (it may still be merging while we scanned; it shares the partial/ticket buffers), then let
+    // the next kernel start filling SMs as our blocks retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // warp 0 (the producer) becomes the merging warp: its list is empty so far
+    // every tile has been consumed: the ring is idle and becomes the merge scratch
+    using Scratch = MergeScratch<kConsumers + 1>;
+    static_assert(sizeof(Scratch) <= sizeof(sm.stage), "ring too small to double as merge scratch");
+    __syncthreads();
+    finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane);
 }
 
 // k-way merge of n_lists top-k lists per query (after the all-gather of the sharded path).
@@ -228,14 +552,57 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t *__restr
     if (lane < static_cast<int>(k)) out[static_cast<size_t>(qi) * k + lane] = top.mine;
 }
 
+template <int kConsumers, int kStages>
+cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
+    using Smem = TmaSmem<kConsumers, kStages>;
+    static bool configured = false;   // per process; the attribute is sticky for the function
+    auto kern = score_topk_scan_tma_kernel<kConsumers, kStages>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem)));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((kConsumers + 1) * 32, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 }  // namespace
 
-uint32_t scan_default_blocks_per_query(int sm_count) { return static_cast<uint32_t>(sm_count) * 2u; }
+uint32_t scan_default_blocks_per_query(int sm_count, int variant) {
+    return static_cast<uint32_t>(sm_count) * (variant == kScanVariantLdg ? 2u : 1u);
+}
 
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, cudaStream_t s) {
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s) {
     dim3 grid(blocks_per_query, nq, 1);
-    score_topk_scan_kernel<<<grid, kScanThreads, 0, s>>>(a);
-    return cudaGetLastError();
+    switch (variant) {
+        case kScanVariantLdg: {
+            static bool configured = false;
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(score_topk_scan_ldg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     static_cast<int>(sizeof(MergeScratch<kLdgWarps>)));
+                if (e != cudaSuccess) return e;
+                configured = true;
+            }
+            score_topk_scan_ldg_kernel<<<grid, kLdgWarps * 32, sizeof(MergeScratch<kLdgWarps>), s>>>(a);
+            return cudaGetLastError();
+        }
+        case kScanVariantTma8x24: return launch_tma<8, 24>(a, grid, s);
+        case kScanVariantTma12x24: return launch_tma<12, 24>(a, grid, s);
+        case kScanVariantTma8x16: return launch_tma<8, 16>(a, grid, s);
+        case kScanVariantTma6x12: return launch_tma<6, 12>(a, grid, s);
+        case kScanVariantTma12x12: return launch_tma<12, 12>(a, grid, s);
+        case kScanVariantTma4x12: return launch_tma<4, 12>(a, grid, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t *out_keys,
