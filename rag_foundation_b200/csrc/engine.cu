@@ -111,11 +111,37 @@ struct PinnedBuf {
     }
 };
 
+struct MappedBuf {   // pinned host memory the GPU writes results into directly (zero-copy)
+    void *h = nullptr;
+    void *d = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (h) cudaFreeHost(h);
+        h = d = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n, 4096);
+        cudaError_t e = cudaHostAlloc(&h, want, cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        e = cudaHostGetDevicePointer(&d, h, 0);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        h = d = nullptr;
+        cap = 0;
+    }
+};
+
 struct SearchCtx {
     cudaStream_t stream = nullptr;
+    MappedBuf m_out;
     PinnedBuf h_in, h_out;
     DeviceBuf d_in, d_out, d_partial, d_tickets;
     uint32_t launches = 0;   // parity selects the sync set
+    uint32_t seq = 0;        // completion sequence number written by the kernel into m_out
 };
 
 // A scan plan resident on the device for rf_search_keys_device (cached per scope + stream).
@@ -165,8 +191,10 @@ struct rf_engine {
     std::atomic<uint64_t> searches{0};
     std::atomic<uint64_t> launches{0};
     uint32_t blocks_override = 0;
-    int scan_variant = rf::kScanVariantTma8x24;
+    int scan_variant = rf::kScanVariantTma6x12;
     unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
+    bool profile = false;                    // RF_PROFILE=1: host-side phase times of rf_search on stderr at destroy
+    std::atomic<uint64_t> prof_ns[4]{}, prof_n{0};
     size_t debug_cap = 0;
 };
 
@@ -296,11 +324,14 @@ void fill_args(rf_engine *e, ScanArgs &a, const uint8_t *d_blob, const PlanBlob 
     a.F = e->F;
     a.seg = e->seg;
     a.ff = e->ff;
-    a.q = q_dev ? q_dev : reinterpret_cast<const int8_t *>(d_blob + b.off_q);
-    a.plans = reinterpret_cast<const ScanPlan *>(d_blob + b.off_plans);
-    a.ext_lo = reinterpret_cast<const uint32_t *>(d_blob + b.off_lo);
-    a.ext_hi = reinterpret_cast<const uint32_t *>(d_blob + b.off_hi);
-    a.ext_tile0 = reinterpret_cast<const uint32_t *>(d_blob + b.off_tile0);
+    a.q = q_dev;
+    if (d_blob) {   // null when the plan (and query) ride in the kernel parameters
+        if (!q_dev) a.q = reinterpret_cast<const int8_t *>(d_blob + b.off_q);
+        a.plans = reinterpret_cast<const ScanPlan *>(d_blob + b.off_plans);
+        a.ext_lo = reinterpret_cast<const uint32_t *>(d_blob + b.off_lo);
+        a.ext_hi = reinterpret_cast<const uint32_t *>(d_blob + b.off_hi);
+        a.ext_tile0 = reinterpret_cast<const uint32_t *>(d_blob + b.off_tile0);
+    }
     a.id_base = static_cast<uint32_t>(e->cfg.id_base);
     a.k = k;
     a.shared_plan = shared ? 1u : 0u;
@@ -348,27 +379,50 @@ struct OutLayout {
     }
 };
 
-// Enqueue blob upload + scan + result download on the context's stream, then wait.
-int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_dev, uint32_t nq, uint32_t k, bool shared,
+// One search on a context: (blob upload unless everything rides in the kernel parameters) + scan;
+// the last block writes ids / scores / cosines straight into mapped pinned host memory, so there
+// is no device-to-host copy to enqueue: launch, wait, hand the results to the caller.
+int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_host, uint32_t nq, uint32_t k, bool shared,
                uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](int slot, std::chrono::steady_clock::time_point from) {
+        const auto now = std::chrono::steady_clock::now();
+        if (e->profile) e->prof_ns[slot] += std::chrono::duration_cast<std::chrono::nanoseconds>(now - from).count();
+        return now;
+    };
     const OutLayout L(nq, k);
     const uint32_t X = pick_blocks(e, nq, b.max_tiles);
-    RF_CUDA(c->h_in.reserve(b.bytes.size()));
-    RF_CUDA(c->d_in.reserve(b.bytes.size()));
-    RF_CUDA(c->h_out.reserve(L.total));
-    RF_CUDA(c->d_out.reserve(L.total));
+    const size_t flag_off = (L.total + 15) & ~static_cast<size_t>(15);   // [seq word, finished-query counter]
+    if (flag_off + 16 > c->m_out.cap) {
+        RF_CUDA(c->m_out.reserve(flag_off + 16));
+        memset(c->m_out.h, 0, c->m_out.cap);
+        c->seq = 0;
+    }
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(nq) * X * k * 8));
     if (static_cast<size_t>(nq) * kSyncBytesPerQuery > c->d_tickets.cap) {
         RF_CUDA(cudaStreamSynchronize(c->stream));
         RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery));
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
-    memcpy(c->h_in.p, b.bytes.data(), b.bytes.size());
-    RF_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, b.bytes.size(), cudaMemcpyHostToDevice, c->stream));
     ScanArgs a{};
-    fill_args(e, a, static_cast<const uint8_t *>(c->d_in.p), b, q_dev, k, shared);
+    fill_args(e, a, nullptr, b, nullptr, k, shared);
     maybe_inline_plan(a, b, nq, shared);
-    uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
+    const bool inline_q = nq == 1;
+    if (inline_q) {
+        memcpy(a.q_inline, q_host, RF_DIM);
+        a.q = nullptr;
+    }
+    if (!(inline_q && a.inline_plan)) {   // queries and/or plans travel as one H2D copy
+        RF_CUDA(c->h_in.reserve(b.bytes.size()));
+        RF_CUDA(c->d_in.reserve(b.bytes.size()));
+        memcpy(c->h_in.p, b.bytes.data(), b.bytes.size());
+        RF_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, b.bytes.size(), cudaMemcpyHostToDevice, c->stream));
+        const uint8_t keep_inline = a.inline_plan;
+        fill_args(e, a, static_cast<const uint8_t *>(c->d_in.p), b, nullptr, k, shared);
+        a.inline_plan = keep_inline;
+        if (inline_q) a.q = nullptr;
+    }
+    uint8_t *d_out = static_cast<uint8_t *>(c->m_out.d);
     a.partial = static_cast<uint64_t *>(c->d_partial.p);
     set_sync_bufs(a, c->d_tickets, c->launches++);
     a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
@@ -376,19 +430,37 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_de
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
+    // The flag words sit right after the results in the same mapped allocation.  flag_off depends
+    // on (nq, k); the counter word is left at 0 by every launch, so moving it is safe.
+    volatile uint32_t *h_flag = reinterpret_cast<volatile uint32_t *>(static_cast<uint8_t *>(c->m_out.h) + flag_off);
+    h_flag[0] = 0;
+    h_flag[1] = 0;
+    a.done_flag = reinterpret_cast<uint32_t *>(d_out + flag_off);
+    a.done_seq = ++c->seq ? c->seq : ++c->seq;
     RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
-    // keys are not needed on the host: copy ids..counts only
-    RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
-                            cudaMemcpyDeviceToHost, c->stream));
-    RF_CUDA(cudaStreamSynchronize(c->stream));
-    const uint8_t *h = static_cast<const uint8_t *>(c->h_out.p);
+    const auto t1 = lap(1, t0);
+    // Spin on the mapped completion word (a PCIe write lands ~1 us after the kernel's last store);
+    // fall back to the stream's status so a failed launch can never hang the caller.
+    for (uint32_t spins = 0; h_flag[0] != a.done_seq; ++spins) {
+        if ((spins & 0x3FFu) == 0x3FFu) {
+            const cudaError_t qe = cudaStreamQuery(c->stream);
+            if (qe == cudaSuccess) break;
+            if (qe != cudaErrorNotReady) return fail(RF_ECUDA, "scan kernel failed: %s", cudaGetErrorString(qe));
+        }
+    }
+    if (h_flag[0] != a.done_seq) RF_CUDA(cudaStreamSynchronize(c->stream));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const auto t2 = lap(2, t1);
+    const uint8_t *h = static_cast<const uint8_t *>(c->m_out.h);
     const size_t n = static_cast<size_t>(nq) * k;
     memcpy(out_ids, h + L.off_ids, n * 8);
     memcpy(out_scores, h + L.off_scores, n * 4);
     if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
     if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(nq) * 4);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
+    lap(3, t2);
+    if (e->profile) e->prof_n += 1;
     return RF_OK;
 }
 
@@ -486,6 +558,7 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
 
     const uint64_t cap = cfg->capacity_rows;
     cudaError_t ce;
+    e->profile = getenv("RF_PROFILE") != nullptr;
     if (getenv("RF_SCAN_DEBUG")) {
         e->debug_cap = 4096 * 8;
         if (cudaMalloc(&e->debug_ts, e->debug_cap * 8) != cudaSuccess) e->debug_ts = nullptr;
@@ -521,11 +594,17 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
 
 int rf_engine_destroy(rf_engine *e) {
     if (!e) return RF_OK;
+    if (e->profile && e->prof_n.load()) {
+        const double n = static_cast<double>(e->prof_n.load());
+        fprintf(stderr, "[rf profile] rf_search x%.0f: plan %.2f us, prepare+launch %.2f us, wait %.2f us, copy-out %.2f us\n", n,
+                e->prof_ns[0].load() / n / 1e3, e->prof_ns[1].load() / n / 1e3, e->prof_ns[2].load() / n / 1e3,
+                e->prof_ns[3].load() / n / 1e3);
+    }
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (SearchCtx *c : e->all_ctx) {
         if (c->stream) cudaStreamDestroy(c->stream);
-        c->h_in.release(); c->h_out.release();
+        c->h_in.release(); c->h_out.release(); c->m_out.release();
         c->d_in.release(); c->d_out.release(); c->d_partial.release(); c->d_tickets.release();
         delete c;
     }
@@ -762,6 +841,7 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (nq == 0) return RF_OK;
     if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    const auto t0 = std::chrono::steady_clock::now();
     PlanBlob b;
     int rc = build_blob(e, q, nq, store_segs, seg_off, false, b);
     if (rc) return rc;
@@ -769,7 +849,8 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
     if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
-    return run_search(e, c, b, nullptr, nq, k, false, out_ids, out_scores, out_cos, out_counts);
+    if (e->profile) e->prof_ns[0] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    return run_search(e, c, b, q, nq, k, false, out_ids, out_scores, out_cos, out_counts);
 }
 
 int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_q) {

@@ -338,6 +338,18 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         a.tile_ctr[qi] = 0;
         stamp(a, 5);
     }
+    if (a.done_flag) {   // host-side searches spin on this word instead of a stream synchronise
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t finished = atomicAdd(a.done_flag + 1, 1u) + 1u;   // queries of this launch done so far
+            if (finished == gridDim.y) {
+                a.done_flag[1] = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t *>(a.done_flag) = a.done_seq;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,7 +367,8 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
     const int warp = threadIdx.x >> 5;
     const int k = static_cast<int>(a.k);
     if (threadIdx.x == 0) stamp(a, 0);
-    const int4 qv = *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16);
+    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16)
+                        : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
     stage_plan(a, qi, bp);
     if (threadIdx.x == 0) stamp(a, 1);
     const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
@@ -430,7 +443,8 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
         mbar_fence_init();
     }
     if (threadIdx.x == 0) stamp(a, 0);
-    const int4 qv = *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16);
+    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16)
+                        : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
     stage_plan(a, qi, sm.bp);  // ends with __syncthreads()
     if (threadIdx.x == 0) stamp(a, 1);
     const BlockPlan &bp = sm.bp;
@@ -578,7 +592,10 @@ cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
 }  // namespace
 
 uint32_t scan_default_blocks_per_query(int sm_count, int variant) {
-    return static_cast<uint32_t>(sm_count) * (variant == kScanVariantLdg ? 2u : 1u);
+    // blocks resident per SM: the 96 KB-ring variants (and ldg) fit two, the big rings one
+    const bool two = variant == kScanVariantLdg || variant == kScanVariantTma6x12 || variant == kScanVariantTma12x12 ||
+                     variant == kScanVariantTma4x12;
+    return static_cast<uint32_t>(sm_count) * (two ? 2u : 1u);
 }
 
 cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s) {

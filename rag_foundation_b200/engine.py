@@ -60,6 +60,7 @@ class Engine:
         self.capacity_rows = int(capacity_rows)
         self._zipf = None
         self._lock = threading.Lock()
+        self._csr_cache = {}
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -157,13 +158,21 @@ class Engine:
         nq = q.shape[0]
         if len(scopes) != nq:
             raise ValueError("one scope per query")
-        segs, off = scopes_to_csr(scopes)
-        ids = np.zeros((nq, k), np.uint64)
-        sc = np.zeros((nq, k), np.int32)
-        cs = np.zeros((nq, k), np.float32)
-        cnt = np.zeros(nq, np.uint32)
-        check(self._L.rf_search(self.handle, _ptr(q), nq, _ptr(segs), _ptr(off), int(k), _ptr(ids), _ptr(sc), _ptr(cs),
-                                _ptr(cnt)))
+        key = tuple(tuple(s) for s in scopes) if nq <= 4 else None
+        csr = self._csr_cache.get(key) if key is not None else None
+        if csr is None:
+            csr = scopes_to_csr(scopes)
+            if key is not None and len(self._csr_cache) < 1024:
+                self._csr_cache[key] = csr
+        segs, off = csr
+        ids = np.empty((nq, k), np.uint64)
+        sc = np.empty((nq, k), np.int32)
+        cs = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        rc = self._L.rf_search(self._h, q.ctypes.data, nq, segs.ctypes.data, off.ctypes.data, k, ids.ctypes.data,
+                               sc.ctypes.data, cs.ctypes.data, cnt.ctypes.data)
+        if rc:
+            check(rc)
         return ids, sc, cs, cnt
 
     def search_text(self, text: bytes, scope: Sequence[int], k: int = 10):
