@@ -148,6 +148,7 @@ struct SearchCtx {
 struct DevicePlan {
     uint64_t epoch = ~0ull;
     DeviceBuf blob, partial, tickets;
+    DeviceBuf gemm_lists, gemm_keys_a, gemm_floors;   // batched tensor-core path scratch
     uint32_t n_ext = 0, max_tiles = 0;
     uint32_t launches = 0;
 };
@@ -191,6 +192,8 @@ struct rf_engine {
     std::atomic<uint64_t> searches{0};
     std::atomic<uint64_t> launches{0};
     uint32_t blocks_override = 0;
+    bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
+    uint32_t gemm_min_queries = 64;
     int scan_variant = rf::kScanVariantTma6x12;
     unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
     bool profile = false;                    // RF_PROFILE=1: host-side phase times of rf_search on stderr at destroy
@@ -497,6 +500,56 @@ uint32_t fnv1a32(const char *s, size_t n) {
     return h;
 }
 
+
+// Batched search on the tensor cores (score_topk_gemm.cu): a first pass over a sample of the
+// extent gives every query a floor (the k-th best key of the sample is a valid lower bound of its
+// final k-th best), the second pass scores the rest with the candidate path rare, and a
+// tournament merge combines the per-slice lists of both passes.  Everything is enqueued on `s`.
+int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
+                uint32_t k, uint64_t *out_keys_dev, cudaStream_t s) {
+    const uint32_t rows = hi - lo;
+    const uint32_t q_groups = (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);
+    const uint32_t slices_full = std::max(1u, static_cast<uint32_t>(e->sm_count) / q_groups);
+    uint32_t sample = std::min(rows / 4, 8192u) / rf::kGemmTileRows * rf::kGemmTileRows;
+    const uint32_t n_a = std::max(1u, std::min(slices_full, sample / rf::kGemmTileRows));
+    const uint32_t n_b = std::max(1u, std::min(slices_full, (rows - sample + rf::kGemmTileRows - 1) / rf::kGemmTileRows));
+    const uint32_t kl = rf::kGemmListK;
+    const size_t keys_bytes = static_cast<size_t>(nq) * kl * 8;
+    if (dp->gemm_lists.cap < rf::gemm_lists_bytes(std::max(n_a, n_b), nq) + keys_bytes || dp->gemm_keys_a.cap < keys_bytes ||
+        dp->gemm_floors.cap < static_cast<size_t>(nq) * 8) {
+        RF_CUDA(cudaStreamSynchronize(s));
+        RF_CUDA(dp->gemm_lists.reserve(rf::gemm_lists_bytes(std::max(n_a, n_b), nq) + keys_bytes));
+        RF_CUDA(dp->gemm_keys_a.reserve(keys_bytes));
+        RF_CUDA(dp->gemm_floors.reserve(static_cast<size_t>(nq) * 8));
+    }
+    uint64_t *lists = static_cast<uint64_t *>(dp->gemm_lists.p);
+    uint64_t *keys_a = static_cast<uint64_t *>(dp->gemm_keys_a.p);
+    uint64_t *floors = static_cast<uint64_t *>(dp->gemm_floors.p);
+    rf::GemmArgs g{};
+    g.seg = e->seg;
+    g.n_scope = plan->n_scope;
+    for (uint32_t i = 0; i < RF_SCOPE_MAX; ++i) g.scope[i] = plan->scope[i];
+    g.nq = nq;
+    g.id_base = static_cast<uint32_t>(e->cfg.id_base);
+    g.out_lists = lists;
+    // pass A: the sample, no floors
+    g.floors = nullptr;
+    g.row_lo = lo;
+    g.row_hi = lo + sample;
+    RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_a, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_a * 2, nq, kl, kl, keys_a, s));
+    RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
+    // pass B: the rest, floors from the sample
+    g.floors = floors;
+    g.row_lo = lo + sample;
+    g.row_hi = hi;
+    RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_b, s));
+    RF_CUDA(cudaMemcpyAsync(lists + static_cast<size_t>(n_b) * 2 * nq * kl, keys_a, keys_bytes, cudaMemcpyDeviceToDevice, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_b * 2 + 1, nq, kl, k, out_keys_dev, s));
+    e->launches.fetch_add(5, std::memory_order_relaxed);
+    return RF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -547,6 +600,8 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     if (e->cfg.n_contexts == 0) e->cfg.n_contexts = 8;
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
+    if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
+    if (const char *s = getenv("RF_GEMM_MIN_QUERIES")) e->gemm_min_queries = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_SCAN_VARIANT")) {
         const int v = atoi(s);
         if (v < 0 || v >= rf::kScanVariantCount) {
@@ -610,6 +665,7 @@ int rf_engine_destroy(rf_engine *e) {
     }
     for (auto &kv : e->dev_plans) {
         kv.second->blob.release(); kv.second->partial.release(); kv.second->tickets.release();
+        kv.second->gemm_lists.release(); kv.second->gemm_keys_a.release(); kv.second->gemm_floors.release();
         delete kv.second;
     }
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
@@ -966,6 +1022,19 @@ int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const 
             RF_CUDA(cudaMemcpy(dp->blob.p, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice));
             dp->epoch = now;
             dp->max_tiles = b.max_tiles;
+        }
+        // ---- batched tensor-core path: many queries, one contiguous extent, k <= 10 ----
+        {
+            const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
+            if (e->gemm_enabled && nq >= e->gemm_min_queries && k <= static_cast<uint32_t>(rf::kGemmListK) && hp->n_ext == 1) {
+                const uint32_t lo = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo);
+                const uint32_t hi = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi);
+                if (hi - lo >= 32768) {
+                    const int rc2 = search_gemm(e, dp, q_dev, nq, hp, lo, hi, k, out_keys_dev, s);
+                    if (rc2 == RF_OK) e->searches.fetch_add(nq, std::memory_order_relaxed);
+                    return rc2;
+                }
+            }
         }
         const uint32_t X = pick_blocks(e, nq, dp->max_tiles);
         const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;

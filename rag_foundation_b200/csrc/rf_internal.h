@@ -72,6 +72,28 @@ cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t n
                               uint64_t *out_keys, cudaStream_t s);
 uint32_t scan_default_blocks_per_query(int sm_count, int variant);
 
+// ---- batched GEMM path (score_topk_gemm.cu) ----------------------------------------------------
+constexpr int kGemmListK = 10;      // top-k kept per (thread, query) in registers; searches with k <= 10 qualify
+constexpr int kGemmMT = 4;          // 128-query M-tiles resident per block (512 queries)
+constexpr int kGemmTileRows = 128;  // chunk rows per B tile
+struct GemmArgs {
+    const uint32_t *seg;        // [rows] store-segment words
+    const uint64_t *floors;     // [nq] per-query lower bound keys, or null
+    uint64_t *out_lists;        // [n_slices * 2, nq, kGemmListK] sorted lists
+    uint32_t scope[RF_SCOPE_MAX];
+    uint32_t n_scope;
+    uint32_t row_lo, row_hi;    // contiguous row range to score
+    uint32_t nq;
+    uint32_t id_base;
+};
+size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq);
+cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
+                                   cudaStream_t s);
+cudaError_t launch_floors_from_keys(const uint64_t *keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *floors, cudaStream_t s);
+// keys: [n_lists, nq, k_in] sorted lists -> out [nq, k_out] (k_out <= k_in <= 32, n_lists <= 1024)
+cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
+                               cudaStream_t s);
+
 cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint8_t *zipf_bucket_dev,
                               int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,
                               cudaStream_t s);

@@ -551,19 +551,33 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane);
 }
 
-// k-way merge of n_lists top-k lists per query (after the all-gather of the sharded path).
-__global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists,
-                                                         uint32_t nq, uint32_t k, uint64_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// k-way merge of n_lists sorted top-k lists per query: one warp per query, two tournament levels
+// (after the all-gather of the sharded path, and after the batched GEMM path's per-slice lists).
+constexpr int kMergeWarps = 2;   // 16 KB of staging per warp
+__global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t nq,
+                                                                       uint32_t k_in, uint32_t k_out, uint64_t *__restrict__ out) {
+    __shared__ uint64_t s_area[kMergeWarps][kWarpArea];
+    __shared__ uint64_t s_level2[kMergeWarps][32 * kListCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qi = blockIdx.x * kMergeWarps + warp;
     if (qi >= nq) return;
-    WarpTopK top;
-    top.reset();
-    for (uint32_t l = 0; l < n_lists; ++l) {
-        const uint64_t key = lane < static_cast<int>(k) ? keys[(static_cast<size_t>(l) * nq + qi) * k + lane] : 0ull;
-        top.consume(key, static_cast<int>(k), lane);
+    const int kin = static_cast<int>(k_in);
+    const int n_groups = static_cast<int>((n_lists + 31) / 32);
+    uint64_t *area = s_area[warp];
+    uint64_t *level2 = s_level2[warp];
+    for (int g = 0; g < n_groups; ++g) {
+        const int lists_here = min(32, static_cast<int>(n_lists) - g * 32);
+        for (int i = lane; i < lists_here * kin; i += 32) {
+            const int l = g * 32 + i / kin, j = i % kin;
+            area[i] = keys[(static_cast<size_t>(l) * nq + qi) * kin + j];
+        }
+        __syncwarp();
+        const uint64_t w = warp_tournament(area, lists_here, kin, kin, lane);
+        if (lane < kin) level2[g * kin + lane] = w;
+        __syncwarp();
     }
-    if (lane < static_cast<int>(k)) out[static_cast<size_t>(qi) * k + lane] = top.mine;
+    const uint64_t w = n_groups == 1 ? level2[lane < kin ? lane : 0] : warp_tournament(level2, n_groups, kin, kin, lane);
+    if (lane < static_cast<int>(k_out)) out[static_cast<size_t>(qi) * k_out + lane] = (lane < kin) ? w : 0ull;
 }
 
 template <int kConsumers, int kStages>
@@ -622,12 +636,16 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
     }
 }
 
+cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
+                               cudaStream_t s) {
+    if (n_lists == 0 || n_lists > 1024 || k_in == 0 || k_in > RF_TOPK_MAX || k_out > k_in) return cudaErrorInvalidValue;
+    merge_lists_kernel<<<(nq + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, 0, s>>>(keys, n_lists, nq, k_in, k_out, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t *out_keys,
                               cudaStream_t s) {
-    const uint32_t warps_per_block = 4;
-    merge_topk_kernel<<<(nq + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(keys, n_lists, nq, k,
-                                                                                                 out_keys);
-    return cudaGetLastError();
+    return launch_merge_lists(keys, n_lists, nq, k, k, out_keys, s);
 }
 
 }  // namespace rf

@@ -1,0 +1,330 @@
+// score_topk_gemm: batched query-vs-chunk scoring as a real GEMM on the 5th-generation tensor
+// cores (tcgen05.mma kind::i8, S8 x S8 -> S32, accumulators in TMEM), with the per-query top-k
+// selection fused into the TMEM epilogue -- the 1024 x 1M score matrix (4 GB) never exists.
+// BASELINE.json configs[2]; RF-1 steps 6-7 (oracle/SPEC.md); the retrieval step of
+// GeminiRag.ask_stream (reference backend/app/services/gemini_rag.py:517-551) for many queries.
+//
+// Orientation.  A = queries (M = 128 rows per MMA), B = chunk rows (N = 128 per MMA), K = 256
+// int8 = 8 MMAs of K = 32.  D[query, chunk] lands in TMEM with lane = query, column = chunk, so an
+// epilogue thread owns ONE query per M-tile and walks its row of scores against that query's own
+// threshold held in a register: no cross-lane reduction.  A block keeps kGemmMT M-tiles (512
+// queries) of Q resident in shared memory (SW128 K-major, loaded once by TMA) and streams its
+// slice of the feature arena through a 3-stage TMA ring; it owns all 512 TMEM columns as four
+// 128-column accumulators (one per M-tile), so the MMA warp runs up to four tiles ahead of the
+// epilogue.  Grid = (chunk slices, query groups of 512).
+//
+// Warp roles (10 warps): 0 = TMA producer + TMEM allocator, 1 = MMA issuer (one elected thread),
+// 2..9 = epilogue: warp w reads TMEM lane quarter w % 4 (hardware rule) and column half (w-2)/4.
+// Per 32-column load an epilogue thread takes the max of its 32 scores; only when it reaches the
+// query's threshold score does the warp enter the candidate path, which walks the union of the
+// lanes' candidate columns (one uniform single-column TMEM load each) and inserts into the
+// thread's sorted top-10, a compare-exchange chain held entirely in registers.  Each thread ends
+// with one list per owned query; the lists of all slices / column halves are merged by
+// merge_topk_kernel (warp tournaments).  Thresholds start from a caller-supplied per-query floor
+// (the engine derives it from a first pass over a sample of the store), which is what keeps the
+// candidate path rare.
+#include <cuda.h>
+
+#include "rf_device.cuh"
+#include "rf_internal.h"
+
+namespace rf {
+
+namespace {
+
+constexpr int kGemmK = kGemmListK;          // list length kept per (thread, query)
+constexpr int kMT = kGemmMT;                // M-tiles (of 128 queries) resident per block
+constexpr int kBN = kGemmTileRows;          // chunk rows per B tile / MMA N
+constexpr int kStagesB = 3;
+constexpr int kKBlockBytes = 128;           // one SW128 swizzle row: 128 int8 of K
+constexpr int kTileKBlock = 128 * kKBlockBytes;   // 16 KB: 128 rows x 128 B
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;
+
+struct GemmSmem {
+    alignas(1024) uint8_t q[kMT][2][kTileKBlock];           // 128 KB: resident query tiles
+    alignas(1024) uint8_t b[kStagesB][2][kTileKBlock];      //  96 KB: feature ring
+    alignas(8) uint64_t q_full;
+    uint64_t full[kStagesB], empty[kStagesB];
+    uint64_t tmem_full[kMT], tmem_empty[kMT];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
+    const uint64_t addr = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return v;
+}
+
+// Sorted (descending) top-kGemmK list in registers.
+struct RegList {
+    uint64_t e[kGemmK];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < kGemmK; ++i) e[i] = 0ull;
+    }
+    // x > e[kGemmK-1] is the caller's business; a compare-exchange chain bubbles x into place
+    __device__ __forceinline__ void insert(uint64_t x) {
+        e[kGemmK - 1] = x;
+#pragma unroll
+        for (int i = kGemmK - 1; i > 0; --i) {
+            const uint64_t hi = e[i] > e[i - 1] ? e[i] : e[i - 1];
+            const uint64_t lo = e[i] > e[i - 1] ? e[i - 1] : e[i];
+            e[i - 1] = hi;
+            e[i] = lo;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t gemm_smem_raw[];
+    GemmSmem &sm = *reinterpret_cast<GemmSmem *>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slice = blockIdx.x, n_slices = gridDim.x, qgroup = blockIdx.y;
+
+    // this block's slice of the row range, in whole tiles
+    const uint32_t total_tiles = (a.row_hi - a.row_lo + kBN - 1) / kBN;
+    const uint32_t t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * slice / n_slices);
+    const uint32_t t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * (slice + 1) / n_slices);
+    const uint32_t n_tiles = t_hi - t_lo;
+    const uint32_t q_base = qgroup * (kMT * 128);
+    const uint32_t q_here = min(static_cast<uint32_t>(kMT * 128), a.nq - q_base);
+    const uint32_t m_tiles = (q_here + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.q_full, 1);
+        for (int s = 0; s < kStagesB; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int m = 0; m < kMT; ++m) { mbar_init(&sm.tmem_full[m], 1); mbar_init(&sm.tmem_empty[m], kEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0 && n_tiles) {
+            mbar_arrive_expect_tx(&sm.q_full, m_tiles * 2 * kTileKBlock);
+            for (uint32_t m = 0; m < m_tiles; ++m)
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_2d(sm.q[m][kb], &map_q, kb * kKBlockBytes, static_cast<int>(q_base + m * 128), &sm.q_full);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t s = t % kStagesB;
+                if (t >= kStagesB) mbar_wait(&sm.empty[s], ((t / kStagesB) - 1) & 1);
+                const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
+                mbar_arrive_expect_tx(&sm.full[s], 2 * kTileKBlock);
+                for (int kb = 0; kb < 2; ++kb) tma_load_2d(sm.b[s][kb], &map_f, kb * kKBlockBytes, static_cast<int>(row0), &sm.full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0 && n_tiles) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+            mbar_wait(&sm.q_full, 0);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t s = t % kStagesB;
+                mbar_wait(&sm.full[s], (t / kStagesB) & 1);
+                tc_fence_after();
+                for (uint32_t m = 0; m < m_tiles; ++m) {
+                    if (t) mbar_wait(&sm.tmem_empty[m], (t - 1) & 1);   // epilogue drained this accumulator
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_i8(tmem + m * kBN, umma_desc_sw128(sm.q[m][kb]) + 2u * k, umma_desc_sw128(sm.b[s][kb]) + 2u * k, idesc,
+                                    (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&sm.tmem_full[m]);
+                }
+                umma_commit(&sm.empty[s]);   // the stage is free once every MMA that reads it has retired
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue =====
+        const int ew = warp - 2;
+        const uint32_t lq = warp & 3;                      // TMEM lane quarter this warp may touch
+        const uint32_t ch = ew >> 2;                       // column half
+        const uint32_t row_in_tile = lq * 32 + lane;       // query row within an M-tile
+        RegList list[kMT];
+        uint64_t thr[kMT];
+        uint32_t n_scope = a.n_scope;
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) {
+            list[m].clear();
+            const uint32_t q = q_base + m * 128 + row_in_tile;
+            thr[m] = (a.floors && q < a.nq) ? a.floors[q] : 0ull;
+            if (q >= a.nq) thr[m] = ~0ull;                 // padding rows never produce candidates
+        }
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
+#pragma unroll
+            for (int m = 0; m < kMT; ++m) {
+                if (static_cast<uint32_t>(m) >= m_tiles) break;
+                mbar_wait(&sm.tmem_full[m], t & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t col0 = ch * 64 + h * 32;                      // chunk column within the tile
+                    const uint32_t taddr = tmem + ((lq * 32u) << 16) + m * kBN + col0;
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    int mx = static_cast<int>(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = max(mx, static_cast<int>(v[j]));
+                    const uint32_t thr_s = static_cast<uint32_t>(thr[m] >> 32);
+                    // scores are >= 0 and < 2^31, so the unsigned compare is exact
+                    if (__any_sync(kFull, static_cast<uint32_t>(mx) >= thr_s && thr[m] != ~0ull)) {
+                        uint32_t cand = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
+                        if (thr[m] == ~0ull) cand = 0;
+                        uint32_t uni = __reduce_or_sync(kFull, cand);
+                        while (uni) {
+                            const int j = __ffs(uni) - 1;
+                            uni &= uni - 1;
+                            const uint32_t sc = tmem_ld1(taddr + j);             // uniform single-column reload
+                            const uint32_t row = row0 + col0 + j;
+                            if ((cand >> j) & 1u) {
+                                const uint64_t key = pack_key(static_cast<int32_t>(sc), a.id_base + row);
+                                if (key > thr[m] && row < a.row_hi) {
+                                    const uint32_t sg = __ldg(a.seg + row);   // rare path; the 4 B/row array stays in L2
+                                    bool ok = false;
+                                    if (sg != kTombstone)
+                                        for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
+                                    if (ok) {
+                                        list[m].insert(key);
+                                        const uint64_t kth = list[m].e[kGemmK - 1];
+                                        if (kth > thr[m]) thr[m] = kth;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tmem_empty[m]);
+            }
+        }
+        // one list per (slice, column half, query)
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) {
+            const uint32_t q = q_base + m * 128 + row_in_tile;
+            if (q < a.nq) {
+                uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * 2 + ch) * a.nq + q) * kGemmK;
+#pragma unroll
+                for (int i = 0; i < kGemmK; ++i) dst[i] = list[m].e[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// floors[q] = k-th best key of query q in `keys` ([nq, k_src] sorted lists), for the next pass.
+__global__ void floors_from_keys_kernel(const uint64_t *__restrict__ keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *__restrict__ floors) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) floors[q] = k <= k_src ? keys[static_cast<size_t>(q) * k_src + (k - 1)] : 0ull;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, 256] int8 row-major -> boxes of 128 rows x 128 bytes, 128-byte swizzle
+bool make_map(CUtensorMap *map, const void *base, uint64_t rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {256, rows};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * 2 * nq * kGemmK * 8; }
+
+cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
+                                   cudaStream_t s) {
+    CUtensorMap map_q, map_f;
+    if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
+    static bool configured = false;
+    const int smem = static_cast<int>(sizeof(GemmSmem)) + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(score_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(n_slices, (a.nq + kMT * 128 - 1) / (kMT * 128), 1);
+    score_topk_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_floors_from_keys(const uint64_t *keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *floors, cudaStream_t s) {
+    floors_from_keys_kernel<<<(nq + 127) / 128, 128, 0, s>>>(keys, nq, k_src, k, floors);
+    return cudaGetLastError();
+}
+
+}  // namespace rf

@@ -440,3 +440,54 @@ def test_concurrent_searches_from_threads(co, zb):
         ts = [threading.Thread(target=work, args=(i,)) for i in range(16)]
         [t.start() for t in ts]; [t.join() for t in ts]
         assert not errs, errs[:1]
+
+
+# ------------------------------------------------------------------ batched tensor-core path (configs[2])
+def _device_batch(e, Q, scope, k):
+    import torch
+    qd = torch.from_numpy(np.ascontiguousarray(Q)).cuda()
+    out = torch.zeros((Q.shape[0], k), dtype=torch.int64, device="cuda")
+    e.search_keys_device(qd.data_ptr(), Q.shape[0], scope, k, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("n_rows,nq,k", [(100_001, 300, 10), (65_536, 128, 10), (200_000, 1024, 10), (150_000, 513, 3), (70_000, 64, 1)])
+def test_gemm_path_parity(co, zb, n_rows, nq, k):
+    """tcgen05 int8 GEMM + fused top-k == oracle, including ragged M-tiles, a ragged last chunk tile
+    and k < 10."""
+    with _engine(n_rows + 200, id_base=7) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=21, start_counter=0, n_rows=n_rows)
+        launches0 = e.stats()["kernel_launches"]
+        F = co.synth_rows(21, 0, n_rows, zb)
+        seg = np.full(n_rows, s, np.uint32)
+        Q = np.stack([co.synth_query(21, i, zb) for i in range(nq)])
+        keys = _device_batch(e, Q, [s], k)
+        assert e.stats()["kernel_launches"] - launches0 == 5, "the batched search should have taken the GEMM path"
+        step = max(1, nq // 48)
+        for i in list(range(0, nq, step)) + [nq - 1]:
+            want = co.score_topk_keys(F, seg, Q[i], [s], k=k, id_base=7)
+            assert keys[i].tolist() == want.tolist(), i
+
+
+def test_gemm_path_mask_and_dense_queries(co, zb):
+    """Tombstoned rows inside the extent, a second store after it, and dense high-magnitude queries
+    (many candidates, many ties)."""
+    rng = np.random.default_rng(4)
+    n = 50_000
+    with _engine(3 * n) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        parts = [co.synth_rows(22, i * n // 2, n // 2, zb) for i in range(4)]
+        e.ingest_features(a, 1, parts[0]); e.ingest_features(a, 2, parts[1]); e.ingest_features(a, 3, parts[2])
+        e.ingest_features(b, 4, parts[3])
+        e.tombstone_doc(2)
+        F = np.concatenate(parts)
+        seg = np.concatenate([np.full(n // 2, a), np.full(n // 2, 0xFFFFFFFF), np.full(n // 2, a), np.full(n // 2, b)]).astype(np.uint32)
+        Q = rng.integers(0, 4, (256, 256)).astype(np.int8)
+        Q[:8] = 127                                   # saturating queries: huge scores
+        Q[8:16] = 0                                   # all-zero queries: every score ties at 0
+        keys = _device_batch(e, Q, [a], 10)
+        for i in list(range(0, 256, 9)) + [0, 8, 255]:
+            want = co.score_topk_keys(F, seg, Q[i], [a], k=10)
+            assert keys[i].tolist() == want.tolist(), i
