@@ -194,6 +194,8 @@ struct rf_engine {
     uint32_t blocks_override = 0;
     bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
     uint32_t gemm_min_queries = 64;
+    uint32_t gemm_sample = 8192;     // rows of the first (floor-finding) pass
+    uint32_t gemm_slices_a = 0;      // 0 = as many as fit
     int scan_variant = rf::kScanVariantTma6x12;
     unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
     bool profile = false;                    // RF_PROFILE=1: host-side phase times of rf_search on stderr at destroy
@@ -510,8 +512,9 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     const uint32_t rows = hi - lo;
     const uint32_t q_groups = (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);
     const uint32_t slices_full = std::max(1u, static_cast<uint32_t>(e->sm_count) / q_groups);
-    uint32_t sample = std::min(rows / 4, 8192u) / rf::kGemmTileRows * rf::kGemmTileRows;
-    const uint32_t n_a = std::max(1u, std::min(slices_full, sample / rf::kGemmTileRows));
+    uint32_t sample = std::min(rows / 4, e->gemm_sample) / rf::kGemmTileRows * rf::kGemmTileRows;
+    uint32_t n_a = std::max(1u, std::min(slices_full, sample / rf::kGemmTileRows));
+    if (e->gemm_slices_a) n_a = std::max(1u, std::min(n_a, e->gemm_slices_a));
     const uint32_t n_b = std::max(1u, std::min(slices_full, (rows - sample + rf::kGemmTileRows - 1) / rf::kGemmTileRows));
     const uint32_t kl = rf::kGemmListK;
     const size_t keys_bytes = static_cast<size_t>(nq) * kl * 8;
@@ -532,20 +535,22 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.nq = nq;
     g.id_base = static_cast<uint32_t>(e->cfg.id_base);
     g.out_lists = lists;
+    g.debug = nullptr;
     // pass A: the sample, no floors
     g.floors = nullptr;
     g.row_lo = lo;
     g.row_hi = lo + sample;
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_a, s));
-    RF_CUDA(rf::launch_merge_lists(lists, n_a * 2, nq, kl, kl, keys_a, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_a, nq, kl, kl, keys_a, s));
     RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
     // pass B: the rest, floors from the sample
     g.floors = floors;
     g.row_lo = lo + sample;
     g.row_hi = hi;
+    g.debug = e->debug_ts;   // RF_SCAN_DEBUG=1: cycle counters of the second pass
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_b, s));
-    RF_CUDA(cudaMemcpyAsync(lists + static_cast<size_t>(n_b) * 2 * nq * kl, keys_a, keys_bytes, cudaMemcpyDeviceToDevice, s));
-    RF_CUDA(rf::launch_merge_lists(lists, n_b * 2 + 1, nq, kl, k, out_keys_dev, s));
+    RF_CUDA(cudaMemcpyAsync(lists + static_cast<size_t>(n_b) * nq * kl, keys_a, keys_bytes, cudaMemcpyDeviceToDevice, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_b + 1, nq, kl, k, out_keys_dev, s));
     e->launches.fetch_add(5, std::memory_order_relaxed);
     return RF_OK;
 }
@@ -601,6 +606,8 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
+    if (const char *s = getenv("RF_GEMM_SAMPLE")) e->gemm_sample = static_cast<uint32_t>(atoi(s));
+    if (const char *s = getenv("RF_GEMM_SLICES_A")) e->gemm_slices_a = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM_MIN_QUERIES")) e->gemm_min_queries = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_SCAN_VARIANT")) {
         const int v = atoi(s);

@@ -79,12 +79,13 @@ constexpr int kGemmTileRows = 128;  // chunk rows per B tile
 struct GemmArgs {
     const uint32_t *seg;        // [rows] store-segment words
     const uint64_t *floors;     // [nq] per-query lower bound keys, or null
-    uint64_t *out_lists;        // [n_slices * 2, nq, kGemmListK] sorted lists
+    uint64_t *out_lists;        // [n_slices, nq, kGemmListK] sorted lists
     uint32_t scope[RF_SCOPE_MAX];
     uint32_t n_scope;
     uint32_t row_lo, row_hi;    // contiguous row range to score
     uint32_t nq;
     uint32_t id_base;
+    unsigned long long *debug;  // diagnostics: [block][8] cycle counters, or null
 };
 size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq);
 cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,

@@ -13,8 +13,9 @@
 // 128-column accumulators (one per M-tile), so the MMA warp runs up to four tiles ahead of the
 // epilogue.  Grid = (chunk slices, query groups of 512).
 //
-// Warp roles (10 warps): 0 = TMA producer + TMEM allocator, 1 = MMA issuer (one elected thread),
-// 2..9 = epilogue: warp w reads TMEM lane quarter w % 4 (hardware rule) and column half (w-2)/4.
+// Warp roles (18 warps): 0 = TMA producer + TMEM allocator, 1 = MMA issuer (one elected thread),
+// 2..17 = epilogue, four warps per accumulator: warp w serves M-tile (w-2)/4 and reads TMEM lane
+// quarter w % 4 (hardware rule), so the four accumulators drain concurrently.
 // Per 32-column load an epilogue thread takes the max of its 32 scores; only when it reaches the
 // query's threshold score does the warp enter the candidate path, which walks the union of the
 // lanes' candidate columns (one uniform single-column TMEM load each) and inserts into the
@@ -38,8 +39,9 @@ constexpr int kBN = kGemmTileRows;          // chunk rows per B tile / MMA N
 constexpr int kStagesB = 3;
 constexpr int kKBlockBytes = 128;           // one SW128 swizzle row: 128 int8 of K
 constexpr int kTileKBlock = 128 * kKBlockBytes;   // 16 KB: 128 rows x 128 B
-constexpr int kGemmThreads = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarpsPerTile = 4;          // one warp per TMEM lane quarter
+constexpr int kEpiWarps = kMT * kEpiWarpsPerTile;   // 16: one group of four warps per accumulator
+constexpr int kGemmThreads = (2 + kEpiWarps) * 32;  // 576
 
 struct GemmSmem {
     alignas(1024) uint8_t q[kMT][2][kTileKBlock];           // 128 KB: resident query tiles
@@ -94,6 +96,20 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
     return v;
 }
 
+// v[j] for a warp-uniform j: a 32-way uniform switch over registers (a single-column TMEM reload
+// would queue behind the other warps' 4 KB accumulator loads).
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+    switch (j) {
+#define RF_PICK(i) case i: return v[i];
+        RF_PICK(0) RF_PICK(1) RF_PICK(2) RF_PICK(3) RF_PICK(4) RF_PICK(5) RF_PICK(6) RF_PICK(7)
+        RF_PICK(8) RF_PICK(9) RF_PICK(10) RF_PICK(11) RF_PICK(12) RF_PICK(13) RF_PICK(14) RF_PICK(15)
+        RF_PICK(16) RF_PICK(17) RF_PICK(18) RF_PICK(19) RF_PICK(20) RF_PICK(21) RF_PICK(22) RF_PICK(23)
+        RF_PICK(24) RF_PICK(25) RF_PICK(26) RF_PICK(27) RF_PICK(28) RF_PICK(29) RF_PICK(30)
+#undef RF_PICK
+        default: return v[31];
+    }
+}
+
 // Sorted (descending) top-kGemmK list in registers.
 struct RegList {
     uint64_t e[kGemmK];
@@ -133,7 +149,7 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     if (threadIdx.x == 0) {
         mbar_init(&sm.q_full, 1);
         for (int s = 0; s < kStagesB; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int m = 0; m < kMT; ++m) { mbar_init(&sm.tmem_full[m], 1); mbar_init(&sm.tmem_empty[m], kEpiWarps); }
+        for (int m = 0; m < kMT; ++m) { mbar_init(&sm.tmem_full[m], 1); mbar_init(&sm.tmem_empty[m], kEpiWarpsPerTile); }
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -166,12 +182,18 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (lane == 0 && n_tiles) {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
             mbar_wait(&sm.q_full, 0);
+            long long w_full = 0, w_empty = 0;
+            const long long c_start = clock64();
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kStagesB;
+                long long c0 = clock64();
                 mbar_wait(&sm.full[s], (t / kStagesB) & 1);
+                w_full += clock64() - c0;
                 tc_fence_after();
                 for (uint32_t m = 0; m < m_tiles; ++m) {
+                    c0 = clock64();
                     if (t) mbar_wait(&sm.tmem_empty[m], (t - 1) & 1);   // epilogue drained this accumulator
+                    w_empty += clock64() - c0;
                     tc_fence_after();
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
@@ -185,83 +207,98 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 umma_commit(&sm.empty[s]);   // the stage is free once every MMA that reads it has retired
             }
+            if (a.debug) {
+                unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+                d[0] = clock64() - c_start; d[1] = w_full; d[2] = w_empty; d[3] = n_tiles;
+            }
         }
         __syncwarp();
     } else {
-        // ===== epilogue =====
-        const int ew = warp - 2;
+        // ===== epilogue: group g = (warp - 2) / 4 owns accumulator / M-tile g =====
+        const uint32_t m = static_cast<uint32_t>(warp - 2) >> 2;
         const uint32_t lq = warp & 3;                      // TMEM lane quarter this warp may touch
-        const uint32_t ch = ew >> 2;                       // column half
-        const uint32_t row_in_tile = lq * 32 + lane;       // query row within an M-tile
-        RegList list[kMT];
-        uint64_t thr[kMT];
-        uint32_t n_scope = a.n_scope;
+        const uint32_t row_in_tile = lq * 32 + lane;       // query row within the M-tile
+        const uint32_t q = q_base + m * 128 + row_in_tile;
+        const uint32_t n_scope = a.n_scope;
+        RegList list;
+        list.clear();
+        uint64_t thr = (a.floors && q < a.nq) ? a.floors[q] : 0ull;
+        const bool live = q < a.nq;                        // padding rows never produce candidates
+        long long w_tfull = 0, w_cand = 0, n_cand = 0;
+        const long long e_start = clock64();
+        if (m < m_tiles) {
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
+                // Tenant mask of the tile's 128 chunk columns, one bit per column, fetched with four
+                // coalesced loads before the accumulator is awaited (the candidate path below never
+                // touches global memory): bit j of ok_mask[h] <=> row row0 + 32 h + j is in scope,
+                // not tombstoned and inside the row range.
+                uint32_t ok_mask[4];
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) {
-            list[m].clear();
-            const uint32_t q = q_base + m * 128 + row_in_tile;
-            thr[m] = (a.floors && q < a.nq) ? a.floors[q] : 0ull;
-            if (q >= a.nq) thr[m] = ~0ull;                 // padding rows never produce candidates
-        }
-        for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
-#pragma unroll
-            for (int m = 0; m < kMT; ++m) {
-                if (static_cast<uint32_t>(m) >= m_tiles) break;
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t row = row0 + h * 32 + lane;
+                    bool ok = false;
+                    if (row < a.row_hi) {
+                        const uint32_t sg = __ldg(a.seg + row);
+                        if (sg != kTombstone)
+                            for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
+                    }
+                    ok_mask[h] = __ballot_sync(kFull, ok);
+                }
+                long long c0 = clock64();
                 mbar_wait(&sm.tmem_full[m], t & 1);
+                w_tfull += clock64() - c0;
                 tc_fence_after();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t col0 = ch * 64 + h * 32;                      // chunk column within the tile
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t col0 = h * 32;                                // chunk column within the tile
                     const uint32_t taddr = tmem + ((lq * 32u) << 16) + m * kBN + col0;
+                    const uint32_t okm = h == 0 ? ok_mask[0] : h == 1 ? ok_mask[1] : h == 2 ? ok_mask[2] : ok_mask[3];
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
                     int mx = static_cast<int>(v[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = max(mx, static_cast<int>(v[j]));
-                    const uint32_t thr_s = static_cast<uint32_t>(thr[m] >> 32);
+                    const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
                     // scores are >= 0 and < 2^31, so the unsigned compare is exact
-                    if (__any_sync(kFull, static_cast<uint32_t>(mx) >= thr_s && thr[m] != ~0ull)) {
+                    if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= thr_s)) {
+                        const long long cc = clock64();
+                        ++n_cand;
                         uint32_t cand = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
-                        if (thr[m] == ~0ull) cand = 0;
+                        cand &= okm;
+                        if (!live) cand = 0;
                         uint32_t uni = __reduce_or_sync(kFull, cand);
                         while (uni) {
                             const int j = __ffs(uni) - 1;
                             uni &= uni - 1;
-                            const uint32_t sc = tmem_ld1(taddr + j);             // uniform single-column reload
-                            const uint32_t row = row0 + col0 + j;
+                            const uint32_t sc = pick32(v, j);                    // j is warp-uniform: a jump, not a reload
                             if ((cand >> j) & 1u) {
-                                const uint64_t key = pack_key(static_cast<int32_t>(sc), a.id_base + row);
-                                if (key > thr[m] && row < a.row_hi) {
-                                    const uint32_t sg = __ldg(a.seg + row);   // rare path; the 4 B/row array stays in L2
-                                    bool ok = false;
-                                    if (sg != kTombstone)
-                                        for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
-                                    if (ok) {
-                                        list[m].insert(key);
-                                        const uint64_t kth = list[m].e[kGemmK - 1];
-                                        if (kth > thr[m]) thr[m] = kth;
-                                    }
+                                const uint64_t key = pack_key(static_cast<int32_t>(sc), a.id_base + row0 + col0 + j);
+                                if (key > thr) {
+                                    list.insert(key);
+                                    const uint64_t kth = list.e[kGemmK - 1];
+                                    if (kth > thr) thr = kth;
                                 }
                             }
                         }
+                        w_cand += clock64() - cc;
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tmem_empty[m]);
             }
-        }
-        // one list per (slice, column half, query)
+            if (a.debug && warp == 2 && lane == 0) {
+                unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+                d[4] = clock64() - e_start; d[5] = w_tfull; d[6] = w_cand; d[7] = n_cand;
+            }
+            // one list per (slice, query)
+            if (live) {
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) {
-            const uint32_t q = q_base + m * 128 + row_in_tile;
-            if (q < a.nq) {
-                uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * 2 + ch) * a.nq + q) * kGemmK;
-#pragma unroll
-                for (int i = 0; i < kGemmK; ++i) dst[i] = list[m].e[i];
+                for (int i = 0; i < kGemmK; ++i) dst[i] = list.e[i];
             }
         }
     }
@@ -304,7 +341,7 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows) {
 
 }  // namespace
 
-size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * 2 * nq * kGemmK * 8; }
+size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * nq * kGemmK * 8; }
 
 cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
                                    cudaStream_t s) {
