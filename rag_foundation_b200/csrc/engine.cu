@@ -194,7 +194,7 @@ struct rf_engine {
     uint32_t blocks_override = 0;
     bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
     uint32_t gemm_min_queries = 64;
-    uint32_t gemm_sample = 8192;     // rows of the first (floor-finding) pass
+    uint32_t gemm_sample = 65536;    // rows of the first (floor-finding) pass
     uint32_t gemm_slices_a = 0;      // 0 = as many as fit
     int scan_variant = rf::kScanVariantTma6x12;
     unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
@@ -504,9 +504,9 @@ uint32_t fnv1a32(const char *s, size_t n) {
 
 
 // Batched search on the tensor cores (score_topk_gemm.cu): a first pass over a sample of the
-// extent gives every query a floor (the k-th best key of the sample is a valid lower bound of its
-// final k-th best), the second pass scores the rest with the candidate path rare, and a
-// tournament merge combines the per-slice lists of both passes.  Everything is enqueued on `s`.
+// extent gives every query a floor (the k-th largest per-group maximum of the sample is a valid
+// lower bound of its final k-th best score), the second pass scores every row with the
+// candidate path rare, and a tournament merge combines the per-slice lists.  All on stream `s`.
 int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
                 uint32_t k, uint64_t *out_keys_dev, cudaStream_t s) {
     const uint32_t rows = hi - lo;
@@ -515,7 +515,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     uint32_t sample = std::min(rows / 4, e->gemm_sample) / rf::kGemmTileRows * rf::kGemmTileRows;
     uint32_t n_a = std::max(1u, std::min(slices_full, sample / rf::kGemmTileRows));
     if (e->gemm_slices_a) n_a = std::max(1u, std::min(n_a, e->gemm_slices_a));
-    const uint32_t n_b = std::max(1u, std::min(slices_full, (rows - sample + rf::kGemmTileRows - 1) / rf::kGemmTileRows));
+    const uint32_t n_b = std::max(1u, std::min(slices_full, (rows + rf::kGemmTileRows - 1) / rf::kGemmTileRows));
     const uint32_t kl = rf::kGemmListK;
     const size_t keys_bytes = static_cast<size_t>(nq) * kl * 8;
     if (dp->gemm_lists.cap < rf::gemm_lists_bytes(std::max(n_a, n_b), nq) + keys_bytes || dp->gemm_keys_a.cap < keys_bytes ||
@@ -536,21 +536,22 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.id_base = static_cast<uint32_t>(e->cfg.id_base);
     g.out_lists = lists;
     g.debug = nullptr;
-    // pass A: the sample, no floors
+    // pass A: group maxima over a sample -> per-query floors (a lower bound of the k-th best score)
     g.floors = nullptr;
+    g.group_max_mode = 1;
     g.row_lo = lo;
     g.row_hi = lo + sample;
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_a, s));
     RF_CUDA(rf::launch_merge_lists(lists, n_a, nq, kl, kl, keys_a, s));
     RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
-    // pass B: the rest, floors from the sample
+    // pass B: every row (the sample included: pass A kept maxima, not chunks), floors from pass A
     g.floors = floors;
-    g.row_lo = lo + sample;
+    g.group_max_mode = 0;
+    g.row_lo = lo;
     g.row_hi = hi;
     g.debug = e->debug_ts;   // RF_SCAN_DEBUG=1: cycle counters of the second pass
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_b, s));
-    RF_CUDA(cudaMemcpyAsync(lists + static_cast<size_t>(n_b) * nq * kl, keys_a, keys_bytes, cudaMemcpyDeviceToDevice, s));
-    RF_CUDA(rf::launch_merge_lists(lists, n_b + 1, nq, kl, k, out_keys_dev, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_b, nq, kl, k, out_keys_dev, s));
     e->launches.fetch_add(5, std::memory_order_relaxed);
     return RF_OK;
 }

@@ -85,6 +85,7 @@ struct GemmArgs {
     uint32_t row_lo, row_hi;    // contiguous row range to score
     uint32_t nq;
     uint32_t id_base;
+    uint32_t group_max_mode;    // 1: floor-finding pass -- keep the top-k of per-32-chunk group maxima, not of chunks
     unsigned long long *debug;  // diagnostics: [block][8] cycle counters, or null
 };
 size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq);

@@ -551,21 +551,20 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane);
 }
 
-// k-way merge of n_lists sorted top-k lists per query: one warp per query, two tournament levels
-// (after the all-gather of the sharded path, and after the batched GEMM path's per-slice lists).
-constexpr int kMergeWarps = 2;   // 16 KB of staging per warp
+// k-way merge of n_lists sorted top-k lists per query (after the all-gather of the sharded path,
+// and after the batched GEMM path's per-slice lists): one block per query, one warp per group of
+// 32 lists (level-1 tournaments run in parallel), warp 0 plays the final over the group winners.
+constexpr int kMergeWarps = 8;
 __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t nq,
                                                                        uint32_t k_in, uint32_t k_out, uint64_t *__restrict__ out) {
-    __shared__ uint64_t s_area[kMergeWarps][kWarpArea];
-    __shared__ uint64_t s_level2[kMergeWarps][32 * kListCap];
+    extern __shared__ __align__(16) uint8_t merge_smem[];   // kMergeWarps areas of 32*k_in keys + level 2 of 32*k_in keys
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t qi = blockIdx.x * kMergeWarps + warp;
-    if (qi >= nq) return;
+    const uint32_t qi = blockIdx.x;
     const int kin = static_cast<int>(k_in);
     const int n_groups = static_cast<int>((n_lists + 31) / 32);
-    uint64_t *area = s_area[warp];
-    uint64_t *level2 = s_level2[warp];
-    for (int g = 0; g < n_groups; ++g) {
+    uint64_t *area = reinterpret_cast<uint64_t *>(merge_smem) + static_cast<size_t>(warp) * 32 * kin;
+    uint64_t *level2 = reinterpret_cast<uint64_t *>(merge_smem) + static_cast<size_t>(kMergeWarps) * 32 * kin;
+    for (int g = warp; g < n_groups; g += kMergeWarps) {
         const int lists_here = min(32, static_cast<int>(n_lists) - g * 32);
         for (int i = lane; i < lists_here * kin; i += 32) {
             const int l = g * 32 + i / kin, j = i % kin;
@@ -576,6 +575,8 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
         if (lane < kin) level2[g * kin + lane] = w;
         __syncwarp();
     }
+    __syncthreads();
+    if (warp != 0) return;
     const uint64_t w = n_groups == 1 ? level2[lane < kin ? lane : 0] : warp_tournament(level2, n_groups, kin, kin, lane);
     if (lane < static_cast<int>(k_out)) out[static_cast<size_t>(qi) * k_out + lane] = (lane < kin) ? w : 0ull;
 }
@@ -639,7 +640,15 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
                                cudaStream_t s) {
     if (n_lists == 0 || n_lists > 1024 || k_in == 0 || k_in > RF_TOPK_MAX || k_out > k_in) return cudaErrorInvalidValue;
-    merge_lists_kernel<<<(nq + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, 0, s>>>(keys, n_lists, nq, k_in, k_out, out);
+    const size_t smem = (static_cast<size_t>(kMergeWarps) + 1) * 32 * k_in * 8;   // <= 72 KB at k_in = 32
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>((kMergeWarps + 1) * 32 * RF_TOPK_MAX * 8));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    merge_lists_kernel<<<nq, kMergeWarps * 32, smem, s>>>(keys, n_lists, nq, k_in, k_out, out);
     return cudaGetLastError();
 }
 

@@ -227,6 +227,12 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         long long w_tfull = 0, w_cand = 0, n_cand = 0;
         const long long e_start = clock64();
         if (m < m_tiles) {
+            uint32_t seg_next[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint32_t row = a.row_lo + t_lo * kBN + h * 32 + lane;
+                seg_next[h] = (n_tiles && row < a.row_hi) ? __ldg(a.seg + row) : kTombstone;
+            }
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
                 // Tenant mask of the tile's 128 chunk columns, one bit per column, fetched with four
@@ -237,13 +243,18 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     const uint32_t row = row0 + h * 32 + lane;
+                    const uint32_t sg = seg_next[h];                 // loaded one tile ahead
                     bool ok = false;
-                    if (row < a.row_hi) {
-                        const uint32_t sg = __ldg(a.seg + row);
-                        if (sg != kTombstone)
-                            for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
-                    }
+                    if (row < a.row_hi && sg != kTombstone)
+                        for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
                     ok_mask[h] = __ballot_sync(kFull, ok);
+                }
+                if (t + 1 < n_tiles) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t row = row0 + kBN + h * 32 + lane;
+                        seg_next[h] = row < a.row_hi ? __ldg(a.seg + row) : kTombstone;
+                    }
                 }
                 long long c0 = clock64();
                 mbar_wait(&sm.tmem_full[m], t & 1);
@@ -256,6 +267,22 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     const uint32_t okm = h == 0 ? ok_mask[0] : h == 1 ? ok_mask[1] : h == 2 ? ok_mask[2] : ok_mask[3];
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
+                    if (a.group_max_mode) {
+                        // Floor-finding pass: the k-th largest of per-group maxima (a group = these
+                        // 32 chunks of this query) is a valid lower bound of the query's k-th best
+                        // score -- k distinct chunks reach it -- and costs one insertion per group
+                        // instead of one per chunk.  Out-of-scope chunks must not raise the bound.
+                        int gm = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) gm = max(gm, ((okm >> j) & 1u) ? static_cast<int>(v[j]) : 0);
+                        const uint64_t key = pack_key(gm, a.id_base + row0 + col0);   // low word only makes groups distinct
+                        if (live && okm != 0u && key > thr) {
+                            list.insert(key);
+                            const uint64_t kth = list.e[kGemmK - 1];
+                            if (kth > thr) thr = kth;
+                        }
+                        continue;
+                    }
                     int mx = static_cast<int>(v[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = max(mx, static_cast<int>(v[j]));
@@ -307,10 +334,11 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-// floors[q] = k-th best key of query q in `keys` ([nq, k_src] sorted lists), for the next pass.
+// floors[q] = (k-th best score of query q in `keys` ([nq, k_src] sorted lists)) << 32, for the next pass.
 __global__ void floors_from_keys_kernel(const uint64_t *__restrict__ keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *__restrict__ floors) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) floors[q] = k <= k_src ? keys[static_cast<size_t>(q) * k_src + (k - 1)] : 0ull;
+    // score word only: the low word of a group-maximum key is a group tag, not a chunk id
+    if (q < nq) floors[q] = k <= k_src ? (keys[static_cast<size_t>(q) * k_src + (k - 1)] & 0xFFFFFFFF00000000ull) : 0ull;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
