@@ -65,12 +65,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
     return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        "l"(da), "l"(db), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -178,9 +184,14 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && n_tiles) {
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow keeps descriptors in
+        // uniform registers); one elected lane issues the tcgen05 instructions =====
+        if (n_tiles) {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+            constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);        // SBO = 1024 B, version 1, SWIZZLE_128B
+            const uint32_t q_lo0 = ((smem_u32(&sm.q[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(&sm.b[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
+            constexpr uint32_t kKBlockStep = kTileKBlock >> 4;                   // descriptor units (16 B) per K-block
             mbar_wait(&sm.q_full, 0);
             long long w_full = 0, w_empty = 0;
             const long long c_start = clock64();
@@ -190,24 +201,32 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 mbar_wait(&sm.full[s], (t / kStagesB) & 1);
                 w_full += clock64() - c0;
                 tc_fence_after();
+                const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t m = 0; m < m_tiles; ++m) {
                     c0 = clock64();
                     if (t) mbar_wait(&sm.tmem_empty[m], (t - 1) & 1);   // epilogue drained this accumulator
                     w_empty += clock64() - c0;
                     tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t q_lo = q_lo0 + m * 2 * kKBlockStep;
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb) {
+                        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_i8(tmem + m * kBN, umma_desc_sw128(sm.q[m][kb]) + 2u * k, umma_desc_sw128(sm.b[s][kb]) + 2u * k, idesc,
-                                    (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (q_lo + kb * kKBlockStep + 2u * k);
+                                const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + kb * kKBlockStep + 2u * k);
+                                if (kb | k) umma_i8<true>(tmem + m * kBN, da, db, idesc);
+                                else umma_i8<false>(tmem + m * kBN, da, db, idesc);
+                            }
                         }
+                        umma_commit(&sm.tmem_full[m]);
                     }
-                    umma_commit(&sm.tmem_full[m]);
+                    __syncwarp();
                 }
-                umma_commit(&sm.empty[s]);   // the stage is free once every MMA that reads it has retired
+                if (elect_one()) umma_commit(&sm.empty[s]);   // the stage is free once every MMA that reads it has retired
+                __syncwarp();
             }
-            if (a.debug) {
+            if (a.debug && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[0] = clock64() - c_start; d[1] = w_full; d[2] = w_empty; d[3] = n_tiles;
             }

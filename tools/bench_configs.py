@@ -64,7 +64,7 @@ def cfg3(n_rows: int, nq: int, reps: int):
         for i in range(ncpu):
             co.score_topk_keys(F, seg, Q[i], [s])
         cpu_q = (time.perf_counter() - t0) / ncpu
-        emit({"config": "cfg3: 1M chunks, batched %d queries, top-10, 1 B200" % nq, "kernel": "score_topk_scan (grid.y = queries)",
+        emit({"config": "cfg3: 1M chunks, batched %d queries, top-10, 1 B200" % nq, "kernel": "score_topk_gemm (tcgen05 kind::i8) unless RF_GEMM=0 / nq < 64, then score_topk_scan",
               "ms_per_batch": ms, "qps": nq / (ms * 1e-3), "chunks_per_s": nq * n_rows / (ms * 1e-3),
               "int8_mac_ops_per_s": 2.0 * nq * n_rows * 256 / (ms * 1e-3), "parity_mismatches_sampled": bad,
               "cpu_oracle_ms_per_query": cpu_q * 1e3, "cpu_threads": co.max_threads()})
