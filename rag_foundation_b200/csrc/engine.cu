@@ -69,7 +69,7 @@ struct Doc {
 };
 
 constexpr uint32_t kMaxExtPerQuery = 64;   // more are coalesced (the row mask keeps it exact)
-constexpr uint32_t kTilesPerBlockTarget = 48;
+constexpr uint32_t kTilesPerBlockTarget = 160;   // ~1.3 MB streamed per block: start-up and merge stay under 10 %
 
 struct DeviceBuf {
     void *p = nullptr;
@@ -364,11 +364,13 @@ void maybe_inline_plan(ScanArgs &a, const PlanBlob &b, uint32_t nq, bool shared)
 // n u32 tile counters.
 constexpr size_t kSyncBytesPerQuery = 2 * 16;
 void set_sync_bufs(ScanArgs &a, const DeviceBuf &buf, uint32_t parity) {
-    const size_t cap_q = buf.cap / kSyncBytesPerQuery;
+    const size_t cap_q = (buf.cap - 8) / kSyncBytesPerQuery;
     uint8_t *base = static_cast<uint8_t *>(buf.p) + (parity & 1u) * cap_q * 16;
     a.floors = reinterpret_cast<uint64_t *>(base);
     a.tickets = reinterpret_cast<uint32_t *>(base + cap_q * 8);
     a.tile_ctr = reinterpret_cast<uint32_t *>(base + cap_q * 12);
+    // one finished-query counter per set sits in the last 8 bytes of the buffer (reserve() adds them)
+    a.done_count = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(buf.p) + buf.cap - 8) + (parity & 1u);
 }
 
 struct OutLayout {
@@ -404,9 +406,9 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
         c->seq = 0;
     }
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(nq) * X * k * 8));
-    if (static_cast<size_t>(nq) * kSyncBytesPerQuery > c->d_tickets.cap) {
+    if (static_cast<size_t>(nq) * kSyncBytesPerQuery + 8 > c->d_tickets.cap) {
         RF_CUDA(cudaStreamSynchronize(c->stream));
-        RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery));
+        RF_CUDA(c->d_tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery + 8));
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     ScanArgs a{};
@@ -427,7 +429,15 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
         a.inline_plan = keep_inline;
         if (inline_q) a.q = nullptr;
     }
-    uint8_t *d_out = static_cast<uint8_t *>(c->m_out.d);
+    // Few queries: results land straight in mapped pinned host memory and the host spins on a
+    // completion word (no copy to enqueue, ~1 us after the last store).  Many queries: one PCIe
+    // write per result word would dominate, so results stay in HBM and come back as one copy.
+    const bool mapped = nq <= 8;
+    if (!mapped) {
+        RF_CUDA(c->d_out.reserve(L.total));
+        RF_CUDA(c->h_out.reserve(L.total));
+    }
+    uint8_t *d_out = static_cast<uint8_t *>(mapped ? c->m_out.d : c->d_out.p);
     a.partial = static_cast<uint64_t *>(c->d_partial.p);
     set_sync_bufs(a, c->d_tickets, c->launches++);
     a.out_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
@@ -435,29 +445,40 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
-    // The flag words sit right after the results in the same mapped allocation.  flag_off depends
-    // on (nq, k); the counter word is left at 0 by every launch, so moving it is safe.
-    volatile uint32_t *h_flag = reinterpret_cast<volatile uint32_t *>(static_cast<uint8_t *>(c->m_out.h) + flag_off);
-    h_flag[0] = 0;
-    h_flag[1] = 0;
-    a.done_flag = reinterpret_cast<uint32_t *>(d_out + flag_off);
-    a.done_seq = ++c->seq ? c->seq : ++c->seq;
-    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
-    e->launches.fetch_add(1, std::memory_order_relaxed);
-    const auto t1 = lap(1, t0);
-    // Spin on the mapped completion word (a PCIe write lands ~1 us after the kernel's last store);
-    // fall back to the stream's status so a failed launch can never hang the caller.
-    for (uint32_t spins = 0; h_flag[0] != a.done_seq; ++spins) {
-        if ((spins & 0x3FFu) == 0x3FFu) {
-            const cudaError_t qe = cudaStreamQuery(c->stream);
-            if (qe == cudaSuccess) break;
-            if (qe != cudaErrorNotReady) return fail(RF_ECUDA, "scan kernel failed: %s", cudaGetErrorString(qe));
+    const uint8_t *h = nullptr;
+    std::chrono::steady_clock::time_point t1;
+    if (mapped) {
+        // The flag word sits right after the results in the same mapped allocation.
+        volatile uint32_t *h_flag = reinterpret_cast<volatile uint32_t *>(static_cast<uint8_t *>(c->m_out.h) + flag_off);
+        h_flag[0] = 0;
+        a.done_flag = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->m_out.d) + flag_off);
+        a.done_seq = ++c->seq ? c->seq : ++c->seq;
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
+        e->launches.fetch_add(1, std::memory_order_relaxed);
+        t1 = lap(1, t0);
+        // Spin on the completion word; fall back to the stream's status so a failed launch can
+        // never hang the caller.
+        for (uint32_t spins = 0; h_flag[0] != a.done_seq; ++spins) {
+            if ((spins & 0x3FFu) == 0x3FFu) {
+                const cudaError_t qe = cudaStreamQuery(c->stream);
+                if (qe == cudaSuccess) break;
+                if (qe != cudaErrorNotReady) return fail(RF_ECUDA, "scan kernel failed: %s", cudaGetErrorString(qe));
+            }
         }
+        if (h_flag[0] != a.done_seq) RF_CUDA(cudaStreamSynchronize(c->stream));
+        h = static_cast<const uint8_t *>(c->m_out.h);
+    } else {
+        a.done_flag = nullptr;
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
+        e->launches.fetch_add(1, std::memory_order_relaxed);
+        RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
+                                cudaMemcpyDeviceToHost, c->stream));
+        t1 = lap(1, t0);
+        RF_CUDA(cudaStreamSynchronize(c->stream));
+        h = static_cast<const uint8_t *>(c->h_out.p);
     }
-    if (h_flag[0] != a.done_seq) RF_CUDA(cudaStreamSynchronize(c->stream));
     std::atomic_thread_fence(std::memory_order_acquire);
     const auto t2 = lap(2, t1);
-    const uint8_t *h = static_cast<const uint8_t *>(c->m_out.h);
     const size_t n = static_cast<size_t>(nq) * k;
     memcpy(out_ids, h + L.off_ids, n * 8);
     memcpy(out_scores, h + L.off_scores, n * 4);
@@ -972,8 +993,8 @@ int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *
     RF_CUDA(c->h_out.reserve(L.total + RF_DIM));
     RF_CUDA(c->d_out.reserve(L.total));
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(X) * k * 8));
-    if (c->d_tickets.cap < kSyncBytesPerQuery) {
-        RF_CUDA(c->d_tickets.reserve(kSyncBytesPerQuery));
+    if (c->d_tickets.cap < kSyncBytesPerQuery + 8) {
+        RF_CUDA(c->d_tickets.reserve(kSyncBytesPerQuery + 8));
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     ScanArgs a{};
@@ -1046,11 +1067,11 @@ int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const 
         }
         const uint32_t X = pick_blocks(e, nq, dp->max_tiles);
         const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
-        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * kSyncBytesPerQuery > dp->tickets.cap) {
+        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * kSyncBytesPerQuery + 8 > dp->tickets.cap) {
             RF_CUDA(cudaStreamSynchronize(s));
             RF_CUDA(dp->partial.reserve(need_partial));
-            if (static_cast<size_t>(nq) * kSyncBytesPerQuery > dp->tickets.cap) {
-                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery));
+            if (static_cast<size_t>(nq) * kSyncBytesPerQuery + 8 > dp->tickets.cap) {
+                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery + 8));
                 RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
             }
         }

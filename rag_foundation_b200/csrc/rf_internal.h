@@ -50,6 +50,7 @@ struct ScanArgs {
     uint32_t inl_hi[8];
     uint32_t inl_tile0[9];
     uint32_t *done_flag;           // mapped host word: set to done_seq after the results are visible to the host (or null)
+    uint32_t *done_count;          // device word (zero between launches): queries of this launch finished so far
     uint32_t done_seq;
     int8_t q_inline[256];          // the query vector itself when q == nullptr (nq == 1, host-side searches)
     unsigned long long *debug_ts;  // diagnostics (RF_SCAN_DEBUG=1): [grid.x][8] globaltimer stamps, else null

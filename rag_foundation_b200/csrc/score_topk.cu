@@ -339,12 +339,14 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         stamp(a, 5);
     }
     if (a.done_flag) {   // host-side searches spin on this word instead of a stream synchronise
-        __threadfence_system();
+        __threadfence_system();   // this query's results are visible to the host
         __syncwarp();
         if (lane == 0) {
-            const uint32_t finished = atomicAdd(a.done_flag + 1, 1u) + 1u;   // queries of this launch done so far
+            // the per-launch counter lives in device memory: an atomic on mapped host memory is a
+            // PCIe round trip per query and serialises a 1024-query batch
+            const uint32_t finished = atomicAdd(a.done_count, 1u) + 1u;
             if (finished == gridDim.y) {
-                a.done_flag[1] = 0;
+                *a.done_count = 0;
                 __threadfence_system();
                 *reinterpret_cast<volatile uint32_t *>(a.done_flag) = a.done_seq;
             }

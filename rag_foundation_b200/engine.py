@@ -153,18 +153,27 @@ class Engine:
 
     # ------------------------------------------------------------------ query
     def search(self, q, scopes: Sequence[Sequence[int]], k: int = 10):
-        """q int8 [nq, 256] (host). -> ids uint64 [nq,k], scores int32, cos float32, counts uint32."""
+        """q int8 [nq, 256] (host). -> ids uint64 [nq,k], scores int32, cos float32, counts uint32.
+
+        `scopes` is one list of store segments per query, or -- for large batches, to skip the
+        Python loop -- the CSR pair (segs uint32 [n], off uint32 [nq + 1]) the C-ABI takes."""
         q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, RF_DIM)
         nq = q.shape[0]
-        if len(scopes) != nq:
-            raise ValueError("one scope per query")
-        key = tuple(tuple(s) for s in scopes) if nq <= 4 else None
-        csr = self._csr_cache.get(key) if key is not None else None
-        if csr is None:
-            csr = scopes_to_csr(scopes)
-            if key is not None and len(self._csr_cache) < 1024:
-                self._csr_cache[key] = csr
-        segs, off = csr
+        if isinstance(scopes, tuple) and len(scopes) == 2 and isinstance(scopes[0], np.ndarray):
+            segs = np.ascontiguousarray(scopes[0], dtype=np.uint32)
+            off = np.ascontiguousarray(scopes[1], dtype=np.uint32)
+            if off.shape != (nq + 1,) or int(off[-1]) > segs.size:
+                raise ValueError("CSR scopes: off must have nq + 1 entries ending within segs")
+        else:
+            if len(scopes) != nq:
+                raise ValueError("one scope per query")
+            key = tuple(tuple(s) for s in scopes) if nq <= 4 else None
+            csr = self._csr_cache.get(key) if key is not None else None
+            if csr is None:
+                csr = scopes_to_csr(scopes)
+                if key is not None and len(self._csr_cache) < 1024:
+                    self._csr_cache[key] = csr
+            segs, off = csr
         ids = np.empty((nq, k), np.uint64)
         sc = np.empty((nq, k), np.int32)
         cs = np.empty((nq, k), np.float32)

@@ -92,11 +92,16 @@ def cfg5(n_stores: int, per_store: int, nq: int, reps: int):
             w_ids, w_sc, _ = co.score_topk(F, np.zeros(per_store, np.uint32), Q[i], [0], id_base=st_i * per_store)
             t_cpu += time.perf_counter() - t0
             bad += int(ids[i].tolist() != w_ids.tolist() or sc[i].tolist() != w_sc.tolist())
+        from rag_foundation_b200.engine import scopes_to_csr
+        csr = scopes_to_csr(scopes)                      # the C-ABI's own scope format
+        ids2, sc2, _, _ = e.search(Q, csr, k=10)
+        bad += int(not (ids2 == ids).all() or not (sc2 == sc).all())
         for _ in range(3):
-            e.search(Q, scopes, k=10)
+            e.search(Q, csr, k=10)
+        reps = max(reps, 20)
         t0 = time.perf_counter()
         for _ in range(reps):
-            e.search(Q, scopes, k=10)
+            e.search(Q, csr, k=10)
         wall_ms = (time.perf_counter() - t0) / reps * 1e3
         alg = nq * per_store * 260
         emit({"config": "cfg5: %d stores x %d chunks, %d store-scoped queries per batch, 1 B200" % (n_stores, per_store, nq),
