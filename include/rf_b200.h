@@ -120,6 +120,16 @@ int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *
                    uint32_t n_segs, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
                    float *out_cos, uint32_t *out_count, int8_t *out_q /* RF_DIM, may be NULL */);
 
+/* rf_search_text restricted further to the global chunk id ranges [ranges[2i], ranges[2i+1])
+ * (sorted, disjoint; n_ranges = 0 means no restriction).  Carries doc-level metadata filters
+ * (ChatRequest.metadataFilter, routes/chat.py:295-335, forwarded as `metadata_filter` to
+ * ask_stream): the host resolves the filter to the matching documents' chunk ranges, the kernel
+ * scans the intersection of those ranges with the scoped stores' extents (row mask still applied). */
+int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs,
+                      uint32_t n_segs, const uint64_t *ranges, uint32_t n_ranges, uint32_t k,
+                      uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_count,
+                      int8_t *out_q /* RF_DIM, may be NULL */);
+
 /* Device-resident variant for pipelines and the sharded (multi-GPU) path: q_dev and out_keys_dev
  * are DEVICE pointers, the work is enqueued on `stream` (a cudaStream_t; NULL = legacy default
  * stream) and the call returns without synchronising.  out_keys_dev: nq x k packed RF-1 keys

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rf_rows_read": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp]),
     "rf_search": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "rf_search_text_in": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_keys_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "rf_featurize_query": (_i32, [_vp, _vp, _sz, _vp]),

@@ -14,6 +14,7 @@ facade over one process-global Registry (engine handle + chunk-text sidecar).
 from __future__ import annotations
 
 import bisect
+import logging
 import os
 import threading
 import time
@@ -48,6 +49,7 @@ class _Doc:
     data: bytes
     custom_metadata: Any = None
     deleted: bool = False
+    meta: Dict[str, Any] = field(default_factory=dict)   # custom_metadata flattened to {key: value}
 
 
 class Registry:
@@ -111,6 +113,39 @@ def contents_to_text(contents: Any) -> str:
                     if isinstance(text, str) and text.strip():
                         return text.strip()
     return str(contents)
+
+
+def normalize_custom_metadata(custom_metadata: Any) -> Dict[str, Any]:
+    """upload_file's `custom_metadata` (gemini_rag.py:314: a list of {"key": k, "string_value" |
+    "numeric_value": v} entries, or a plain dict) -> {key: value}."""
+    out: Dict[str, Any] = {}
+    if isinstance(custom_metadata, dict):
+        out.update(custom_metadata)
+    elif isinstance(custom_metadata, (list, tuple)):
+        for item in custom_metadata:
+            if isinstance(item, dict) and "key" in item:
+                for vk in ("string_value", "numeric_value", "value"):
+                    if vk in item:
+                        out[str(item["key"])] = item[vk]
+                        break
+    return out
+
+
+def doc_matches(meta: Dict[str, Any], metadata_filter: Optional[Dict[str, Any]]) -> bool:
+    """`metadata_filter` as validated upstream (routes/chat.py:295-335): {key: scalar | [scalars]};
+    every key must match (a list means any-of); documents without the key do not match."""
+    if not metadata_filter:
+        return True
+    if not isinstance(metadata_filter, dict):
+        return False
+    for key, want in metadata_filter.items():
+        if key not in meta:
+            return False
+        have = meta[key]
+        wants = want if isinstance(want, (list, tuple, set)) else [want]
+        if not any(have == w or str(have) == str(w) for w in wants):
+            return False
+    return True
 
 
 def _get_response_name(response: Any, *, context: str) -> str:  # gemini_rag.py:96-102
@@ -186,7 +221,7 @@ class B200Rag:
                 reg.ops[op_name] = {"done": True, "error": str(exc)}
             raise
         doc = _Doc(doc_id, store_name, display_name or os.path.basename(file_path), file_id, first, n_chunks, spans,
-                   data, custom_metadata)
+                   data, custom_metadata, meta=normalize_custom_metadata(custom_metadata))
         with reg.lock:
             reg.docs[doc_id] = doc
             reg.doc_by_file[file_id] = doc_id
@@ -219,8 +254,10 @@ class B200Rag:
             reg.engine.tombstone_doc(doc.doc_id)
 
     # -------- Query (gemini_rag.py:472-551, 656-694) --------
-    def retrieve(self, text: str, store_names: Sequence[str], k: Optional[int] = None) -> List[dict]:
-        """Top-k grounding contexts for `text` within `store_names`, rank order."""
+    def retrieve(self, text: str, store_names: Sequence[str], k: Optional[int] = None,
+                 metadata_filter: Optional[Dict[str, Any]] = None) -> List[dict]:
+        """Top-k grounding contexts for `text` within `store_names`, rank order.  A metadata filter
+        narrows the scan to the chunk ranges of the matching documents (second mask)."""
         reg = self._reg
         segs = []
         for s in store_names:
@@ -229,7 +266,15 @@ class B200Rag:
                 segs.append(seg)
         if not segs:
             return []
-        ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k)
+        ranges = None
+        if metadata_filter:
+            names = set(store_names)
+            with reg.lock:
+                ranges = sorted((d.first_chunk, d.first_chunk + d.n_chunks) for d in reg.docs.values()
+                                if not d.deleted and d.n_chunks and d.store_name in names and doc_matches(d.meta, metadata_filter))
+            if not ranges:
+                return []
+        ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges)
         out = []
         for gid, sc, c in zip(ids.tolist(), scores.tolist(), cos.tolist()):
             hit = reg.chunk_to_doc(int(gid))
@@ -245,12 +290,12 @@ class B200Rag:
 
     def ask(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
             system: str | None = None) -> Any:
-        return build_final_response(self.retrieve(contents_to_text(contents), store_names))
+        return build_final_response(self.retrieve(contents_to_text(contents), store_names, metadata_filter=metadata_filter))
 
     def ask_stream(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
                    system: str | None = None) -> Generator:
         text = contents_to_text(contents)
-        grounding = self.retrieve(text, store_names)   # the GPU work; no lock is held across the yields
+        grounding = self.retrieve(text, store_names, metadata_filter=metadata_filter)   # the GPU work; no lock is held across the yields
         lead = grounding[0]["text"].strip().splitlines()[0][:200] if grounding else "no matching passages"
         yield SimpleNamespace(text=f"[b200-retrieval] {lead}", candidates=None,
                               usage_metadata=SimpleNamespace(prompt_token_count=0, candidates_token_count=0))
@@ -277,7 +322,10 @@ class B200Rag:
                     out.append({"index": i, "source_type": "web", "uri": getattr(web, "uri", None),
                                 "title": getattr(web, "title", None), "snippet": None, "store": None})
             return out
-        except (AttributeError, KeyError, IndexError, TypeError):
+        except (AttributeError, KeyError, IndexError, TypeError) as e:
+            # same observable behaviour as the reference (gemini_rag.py:589-595): warn and return what we have
+            logging.warning(f"Failed to extract citations: {e}",
+                            extra={"response_type": type(response).__name__, "has_candidates": hasattr(response, "candidates")})
             return out
 
     @staticmethod

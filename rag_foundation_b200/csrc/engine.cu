@@ -245,8 +245,20 @@ void gather_extents(rf_engine *e, const uint32_t *segs, uint32_t n_segs, std::ve
 }
 
 // Build the launch blob for nq queries with CSR scopes.  q may be null (device-resident queries).
+// Keep only the parts of `ext` (sorted, disjoint rows) that fall inside `lim` (sorted, disjoint rows).
+void intersect_extents(std::vector<Extent> &ext, const std::vector<Extent> &lim) {
+    std::vector<Extent> out;
+    size_t i = 0, j = 0;
+    while (i < ext.size() && j < lim.size()) {
+        const uint32_t lo = std::max(ext[i].lo, lim[j].lo), hi = std::min(ext[i].hi, lim[j].hi);
+        if (lo < hi) out.push_back({lo, hi});
+        if (ext[i].hi < lim[j].hi) ++i; else ++j;
+    }
+    ext.swap(out);
+}
+
 int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off,
-               bool shared_scope, PlanBlob &b) {
+               bool shared_scope, PlanBlob &b, const std::vector<Extent> *restrict_rows = nullptr) {
     std::vector<ScanPlan> plans(shared_scope ? 1 : nq);
     std::vector<uint32_t> lo, hi, tile0;
     std::vector<Extent> ext;
@@ -261,6 +273,13 @@ int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store
             p.n_scope = s1 - s0;
             for (uint32_t j = 0; j < RF_SCOPE_MAX; ++j) p.scope[j] = j < p.n_scope ? store_segs[s0 + j] : RF_TOMBSTONE;
             gather_extents(e, store_segs + s0, p.n_scope, ext);
+            if (restrict_rows) {
+                intersect_extents(ext, *restrict_rows);
+                // Unlike store extents these cannot be widened (the row mask knows stores, not
+                // documents): callers split long range lists over several calls (engine.py does).
+                if (ext.size() > kMaxExtPerQuery)
+                    return fail(RF_EINVAL, "row restriction leaves %zu extents (max %u per call)", ext.size(), kMaxExtPerQuery);
+            }
             p.ext_off = static_cast<uint32_t>(lo.size());
             p.n_ext = static_cast<uint32_t>(ext.size());
             uint32_t tiles = 0;
@@ -962,12 +981,30 @@ int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_
 
 int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs, uint32_t k,
                    uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_count, int8_t *out_q) {
-    if (!e || (!utf8 && n) || !out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+    return rf_search_text_in(e, utf8, n, store_segs, n_segs, nullptr, 0, k, out_ids, out_scores, out_cos, out_count, out_q);
+}
+
+int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
+                      const uint64_t *ranges, uint32_t n_ranges, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
+                      float *out_cos, uint32_t *out_count, int8_t *out_q) {
+    if (!e || (!utf8 && n) || !out_ids || !out_scores || (!ranges && n_ranges)) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (n > (1u << 26)) return fail(RF_EINVAL, "query text too long");
+    std::vector<Extent> lim;
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+        const uint64_t lo = ranges[2 * i], hi = ranges[2 * i + 1];
+        if (hi < lo || (i && lo < ranges[2 * i - 1])) return fail(RF_EINVAL, "ranges must be sorted and disjoint");
+        const uint64_t base = e->cfg.id_base, cap = e->cfg.capacity_rows;
+        const uint64_t rlo = lo > base ? lo - base : 0, rhi = hi > base ? hi - base : 0;
+        if (rlo < rhi && rlo < cap) {
+            const uint32_t l32 = static_cast<uint32_t>(rlo), h32 = static_cast<uint32_t>(std::min(rhi, cap));
+            if (!lim.empty() && lim.back().hi == l32) lim.back().hi = h32;   // adjacent documents merge
+            else lim.push_back({l32, h32});
+        }
+    }
     const uint32_t seg_off[2] = {0, n_segs};
     PlanBlob b;
-    int rc = build_blob(e, nullptr, 1, store_segs, seg_off, false, b);
+    int rc = build_blob(e, nullptr, 1, store_segs, seg_off, false, b, n_ranges ? &lim : nullptr);
     if (rc) return rc;
     SearchCtx *c = ctx_acquire(e);
     if (!c) return fail(RF_EBUSY, "no search context free after 5 s");

@@ -48,6 +48,8 @@ def scopes_to_csr(scopes: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarr
 class Engine:
     """One GPU's share of the chunk index (feature arena in HBM + store extents)."""
 
+    RANGES_PER_CALL = 16   # row-range restrictions per launch (the kernel plan holds 64 extents)
+
     def __init__(self, capacity_rows: int, device: int = 0, id_base: int = 0, n_contexts: int = 8):
         self._L = lib()
         cfg = _capi.rf_config(C.sizeof(_capi.rf_config), int(device), RF_DIM, int(n_contexts), int(capacity_rows),
@@ -184,9 +186,24 @@ class Engine:
             check(rc)
         return ids, sc, cs, cnt
 
-    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10):
-        """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [256]   (m <= k results)."""
+    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None):
+        """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [256]   (m <= k results).
+
+        `ranges`: optional sorted, disjoint [(lo, hi), ...] global chunk id ranges to stay inside
+        (doc-level metadata filters)."""
         text = bytes(text)
+        rng = None
+        if ranges is not None:
+            rng = np.ascontiguousarray(np.asarray(list(ranges), dtype=np.uint64).reshape(-1, 2))
+            if rng.shape[0] == 0:
+                return (np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32), self.featurize_query(text))
+            if rng.shape[0] > self.RANGES_PER_CALL:   # many matching documents: several launches, merged here
+                parts = [self.search_text(text, scope, k, ranges=rng[i:i + self.RANGES_PER_CALL])
+                         for i in range(0, rng.shape[0], self.RANGES_PER_CALL)]
+                ids = np.concatenate([p[0] for p in parts]); sc = np.concatenate([p[1] for p in parts])
+                cs = np.concatenate([p[2] for p in parts])
+                order = np.lexsort((ids, -sc.astype(np.int64)))[:k]   # (score desc, id asc): the RF-1 order
+                return ids[order], sc[order], cs[order], parts[0][3]
         segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
         ids = np.zeros(k, np.uint64)
         sc = np.zeros(k, np.int32)
@@ -194,8 +211,9 @@ class Engine:
         cnt = C.c_uint32()
         q = np.zeros(RF_DIM, np.int8)
         buf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0")
-        check(self._L.rf_search_text(self.handle, C.addressof(buf), len(text), _ptr(segs), len(scope), int(k), _ptr(ids),
-                                     _ptr(sc), _ptr(cs), C.byref(cnt), _ptr(q)))
+        check(self._L.rf_search_text_in(self.handle, C.addressof(buf), len(text), _ptr(segs), len(scope), _ptr(rng),
+                                        0 if rng is None else rng.shape[0], int(k), _ptr(ids), _ptr(sc), _ptr(cs),
+                                        C.byref(cnt), _ptr(q)))
         m = int(cnt.value)
         return ids[:m], sc[:m], cs[:m], q
 

@@ -44,8 +44,9 @@ class ScriptedEngine:
     def tombstone_doc(self, doc_id):
         self.tombstoned.append(doc_id)
 
-    def search_text(self, text, scope, k):
+    def search_text(self, text, scope, k, ranges=None):
         self.last_query = (text, list(scope), k)
+        self.last_ranges = ranges
         ids = np.array([h[0] for h in self.hits[:k]], np.uint64)
         sc = np.array([h[1] for h in self.hits[:k]], np.int32)
         cs = np.array([0.5] * len(ids), np.float32)
@@ -176,3 +177,36 @@ def test_upload_failure_is_visible_in_op_status(rag, tmp_path):
         rag.upload_file(store, str(p))
     ops = list(rag._reg.ops.items())
     assert len(ops) == 1 and rag.op_status(ops[0][0])["error"] == "arena full"   # ingestion.py:132-133 raises on it
+
+
+def test_metadata_helpers():
+    m = ad.normalize_custom_metadata([{"key": "team", "string_value": "ops"}, {"key": "year", "numeric_value": 2024}, {"bad": 1}])
+    assert m == {"team": "ops", "year": 2024}
+    assert ad.normalize_custom_metadata({"a": 1}) == {"a": 1} and ad.normalize_custom_metadata(None) == {}
+    assert ad.doc_matches(m, None) and ad.doc_matches(m, {})
+    assert ad.doc_matches(m, {"team": "ops"}) and ad.doc_matches(m, {"team": ["dev", "ops"], "year": 2024})
+    assert ad.doc_matches(m, {"year": "2024"})                      # upstream coerces values to strings or numbers
+    assert not ad.doc_matches(m, {"team": "dev"}) and not ad.doc_matches(m, {"missing": "x"})
+    assert not ad.doc_matches(m, "team = ops")                       # only the validated dict form is accepted
+
+
+def test_metadata_filter_narrows_to_matching_documents(rag, tmp_path):
+    store = rag.create_store("s")
+    for i, team in enumerate(["ops", "dev", "ops"]):
+        p = tmp_path / f"d{i}.txt"
+        p.write_text(" ".join(f"w{j}" for j in range(200)))          # 2 chunks each
+        rag.upload_file(store, str(p), display_name=f"d{i}.txt", custom_metadata=[{"key": "team", "string_value": team}])
+    seen = {}
+
+    def search_text(text, scope, k, ranges=None):
+        seen["ranges"] = ranges
+        return np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(256, np.int8)
+    rag._reg.engine.search_text = search_text
+    rag.retrieve("q", [store], metadata_filter={"team": "ops"})
+    assert seen["ranges"] == [(0, 2), (4, 6)]
+    rag.retrieve("q", [store], metadata_filter=None)
+    assert seen["ranges"] is None
+    seen.clear()
+    assert rag.retrieve("q", [store], metadata_filter={"team": "nobody"}) == [] and "ranges" not in seen
+    list(rag.ask_stream(contents="q", store_names=[store], metadata_filter={"team": ["dev"]}, model="m"))
+    assert seen["ranges"] == [(2, 4)]

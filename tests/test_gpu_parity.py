@@ -491,3 +491,29 @@ def test_gemm_path_mask_and_dense_queries(co, zb):
         for i in list(range(0, 256, 9)) + [0, 8, 255]:
             want = co.score_topk_keys(F, seg, Q[i], [a], k=10)
             assert keys[i].tolist() == want.tolist(), i
+
+
+# ------------------------------------------------------------------ doc-level row restriction (metadata filters)
+def test_search_text_in_ranges(co, zb):
+    n = 30_000
+    with _engine(n) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        F = co.synth_rows(31, 0, n, zb)
+        e.ingest_features(a, 1, F[:10_000]); e.ingest_features(b, 2, F[10_000:20_000]); e.ingest_features(a, 3, F[20_000:])
+        seg = np.concatenate([np.full(10_000, a), np.full(10_000, b), np.full(10_000, a)]).astype(np.uint32)
+        text = b"1786 23 4479 313 12 7 1318 21"
+        q = co.query_vector(text)
+        for ranges in ([(100, 5_000)], [(0, 33), (9_990, 20_010), (29_999, 30_000)], [(10_000, 20_000)],
+                       [(i * 500, i * 500 + 37) for i in range(60)]):           # 60 ranges: split over several launches
+            ids, sc, cs, q_gpu = e.search_text(text, [a], 10, ranges=ranges)
+            assert (q_gpu == q).all()
+            keys = np.concatenate([co.score_topk_keys(F, seg, q, [a], k=10, row_lo=lo, row_hi=hi) for lo, hi in ranges])
+            want = co.merge_topk(keys, 10)
+            want = want[want != 0]
+            from rag_foundation_b200 import unpack_keys
+            w_ids, w_sc, _ = unpack_keys(want)
+            assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist(), ranges[:2]
+        ids, sc, cs, _ = e.search_text(text, [a], 10, ranges=[])
+        assert len(ids) == 0
+        with pytest.raises(RuntimeError):
+            e.search_text(text, [a], 10, ranges=[(50, 60), (10, 20)])          # unsorted
