@@ -101,6 +101,15 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
 /* GeminiRag.delete_document_from_store (gemini_rag.py:354-424, 699-702). */
 int rf_doc_tombstone(rf_engine *e, uint64_t doc_id);
 
+/* ---- durability: the HBM index is volatile and the reference deletes uploads
+ * after ingest (services/ingestion.py:341), so the engine can write / read a snapshot file:
+ * header {magic "RFB2SNP1", dim, n_rows, id_base, n_stores, n_docs}, store table (name, dropped,
+ * extents), document table (id, store, extents), then int8 rows, uint32 segment words, int32 norms.
+ * rf_snapshot_load needs a freshly created engine (no rows, no stores) with capacity >= n_rows and
+ * the same id_base. */
+int rf_snapshot_save(rf_engine *e, const char *path);
+int rf_snapshot_load(rf_engine *e, const char *path);
+
 /* Copy rows [first, first+n) back to the host (tests / snapshots): any of the outputs may be NULL. */
 int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uint32_t *store_seg,
                  int32_t *ff);

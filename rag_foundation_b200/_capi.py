@@ -47,6 +47,8 @@ SIGNATURES = {
     "rf_ingest_features": (_i32, [_vp, _u32, _u64, _vp, _u64, _i32, C.POINTER(_u64)]),
     "rf_ingest_synthetic": (_i32, [_vp, _u32, _u64, _u64, _u64, _u64, _vp, C.POINTER(_u64)]),
     "rf_doc_tombstone": (_i32, [_vp, _u64]),
+    "rf_snapshot_save": (_i32, [_vp, C.c_char_p]),
+    "rf_snapshot_load": (_i32, [_vp, C.c_char_p]),
     "rf_rows_read": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp]),
     "rf_search": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),

@@ -76,6 +76,33 @@ class Registry:
             return d, chunk_id - d.first_chunk
 
 
+    # ---- durability: engine snapshot + the chunk-text sidecar ----
+    def save(self, directory: str) -> None:
+        import pickle
+        os.makedirs(directory, exist_ok=True)
+        with self.lock:
+            self.engine.save_snapshot(os.path.join(directory, "index.rfsnap"))
+            side = {"docs": self.docs, "doc_by_file": self.doc_by_file, "first_chunks": self.first_chunks,
+                    "first_chunk_doc": self.first_chunk_doc, "ops": self.ops, "next_doc": self.next_doc}
+            tmp = os.path.join(directory, "sidecar.pkl.tmp")
+            with open(tmp, "wb") as f:
+                pickle.dump(side, f, protocol=pickle.HIGHEST_PROTOCOL)
+            os.replace(tmp, os.path.join(directory, "sidecar.pkl"))
+
+    @classmethod
+    def load(cls, engine: Engine, directory: str) -> "Registry":
+        """`engine` must be freshly created (empty).  The sidecar is this process's own pickle."""
+        import pickle
+        engine.load_snapshot(os.path.join(directory, "index.rfsnap"))
+        reg = cls(engine)
+        with open(os.path.join(directory, "sidecar.pkl"), "rb") as f:
+            side = pickle.load(f)
+        reg.docs, reg.doc_by_file = side["docs"], side["doc_by_file"]
+        reg.first_chunks, reg.first_chunk_doc = side["first_chunks"], side["first_chunk_doc"]
+        reg.ops, reg.next_doc = side["ops"], side["next_doc"]
+        return reg
+
+
 _registry: Optional[Registry] = None
 _registry_lock = threading.Lock()
 

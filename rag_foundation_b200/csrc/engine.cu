@@ -926,6 +926,118 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
     return RF_OK;
 }
 
+namespace {
+struct SnapHeader {
+    char magic[8];
+    uint32_t dim, reserved;
+    uint64_t n_rows, id_base, n_stores, n_docs;
+};
+bool put(FILE *f, const void *p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+bool get(FILE *f, void *p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+struct FileCloser {
+    FILE *f;
+    ~FileCloser() { if (f) fclose(f); }
+};
+constexpr size_t kSnapChunk = 64u << 20;
+}  // namespace
+
+int rf_snapshot_save(rf_engine *e, const char *path) {
+    if (!e || !path) return fail(RF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> ing(e->ingest_mu);          // no appends / tombstones while we copy
+    std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(RF_EINVAL, "cannot open %s for writing", path);
+    FileCloser fc{f};
+    SnapHeader h{};
+    memcpy(h.magic, "RFB2SNP1", 8);
+    h.dim = RF_DIM;
+    h.n_rows = e->n_rows;
+    h.id_base = e->cfg.id_base;
+    h.n_stores = e->stores.size();
+    h.n_docs = e->docs.size();
+    bool ok = put(f, &h, sizeof h);
+    for (const Store &s : e->stores) {
+        const uint32_t len = static_cast<uint32_t>(s.name.size()), dropped = s.dropped ? 1u : 0u, n_ext = static_cast<uint32_t>(s.ext.size());
+        ok = ok && put(f, &len, 4) && put(f, s.name.data(), len) && put(f, &dropped, 4) && put(f, &n_ext, 4) && put(f, s.ext.data(), n_ext * sizeof(Extent));
+    }
+    for (const auto &kv : e->docs) {
+        const uint32_t n_ext = static_cast<uint32_t>(kv.second.ext.size());
+        ok = ok && put(f, &kv.first, 8) && put(f, &kv.second.store, 4) && put(f, &n_ext, 4) && put(f, kv.second.ext.data(), n_ext * sizeof(Extent));
+    }
+    if (!ok) return fail(RF_EINVAL, "write to %s failed", path);
+    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(e->n_rows * RF_DIM, 1)));
+    const struct { const void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
+    for (const auto &arr : arrays) {
+        const size_t total = e->n_rows * arr.elt;
+        for (size_t off = 0; off < total; off += buf.size()) {
+            const size_t n = std::min(buf.size(), total - off);
+            RF_CUDA(cudaMemcpy(buf.data(), static_cast<const uint8_t *>(arr.base) + off, n, cudaMemcpyDeviceToHost));
+            if (!put(f, buf.data(), n)) return fail(RF_EINVAL, "write to %s failed", path);
+        }
+    }
+    return RF_OK;
+}
+
+int rf_snapshot_load(rf_engine *e, const char *path) {
+    if (!e || !path) return fail(RF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> ing(e->ingest_mu);
+    std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+    if (e->n_rows || !e->stores.empty()) return fail(RF_EINVAL, "snapshots load into an empty engine");
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(RF_ENOTFOUND, "cannot open %s", path);
+    FileCloser fc{f};
+    SnapHeader h{};
+    if (!get(f, &h, sizeof h) || memcmp(h.magic, "RFB2SNP1", 8) != 0 || h.dim != RF_DIM) return fail(RF_EINVAL, "%s is not an RF-1 snapshot", path);
+    if (h.n_rows > e->cfg.capacity_rows) return fail(RF_ECAPACITY, "snapshot holds %llu rows, engine capacity is %llu", (unsigned long long)h.n_rows, (unsigned long long)e->cfg.capacity_rows);
+    if (h.id_base != e->cfg.id_base) return fail(RF_EINVAL, "snapshot id_base %llu != engine id_base %llu", (unsigned long long)h.id_base, (unsigned long long)e->cfg.id_base);
+    std::vector<Store> stores(h.n_stores);
+    bool ok = true;
+    for (Store &s : stores) {
+        uint32_t len = 0, dropped = 0, n_ext = 0;
+        ok = ok && get(f, &len, 4) && len < (1u << 20);
+        if (!ok) break;
+        s.name.resize(len);
+        ok = get(f, &s.name[0], len) && get(f, &dropped, 4) && get(f, &n_ext, 4) && n_ext <= h.n_rows + 1;
+        if (!ok) break;
+        s.dropped = dropped != 0;
+        s.ext.resize(n_ext);
+        ok = get(f, s.ext.data(), n_ext * sizeof(Extent));
+    }
+    std::unordered_map<uint64_t, Doc> docs;
+    for (uint64_t i = 0; ok && i < h.n_docs; ++i) {
+        uint64_t id = 0;
+        uint32_t store = 0, n_ext = 0;
+        ok = get(f, &id, 8) && get(f, &store, 4) && get(f, &n_ext, 4) && n_ext <= h.n_rows + 1;
+        if (!ok) break;
+        Doc d;
+        d.store = store;
+        d.ext.resize(n_ext);
+        ok = get(f, d.ext.data(), n_ext * sizeof(Extent));
+        docs.emplace(id, std::move(d));
+    }
+    if (!ok) return fail(RF_EINVAL, "%s is truncated or corrupt", path);
+    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(h.n_rows * RF_DIM, 1)));
+    const struct { void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
+    for (const auto &arr : arrays) {
+        const size_t total = h.n_rows * arr.elt;
+        for (size_t off = 0; off < total; off += buf.size()) {
+            const size_t n = std::min(buf.size(), total - off);
+            if (!get(f, buf.data(), n)) return fail(RF_EINVAL, "%s is truncated", path);
+            RF_CUDA(cudaMemcpy(static_cast<uint8_t *>(arr.base) + off, buf.data(), n, cudaMemcpyHostToDevice));
+        }
+    }
+    e->stores.swap(stores);
+    e->store_by_name.clear();
+    for (uint32_t i = 0; i < e->stores.size(); ++i)
+        if (!e->stores[i].dropped) e->store_by_name.emplace(e->stores[i].name, i);
+    e->docs.swap(docs);
+    e->n_rows = h.n_rows;
+    e->epoch.fetch_add(1);
+    return RF_OK;
+}
+
 int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uint32_t *store_seg, int32_t *ff) {
     if (!e) return fail(RF_EINVAL, "null argument");
     {

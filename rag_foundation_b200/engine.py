@@ -146,6 +146,13 @@ class Engine:
     def tombstone_doc(self, doc_id: int) -> None:
         check(self._L.rf_doc_tombstone(self.handle, int(doc_id)))
 
+    def save_snapshot(self, path: str) -> None:
+        check(self._L.rf_snapshot_save(self.handle, os.fsencode(path)))
+
+    def load_snapshot(self, path: str) -> None:
+        """Into a freshly created engine (same id_base, capacity >= the snapshot's rows)."""
+        check(self._L.rf_snapshot_load(self.handle, os.fsencode(path)))
+
     def read_rows(self, first_row: int, n: int):
         F = np.zeros((n, RF_DIM), np.int8)
         seg = np.zeros(n, np.uint32)
