@@ -360,6 +360,11 @@ class B200Rag:
         return str(uuid.uuid4()), str(uuid.uuid4())
 
 
-def get_rag_client() -> B200Rag:
-    """What gemini_rag.get_rag_client() (:721-725) returns when RAG_BACKEND=b200."""
+def get_rag_client():
+    """What gemini_rag.get_rag_client() (:721-725) returns when RAG_BACKEND=b200:
+    the in-process adapter, or -- when RAG_B200_SOCKET names the engine daemon's socket -- the
+    client that forwards to it (server.py), so several API / worker processes share one index."""
+    if os.environ.get("RAG_B200_SOCKET"):
+        from .server import RemoteB200Rag
+        return RemoteB200Rag()
     return B200Rag()

@@ -119,3 +119,41 @@ def test_snapshot_round_trip(tmp_path, golden_dir):
             e.load_snapshot(str(tmp_path / "snap" / "index.rfsnap"))             # capacity too small
         finally:
             e.close()
+
+
+@pytest.mark.timeout(180)
+def test_daemon_with_real_engine_and_concurrent_clients(tmp_path, golden_dir):
+    """SURVEY 8f-1 on the GPU: one daemon owns the engine, several client threads (the reference
+    runs one daemon thread per stream, routes/chat.py:520) query it at once."""
+    import threading
+    from rag_foundation_b200 import Engine
+    from rag_foundation_b200 import adapter as ad
+    from rag_foundation_b200.server import RemoteB200Rag, Server
+
+    g = json.load(open(os.path.join(golden_dir, "rf1_golden.json")))
+    wire = json.load(open(os.path.join(golden_dir, "config1_wire.json")))
+    reg = ad.Registry(Engine(capacity_rows=4096, n_contexts=4))
+    srv = Server(str(tmp_path / "rag.sock"), reg).start()
+    try:
+        rag = RemoteB200Rag(str(tmp_path / "rag.sock"))
+        store = rag.create_store("demo")
+        p = tmp_path / "sample-report.md"
+        p.write_bytes(g["sample_report"]["text"].encode("utf-8"))
+        rag.upload_file(store, str(p), display_name="sample-report.md")
+        local = ad.B200Rag(registry=reg).retrieve(wire["demo_query"], [store])
+        assert local and local[0]["title"] == "sample-report.md"
+        errs = []
+
+        def client():
+            try:
+                r = RemoteB200Rag(str(tmp_path / "rag.sock"))
+                for _ in range(20):
+                    assert r.retrieve(wire["demo_query"], [store]) == local
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+        ts = [threading.Thread(target=client) for _ in range(8)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs[:1]
+    finally:
+        srv.close()
+        reg.engine.close()
