@@ -7,7 +7,8 @@ top-10 retrieval, with the fraction of the HBM roofline and the CPU oracle timed
   python bench.py --impl reference ...                     # the CPU arm (RF-1 C oracle, all host cores)
 
 A step is ONE query through the hot path: the fused score + top-10 kernel over every chunk in
-scope (at N > 1: per-rank scan, one NCCL all-gather of the packed keys, the merge kernel).
+scope (at N > 1: per-rank scan with the top-k exchange fused into the kernel over NVLink peer
+memory; `--exchange nccl` selects the all-gather + merge-kernel path instead).
 `value` is chunks scored per second over all GPUs with inputs resident in HBM, timed with CUDA
 events on the launching stream (max over ranks).  `e2e` is the same metric through the public
 C-ABI call with HOST buffers (query upload and result download inside the timed region).
@@ -217,7 +218,7 @@ def run_b200(args) -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     from rag_foundation_b200 import Engine
-    from rag_foundation_b200.sharded import ShardedSearcher, shard_range
+    from rag_foundation_b200.sharded import FusedShardedSearcher, ShardedSearcher, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,7 +240,17 @@ def run_b200(args) -> None:
     eng = Engine(capacity_rows=hi - lo, device=local_rank, id_base=lo)
     seg = eng.open_store("fileSearchStores/bench")
     eng.ingest_synthetic(seg, 0, seed=SEED, start_counter=lo, n_rows=hi - lo)
-    searcher = ShardedSearcher.for_engine(eng)
+    searcher = ShardedSearcher.for_engine(eng)          # NCCL all-gather + merge kernel
+    exchange = "single GPU"
+    if world > 1:
+        exchange = "nccl all-gather + merge kernel"
+        if args.exchange == "fused":
+            try:    # compute + collective in one kernel over NVLink peer memory (symmetric memory)
+                searcher = FusedShardedSearcher(eng, nq_cap=8, k=10)
+                exchange = "fused in the scan kernel: NVLink peer stores + flags (symmetric memory), no collective launch"
+            except Exception as exc:   # noqa: BLE001
+                if rank == 0:
+                    print(f"bench.py: fused exchange unavailable ({exc}); using NCCL", file=sys.stderr)
 
     Qh = make_queries(N_DISTINCT_QUERIES)
     Qd = torch.from_numpy(Qh).to(dev)
@@ -252,7 +263,7 @@ def run_b200(args) -> None:
         if n_gpus == 1:
             eng.search_keys_device(q.data_ptr(), 1, [seg], k, out_keys[qi].data_ptr(), stream.cuda_stream)
         else:
-            out_keys[qi] = searcher.search_keys(q, [seg], k)[0]
+            searcher.search_keys(q, [seg], k, out=out_keys[qi:qi + 1])
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -338,6 +349,8 @@ def run_b200(args) -> None:
         if n_gpus == 1 and not args.no_cpu_baseline:
             cpu = cpu_oracle_leg(n_total, args.cpu_budget_s, Qh, gpu_keys=keys_host if steps + warmup >= N_DISTINCT_QUERIES else None)
         workload = workload_name(n_gpus) if not args.chunks else f"custom: {n_total} chunks over {n_gpus} GPU(s)"
+        if world > 1 and isinstance(searcher, FusedShardedSearcher) and searcher.timed_out():
+            raise SystemExit("bench.py: a peer's top-k never arrived (fused exchange timed out)")
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if n_gpus > 1 else "weak",
@@ -345,7 +358,7 @@ def run_b200(args) -> None:
             "config": {"workload": workload, "chunks": n_total, "chunks_per_gpu": shard_rows, "dim": 256, "k": k,
                        "queries_per_step": 1, "seed": SEED,
                        "l2": f"inputs larger than L2: each step streams {shard_rows * BYTES_PER_CHUNK / 1e6:.0f} MB per GPU (L2 = 126 MB); no flush",
-                       "parallelism": "single GPU" if n_gpus == 1 else f"chunk-sharded x{n_gpus}, NCCL all-gather of packed top-k keys + merge kernel"},
+                       "parallelism": "single GPU" if n_gpus == 1 else f"chunk-sharded x{n_gpus}; top-k exchange: {exchange}"},
             "qps": steps / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": load_traffic("cfg2" if n_gpus == 1 else "cfg4"),
@@ -374,6 +387,7 @@ def main() -> None:
     ap.add_argument("--chunks", type=int, default=0, help="override the corpus size (not the headline workload)")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU top-k exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

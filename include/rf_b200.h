@@ -146,6 +146,30 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
 int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
                           uint32_t n_segs, uint32_t k, uint64_t *out_keys_dev, void *stream);
 
+/* Fused variant of the sharded search: local scan + top-k EXCHANGE in one pass over NVLink peer
+ * memory, no collective launch.  Every rank passes the same exchange description: keys_ptrs[r] /
+ * flag_ptrs[r] are this process's mappings of rank r's gather buffer ([4][world][nq_cap][k] u64)
+ * and flag array ([4][world][nq_cap] u32, zero-initialised), e.g. from a symmetric-memory
+ * rendezvous; `seq` must be the same on all ranks and increase by one per call (four buffers,
+ * slot = seq % 4).  ONE kernel per call does both halves: the block that finishes a query stores its
+ * k keys into every rank's buffer and releases a flag there, then acquires all ranks' flags in its
+ * own buffer (the peers' kernels run concurrently on their GPUs; bounded wait: out_keys_dev is
+ * zeroed and *timeout_flag_dev set to 1 if a peer does not arrive within ~2 s) and merges into
+ * out_keys_dev [nq, k].  Collective semantics: all ranks must call it, on one stream each. */
+typedef struct rf_peer_exchange {
+    uint32_t struct_size;
+    uint32_t rank, world;      /* world <= 8 */
+    uint32_t nq_cap;           /* queries the buffers are sized for */
+    uint32_t k;                /* keys per list the buffers are sized for (== k of the call) */
+    uint32_t seq;              /* > 0, +1 per call, identical on every rank */
+    const uint64_t *keys_ptrs; /* HOST array [world] of device pointers */
+    const uint64_t *flag_ptrs; /* HOST array [world] of device pointers */
+    uint32_t *timeout_flag_dev;
+} rf_peer_exchange;
+int rf_search_keys_device_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                uint32_t n_segs, uint32_t k, const rf_peer_exchange *px,
+                                uint64_t *out_keys_dev, void *stream);
+
 /* k-way merge after the all-gather of the sharded path: keys_dev is n_lists x nq x k packed keys
  * (device), out_keys_dev nq x k.  Enqueued on `stream`, no synchronisation. */
 int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq,

@@ -24,6 +24,12 @@ class rf_config(C.Structure):
                 ("n_contexts", C.c_uint32), ("capacity_rows", C.c_uint64), ("id_base", C.c_uint64)]
 
 
+class rf_peer_exchange(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("nq_cap", C.c_uint32),
+                ("k", C.c_uint32), ("seq", C.c_uint32), ("keys_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p),
+                ("timeout_flag_dev", C.c_void_p)]
+
+
 class rf_stats(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("capacity_rows", C.c_uint64), ("n_stores", C.c_uint64),
                 ("n_docs", C.c_uint64), ("hbm_bytes", C.c_uint64), ("searches", C.c_uint64),
@@ -54,6 +60,7 @@ SIGNATURES = {
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_text_in": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_keys_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
+    "rf_search_keys_device_fused": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "rf_featurize_query": (_i32, [_vp, _vp, _sz, _vp]),
 }

@@ -1172,8 +1172,25 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
     return RF_OK;
 }
 
+static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
+                                   uint32_t k, uint64_t *out_keys_dev, void *stream, const rf_peer_exchange *px);
+
 int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
                           uint32_t k, uint64_t *out_keys_dev, void *stream) {
+    return search_keys_device_impl(e, q_dev, nq, store_segs, n_segs, k, out_keys_dev, stream, nullptr);
+}
+
+int rf_search_keys_device_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
+                                uint32_t k, const rf_peer_exchange *px, uint64_t *out_keys_dev, void *stream) {
+    if (!px || px->struct_size != sizeof(rf_peer_exchange)) return fail(RF_EINVAL, "bad rf_peer_exchange");
+    if (px->world == 0 || px->world > 8 || px->rank >= px->world) return fail(RF_EINVAL, "world must be in [1, 8] and rank < world");
+    if (!px->keys_ptrs || !px->flag_ptrs || !px->timeout_flag_dev) return fail(RF_EINVAL, "null exchange buffer");
+    if (nq > px->nq_cap || k != px->k || px->seq == 0) return fail(RF_EINVAL, "exchange buffers are sized for nq <= %u, k == %u, seq > 0", px->nq_cap, px->k);
+    return search_keys_device_impl(e, q_dev, nq, store_segs, n_segs, k, out_keys_dev, stream, px);
+}
+
+static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
+                                   uint32_t k, uint64_t *out_keys_dev, void *stream, const rf_peer_exchange *px) {
     if (!e || !q_dev || !out_keys_dev) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (nq == 0) return RF_OK;
@@ -1204,7 +1221,7 @@ int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const 
         // ---- batched tensor-core path: many queries, one contiguous extent, k <= 10 ----
         {
             const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
-            if (e->gemm_enabled && nq >= e->gemm_min_queries && k <= static_cast<uint32_t>(rf::kGemmListK) && hp->n_ext == 1) {
+            if (!px && e->gemm_enabled && nq >= e->gemm_min_queries && k <= static_cast<uint32_t>(rf::kGemmListK) && hp->n_ext == 1) {
                 const uint32_t lo = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo);
                 const uint32_t hi = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi);
                 if (hi - lo >= 32768) {
@@ -1230,6 +1247,27 @@ int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const 
         a.partial = static_cast<uint64_t *>(dp->partial.p);
         set_sync_bufs(a, dp->tickets, dp->launches++);
         a.out_keys = out_keys_dev;
+        if (px) {
+            // fused exchange: the scan publishes into every rank's gather buffer, the merge waits on flags
+            const size_t slot = px->seq & 3u;   // four buffers: a rank is never more than three calls ahead of a peer's merge
+            const size_t keys_off = slot * px->world * px->nq_cap * static_cast<size_t>(k);
+            const size_t flag_off = slot * px->world * static_cast<size_t>(px->nq_cap);
+            for (uint32_t r = 0; r < px->world; ++r) {
+                a.px_keys[r] = reinterpret_cast<uint64_t *>(px->keys_ptrs[r]) + keys_off;
+                a.px_flags[r] = reinterpret_cast<uint32_t *>(px->flag_ptrs[r]) + flag_off;
+            }
+            a.px_rank = px->rank;
+            a.px_world = px->world;
+            a.px_seq = px->seq;
+            a.px_nq_cap = px->nq_cap;
+            a.px_out = out_keys_dev;
+            a.px_timeout = px->timeout_flag_dev;
+            if (static_cast<size_t>(nq) * k * 8 > dp->gemm_keys_a.cap) {          // the local (pre-merge) list
+                RF_CUDA(cudaStreamSynchronize(s));
+                RF_CUDA(dp->gemm_keys_a.reserve(static_cast<size_t>(nq) * k * 8));
+            }
+            a.out_keys = static_cast<uint64_t *>(dp->gemm_keys_a.p);
+        }
         RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
     }
     e->launches.fetch_add(1, std::memory_order_relaxed);

@@ -49,6 +49,14 @@ struct ScanArgs {
     uint32_t inl_lo[8];
     uint32_t inl_hi[8];
     uint32_t inl_tile0[9];
+    // Fused top-k exchange over NVLink peer memory (sharded search): when px_world > 1 the block
+    // that finishes a query stores its k keys into every rank's gather buffer and then releases
+    // a per-(rank, query) flag there; merge_wait_kernel on each rank acquires the flags and merges.
+    uint64_t *px_keys[8];          // rank r's gather buffer [world][px_nq_cap][k] (peer-mapped pointers)
+    uint32_t *px_flags[8];         // rank r's flags [world][px_nq_cap]
+    uint32_t px_rank, px_world, px_seq, px_nq_cap;
+    uint64_t *px_out;              // [nq, k] merged result of all ranks (this rank's copy)
+    uint32_t *px_timeout;          // set to 1 if a peer's keys did not arrive within the wait bound
     uint32_t *done_flag;           // mapped host word: set to done_seq after the results are visible to the host (or null)
     uint32_t *done_count;          // device word (zero between launches): queries of this launch finished so far
     uint32_t done_seq;

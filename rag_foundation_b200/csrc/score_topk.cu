@@ -331,6 +331,45 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
             a.out_cos[o] = c;
         }
     }
+    if (a.px_world > 1) {
+        // ---- fused exchange (sharded search): compute + collective in this one kernel.  This
+        // rank's top-k of query qi goes straight into every rank's gather buffer over NVLink
+        // (peer-mapped stores), one release store per peer publishes it; then lane r acquires rank
+        // r's flag (the peers' scan kernels run concurrently on their own GPUs; the wait is
+        // bounded) and the warp plays the tournament over the `world` lists in the local buffer.
+        if (lane < k) {
+            const size_t slot = (static_cast<size_t>(a.px_rank) * a.px_nq_cap + qi) * k + lane;
+            for (uint32_t p = 0; p < a.px_world; ++p) a.px_keys[p][slot] = key;
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < static_cast<int>(a.px_world)) {
+            uint32_t *flag = a.px_flags[lane] + static_cast<size_t>(a.px_rank) * a.px_nq_cap + qi;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.px_seq) : "memory");
+        }
+        bool arrived = true;
+        if (lane < static_cast<int>(a.px_world)) {
+            const uint32_t *flag = a.px_flags[a.px_rank] + static_cast<size_t>(lane) * a.px_nq_cap + qi;
+            const long long t0 = clock64();
+            uint32_t v;
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v == a.px_seq) break;
+                if (clock64() - t0 > (4ll << 30)) { arrived = false; break; }   // ~2 s: fail loudly, never hang
+            }
+        }
+        arrived = __all_sync(kFull, arrived);
+        uint64_t *lists = ms.level2;
+        const uint64_t *gather = a.px_keys[a.px_rank];
+        for (int i = lane; i < static_cast<int>(a.px_world) * k; i += 32) {
+            const int r = i / k, j = i % k;
+            lists[i] = __ldcg(gather + (static_cast<size_t>(r) * a.px_nq_cap + qi) * k + j);   // peers wrote into L2
+        }
+        __syncwarp();
+        const uint64_t merged = warp_tournament(lists, static_cast<int>(a.px_world), k, k, lane);
+        if (lane < k) a.px_out[static_cast<size_t>(qi) * k + lane] = arrived ? merged : 0ull;
+        if (!arrived && lane == 0) atomicExch(a.px_timeout, 1u);
+    }
     if (lane == 0) {
         if (a.out_counts) a.out_counts[qi] = __popc(found);
         a.tickets[qi] = 0;  // ready for the next launch that uses this sync set

@@ -237,6 +237,17 @@ class Engine:
         check(self._L.rf_search_keys_device(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k),
                                             int(out_keys_ptr), int(stream) or None))
 
+    def search_keys_device_fused(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int, stream: int,
+                                 rank: int, world: int, nq_cap: int, seq: int, keys_ptrs: np.ndarray, flag_ptrs: np.ndarray,
+                                 timeout_flag_ptr: int) -> None:
+        """Sharded search with the top-k exchange fused into the kernels (NVLink peer stores +
+        flags) instead of an NCCL all-gather; see rf_search_keys_device_fused in rf_b200.h."""
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        px = _capi.rf_peer_exchange(C.sizeof(_capi.rf_peer_exchange), int(rank), int(world), int(nq_cap), int(k), int(seq),
+                                    keys_ptrs.ctypes.data, flag_ptrs.ctypes.data, int(timeout_flag_ptr))
+        check(self._L.rf_search_keys_device_fused(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k), C.byref(px),
+                                                  int(out_keys_ptr), int(stream) or None))
+
     def merge_topk_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, out_keys_ptr: int, stream: int = 0) -> None:
         check(self._L.rf_merge_topk_device(self.handle, int(keys_ptr), int(n_lists), int(nq), int(k), int(out_keys_ptr),
                                            int(stream) or None))

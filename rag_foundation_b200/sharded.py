@@ -64,17 +64,75 @@ class ShardedSearcher:
 
         return cls(local_search, merge, group)
 
-    def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: int = 10) -> torch.Tensor:
+    def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: int = 10, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """q int8 [nq, 256] (replicated on every rank) -> merged packed keys int64 [nq, k] on every rank."""
         local = self.local_search(q, scope, k)
         if self.world == 1:
+            if out is not None:
+                out.copy_(local)
+                return out
             return local
         shape = (self.world, local.shape[0], k)
         if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != local.device:
             self._gather_buf = torch.empty(shape, dtype=torch.int64, device=local.device)
         # rank-major concatenation along dim 0 (the form both NCCL and gloo accept)
         dist.all_gather_into_tensor(self._gather_buf.view(shape[0] * shape[1], k), local.contiguous(), group=self.group)
-        return self.merge(self._gather_buf, k)
+        merged = self.merge(self._gather_buf, k)
+        if out is not None:
+            out.copy_(merged)
+            return out
+        return merged
 
     def search(self, q: torch.Tensor, scope: Sequence[int], k: int = 10):
+        return unpack_keys_torch(self.search_keys(q, scope, k))
+
+
+class FusedShardedSearcher:
+    """Sharded search with the exchange fused into the scan kernel: its finishing block stores the
+    rank's top-k straight into every rank's gather buffer over NVLink (symmetric memory from
+    torch.distributed._symmetric_memory), releases a flag, acquires the peers' flags and merges --
+    compute and collective in ONE kernel, no NCCL launch on the data path.  Same results as
+    ShardedSearcher (the packed key is a total order)."""
+
+    def __init__(self, engine, nq_cap: int = 64, k: int = 10, group: Optional[dist.ProcessGroup] = None):
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm_mem
+        self.engine = engine
+        self.k = k
+        self.nq_cap = nq_cap
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("the fused exchange serves the GPUs of one box (world <= 8)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._keys = symm_mem.empty((4 * self.world * nq_cap * k,), dtype=torch.int64, device=dev)
+        self._flags = symm_mem.empty((4 * self.world * nq_cap,), dtype=torch.int32, device=dev)
+        self._keys.zero_()
+        self._flags.zero_()
+        self._hk = symm_mem.rendezvous(self._keys, self.group)
+        self._hf = symm_mem.rendezvous(self._flags, self.group)
+        self._keys_ptrs = np.asarray([int(p) for p in self._hk.buffer_ptrs], dtype=np.uint64)
+        self._flag_ptrs = np.asarray([int(p) for p in self._hf.buffer_ptrs], dtype=np.uint64)
+        self._timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._seq = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)          # every rank has zeroed its flags before anyone publishes
+
+    def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: Optional[int] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        k = k or self.k
+        assert k == self.k and q.shape[0] <= self.nq_cap and q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
+        if out is None:
+            out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        self._seq += 1
+        self.engine.search_keys_device_fused(q.data_ptr(), q.shape[0], scope, k, out.data_ptr(),
+                                             torch.cuda.current_stream(q.device).cuda_stream, self.rank, self.world,
+                                             self.nq_cap, self._seq, self._keys_ptrs, self._flag_ptrs, self._timeout.data_ptr())
+        return out
+
+    def timed_out(self) -> bool:
+        return bool(self._timeout.item())
+
+    def search(self, q: torch.Tensor, scope: Sequence[int], k: Optional[int] = None):
         return unpack_keys_torch(self.search_keys(q, scope, k))
