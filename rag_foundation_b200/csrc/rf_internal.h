@@ -8,6 +8,20 @@
 
 namespace rf {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per
+// device, and one process may own engines on several GPUs.  Benign if two threads race.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes) {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
 constexpr uint32_t kScanTileRows = 32;  // rows per warp step of the scan kernel (== rf::kTileRows)
 
 // One query's scan plan (device memory).  The rows to scan are the union of `n_ext` extents
@@ -74,7 +88,8 @@ enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, de
     kScanVariantTma6x12 = 4,    // 96 KB ring: two blocks per SM
     kScanVariantTma12x12 = 5,
     kScanVariantTma4x12 = 6,
-    kScanVariantCount = 7
+    kScanVariantTma4x8 = 7,     // 64 KB ring: three blocks per SM
+    kScanVariantCount = 8
 };
 cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s);
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,

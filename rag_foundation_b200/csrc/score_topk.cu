@@ -625,13 +625,8 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
 template <int kConsumers, int kStages>
 cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
     using Smem = TmaSmem<kConsumers, kStages>;
-    static bool configured = false;   // per process; the attribute is sticky for the function
     auto kern = score_topk_scan_tma_kernel<kConsumers, kStages>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem)));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(kern, static_cast<int>(sizeof(Smem))); e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((kConsumers + 1) * 32, 1, 1);
@@ -651,6 +646,7 @@ uint32_t scan_default_blocks_per_query(int sm_count, int variant) {
     // blocks resident per SM: the 96 KB-ring variants (and ldg) fit two, the big rings one
     const bool two = variant == kScanVariantLdg || variant == kScanVariantTma6x12 || variant == kScanVariantTma12x12 ||
                      variant == kScanVariantTma4x12;
+    if (variant == kScanVariantTma4x8) return static_cast<uint32_t>(sm_count) * 3u;   // 64 KB rings: three per SM
     return static_cast<uint32_t>(sm_count) * (two ? 2u : 1u);
 }
 
@@ -658,13 +654,9 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
     dim3 grid(blocks_per_query, nq, 1);
     switch (variant) {
         case kScanVariantLdg: {
-            static bool configured = false;
-            if (!configured) {
-                cudaError_t e = cudaFuncSetAttribute(score_topk_scan_ldg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     static_cast<int>(sizeof(MergeScratch<kLdgWarps>)));
-                if (e != cudaSuccess) return e;
-                configured = true;
-            }
+            if (cudaError_t e = ensure_dynamic_smem(score_topk_scan_ldg_kernel, static_cast<int>(sizeof(MergeScratch<kLdgWarps>)));
+                e != cudaSuccess)
+                return e;
             score_topk_scan_ldg_kernel<<<grid, kLdgWarps * 32, sizeof(MergeScratch<kLdgWarps>), s>>>(a);
             return cudaGetLastError();
         }
@@ -674,6 +666,7 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
         case kScanVariantTma6x12: return launch_tma<6, 12>(a, grid, s);
         case kScanVariantTma12x12: return launch_tma<12, 12>(a, grid, s);
         case kScanVariantTma4x12: return launch_tma<4, 12>(a, grid, s);
+        case kScanVariantTma4x8: return launch_tma<4, 8>(a, grid, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -682,13 +675,8 @@ cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t 
                                cudaStream_t s) {
     if (n_lists == 0 || n_lists > 1024 || k_in == 0 || k_in > RF_TOPK_MAX || k_out > k_in) return cudaErrorInvalidValue;
     const size_t smem = (static_cast<size_t>(kMergeWarps) + 1) * 32 * k_in * 8;   // <= 72 KB at k_in = 32
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>((kMergeWarps + 1) * 32 * RF_TOPK_MAX * 8));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(merge_lists_kernel, static_cast<int>((kMergeWarps + 1) * 32 * RF_TOPK_MAX * 8)); e != cudaSuccess)
+        return e;
     merge_lists_kernel<<<nq, kMergeWarps * 32, smem, s>>>(keys, n_lists, nq, k_in, k_out, out);
     return cudaGetLastError();
 }

@@ -18,12 +18,17 @@
 // quarter w % 4 (hardware rule), so the four accumulators drain concurrently.
 // Per 32-column load an epilogue thread takes the max of its 32 scores; only when it reaches the
 // query's threshold score does the warp enter the candidate path, which walks the union of the
-// lanes' candidate columns (one uniform single-column TMEM load each) and inserts into the
-// thread's sorted top-10, a compare-exchange chain held entirely in registers.  Each thread ends
-// with one list per owned query; the lists of all slices / column halves are merged by
-// merge_topk_kernel (warp tournaments).  Thresholds start from a caller-supplied per-query floor
-// (the engine derives it from a first pass over a sample of the store), which is what keeps the
-// candidate path rare.
+// lanes' candidate columns (a warp-uniform register pick each; the tenant mask of the tile's 128
+// columns was fetched one tile ahead as four ballots) and inserts into the thread's sorted top-10,
+// a compare-exchange chain held entirely in registers.  Each thread ends with one list for its
+// query; the lists of all slices are merged by merge_lists_kernel (warp tournaments).
+//
+// Two passes (engine.cu:search_gemm).  Pass A (group_max_mode) runs the same GEMM over a sample of
+// the rows but keeps, per query, the top-k of per-32-chunk GROUP MAXIMA: its k-th value is a valid
+// lower bound of the query's final k-th best score (k distinct chunks reach it) and costs one
+// insertion per group.  Pass B scores every row with those floors, so the candidate path is rare.
+// What bounds pass B (profiles/gemm_timeline_r01.txt): reading the accumulators back -- 4 B of
+// TMEM per score at ~64 B/clk/SM is 4096 cycles per 128 x 512 tile against 2048 cycles of MMA.
 #include <cuda.h>
 
 #include "rf_device.cuh"
@@ -95,13 +100,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return v;
-}
-
 // v[j] for a warp-uniform j: a 32-way uniform switch over registers (a single-column TMEM reload
 // would queue behind the other warps' 4 KB accumulator loads).
 __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
@@ -394,13 +392,8 @@ cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const
                                    cudaStream_t s) {
     CUtensorMap map_q, map_f;
     if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
-    static bool configured = false;
     const int smem = static_cast<int>(sizeof(GemmSmem)) + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(score_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_kernel, smem); e != cudaSuccess) return e;
     dim3 grid(n_slices, (a.nq + kMT * 128 - 1) / (kMT * 128), 1);
     score_topk_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
     return cudaGetLastError();

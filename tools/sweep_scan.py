@@ -20,7 +20,7 @@ F = co.synth_rows(0, 0, N, zb)
 seg0 = np.zeros(N, np.uint32)
 Q = np.stack([co.synth_query(0, i, zb) for i in range(64)])
 want = [co.score_topk_keys(F, seg0, Q[i], [0]).tolist() for i in range(4)]
-names = {0: "ldg8x2", 1: "tma8x24", 2: "tma12x24", 3: "tma8x16", 4: "tma6x12", 5: "tma12x12", 6: "tma4x12"}
+names = {0: "ldg8x2", 1: "tma8x24", 2: "tma12x24", 3: "tma8x16", 4: "tma6x12", 5: "tma12x12", 6: "tma4x12", 7: "tma4x8"}
 configs = []
 for v in [int(x) for x in os.environ.get("SWEEP_VARIANTS", "0,1,2,3,4").split(",")]:
     for mult in [float(x) for x in os.environ.get("SWEEP_MULTS", "1,2,3,4").split(",")]:
