@@ -575,6 +575,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.nq = nq;
     g.id_base = static_cast<uint32_t>(e->cfg.id_base);
     g.out_lists = lists;
+    g.lists_per_slice = rf::gemm_lists_per_slice(nq);
     g.debug = nullptr;
     // pass A: group maxima over a sample -> per-query floors (a lower bound of the k-th best score)
     g.floors = nullptr;
@@ -582,7 +583,8 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.row_lo = lo;
     g.row_hi = lo + sample;
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_a, s));
-    RF_CUDA(rf::launch_merge_lists(lists, n_a, nq, kl, kl, keys_a, s));
+    const uint32_t lps = rf::gemm_lists_per_slice(nq);
+    RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s));
     RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
     // pass B: every row (the sample included: pass A kept maxima, not chunks), floors from pass A
     g.floors = floors;
@@ -591,7 +593,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.row_hi = hi;
     g.debug = e->debug_ts;   // RF_SCAN_DEBUG=1: cycle counters of the second pass
     RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_b, s));
-    RF_CUDA(rf::launch_merge_lists(lists, n_b, nq, kl, k, out_keys_dev, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_b * lps, nq, kl, k, out_keys_dev, s));
     e->launches.fetch_add(5, std::memory_order_relaxed);
     return RF_OK;
 }

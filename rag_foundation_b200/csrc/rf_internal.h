@@ -103,15 +103,19 @@ constexpr int kGemmTileRows = 128;  // chunk rows per B tile
 struct GemmArgs {
     const uint32_t *seg;        // [rows] store-segment words
     const uint64_t *floors;     // [nq] per-query lower bound keys, or null
-    uint64_t *out_lists;        // [n_slices, nq, kGemmListK] sorted lists
+    uint64_t *out_lists;        // [n_slices * gemm_lists_per_slice(nq), nq, kGemmListK] sorted lists
     uint32_t scope[RF_SCOPE_MAX];
     uint32_t n_scope;
     uint32_t row_lo, row_hi;    // contiguous row range to score
     uint32_t nq;
     uint32_t id_base;
+    uint32_t lists_per_slice;   // = gemm_lists_per_slice(nq): accumulator replicas per M-tile
     uint32_t group_max_mode;    // 1: floor-finding pass -- keep the top-k of per-32-chunk group maxima, not of chunks
     unsigned long long *debug;  // diagnostics: [block][8] cycle counters, or null
 };
+// accumulator replicas per M-tile when a block holds fewer than four M-tiles (1 -> 4, 2 -> 2, else 1)
+__host__ __device__ inline uint32_t gemm_replicas(uint32_t m_tiles) { return m_tiles == 1 ? 4u : m_tiles == 2 ? 2u : 1u; }
+uint32_t gemm_lists_per_slice(uint32_t nq);   // lists each slice writes per query (= replicas)
 size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq);
 cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
                                    cudaStream_t s);

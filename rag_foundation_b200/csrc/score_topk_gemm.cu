@@ -29,6 +29,8 @@
 // insertion per group.  Pass B scores every row with those floors, so the candidate path is rare.
 // What bounds pass B (profiles/gemm_timeline_r01.txt): reading the accumulators back -- 4 B of
 // TMEM per score at ~64 B/clk/SM is 4096 cycles per 128 x 512 tile against 2048 cycles of MMA.
+#include <algorithm>
+
 #include <cuda.h>
 
 #include "rf_device.cuh"
@@ -149,6 +151,9 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const uint32_t q_base = qgroup * (kMT * 128);
     const uint32_t q_here = min(static_cast<uint32_t>(kMT * 128), a.nq - q_base);
     const uint32_t m_tiles = (q_here + 127) / 128;
+    // Fewer than four M-tiles: the spare accumulators take alternate chunk tiles of the same M-tile,
+    // so all four epilogue groups (and the MMA look-ahead) stay busy for small batches.
+    const uint32_t reps = a.lists_per_slice;   // host-chosen so every block of the launch agrees: > 1 only with one query group
 
     if (threadIdx.x == 0) {
         mbar_init(&sm.q_full, 1);
@@ -201,8 +206,9 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t m = 0; m < m_tiles; ++m) {
+                    const uint32_t acc = m + m_tiles * (t % reps);      // accumulator (and epilogue group) of this unit
                     c0 = clock64();
-                    if (t) mbar_wait(&sm.tmem_empty[m], (t - 1) & 1);   // epilogue drained this accumulator
+                    if (t >= reps) mbar_wait(&sm.tmem_empty[acc], ((t / reps) - 1) & 1);   // epilogue drained this accumulator
                     w_empty += clock64() - c0;
                     tc_fence_after();
                     if (elect_one()) {
@@ -213,11 +219,11 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (q_lo + kb * kKBlockStep + 2u * k);
                                 const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + kb * kKBlockStep + 2u * k);
-                                if (kb | k) umma_i8<true>(tmem + m * kBN, da, db, idesc);
-                                else umma_i8<false>(tmem + m * kBN, da, db, idesc);
+                                if (kb | k) umma_i8<true>(tmem + acc * kBN, da, db, idesc);
+                                else umma_i8<false>(tmem + acc * kBN, da, db, idesc);
                             }
                         }
-                        umma_commit(&sm.tmem_full[m]);
+                        umma_commit(&sm.tmem_full[acc]);
                     }
                     __syncwarp();
                 }
@@ -231,8 +237,11 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         __syncwarp();
     } else {
-        // ===== epilogue: group g = (warp - 2) / 4 owns accumulator / M-tile g =====
-        const uint32_t m = static_cast<uint32_t>(warp - 2) >> 2;
+        // ===== epilogue: group g = (warp - 2) / 4 owns accumulator g, i.e. M-tile g % m_tiles and
+        // the chunk tiles t with t % reps == g / m_tiles =====
+        const uint32_t g = static_cast<uint32_t>(warp - 2) >> 2;
+        const uint32_t m = reps > 1 ? g % m_tiles : g;
+        const uint32_t rep = reps > 1 ? g / m_tiles : 0;
         const uint32_t lq = warp & 3;                      // TMEM lane quarter this warp may touch
         const uint32_t row_in_tile = lq * 32 + lane;       // query row within the M-tile
         const uint32_t q = q_base + m * 128 + row_in_tile;
@@ -243,14 +252,14 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const bool live = q < a.nq;                        // padding rows never produce candidates
         long long w_tfull = 0, w_cand = 0, n_cand = 0;
         const long long e_start = clock64();
-        if (m < m_tiles) {
+        if (g < m_tiles * reps) {
             uint32_t seg_next[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const uint32_t row = a.row_lo + t_lo * kBN + h * 32 + lane;
-                seg_next[h] = (n_tiles && row < a.row_hi) ? __ldg(a.seg + row) : kTombstone;
+                const uint32_t row = a.row_lo + (t_lo + rep) * kBN + h * 32 + lane;
+                seg_next[h] = (rep < n_tiles && row < a.row_hi) ? __ldg(a.seg + row) : kTombstone;
             }
-            for (uint32_t t = 0; t < n_tiles; ++t) {
+            for (uint32_t t = rep; t < n_tiles; t += reps) {
                 const uint32_t row0 = a.row_lo + (t_lo + t) * kBN;
                 // Tenant mask of the tile's 128 chunk columns, one bit per column, fetched with four
                 // coalesced loads before the accumulator is awaited (the candidate path below never
@@ -266,21 +275,21 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
                     ok_mask[h] = __ballot_sync(kFull, ok);
                 }
-                if (t + 1 < n_tiles) {
+                if (t + reps < n_tiles) {
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
-                        const uint32_t row = row0 + kBN + h * 32 + lane;
+                        const uint32_t row = row0 + reps * kBN + h * 32 + lane;
                         seg_next[h] = row < a.row_hi ? __ldg(a.seg + row) : kTombstone;
                     }
                 }
                 long long c0 = clock64();
-                mbar_wait(&sm.tmem_full[m], t & 1);
+                mbar_wait(&sm.tmem_full[g], (t / reps) & 1);
                 w_tfull += clock64() - c0;
                 tc_fence_after();
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
                     const uint32_t col0 = h * 32;                                // chunk column within the tile
-                    const uint32_t taddr = tmem + ((lq * 32u) << 16) + m * kBN + col0;
+                    const uint32_t taddr = tmem + ((lq * 32u) << 16) + g * kBN + col0;
                     const uint32_t okm = h == 0 ? ok_mask[0] : h == 1 ? ok_mask[1] : h == 2 ? ok_mask[2] : ok_mask[3];
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
@@ -332,15 +341,15 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tmem_empty[m]);
+                if (lane == 0) mbar_arrive(&sm.tmem_empty[g]);
             }
             if (a.debug && warp == 2 && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[4] = clock64() - e_start; d[5] = w_tfull; d[6] = w_cand; d[7] = n_cand;
             }
-            // one list per (slice, query)
+            // one list per (slice, replica, query)
             if (live) {
-                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+                uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * reps + rep) * a.nq + q) * kGemmK;
 #pragma unroll
                 for (int i = 0; i < kGemmK; ++i) dst[i] = list.e[i];
             }
@@ -386,7 +395,11 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows) {
 
 }  // namespace
 
-size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * nq * kGemmK * 8; }
+uint32_t gemm_lists_per_slice(uint32_t nq) {
+    const uint32_t m_tiles_max = std::min<uint32_t>((nq + 127) / 128, kGemmMT);   // every query group of a launch has this many, or fewer in the last
+    return nq > static_cast<uint32_t>(kGemmMT) * 128 ? 1u : gemm_replicas(m_tiles_max);
+}
+size_t gemm_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * gemm_lists_per_slice(nq) * nq * kGemmK * 8; }
 
 cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
                                    cudaStream_t s) {
