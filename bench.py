@@ -245,12 +245,16 @@ def run_b200(args) -> None:
     if world > 1:
         exchange = "nccl all-gather + merge kernel"
         if args.exchange == "fused":
+            fused = None
             try:    # compute + collective in one kernel over NVLink peer memory (symmetric memory)
-                searcher = FusedShardedSearcher(eng, nq_cap=8, k=10)
-                exchange = "fused in the scan kernel: NVLink peer stores + flags (symmetric memory), no collective launch"
+                fused = FusedShardedSearcher(eng, nq_cap=8, k=10)
             except Exception as exc:   # noqa: BLE001
-                if rank == 0:
-                    print(f"bench.py: fused exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+                print(f"bench.py: rank {rank}: fused exchange unavailable ({exc})", file=sys.stderr)
+            ok = torch.tensor([1 if fused is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank or none
+            if int(ok.item()):
+                searcher = fused
+                exchange = "fused in the scan kernel: NVLink peer stores + flags (symmetric memory), no collective launch"
 
     Qh = make_queries(N_DISTINCT_QUERIES)
     Qd = torch.from_numpy(Qh).to(dev)
@@ -270,6 +274,35 @@ def run_b200(args) -> None:
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
+
+    # size-independent check at N > 1: the fused NVLink exchange and the NCCL all-gather + merge
+    # kernel must return identical packed keys, and the winners' scores must match a CPU re-scoring
+    # of exactly those rows (regenerated from their counters by the oracle on rank 0)
+    exchange_check = None
+    if world > 1:
+        nccl_ref = ShardedSearcher.for_engine(eng)
+        agree = 1
+        first_keys = None
+        for qi in range(4):
+            a_keys = searcher.search_keys(Qd[qi:qi + 1], [seg], k).clone()
+            b_keys = nccl_ref.search_keys(Qd[qi:qi + 1], [seg], k)
+            agree &= int(torch.equal(a_keys, b_keys))
+            if qi == 0:
+                first_keys = a_keys.cpu().numpy().view(np.uint64)[0]
+        t_ag = torch.tensor([agree], device=dev)
+        dist.all_reduce(t_ag, op=dist.ReduceOp.MIN)
+        exchange_check = {"fused_equals_nccl": bool(int(t_ag.item()))}
+        if rank == 0:
+            from oracle import c_oracle as co, rf1
+            zb = rf1.zipf_bucket_table()
+            ok = True
+            for key in first_keys:
+                if int(key) == 0:
+                    continue
+                gid = 0xFFFFFFFF - (int(key) & 0xFFFFFFFF)
+                row = co.synth_rows(SEED, gid, 1, zb)[0]
+                ok &= int(row.astype(np.int32) @ Qh[0].astype(np.int32)) == int(key) >> 32
+            exchange_check["winner_scores_match_cpu_rescoring"] = bool(ok)
 
     steps, warmup = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
@@ -372,6 +405,8 @@ def run_b200(args) -> None:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if exchange_check is not None:
+            line["exchange_check"] = exchange_check
         print(json.dumps(line))
     eng.close()
     if world > 1:
