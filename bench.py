@@ -332,6 +332,22 @@ def run_b200(args) -> None:
         sync_all()
         kernel_ms = ek0.elapsed_time(ek1) / kq
 
+        # ---- isolated launches (a lone caller's latency: no overlap with a neighbouring query)
+        lat_us = []
+        for i in range(min(200, max(steps, 20))):
+            qi = i % N_DISTINCT_QUERIES
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a0.record(stream)
+            if n_gpus == 1:
+                eng.search_keys_device(Qd[qi:qi + 1].data_ptr(), 1, [seg], k, scratch.data_ptr(), stream.cuda_stream)
+            else:
+                searcher.search_keys(Qd[qi:qi + 1], [seg], k, out=scratch)
+            a1.record(stream)
+            a1.synchronize()
+            lat_us.append(a0.elapsed_time(a1) * 1e3)
+        sync_all()
+
         # ---- e2e: the public C-ABI call with HOST buffers (query H2D + result D2H inside)
         e2e_steps = max(10, min(steps, 2000))
         if n_gpus == 1:
@@ -345,6 +361,19 @@ def run_b200(args) -> None:
             e2e_s = time.perf_counter() - t0
             h2d = 256 + 80 + 16 + 16 + 16   # query row + ScanPlan + one extent (lo, hi, tile prefix), 16-byte aligned
             d2h = k * (8 + 4 + 4) + 4
+            # the reference serves up to 50 concurrent streams per process (routes/chat.py:40): the
+            # same call from 4 host threads (each search owns a context + stream; ctypes drops the GIL)
+            n_thr, per_thr = 4, max(50, e2e_steps // 4)
+
+            def _client(tid):
+                for i in range(per_thr):
+                    qi = (tid * 17 + i) % N_DISTINCT_QUERIES
+                    eng.search(Qh[qi:qi + 1], [[seg]], k=k)
+            ths = [threading.Thread(target=_client, args=(t,)) for t in range(n_thr)]
+            t0 = time.perf_counter()
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            e2e_conc_qps = n_thr * per_thr / (time.perf_counter() - t0)
         else:
             pinned_q = torch.from_numpy(Qh).pin_memory()
             host_out = torch.zeros((1, k), dtype=torch.int64).pin_memory()
@@ -365,6 +394,7 @@ def run_b200(args) -> None:
             sync_all()
             e2e_s = time.perf_counter() - t0
             h2d, d2h = 256, k * 8
+            e2e_conc_qps = None
 
     t = torch.tensor([ms, kernel_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -400,7 +430,9 @@ def run_b200(args) -> None:
                          "frac_of_8TBps": achieved / 8000.0},
             "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "qps": e2e_steps / e2e_s, "ms_per_query": 1e3 * e2e_s / e2e_steps,
-                    "steps": e2e_steps, "api": "rf_search (C-ABI, host buffers)" if n_gpus == 1 else "ShardedSearcher.search_keys with pinned host query/result"},
+                    "steps": e2e_steps, "qps_4_host_threads": e2e_conc_qps, "api": "rf_search (C-ABI, host buffers)" if n_gpus == 1 else "ShardedSearcher.search_keys with pinned host query/result"},
+            "isolated_launch_latency_us": {"p50": float(np.percentile(lat_us, 50)), "p95": float(np.percentile(lat_us, 95)),
+                                           "n": len(lat_us), "note": "one query at a time with a device sync between launches (device-resident query)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu is not None:

@@ -29,7 +29,9 @@ def load_zipf_vocab() -> np.ndarray:
 
 
 def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
-    return None if a is None else a.ctypes.data
+    # __array_interface__ is ~10x cheaper than .ctypes.data (no ctypes helper object); it matters
+    # on the single-query path, where the whole call is tens of microseconds
+    return None if a is None else a.__array_interface__["data"][0]
 
 
 def scopes_to_csr(scopes: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
@@ -187,8 +189,7 @@ class Engine:
         sc = np.empty((nq, k), np.int32)
         cs = np.empty((nq, k), np.float32)
         cnt = np.empty(nq, np.uint32)
-        rc = self._L.rf_search(self._h, q.ctypes.data, nq, segs.ctypes.data, off.ctypes.data, k, ids.ctypes.data,
-                               sc.ctypes.data, cs.ctypes.data, cnt.ctypes.data)
+        rc = self._L.rf_search(self._h, _ptr(q), nq, _ptr(segs), _ptr(off), k, _ptr(ids), _ptr(sc), _ptr(cs), _ptr(cnt))
         if rc:
             check(rc)
         return ids, sc, cs, cnt
