@@ -198,6 +198,7 @@ struct rf_engine {
     uint32_t gemm_slices_a = 0;      // 0 = as many as fit
     int scan_variant = rf::kScanVariantTma6x12;
     unsigned long long *debug_ts = nullptr;  // RF_SCAN_DEBUG=1 (diagnostics)
+    uint32_t dbg_flags = 0;                  // RF_SCAN_DBG (diagnostics)
     bool profile = false;                    // RF_PROFILE=1: host-side phase times of rf_search on stderr at destroy
     std::atomic<uint64_t> prof_ns[4]{}, prof_n{0};
     size_t debug_cap = 0;
@@ -361,6 +362,7 @@ void fill_args(rf_engine *e, ScanArgs &a, const uint8_t *d_blob, const PlanBlob 
     a.shared_plan = shared ? 1u : 0u;
     a.inline_plan = 0;
     a.debug_ts = e->debug_ts;
+    a.dbg_flags = e->dbg_flags;
 }
 
 // Single plan with few extents: copy it into the kernel parameters (host copy of the blob).
@@ -664,6 +666,7 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     const uint64_t cap = cfg->capacity_rows;
     cudaError_t ce;
     e->profile = getenv("RF_PROFILE") != nullptr;
+    if (const char *s = getenv("RF_SCAN_DBG")) e->dbg_flags = static_cast<uint32_t>(atoi(s));
     if (getenv("RF_SCAN_DEBUG")) {
         e->debug_cap = 4096 * 8;
         if (cudaMalloc(&e->debug_ts, e->debug_cap * 8) != cudaSuccess) e->debug_ts = nullptr;

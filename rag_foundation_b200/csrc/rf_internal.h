@@ -75,6 +75,7 @@ struct ScanArgs {
     uint32_t *done_count;          // device word (zero between launches): queries of this launch finished so far
     uint32_t done_seq;
     int8_t q_inline[256];          // the query vector itself when q == nullptr (nq == 1, host-side searches)
+    uint32_t dbg_flags;            // diagnostics (RF_SCAN_DBG): 1 = no seg bulk copy, 2 = static round-robin tiles instead of stealing
     unsigned long long *debug_ts;  // diagnostics (RF_SCAN_DEBUG=1): [grid.x][8] globaltimer stamps, else null
 };
 constexpr uint32_t kInlineExt = 8;

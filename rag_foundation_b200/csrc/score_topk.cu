@@ -514,7 +514,10 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
             uint32_t seen = static_tiles;                       // last counter value this lane saw
             while (true) {
                 if (round) mbar_wait(&sm.empty[lane], (round - 1) & 1);
-                if (next == chunk_end) {
+                if (next == chunk_end && (a.dbg_flags & 2u)) {   // diagnostics: static round-robin
+                    next += static_tiles - 1;
+                    chunk_end = next + 1;
+                } else if (next == chunk_end) {
                     const uint32_t left = seen < total_tiles ? total_tiles - seen : 0u;
                     const uint32_t want = max(1u, min(static_cast<uint32_t>(kChunkTiles), left / (2u * lanes_total)));
                     seen = static_tiles + atomicAdd(tile_ctr, want);
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
                 ++next;
                 const uint32_t rows = min(static_cast<uint32_t>(kTileRows), row_end - row0);
                 // the 32 store-segment words ride along when their 128 bytes are 16-byte aligned
-                const bool seg_copy = rows == kTileRows && (row0 & 3u) == 0u;
+                const bool seg_copy = rows == kTileRows && (row0 & 3u) == 0u && !(a.dbg_flags & 1u);
                 sm.st_row0[lane] = row0;
                 sm.st_rows[lane] = rows | (seg_copy ? 0x100u : 0u);
                 mbar_arrive_expect_tx(&sm.full[lane], rows * kRowBytes + (seg_copy ? 128u : 0u));   // release: publishes st_*

@@ -517,3 +517,27 @@ def test_search_text_in_ranges(co, zb):
         assert len(ids) == 0
         with pytest.raises(RuntimeError):
             e.search_text(text, [a], 10, ranges=[(50, 60), (10, 20)])          # unsorted
+
+
+def test_back_to_back_queries_overlap_safely(co, zb):
+    """64 different queries enqueued back to back on one stream with no synchronisation: under
+    programmatic dependent launch each query's scan overlaps the previous query's merge tail, and
+    the two alternating sync sets must keep them apart."""
+    import torch
+    n = 300_000
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=17, start_counter=0, n_rows=n)
+        F = co.synth_rows(17, 0, n, zb)
+        seg = np.full(n, s, np.uint32)
+        Q = np.stack([co.synth_query(17, i, zb) for i in range(64)])
+        qd = torch.from_numpy(Q).cuda()
+        out = torch.zeros((64, 10), dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for rep in range(3):
+            for i in range(64):
+                e.search_keys_device(qd[i:i + 1].data_ptr(), 1, [s], 10, out[i].data_ptr(), st)
+        torch.cuda.synchronize()
+        keys = out.cpu().numpy().view(np.uint64)
+        for i in range(64):
+            assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], [s]).tolist(), i
