@@ -27,8 +27,9 @@
 // the rows but keeps, per query, the top-k of per-32-chunk GROUP MAXIMA: its k-th value is a valid
 // lower bound of the query's final k-th best score (k distinct chunks reach it) and costs one
 // insertion per group.  Pass B scores every row with those floors, so the candidate path is rare.
-// What bounds pass B (profiles/gemm_timeline_r01.txt): reading the accumulators back -- 4 B of
-// TMEM per score at ~64 B/clk/SM is 4096 cycles per 128 x 512 tile against 2048 cycles of MMA.
+// What bounds pass B (profiles/gemm_timeline_r01.txt): the MMA's operand fetch -- both operands
+// come from shared memory (SS mode, 8 KB per 128x128x32 MMA), which paces each MMA at ~128 cycles
+// against 64 cycles of tensor-pipe time; TMEM read-back sustains 468 B/clk/SM and is not the limit.
 #include <algorithm>
 
 #include <cuda.h>
