@@ -572,6 +572,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     uint64_t *floors = static_cast<uint64_t *>(dp->gemm_floors.p);
     rf::GemmArgs g{};
     g.seg = e->seg;
+    g.q = q_dev;
     g.n_scope = plan->n_scope;
     for (uint32_t i = 0; i < RF_SCOPE_MAX; ++i) g.scope[i] = plan->scope[i];
     g.nq = nq;

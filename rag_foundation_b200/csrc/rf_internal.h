@@ -103,6 +103,7 @@ constexpr int kGemmMT = 4;          // 128-query M-tiles resident per block (512
 constexpr int kGemmTileRows = 128;  // chunk rows per B tile
 struct GemmArgs {
     const uint32_t *seg;        // [rows] store-segment words
+    const int8_t *q;            // [nq, 256] query vectors (device)
     const uint64_t *floors;     // [nq] per-query lower bound keys, or null
     uint64_t *out_lists;        // [n_slices * gemm_lists_per_slice(nq), nq, kGemmListK] sorted lists
     uint32_t scope[RF_SCOPE_MAX];
@@ -110,7 +111,7 @@ struct GemmArgs {
     uint32_t row_lo, row_hi;    // contiguous row range to score
     uint32_t nq;
     uint32_t id_base;
-    uint32_t lists_per_slice;   // = gemm_lists_per_slice(nq): accumulator replicas per M-tile
+    uint32_t lists_per_slice;   // = gemm_lists_per_slice(nq)
     uint32_t group_max_mode;    // 1: floor-finding pass -- keep the top-k of per-32-chunk group maxima, not of chunks
     unsigned long long *debug;  // diagnostics: [block][8] cycle counters, or null
 };
