@@ -541,3 +541,102 @@ def test_back_to_back_queries_overlap_safely(co, zb):
         keys = out.cpu().numpy().view(np.uint64)
         for i in range(64):
             assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], [s]).tolist(), i
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes, size-independent properties
+@pytest.mark.timeout(900)
+def test_full_size_100m_chunks_properties(co, zb):
+    """configs[3]'s corpus (100 M chunks, 26 GB) on ONE GPU.  The CPU oracle cannot scan it in
+    seconds, so the checks are size-independent: (a) every winner's score equals a CPU re-scoring
+    of exactly that row (rows are regenerated from their counters); (b) the list is strictly ordered
+    by the RF-1 key; (c) the same corpus split over four engines with id bases, merged by the
+    merge kernel, gives the identical keys (two different decompositions of the scan agree);
+    (d) the first million rows, which the oracle can scan, contribute exactly the oracle's top-10
+    when the scope is narrowed to them by tombstoning nothing and searching a 1 M-row twin."""
+    import torch
+    from rag_foundation_b200 import unpack_keys
+    n = 100_000_000
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60 * (1 << 30):
+        pytest.skip("needs ~56 GB of free HBM")
+    Q = np.stack([co.synth_query(0, i, zb) for i in range(4)])
+    qd = torch.from_numpy(Q).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/all")
+        e.ingest_synthetic(s, 0, seed=0, start_counter=0, n_rows=n)
+        out = torch.zeros((4, 10), dtype=torch.int64, device="cuda")
+        for i in range(4):
+            e.search_keys_device(qd[i:i + 1].data_ptr(), 1, [s], 10, out[i].data_ptr(), stream)
+        torch.cuda.synchronize()
+        whole = out.cpu().numpy().view(np.uint64)
+        ids_h, sc_h, cs_h, cnt_h = e.search(Q, [[s]] * 4, k=10)            # host path agrees with the device path
+    for i in range(4):
+        ids, sc, valid = unpack_keys(whole[i])
+        assert valid.all() and ids_h[i].tolist() == ids.tolist() and sc_h[i].tolist() == sc.tolist()
+        assert all(int(whole[i][j]) > int(whole[i][j + 1]) for j in range(9))                       # (b)
+        for gid, score in zip(ids.tolist(), sc.tolist()):                                            # (a)
+            row = co.synth_rows(0, int(gid), 1, zb)[0]
+            assert int(row.astype(np.int32) @ Q[i].astype(np.int32)) == score
+    # (c) four shards + merge kernel
+    parts = torch.zeros((4, 4, 10), dtype=torch.int64, device="cuda")
+    engines = []
+    try:
+        for r in range(4):
+            lo, hi = r * (n // 4), (r + 1) * (n // 4)
+            er = _engine(hi - lo, id_base=lo)
+            engines.append(er)
+            sr = er.open_store("fileSearchStores/all")
+            er.ingest_synthetic(sr, 0, seed=0, start_counter=lo, n_rows=hi - lo)
+            for i in range(4):
+                er.search_keys_device(qd[i:i + 1].data_ptr(), 1, [sr], 10, parts[r, i].data_ptr(), stream)
+        merged = torch.zeros((4, 10), dtype=torch.int64, device="cuda")
+        engines[0].merge_topk_device(parts.data_ptr(), 4, 4, 10, merged.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert (merged.cpu().numpy().view(np.uint64) == whole).all()
+    finally:
+        for er in engines:
+            er.close()
+    # (d) the oracle's own scan of the first 1 M rows vs a 1 M-row engine of the same counters
+    F = co.synth_rows(0, 0, 1_000_000, zb)
+    with _engine(1_000_000) as e1:
+        s1 = e1.open_store("fileSearchStores/all")
+        e1.ingest_synthetic(s1, 0, seed=0, start_counter=0, n_rows=1_000_000)
+        ids1, sc1, _, _ = e1.search(Q, [[s1]] * 4, k=10)
+    for i in range(4):
+        w_ids, w_sc, _ = co.score_topk(F, np.zeros(1_000_000, np.uint32), Q[i], [0])
+        assert ids1[i].tolist() == w_ids.tolist() and sc1[i].tolist() == w_sc.tolist()
+        # every whole-corpus winner that lives in the first million must be in the 1 M top-10
+        ids, _, _ = unpack_keys(whole[i])
+        assert set(int(x) for x in ids if x < 1_000_000) <= set(w_ids.tolist())
+
+
+@pytest.mark.timeout(900)
+def test_full_size_multi_tenant_batch(co, zb):
+    """configs[4] at full size: 10 000 stores x 10 000 chunks (26 GB), 1024 store-scoped queries in
+    one call; every 8th answer is checked against the oracle's scan of just that store (10 k rows,
+    regenerated from its counters), and every answer must stay inside its store (tenant mask)."""
+    import torch
+    from rag_foundation_b200.engine import scopes_to_csr
+    free, _total = torch.cuda.mem_get_info()
+    if free < 30 * (1 << 30):
+        pytest.skip("needs ~28 GB of free HBM")
+    n_stores, per, nq = 10_000, 10_000, 1024
+    rng = np.random.default_rng(9)
+    with _engine(n_stores * per) as e:
+        first = e.open_store("fileSearchStores/t0")
+        for i in range(1, n_stores):
+            e.open_store(f"fileSearchStores/t{i}")
+        e.ingest_synthetic(first, per, seed=5, start_counter=0, n_rows=n_stores * per)
+        stores = rng.integers(0, n_stores, nq)
+        scopes = [[int(first + st)] for st in stores]
+        Q = np.stack([co.synth_query(5, i, zb) for i in range(nq)])
+        ids, sc, cs, cnt = e.search(Q, scopes_to_csr(scopes), k=10)
+        assert (cnt == 10).all()
+        lo = (stores * per)[:, None]
+        assert ((ids >= lo) & (ids < lo + per)).all(), "a citation left its tenant's store"
+        for i in range(0, nq, 8):
+            st = int(stores[i])
+            F = co.synth_rows(5, st * per, per, zb)
+            w_ids, w_sc, _ = co.score_topk(F, np.zeros(per, np.uint32), Q[i], [0], id_base=st * per)
+            assert ids[i].tolist() == w_ids.tolist() and sc[i].tolist() == w_sc.tolist(), i
