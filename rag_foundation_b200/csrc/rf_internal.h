@@ -9,16 +9,25 @@
 namespace rf {
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per
-// device, and one process may own engines on several GPUs.  Benign if two threads race.
+// device, and one process may own engines on several GPUs.  Keyed by the function's address (kernels
+// of one signature share a C++ type).  Benign if two threads race.
 template <typename Kernel>
 inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes) {
-    static bool done[64] = {};
+    struct Seen { const void *fn; int dev; };
+    static Seen seen[256];
+    static int n_seen = 0;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    const void *fn = reinterpret_cast<const void *>(kern);
+    const int n = n_seen;
+    for (int i = 0; i < n; ++i)
+        if (seen[i].fn == fn && seen[i].dev == dev) return cudaSuccess;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    if (e == cudaSuccess && n < 256) {
+        seen[n] = {fn, dev};
+        n_seen = n + 1;
+    }
     return e;
 }
 

@@ -540,6 +540,7 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
                 mbar_arrive_expect_tx(&sm.full[lane], rows * kRowBytes + (seg_copy ? 128u : 0u));   // release: publishes st_*
                 bulk_g2s(sm.stage[lane], a.F + static_cast<size_t>(row0) * kRowBytes, rows * kRowBytes, &sm.full[lane]);
                 if (seg_copy) bulk_g2s(sm.st_seg[lane], a.seg + row0, 128u, &sm.full[lane]);
+                if (round == 0 && lane == 0) stamp(a, 7);
                 ++round;
             }
         }

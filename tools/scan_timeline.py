@@ -36,10 +36,10 @@ for v, blocks in [(int(x.split(":")[0]), int(x.split(":")[1])) for x in os.envir
             rel = (t - t0) / 1e3
             last = t[:, 5].max()
             lb = int(t[:, 5].argmax())
-            extra = (t[lb, 4] - t0) / 1e3, (t[lb, 6] - t0) / 1e3, 0
+            extra = (t[lb, 4] - t0) / 1e3, (t[lb, 6] - t0) / 1e3, float(np.mean(rel[:, 7]))
             rows.append([rel[:, 0].max(), rel[:, 1].mean(), rel[:, 1].max(), rel[:, 2].mean(), rel[:, 2].max(),
                          np.median(rel[:, 3]), rel[:, 3].min(), rel[:, 3].max(), rel[:, 4].max(), (last - t0) / 1e3])
         r = np.median(np.array(rows), axis=0)
         print(f"variant {v} blocks {blocks} rows {N} (us from first block entry): last-entry {r[0]:.1f} | plan mean {r[1]:.1f} max {r[2]:.1f} | "
               f"first-tile mean {r[3]:.1f} max {r[4]:.1f} | loop-done med {r[5]:.1f} min {r[6]:.1f} max {r[7]:.1f} | "
-              f"partial published max {r[8]:.1f} | answer {r[9]:.1f} | last block: published {extra[0]:.1f} filtered {extra[1]:.1f} pool {extra[2]}", flush=True)
+              f"partial published max {r[8]:.1f} | answer {r[9]:.1f} | last block: published {extra[0]:.1f} level-1 done {extra[1]:.1f} | producer issued first copy at {extra[2]:.2f}", flush=True)
