@@ -121,8 +121,8 @@ class Engine:
         # a kept token needs >= 1 byte + 1 separator; a chunk past the first needs 112 new tokens
         max_spans = (len(data) // 2 + 1 + 111) // 112 + 1 if want_spans else 0
         spans = np.zeros((max(max_spans, 1), 2), np.int64)
-        buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
-        check(self._L.rf_ingest_text(self.handle, int(seg), int(doc_id), C.addressof(buf), len(data), C.byref(first),
+        # a bytes object goes to a void* parameter as a pointer to its own buffer: no copy
+        check(self._L.rf_ingest_text(self.handle, int(seg), int(doc_id), data or b"\0", len(data), C.byref(first),
                                      C.byref(nch), _ptr(spans) if want_spans else None, max_spans))
         n = int(nch.value)
         return int(first.value), n, spans[:n].copy()
@@ -218,8 +218,7 @@ class Engine:
         cs = np.zeros(k, np.float32)
         cnt = C.c_uint32()
         q = np.zeros(RF_DIM, np.int8)
-        buf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0")
-        check(self._L.rf_search_text_in(self.handle, C.addressof(buf), len(text), _ptr(segs), len(scope), _ptr(rng),
+        check(self._L.rf_search_text_in(self.handle, text or b"\0", len(text), _ptr(segs), len(scope), _ptr(rng),
                                         0 if rng is None else rng.shape[0], int(k), _ptr(ids), _ptr(sc), _ptr(cs),
                                         C.byref(cnt), _ptr(q)))
         m = int(cnt.value)
@@ -228,8 +227,7 @@ class Engine:
     def featurize_query(self, text: bytes) -> np.ndarray:
         text = bytes(text)
         q = np.zeros(RF_DIM, np.int8)
-        buf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0")
-        check(self._L.rf_featurize_query(self.handle, C.addressof(buf), len(text), _ptr(q)))
+        check(self._L.rf_featurize_query(self.handle, text or b"\0", len(text), _ptr(q)))
         return q
 
     def search_keys_device(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int,
