@@ -605,6 +605,9 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
 
 extern "C" {
 
+static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
+                                   uint32_t k, uint64_t *out_keys_dev, void *stream, const rf_peer_exchange *px);
+
 const char *rf_strerror(int code) {
     switch (code) {
         case RF_OK: return "ok";
@@ -1064,6 +1067,48 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
     if (nq == 0) return RF_OK;
     if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
     const auto t0 = std::chrono::steady_clock::now();
+    // A large batch whose queries all have the same scope takes the device-resident route (and
+    // with it the tensor-core path when it qualifies): one H2D of the queries, the batched search,
+    // an unpack kernel, one D2H of the results.
+    if (nq >= e->gemm_min_queries && e->gemm_enabled) {
+        const uint32_t n0 = seg_off[1] - seg_off[0];
+        bool same = n0 <= RF_SCOPE_MAX;
+        for (uint32_t i = 1; same && i < nq; ++i) {
+            same = seg_off[i + 1] - seg_off[i] == n0;
+            for (uint32_t j = 0; same && j < n0; ++j) same = store_segs[seg_off[i] + j] == store_segs[seg_off[0] + j];
+        }
+        if (same) {
+            SearchCtx *c = ctx_acquire(e);
+            if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
+            CtxGuard g{e, c};
+            RF_CUDA(cudaSetDevice(e->cfg.device));
+            const OutLayout L(nq, k);
+            const size_t q_bytes = static_cast<size_t>(nq) * RF_DIM;
+            RF_CUDA(c->h_in.reserve(q_bytes));
+            RF_CUDA(c->d_in.reserve(q_bytes));
+            RF_CUDA(c->d_out.reserve(L.total));
+            RF_CUDA(c->h_out.reserve(L.total));
+            memcpy(c->h_in.p, q, q_bytes);
+            RF_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, q_bytes, cudaMemcpyHostToDevice, c->stream));
+            uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
+            uint64_t *d_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
+            int rc = search_keys_device_impl(e, static_cast<const int8_t *>(c->d_in.p), nq, store_segs + seg_off[0], n0, k, d_keys, c->stream, nullptr);
+            if (rc) return rc;
+            RF_CUDA(rf::launch_unpack_keys(d_keys, static_cast<const int8_t *>(c->d_in.p), e->ff, static_cast<uint32_t>(e->cfg.id_base), nq, k,
+                                           reinterpret_cast<uint64_t *>(d_out + L.off_ids), reinterpret_cast<int32_t *>(d_out + L.off_scores),
+                                           reinterpret_cast<float *>(d_out + L.off_cos), reinterpret_cast<uint32_t *>(d_out + L.off_counts), c->stream));
+            e->launches.fetch_add(1, std::memory_order_relaxed);
+            RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
+            RF_CUDA(cudaStreamSynchronize(c->stream));
+            const uint8_t *h = static_cast<const uint8_t *>(c->h_out.p);
+            const size_t n = static_cast<size_t>(nq) * k;
+            memcpy(out_ids, h + L.off_ids, n * 8);
+            memcpy(out_scores, h + L.off_scores, n * 4);
+            if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
+            if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(nq) * 4);
+            return RF_OK;
+        }
+    }
     PlanBlob b;
     int rc = build_blob(e, q, nq, store_segs, seg_off, false, b);
     if (rc) return rc;
@@ -1177,9 +1222,6 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
     e->searches.fetch_add(1);
     return RF_OK;
 }
-
-static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
-                                   uint32_t k, uint64_t *out_keys_dev, void *stream, const rf_peer_exchange *px);
 
 int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
                           uint32_t k, uint64_t *out_keys_dev, void *stream) {

@@ -102,6 +102,9 @@ enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, de
     kScanVariantCount = 8
 };
 cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s);
+// packed keys [nq, k] -> ids / scores / cosines / counts (host-visible result layout); q: [nq, 256] device
+cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
+                               uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s);
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,
                               uint64_t *out_keys, cudaStream_t s);
 uint32_t scan_default_blocks_per_query(int sm_count, int variant);

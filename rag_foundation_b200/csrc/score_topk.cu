@@ -626,6 +626,42 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
     if (lane < static_cast<int>(k_out)) out[static_cast<size_t>(qi) * k_out + lane] = (lane < kin) ? w : 0ull;
 }
 
+// Packed keys -> the result arrays a host caller gets (same arithmetic as finish_query: RF-1 step 8
+// for the cosine).  One warp per query.
+__global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__restrict__ keys, const int8_t *__restrict__ q,
+                                                          const int32_t *__restrict__ ff, uint32_t id_base, uint32_t nq, uint32_t k,
+                                                          uint64_t *__restrict__ out_ids, int32_t *__restrict__ out_scores,
+                                                          float *__restrict__ out_cos, uint32_t *__restrict__ out_counts) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int2 qv = *reinterpret_cast<const int2 *>(q + static_cast<size_t>(qi) * kDim + lane * 8);
+    int qq = __dp4a(qv.x, qv.x, 0);
+    qq = __dp4a(qv.y, qv.y, qq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
+    const uint64_t key = lane < static_cast<int>(k) ? keys[static_cast<size_t>(qi) * k + lane] : 0ull;
+    const unsigned found = __ballot_sync(kFull, key != 0ull);
+    if (lane < static_cast<int>(k)) {
+        const size_t o = static_cast<size_t>(qi) * k + lane;
+        const uint32_t gid = key_gid(key);
+        const int32_t sc = key_score(key);
+        out_ids[o] = key ? static_cast<uint64_t>(gid) : ~0ull;
+        out_scores[o] = key ? sc : 0;
+        if (out_cos) {
+            float c = 0.0f;
+            if (key && ff) {
+                const float nq_ = sqrtf(static_cast<float>(qq));
+                const float nf = sqrtf(static_cast<float>(__ldg(ff + (gid - id_base))));
+                const float den = __fmul_rn(nq_, nf);
+                c = den == 0.0f ? 0.0f : __fdiv_rn(static_cast<float>(sc), den);
+            }
+            out_cos[o] = c;
+        }
+    }
+    if (lane == 0 && out_counts) out_counts[qi] = __popc(found);
+}
+
 template <int kConsumers, int kStages>
 cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
     using Smem = TmaSmem<kConsumers, kStages>;
@@ -682,6 +718,12 @@ cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t 
     if (cudaError_t e = ensure_dynamic_smem(merge_lists_kernel, static_cast<int>((kMergeWarps + 1) * 32 * RF_TOPK_MAX * 8)); e != cudaSuccess)
         return e;
     merge_lists_kernel<<<nq, kMergeWarps * 32, smem, s>>>(keys, n_lists, nq, k_in, k_out, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
+                               uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s) {
+    unpack_keys_kernel<<<(nq + 3) / 4, 128, 0, s>>>(keys, q, ff, id_base, nq, k, out_ids, out_scores, out_cos, out_counts);
     return cudaGetLastError();
 }
 

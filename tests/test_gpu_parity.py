@@ -640,3 +640,30 @@ def test_full_size_multi_tenant_batch(co, zb):
             F = co.synth_rows(5, st * per, per, zb)
             w_ids, w_sc, _ = co.score_topk(F, np.zeros(per, np.uint32), Q[i], [0], id_base=st * per)
             assert ids[i].tolist() == w_ids.tolist() and sc[i].tolist() == w_sc.tolist(), i
+
+
+def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
+    """rf_search (host buffers) with >= 64 queries that share one scope: one upload of the queries,
+    the batched GEMM search, an unpack kernel, one download -- same ids / scores / cosines as the
+    oracle, and a mixed-scope batch of the same size still goes through the scan kernel."""
+    n, nq = 120_000, 200
+    with _engine(n + 5000) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        e.ingest_synthetic(a, 0, seed=23, start_counter=0, n_rows=n)
+        e.ingest_synthetic(b, 0, seed=24, start_counter=0, n_rows=5000)
+        F, ff = co.synth_rows(23, 0, n, zb, with_ff=True)
+        Fb, ffb = co.synth_rows(24, 0, 5000, zb, with_ff=True)
+        Fall = np.concatenate([F, Fb]); ffall = np.concatenate([ff, ffb])
+        seg = np.concatenate([np.full(n, a), np.full(5000, b)]).astype(np.uint32)
+        Q = np.stack([co.synth_query(23, i, zb) for i in range(nq)])
+        l0 = e.stats()["kernel_launches"]
+        ids, sc, cs, cnt = e.search(Q, [[a]] * nq, k=10)
+        assert e.stats()["kernel_launches"] - l0 == 6, "expected 5 GEMM-path launches + the unpack kernel"
+        for i in range(0, nq, 7):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], [a], 10, 0, ffall)
+        scopes = [[a] if i % 2 else [b] for i in range(nq)]
+        l0 = e.stats()["kernel_launches"]
+        ids, sc, cs, cnt = e.search(Q, scopes, k=10)
+        assert e.stats()["kernel_launches"] - l0 == 1
+        for i in range(0, nq, 11):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], scopes[i], 10, 0, ffall)
