@@ -178,6 +178,28 @@ int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_list
 /* Query featurisation alone (text -> int8[RF_DIM] on the GPU), host buffers. */
 int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_q);
 
+/* ---- RF-1w: the IDF-weighted scoring variant (oracle/SPEC.md).  The reference has
+ * no counterpart: it is the relevance variant its benchmark harness (scripts/benchmark/metrics.py:
+ * 73-92, citation_hit) would grade.  Only the query vector changes, so the search kernels and the
+ * packed keys are the plain RF-1 ones.
+ *
+ * rf_scope_df: per-bucket document frequencies of the scope's live rows, one streaming GPU pass
+ * (cached per scope until the next ingest / delete).  out_df: RF_DIM u64 (HOST), *out_n: live rows.
+ * rf_scope_df_device: the same sums ADDED into df_dev[0 .. RF_DIM) and the row count into
+ * df_dev[RF_DIM] (DEVICE, caller zeroes), enqueued on `stream` without synchronising -- the form
+ * the sharded path all-reduces over the ranks before taking the weights. */
+int rf_scope_df(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint64_t *out_df, uint64_t *out_n);
+int rf_scope_df_device(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint64_t *df_dev, void *stream);
+/* Pure integer host functions: weights w[d] in [4, 31] from (df, n); qw[d] = min(q[d] * w[d], 127). */
+int rf_idf_weights(const uint64_t *df, uint64_t n, uint32_t dim, uint8_t *out_w);
+int rf_weight_query(const int8_t *q, const uint8_t *w, uint32_t dim, int8_t *out_qw);
+/* rf_search_text_in with the query vector weighted on the GPU by `weights` (RF_DIM u8, HOST; NULL =
+ * plain RF-1).  out_q receives the weighted vector. */
+int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs,
+                     uint32_t n_segs, const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights,
+                     uint32_t k, uint64_t *out_ids, int32_t *out_scores, float *out_cos,
+                     uint32_t *out_count, int8_t *out_q /* RF_DIM, may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,12 @@ def lib() -> C.CDLL:
         L.rf1_synth_rows.argtypes = [u64, u64, i64, vp, vp, vp, i32]
         L.rf1_synth_query.restype = None
         L.rf1_synth_query.argtypes = [u64, u64, i32, vp, vp]
+        L.rf1_bucket_df.restype = i64
+        L.rf1_bucket_df.argtypes = [vp, vp, i64, vp, i32, vp]
+        L.rf1_idf_weights.restype = None
+        L.rf1_idf_weights.argtypes = [vp, u64, vp]
+        L.rf1_weight_query.restype = None
+        L.rf1_weight_query.argtypes = [vp, vp, vp]
         _lib = L
     return _lib
 
@@ -150,6 +156,30 @@ def synth_query(seed, qi, zb, n_tokens=8):
     q = np.zeros(D, np.int8)
     lib().rf1_synth_query(seed, qi, n_tokens, _p(zb), _p(q))
     return q
+
+
+def bucket_df(F, store_seg, scope):
+    F = np.ascontiguousarray(F, np.int8)
+    seg = np.ascontiguousarray(store_seg, np.uint32)
+    sc = np.ascontiguousarray(list(scope), np.uint32)
+    df = np.zeros(D, np.uint64)
+    n = lib().rf1_bucket_df(_p(F), _p(seg), len(F), _p(sc), len(sc), _p(df))
+    return df, int(n)
+
+
+def idf_weights(df, n):
+    df = np.ascontiguousarray(df, np.uint64)
+    w = np.zeros(D, np.uint8)
+    lib().rf1_idf_weights(_p(df), int(n), _p(w))
+    return w
+
+
+def weight_query(q, w):
+    q = np.ascontiguousarray(q, np.int8)
+    w = np.ascontiguousarray(w, np.uint8)
+    out = np.zeros(D, np.int8)
+    lib().rf1_weight_query(_p(q), _p(w), _p(out))
+    return out
 
 
 def dot_isa() -> str:

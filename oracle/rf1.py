@@ -173,6 +173,27 @@ def cosine(score, qq, ff) -> np.ndarray:
     return out
 
 
+# ----------------------------------------------------------------------------- RF-1w (SPEC.md "IDF-weighted variant")
+def bucket_df(F, store_seg, scope: Sequence[int]):
+    """-> (df uint64 [D], n): per-bucket document frequency over the live rows of the scope."""
+    store_seg = np.asarray(store_seg, dtype=np.uint32)
+    ok = np.isin(store_seg, np.asarray(list(scope), dtype=np.uint32)) & (store_seg != TOMBSTONE)
+    return (np.asarray(F)[ok] > 0).sum(axis=0).astype(np.uint64), int(ok.sum())
+
+
+def idf_weights(df, n: int) -> np.ndarray:
+    w = np.zeros(len(df), dtype=np.uint8)
+    for d, x in enumerate(df):
+        r = ((int(n) + 1) * 256) // (int(x) + 1)
+        lg = r.bit_length() - 1
+        w[d] = min(4 + 4 * (lg - 8) + ((r >> (lg - 2)) & 3), 31)
+    return w
+
+
+def weight_query(q, w) -> np.ndarray:
+    return np.minimum(np.asarray(q, dtype=np.int32) * np.asarray(w, dtype=np.int32), 127).astype(np.int8)
+
+
 # ----------------------------------------------------------------------------- synthetic corpora
 def load_zipf_vocab() -> np.ndarray:
     t = np.fromfile(ZIPF_PATH, dtype="<u2")

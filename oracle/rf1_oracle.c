@@ -287,6 +287,37 @@ int rf1_merge_topk(const uint64_t *keys, int64_t n, int k, uint64_t *out) {
     return m;
 }
 
+/* ---- RF-1w (SPEC.md "IDF-weighted variant"): document frequencies, weights, weighted query ---- */
+int64_t rf1_bucket_df(const int8_t *F, const uint32_t *store_seg, int64_t n_rows, const uint32_t *scope, int n_scope,
+                      uint64_t *df /* [RF1_D] */) {
+    int64_t n = 0;
+    memset(df, 0, sizeof(uint64_t) * RF1_D);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        if (!in_scope(store_seg[r], scope, n_scope)) continue;
+        ++n;
+        const int8_t *row = F + r * RF1_D;
+        for (int d = 0; d < RF1_D; ++d) df[d] += row[d] > 0;
+    }
+    return n;
+}
+
+void rf1_idf_weights(const uint64_t *df, uint64_t n, uint8_t *w /* [RF1_D] */) {
+    for (int d = 0; d < RF1_D; ++d) {
+        const uint64_t r = ((n + 1) * 256) / (df[d] + 1);
+        int lg = 63;
+        while (!(r >> lg)) --lg;
+        const uint64_t v = 4 + 4 * (uint64_t)(lg - 8) + ((r >> (lg - 2)) & 3);
+        w[d] = (uint8_t)(v < 31 ? v : 31);
+    }
+}
+
+void rf1_weight_query(const int8_t *q, const uint8_t *w, int8_t *qw) {
+    for (int d = 0; d < RF1_D; ++d) {
+        const int v = (int)q[d] * (int)w[d];
+        qw[d] = (int8_t)(v < 127 ? v : 127);
+    }
+}
+
 /* ------------------------------------------------------------------ synthetic corpora */
 static inline uint64_t mix64(uint64_t seed, uint64_t a, uint64_t b) {
     uint64_t x = seed * 0x9E3779B97F4A7C15ull + a * 0xBF58476D1CE4E5B9ull + b * 0x94D049BB133111EBull

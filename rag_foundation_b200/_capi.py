@@ -63,6 +63,11 @@ SIGNATURES = {
     "rf_search_keys_device_fused": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "rf_featurize_query": (_i32, [_vp, _vp, _sz, _vp]),
+    "rf_scope_df": (_i32, [_vp, _vp, _u32, _vp, C.POINTER(_u64)]),
+    "rf_scope_df_device": (_i32, [_vp, _vp, _u32, _vp, _vp]),
+    "rf_idf_weights": (_i32, [_vp, _u64, _u32, _vp]),
+    "rf_weight_query": (_i32, [_vp, _vp, _u32, _vp]),
+    "rf_search_text_w": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -200,11 +200,16 @@ def build_final_response(grounding: Sequence[dict]) -> Any:
 class B200Rag:
     """GeminiRag-shaped retriever backed by the B200 engine."""
 
-    def __init__(self, registry: Optional[Registry] = None, top_k: int = TOPK_DEFAULT) -> None:
+    def __init__(self, registry: Optional[Registry] = None, top_k: int = TOPK_DEFAULT,
+                 scoring: Optional[str] = None) -> None:
         self._reg = registry or get_registry()
         self.is_mock = True          # main.py:385 skips the remote health probe when truthy
         self.is_b200 = True
         self.top_k = top_k
+        # "tf" = RF-1, "idf" = RF-1w (query buckets weighted by the scope's inverse document frequency)
+        self.scoring = (scoring or os.environ.get("RAG_B200_SCORING", "tf")).lower()
+        if self.scoring not in ("tf", "idf"):
+            raise ValueError(f"RAG_B200_SCORING must be 'tf' or 'idf', not {self.scoring!r}")
 
     # -------- Stores (gemini_rag.py:268-304, 607-612, 696-697) --------
     def list_stores(self) -> List[Any]:
@@ -301,7 +306,12 @@ class B200Rag:
                                 if not d.deleted and d.n_chunks and d.store_name in names and doc_matches(d.meta, metadata_filter))
             if not ranges:
                 return []
-        ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges)
+        weights = reg.engine.scope_weights(segs) if self.scoring == "idf" else None
+        if weights is None:   # (keeps the call shape of engines that predate the weighted variant)
+            ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges)
+        else:
+            ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges,
+                                                          weights=weights)
         out = []
         for gid, sc, c in zip(ids.tolist(), scores.tolist(), cos.tolist()):
             hit = reg.chunk_to_doc(int(gid))

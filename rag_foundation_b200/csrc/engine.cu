@@ -176,6 +176,9 @@ struct rf_engine {
     std::unordered_map<uint64_t, Doc> docs;
     uint64_t n_rows = 0;             // published rows
     std::atomic<uint64_t> epoch{0};  // bumps whenever extents change
+    std::atomic<uint64_t> tomb_gen{0};   // bumps whenever rows are tombstoned
+    std::mutex df_mu;                // RF-1w statistics cache: scope -> (generation, df[256] + n)
+    std::map<std::vector<uint32_t>, std::pair<uint64_t, std::vector<uint64_t>>> df_cache;
 
     std::mutex ingest_mu;            // one ingest at a time (shared scratch + append cursor)
     cudaStream_t ingest_stream = nullptr;
@@ -791,6 +794,7 @@ static int tombstone_extents(rf_engine *e, const std::vector<Extent> &ext) {
     for (const Extent &x : ext)
         RF_CUDA(cudaMemsetAsync(e->seg + x.lo, 0xFF, static_cast<size_t>(x.hi - x.lo) * 4, e->ingest_stream));
     RF_CUDA(cudaStreamSynchronize(e->ingest_stream));
+    e->tomb_gen.fetch_add(1);
     return RF_OK;
 }
 
@@ -1134,7 +1138,7 @@ int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_
     uint8_t *d_text = static_cast<uint8_t *>(c->d_in.p);
     int8_t *d_q = reinterpret_cast<int8_t *>(d_text + text_pad);
     if (n) RF_CUDA(cudaMemcpyAsync(d_text, c->h_in.p, n, cudaMemcpyHostToDevice, c->stream));
-    RF_CUDA(rf::launch_featurize_query(d_text, static_cast<uint32_t>(n), d_q, c->stream));
+    RF_CUDA(rf::launch_featurize_query(d_text, static_cast<uint32_t>(n), nullptr, d_q, c->stream));
     e->launches.fetch_add(1);
     RF_CUDA(cudaMemcpyAsync(c->h_in.p, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
     RF_CUDA(cudaStreamSynchronize(c->stream));
@@ -1150,6 +1154,12 @@ int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *
 int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
                       const uint64_t *ranges, uint32_t n_ranges, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
                       float *out_cos, uint32_t *out_count, int8_t *out_q) {
+    return rf_search_text_w(e, utf8, n, store_segs, n_segs, ranges, n_ranges, nullptr, k, out_ids, out_scores, out_cos, out_count, out_q);
+}
+
+int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
+                     const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k, uint64_t *out_ids,
+                     int32_t *out_scores, float *out_cos, uint32_t *out_count, int8_t *out_q) {
     if (!e || (!utf8 && n) || !out_ids || !out_scores || (!ranges && n_ranges)) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (n > (1u << 26)) return fail(RF_EINVAL, "query text too long");
@@ -1176,16 +1186,18 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
     // blob, query text and the query vector share the context's input buffer: one H2D copy
     const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
     const size_t blob_pad = (b.bytes.size() + 255) & ~static_cast<size_t>(255);
-    const size_t need = blob_pad + text_pad + RF_DIM;
+    const size_t w_pad = weights ? RF_DIM : 0;   // [blob | weights | text | query vector]
+    const size_t need = blob_pad + w_pad + text_pad + RF_DIM;
     RF_CUDA(c->h_in.reserve(need));
     RF_CUDA(c->d_in.reserve(need));
     uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
     uint8_t *d = static_cast<uint8_t *>(c->d_in.p);
     memcpy(h, b.bytes.data(), b.bytes.size());
-    if (n) memcpy(h + blob_pad, utf8, n);
-    RF_CUDA(cudaMemcpyAsync(d, h, blob_pad + n, cudaMemcpyHostToDevice, c->stream));
-    int8_t *d_q = reinterpret_cast<int8_t *>(d + blob_pad + text_pad);
-    RF_CUDA(rf::launch_featurize_query(d + blob_pad, static_cast<uint32_t>(n), d_q, c->stream));
+    if (weights) memcpy(h + blob_pad, weights, RF_DIM);
+    if (n) memcpy(h + blob_pad + w_pad, utf8, n);
+    RF_CUDA(cudaMemcpyAsync(d, h, blob_pad + w_pad + n, cudaMemcpyHostToDevice, c->stream));
+    int8_t *d_q = reinterpret_cast<int8_t *>(d + blob_pad + w_pad + text_pad);
+    RF_CUDA(rf::launch_featurize_query(d + blob_pad + w_pad, static_cast<uint32_t>(n), weights ? d + blob_pad : nullptr, d_q, c->stream));
     e->launches.fetch_add(1);
 
     const OutLayout L(1, k);
@@ -1220,6 +1232,102 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
     if (out_count) memcpy(out_count, ho + L.off_counts, 4);
     if (out_q) memcpy(out_q, ho + L.total, RF_DIM);
     e->searches.fetch_add(1);
+    return RF_OK;
+}
+
+// ---- RF-1w statistics ------------------------------------------------------------------------------
+static int fill_df_args(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, rf::DfArgs &a) {
+    if (n_segs > RF_SCOPE_MAX) return fail(RF_EINVAL, "scope has %u segments (max %u)", n_segs, RF_SCOPE_MAX);
+    memset(&a, 0, sizeof a);
+    a.F = e->F;
+    a.seg = e->seg;
+    a.n_scope = n_segs;
+    for (uint32_t j = 0; j < RF_SCOPE_MAX; ++j) a.scope[j] = j < n_segs ? store_segs[j] : RF_TOMBSTONE;
+    std::vector<Extent> ext;
+    {
+        std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+        gather_extents(e, store_segs, n_segs, ext);
+    }
+    static_assert(rf::kDfMaxExtents >= kMaxExtPerQuery, "extent list must fit the kernel parameters");
+    a.n_ext = static_cast<uint32_t>(ext.size());
+    uint32_t rows = 0;
+    for (uint32_t i = 0; i < a.n_ext; ++i) {
+        a.lo[i] = ext[i].lo;
+        a.prefix[i] = rows;
+        rows += ext[i].hi - ext[i].lo;
+    }
+    a.prefix[a.n_ext] = rows;
+    return RF_OK;
+}
+
+int rf_scope_df_device(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint64_t *df_dev, void *stream) {
+    if (!e || (!store_segs && n_segs) || !df_dev) return fail(RF_EINVAL, "null argument");
+    rf::DfArgs a;
+    int rc = fill_df_args(e, store_segs, n_segs, a);
+    if (rc) return rc;
+    a.out = reinterpret_cast<unsigned long long *>(df_dev);
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    RF_CUDA(rf::launch_bucket_df(a, e->sm_count, static_cast<cudaStream_t>(stream)));
+    if (a.prefix[a.n_ext]) e->launches.fetch_add(1, std::memory_order_relaxed);
+    return RF_OK;
+}
+
+int rf_scope_df(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint64_t *out_df, uint64_t *out_n) {
+    if (!e || (!store_segs && n_segs) || !out_df || !out_n) return fail(RF_EINVAL, "null argument");
+    std::vector<uint32_t> key(store_segs, store_segs + n_segs);
+    std::sort(key.begin(), key.end());
+    key.erase(std::unique(key.begin(), key.end()), key.end());
+    const uint64_t gen = e->epoch.load() + e->tomb_gen.load();   // both only grow
+    {
+        std::lock_guard<std::mutex> lk(e->df_mu);
+        auto it = e->df_cache.find(key);
+        if (it != e->df_cache.end() && it->second.first == gen) {
+            memcpy(out_df, it->second.second.data(), RF_DIM * 8);
+            *out_n = it->second.second[RF_DIM];
+            return RF_OK;
+        }
+    }
+    SearchCtx *c = ctx_acquire(e);
+    if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
+    CtxGuard g{e, c};
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t bytes = (RF_DIM + 1) * 8;
+    RF_CUDA(c->d_out.reserve(bytes));
+    RF_CUDA(c->h_out.reserve(bytes));
+    RF_CUDA(cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream));
+    int rc = rf_scope_df_device(e, store_segs, n_segs, static_cast<uint64_t *>(c->d_out.p), c->stream);
+    if (rc) return rc;
+    RF_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t *h = static_cast<const uint64_t *>(c->h_out.p);
+    memcpy(out_df, h, RF_DIM * 8);
+    *out_n = h[RF_DIM];
+    {
+        std::lock_guard<std::mutex> lk(e->df_mu);
+        if (e->df_cache.size() > 4096) e->df_cache.clear();
+        e->df_cache[key] = {gen, std::vector<uint64_t>(h, h + RF_DIM + 1)};
+    }
+    return RF_OK;
+}
+
+int rf_idf_weights(const uint64_t *df, uint64_t n, uint32_t dim, uint8_t *out_w) {
+    if (!df || !out_w) return fail(RF_EINVAL, "null argument");
+    if (n >= (1ull << 55)) return fail(RF_EINVAL, "row count out of range");
+    for (uint32_t d = 0; d < dim; ++d) {
+        if (df[d] > n) return fail(RF_EINVAL, "df[%u] exceeds the row count", d);
+        const uint64_t r = ((n + 1) << 8) / (df[d] + 1);          // >= 256
+        const int lg = 63 - __builtin_clzll(r);
+        out_w[d] = static_cast<uint8_t>(std::min<uint64_t>(4 + 4 * static_cast<uint64_t>(lg - 8) + ((r >> (lg - 2)) & 3), 31));
+    }
+    return RF_OK;
+}
+
+int rf_weight_query(const int8_t *q, const uint8_t *w, uint32_t dim, int8_t *out_qw) {
+    if (!q || !w || !out_qw) return fail(RF_EINVAL, "null argument");
+    for (uint32_t d = 0; d < dim; ++d) {
+        if (q[d] < 0) return fail(RF_EINVAL, "query features are counts (>= 0)");
+        out_qw[d] = static_cast<int8_t>(std::min<int>(static_cast<int>(q[d]) * w[d], 127));
+    }
     return RF_OK;
 }
 

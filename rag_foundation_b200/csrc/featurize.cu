@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
 // Query featurisation (RF-1 step 5): no chunking, so no token ordinals are needed -- one block
 // histograms every kept token of the (<= 32 KB, routes/chat.py:48) query text.
 __global__ void __launch_bounds__(256) featurize_query_kernel(const uint8_t *__restrict__ text, uint32_t n,
+                                                              const uint8_t *__restrict__ weights,
                                                               int8_t *__restrict__ q_out) {
     __shared__ uint32_t hist[kDim];
     hist[threadIdx.x] = 0;
@@ -234,7 +235,66 @@ __global__ void __launch_bounds__(256) featurize_query_kernel(const uint8_t *__r
         atomicAdd(&hist[h & (kDim - 1)], 1u);
     }
     __syncthreads();
-    q_out[threadIdx.x] = static_cast<int8_t>(min(hist[threadIdx.x], 127u));
+    const uint32_t tf = min(hist[threadIdx.x], 127u);
+    q_out[threadIdx.x] = static_cast<int8_t>(weights ? min(tf * weights[threadIdx.x], 127u) : tf);
+}
+
+// RF-1w document frequencies (oracle/SPEC.md "IDF-weighted variant").  A warp takes four rows per
+// step; a lane owns eight adjacent buckets (one 8-byte load per row).  Features are counts in
+// [0, 127], so (x + 0x7F7F7F7F) has bit 7 of a byte set exactly when that byte is non-zero: the
+// per-byte flags accumulate packed, four buckets per register, and are spilled into 32-bit
+// counters every 252 rows.  HBM-bound: 260 B per row, read once.
+__global__ void __launch_bounds__(256) bucket_df_kernel(const __grid_constant__ DfArgs a) {
+    __shared__ unsigned int acc[kDim + 1];
+    for (int i = threadIdx.x; i <= kDim; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t total = a.prefix[a.n_ext];
+    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t p0 = 0, p1 = 0, pending = 0, live = 0;
+    auto spill = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cnt[j] += (p0 >> (8 * j)) & 0xFF;
+            cnt[4 + j] += (p1 >> (8 * j)) & 0xFF;
+        }
+        p0 = p1 = pending = 0;
+    };
+    uint32_t e = 0;
+    for (uint64_t v0 = static_cast<uint64_t>(warp) * 4; v0 < total; v0 += static_cast<uint64_t>(warps_total) * 4) {
+        int2 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            x[j] = make_int2(0, 0);
+            const uint64_t v = v0 + j;
+            if (v >= total) continue;
+            while (v >= a.prefix[e + 1]) ++e;
+            const uint32_t row = a.lo[e] + static_cast<uint32_t>(v - a.prefix[e]);
+            const uint32_t sg = __ldg(a.seg + row);
+            bool ok = false;
+            for (uint32_t t = 0; t < a.n_scope; ++t) ok |= (a.scope[t] == sg);
+            if (!ok || sg == RF_TOMBSTONE) continue;
+            ++live;
+            x[j] = __ldg(reinterpret_cast<const int2 *>(a.F + static_cast<size_t>(row) * kRowBytes) + lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            p0 += ((static_cast<uint32_t>(x[j].x) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+            p1 += ((static_cast<uint32_t>(x[j].y) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+        }
+        pending += 4;
+        if (pending >= 252) spill();
+    }
+    spill();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (cnt[j]) atomicAdd(&acc[lane * 8 + j], cnt[j]);
+    if (lane == 0 && live) atomicAdd(&acc[kDim], live);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= kDim; i += blockDim.x)
+        if (acc[i]) atomicAdd(a.out + i, static_cast<unsigned long long>(acc[i]));
 }
 
 __global__ void __launch_bounds__(256) row_meta_kernel(const int8_t *__restrict__ F, uint64_t n_rows,
@@ -288,8 +348,17 @@ cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, u
     return cudaGetLastError();
 }
 
-cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, int8_t *q_out, cudaStream_t s) {
-    featurize_query_kernel<<<1, 256, 0, s>>>(text_dev, n_bytes, q_out);
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, cudaStream_t s) {
+    featurize_query_kernel<<<1, 256, 0, s>>>(text_dev, n_bytes, weights, q_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bucket_df(const DfArgs &a, int sm_count, cudaStream_t s) {
+    const uint32_t total = a.prefix[a.n_ext];
+    if (total == 0) return cudaSuccess;
+    const uint32_t want = (total + 8 * 4 * 16 - 1) / (8 * 4 * 16);   // >= 16 steps per warp before another block pays off
+    const uint32_t blocks = std::max(1u, std::min(want, static_cast<uint32_t>(sm_count) * 8u));
+    bucket_df_kernel<<<blocks, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

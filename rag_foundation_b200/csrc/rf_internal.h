@@ -156,7 +156,21 @@ cudaError_t launch_tokenize(const FeaturizeWork &w, size_t n_bytes, cudaStream_t
 cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
                                     int32_t *ff, uint32_t *seg, uint32_t store_seg, int64_t *spans_dev,
                                     cudaStream_t s);
-cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, int8_t *q_out, cudaStream_t s);
+// weights: [256] u8 device (RF-1w) or null (plain RF-1)
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, cudaStream_t s);
+// RF-1w statistics: out[d] += rows of the extents that are in scope and have F[row, d] > 0 (d < 256);
+// out[256] += rows in scope.  One streaming pass over the extents' rows.
+constexpr uint32_t kDfMaxExtents = 64;
+struct DfArgs {
+    const int8_t *F;
+    const uint32_t *seg;
+    unsigned long long *out;            // [257] device, accumulated into (caller zeroes)
+    uint32_t n_ext, n_scope;
+    uint32_t scope[RF_SCOPE_MAX];
+    uint32_t lo[kDfMaxExtents];
+    uint32_t prefix[kDfMaxExtents + 1]; // rows before extent i; prefix[n_ext] = total
+};
+cudaError_t launch_bucket_df(const DfArgs &a, int sm_count, cudaStream_t s);
 // ff[r] = sum of squares of row r, seg[r] = store_seg, for rows appended as raw features
 cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
                             cudaStream_t s);

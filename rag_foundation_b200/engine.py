@@ -194,19 +194,26 @@ class Engine:
             check(rc)
         return ids, sc, cs, cnt
 
-    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None):
+    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None, weights=None):
         """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [256]   (m <= k results).
 
         `ranges`: optional sorted, disjoint [(lo, hi), ...] global chunk id ranges to stay inside
-        (doc-level metadata filters)."""
+        (doc-level metadata filters).  `weights`: optional uint8 [256] RF-1w bucket weights
+        (`idf_weights`); the returned q is then the weighted vector."""
         text = bytes(text)
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.uint8)
+            if weights.shape != (RF_DIM,):
+                raise ValueError(f"weights must be uint8 [{RF_DIM}]")
         rng = None
         if ranges is not None:
             rng = np.ascontiguousarray(np.asarray(list(ranges), dtype=np.uint64).reshape(-1, 2))
             if rng.shape[0] == 0:
-                return (np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32), self.featurize_query(text))
+                q0 = self.featurize_query(text)
+                return (np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32),
+                        q0 if weights is None else self.weight_query(q0, weights))
             if rng.shape[0] > self.RANGES_PER_CALL:   # many matching documents: several launches, merged here
-                parts = [self.search_text(text, scope, k, ranges=rng[i:i + self.RANGES_PER_CALL])
+                parts = [self.search_text(text, scope, k, ranges=rng[i:i + self.RANGES_PER_CALL], weights=weights)
                          for i in range(0, rng.shape[0], self.RANGES_PER_CALL)]
                 ids = np.concatenate([p[0] for p in parts]); sc = np.concatenate([p[1] for p in parts])
                 cs = np.concatenate([p[2] for p in parts])
@@ -218,9 +225,9 @@ class Engine:
         cs = np.zeros(k, np.float32)
         cnt = C.c_uint32()
         q = np.zeros(RF_DIM, np.int8)
-        check(self._L.rf_search_text_in(self.handle, text or b"\0", len(text), _ptr(segs), len(scope), _ptr(rng),
-                                        0 if rng is None else rng.shape[0], int(k), _ptr(ids), _ptr(sc), _ptr(cs),
-                                        C.byref(cnt), _ptr(q)))
+        check(self._L.rf_search_text_w(self.handle, text or b"\0", len(text), _ptr(segs), len(scope), _ptr(rng),
+                                       0 if rng is None else rng.shape[0], _ptr(weights), int(k), _ptr(ids), _ptr(sc),
+                                       _ptr(cs), C.byref(cnt), _ptr(q)))
         m = int(cnt.value)
         return ids[:m], sc[:m], cs[:m], q
 
@@ -229,6 +236,37 @@ class Engine:
         q = np.zeros(RF_DIM, np.int8)
         check(self._L.rf_featurize_query(self.handle, text or b"\0", len(text), _ptr(q)))
         return q
+
+    # ---- RF-1w (IDF-weighted variant, oracle/SPEC.md) ------------------------------------------
+    def scope_df(self, scope: Sequence[int]) -> Tuple[np.ndarray, int]:
+        """-> (df uint64 [256], n): per-bucket document frequencies over the scope's live rows."""
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        df = np.zeros(RF_DIM, np.uint64)
+        n = C.c_uint64()
+        check(self._L.rf_scope_df(self.handle, _ptr(segs), len(scope), _ptr(df), C.byref(n)))
+        return df, int(n.value)
+
+    def scope_df_device(self, scope: Sequence[int], df_ptr: int, stream: int = 0) -> None:
+        """Adds the scope's df[256] and row count into the 257 u64 at device pointer `df_ptr`."""
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        check(self._L.rf_scope_df_device(self.handle, _ptr(segs), len(scope), df_ptr, stream))
+
+    def idf_weights(self, df: np.ndarray, n: int) -> np.ndarray:
+        df = np.ascontiguousarray(df, dtype=np.uint64)
+        w = np.zeros(RF_DIM, np.uint8)
+        check(self._L.rf_idf_weights(_ptr(df), int(n), RF_DIM, _ptr(w)))
+        return w
+
+    def scope_weights(self, scope: Sequence[int]) -> np.ndarray:
+        return self.idf_weights(*self.scope_df(scope))
+
+    def weight_query(self, q: np.ndarray, w: np.ndarray) -> np.ndarray:
+        q = np.ascontiguousarray(q, dtype=np.int8)
+        w = np.ascontiguousarray(w, dtype=np.uint8)
+        out = np.zeros_like(q)
+        for row_in, row_out in zip(q.reshape(-1, RF_DIM), out.reshape(-1, RF_DIM)):
+            check(self._L.rf_weight_query(_ptr(row_in), _ptr(w), RF_DIM, _ptr(row_out)))
+        return out
 
     def search_keys_device(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int,
                            stream: int = 0) -> None:

@@ -34,11 +34,36 @@ def unpack_keys_torch(keys: torch.Tensor):
     return ids, scores, valid
 
 
+def allreduce_scope_weights(local_df: Callable[[Sequence[int]], torch.Tensor], weights_fn, scope: Sequence[int],
+                            group: Optional[dist.ProcessGroup] = None):
+    """RF-1w weights of a sharded corpus (oracle/SPEC.md): every rank counts its own shard
+    (`local_df(scope)` -> int64 [257]: df per bucket, then the live row count), ONE integer
+    all-reduce (sum) makes the statistic global, and `weights_fn(df, n)` turns it into the uint8 [256]
+    weights -- identical on every rank, so the merged ranking equals the single-engine one."""
+    stat = local_df(scope)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stat, op=dist.ReduceOp.SUM, group=group)
+    host = stat.cpu().numpy()
+    return weights_fn(host[:-1].astype("uint64"), int(host[-1]))
+
+
+def engine_local_df(engine) -> Callable[[Sequence[int]], torch.Tensor]:
+    def local_df(scope: Sequence[int]) -> torch.Tensor:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        stat = torch.zeros(257, dtype=torch.int64, device=dev)
+        engine.scope_df_device(scope, stat.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return stat
+    return local_df
+
+
 class ShardedSearcher:
     def __init__(self, local_search: Callable[[torch.Tensor, Sequence[int], int], torch.Tensor],
-                 merge: Callable[[torch.Tensor, int], torch.Tensor], group: Optional[dist.ProcessGroup] = None):
+                 merge: Callable[[torch.Tensor, int], torch.Tensor], group: Optional[dist.ProcessGroup] = None,
+                 local_df: Optional[Callable[[Sequence[int]], torch.Tensor]] = None, weights_fn=None):
         self.local_search = local_search
         self.merge = merge
+        self.local_df = local_df
+        self.weights_fn = weights_fn
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -62,7 +87,13 @@ class ShardedSearcher:
                                      torch.cuda.current_stream(gathered.device).cuda_stream)
             return out
 
-        return cls(local_search, merge, group)
+        return cls(local_search, merge, group, local_df=engine_local_df(engine), weights_fn=engine.idf_weights)
+
+    def scope_weights(self, scope: Sequence[int]):
+        """uint8 [256] RF-1w weights from the corpus-wide document frequencies (see allreduce_scope_weights)."""
+        if self.local_df is None or self.weights_fn is None:
+            raise RuntimeError("this searcher was built without the document-frequency callables")
+        return allreduce_scope_weights(self.local_df, self.weights_fn, scope, self.group)
 
     def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: int = 10, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """q int8 [nq, 256] (replicated on every rank) -> merged packed keys int64 [nq, k] on every rank."""
@@ -130,6 +161,9 @@ class FusedShardedSearcher:
                                              torch.cuda.current_stream(q.device).cuda_stream, self.rank, self.world,
                                              self.nq_cap, self._seq, self._keys_ptrs, self._flag_ptrs, self._timeout.data_ptr())
         return out
+
+    def scope_weights(self, scope: Sequence[int]):
+        return allreduce_scope_weights(engine_local_df(self.engine), self.engine.idf_weights, scope, self.group)
 
     def timed_out(self) -> bool:
         return bool(self._timeout.item())

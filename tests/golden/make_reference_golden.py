@@ -35,6 +35,23 @@ def normalize_cases():
     return [{"text": t, "normalized": metrics._normalize(t)} for t in texts]
 
 
+def metrics_cases():
+    """scripts/benchmark/metrics.py citation_hit / extract_gold_doc_ids / p95 on fixed inputs (pins the
+    grading functions tools/quality_eval.py restates)."""
+    sys.path.insert(0, os.path.join(REF, "scripts", "benchmark"))
+    import metrics
+    recs = [{"gold_docs": ["A.md", "b.md"]}, {"supporting_docs": [{"doc_id": "x.txt"}, {"nope": 1}, "str", {"doc_id": ""}]},
+            {"gold_docs": [], "supporting_docs": [{"doc_id": "y"}]}, {}, {"supporting_docs": None}]
+    cits = [[], None, [{"title": "a.md"}], [{"doc_id": "B.MD", "title": "zzz"}], [{"sourceId": "cit-0", "title": "a.md"}],
+            [{"uri": "chunk://s/1/0#5", "title": "a.md"}], [{"title": "q"}, {"title": "A.MD"}], [{"doc_id": "", "sourceId": None, "uri": "", "title": "b.md"}],
+            [{"doc_id": 7}], [{}]]
+    golds = [["A.md", "b.md"], [], ["7"], ["chunk://S/1/0#5"]]
+    series = [[], [5.0], [1.0, 2.0], [3.0, 1.0, 2.0, 10.0], [float(i) for i in range(21)], [0.5] * 7 + [9.25]]
+    return {"extract_gold_doc_ids": [{"rec": r, "want": metrics.extract_gold_doc_ids(r)} for r in recs],
+            "citation_hit": [{"citations": c, "gold": g, "want": metrics.citation_hit(c, g)} for c in cits for g in golds],
+            "p95": [{"values": v, "want": metrics.p95(v)} for v in series]}
+
+
 def wire_case():
     os.environ.update(ENVIRONMENT="test", GEMINI_MOCK_MODE="true", JWT_SECRET="x" * 64,
                       GEMINI_API_KEY="fake-key-for-tests")
@@ -94,4 +111,6 @@ if __name__ == "__main__":
         json.dump(normalize_cases(), f, indent=1, ensure_ascii=True)
     with open(os.path.join(HERE, "config1_wire.json"), "w") as f:
         json.dump(wire_case(), f, indent=1, ensure_ascii=True)
-    print("wrote normalize_golden.json, config1_wire.json")
+    with open(os.path.join(HERE, "benchmark_metrics_golden.json"), "w") as f:
+        json.dump(metrics_cases(), f, indent=1, ensure_ascii=True)
+    print("wrote normalize_golden.json, config1_wire.json, benchmark_metrics_golden.json")

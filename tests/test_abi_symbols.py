@@ -75,3 +75,26 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "librf1_oracle" not in src, f
+
+
+def test_rf1w_host_functions_match_the_oracle():
+    """rf_idf_weights / rf_weight_query are pure host functions of the C-ABI: callable without a GPU."""
+    import ctypes as C
+
+    import numpy as np
+
+    from oracle import c_oracle as co
+    from rag_foundation_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 77, 10_000, 10 ** 8):
+        df = rng.integers(0, n + 1, 256).astype(np.uint64)
+        w = np.zeros(256, np.uint8)
+        assert L.rf_idf_weights(df.ctypes.data, n, 256, w.ctypes.data) == 0
+        assert (w == co.idf_weights(df, n)).all()
+        q = rng.integers(0, 9, 256).astype(np.int8)
+        qw = np.zeros(256, np.int8)
+        assert L.rf_weight_query(q.ctypes.data, w.ctypes.data, 256, qw.ctypes.data) == 0
+        assert (qw == co.weight_query(q, w)).all()
+    bad = np.full(256, 5, np.uint64)
+    assert L.rf_idf_weights(bad.ctypes.data, 4, 256, w.ctypes.data) == _capi.RF_EINVAL   # df > n

@@ -157,3 +157,42 @@ def test_daemon_with_real_engine_and_concurrent_clients(tmp_path, golden_dir):
     finally:
         srv.close()
         reg.engine.close()
+
+
+def test_idf_scoring_through_the_adapter_and_quality_eval(tmp_path):
+    """RAG_B200_SCORING=idf (RF-1w): citations rank as the oracle's weighted ranking says, the plain
+    adapter on the same registry is unchanged, and the reference-style citation grading runs end to end."""
+    import importlib.util
+    from oracle import c_oracle as co
+    from rag_foundation_b200 import Engine
+    from rag_foundation_b200 import adapter as ad
+    spec = importlib.util.spec_from_file_location("quality_eval", os.path.join(os.path.dirname(__file__), "..", "tools", "quality_eval.py"))
+    qe = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(qe)
+
+    docs, questions = qe.make_labelled_set(150, 60, seed=4)
+    reg = ad.Registry(Engine(capacity_rows=8192))
+    try:
+        res = qe.run_eval(lambda scoring: ad.B200Rag(registry=reg, scoring=scoring), docs, questions)
+        # an independent numpy model of RF-1 / RF-1w over the same labelled set grades identically
+        model = qe.model_dim_sweep(docs, questions, dims=(256,))["256"]
+        for mode in ("tf", "idf"):
+            assert res["scoring"][mode]["citation_hit_rate"] == pytest.approx(model[mode], abs=1e-12), (res, model)
+        assert res["scoring"]["idf"]["citation_hit_rate"] > res["scoring"]["tf"]["citation_hit_rate"] > 0
+        rag_idf, rag_tf = ad.B200Rag(registry=reg, scoring="idf"), ad.B200Rag(registry=reg, scoring="tf")
+        store = next(iter({d.store_name for d in reg.docs.values()}))
+        seg = reg.engine.lookup_store(store)
+        n_rows = reg.engine.stats()["n_rows"]
+        F, sg, ff = reg.engine.read_rows(0, n_rows)
+        w = co.idf_weights(*co.bucket_df(F, sg, [seg]))
+        assert (reg.engine.scope_weights([seg]) == w).all()
+        for rec in questions[:12]:
+            q = co.query_vector(rec["question"].encode())
+            for rag, qv in ((rag_tf, q), (rag_idf, co.weight_query(q, w))):
+                got = rag.retrieve(rec["question"], [store])
+                w_ids, w_sc, _ = co.score_topk(F, sg, qv, [seg], ff=ff)
+                assert [g["chunk_id"] for g in got] == w_ids.tolist() and [g["score"] for g in got] == w_sc.tolist()
+        with pytest.raises(ValueError):
+            ad.B200Rag(registry=reg, scoring="bm25")
+    finally:
+        reg.engine.close()

@@ -309,6 +309,11 @@ def test_sharded_searcher_single_process_two_engines(co, zb):
         for i in range(4):
             w_ids, w_sc, _ = co.score_topk(F, np.zeros(n, np.uint32), Q[i], [0])
             assert ids[i].tolist() == w_ids.tolist() and sc[i].tolist() == w_sc.tolist()
+        # RF-1w: the shards' device-side statistics add up to the whole corpus's
+        from rag_foundation_b200.sharded import engine_local_df
+        stat = sum(engine_local_df(e)([0]) for e in engines).cpu().numpy()
+        w_df, w_n = co.bucket_df(F, np.zeros(n, np.uint32), [0])
+        assert int(stat[-1]) == w_n and (stat[:-1].astype(np.uint64) == w_df).all()
     finally:
         for e in engines:
             e.close()
@@ -667,3 +672,83 @@ def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
         assert e.stats()["kernel_launches"] - l0 == 1
         for i in range(0, nq, 11):
             _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], scopes[i], 10, 0, ffall)
+
+
+# ------------------------------------------------------------------ RF-1w (IDF-weighted variant)
+def test_scope_df_and_weights_match_oracle(co, zb):
+    """Document frequencies over interleaved stores (many extents), after tombstones and a dropped
+    store, with the cache refreshed by every change; weights are the C-ABI's own host function."""
+    rng = np.random.default_rng(8)
+    with _engine(80_000) as e:
+        stores = [e.open_store(f"fileSearchStores/t{i}") for i in range(4)]
+        F_all, seg_all = [], []
+        start = 0
+        for d in range(150):
+            s = int(rng.integers(0, 4)); n = int(rng.integers(1, 500))
+            rows = co.synth_rows(12, start, n, zb)
+            e.ingest_features(stores[s], d + 1, rows)
+            F_all.append(rows); seg_all.append(np.full(n, stores[s], np.uint32)); start += n
+        F = np.concatenate(F_all); seg = np.concatenate(seg_all)
+
+        def check_all():
+            for scope in ([stores[0]], [stores[1], stores[3]], stores, [stores[2], stores[2]], [99], []):
+                df, n = e.scope_df(scope)
+                w_df, w_n = co.bucket_df(F, seg, scope)
+                assert n == w_n and (df == w_df).all(), scope
+                assert (e.idf_weights(df, n) == co.idf_weights(w_df, w_n)).all()
+                df2, n2 = e.scope_df(scope)                     # second call: served from the cache
+                assert n2 == n and (df2 == df).all()
+        check_all()
+        lo = 0
+        for d, rows in enumerate(F_all, start=1):
+            if d in (5, 60, 149):
+                e.tombstone_doc(d)
+                seg[lo:lo + len(rows)] = 0xFFFFFFFF
+            lo += len(rows)
+        check_all()
+        e.drop_store(stores[3]); seg[seg == stores[3]] = 0xFFFFFFFF
+        extra = co.synth_rows(12, start, 3000, zb)
+        e.ingest_features(stores[0], 1000, extra)
+        F = np.concatenate([F, extra]); seg = np.concatenate([seg, np.full(3000, stores[0], np.uint32)])
+        check_all()
+
+
+def test_scope_df_one_million_rows(co, zb):
+    n = 1_000_000
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=0, start_counter=0, n_rows=n)
+        df, live = e.scope_df([s])
+        F = co.synth_rows(0, 0, n, zb)
+        w_df, w_n = co.bucket_df(F, np.zeros(n, np.uint32), [0])
+        assert live == w_n == n and (df == w_df).all()
+
+
+def test_weighted_text_search_matches_oracle(co, zb, rf1):
+    """rf_search_text_w: the query is tokenised, hashed AND weighted on the GPU; ids / scores / cosines
+    equal the oracle's RF-1w ranking, also inside a metadata range restriction."""
+    n = 40_000
+    with _engine(n) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        F, ff = co.synth_rows(41, 0, n, zb, with_ff=True)
+        e.ingest_features(a, 1, F[:25_000]); e.ingest_features(b, 2, F[25_000:])
+        seg = np.concatenate([np.full(25_000, a), np.full(15_000, b)]).astype(np.uint32)
+        for scope in ([a], [b], [a, b]):
+            w = e.scope_weights(scope)
+            assert (w == co.idf_weights(*co.bucket_df(F, seg, scope))).all()
+            for text in (b"1786 23 4479 313 12 7 1318 21", b"7 7 7 7 7 7 7 7 12 the 12", b"", b"zzz"):
+                qw = co.weight_query(co.query_vector(text), w)
+                ids, sc, cs, q_gpu = e.search_text(text, scope, 10, weights=w)
+                assert (q_gpu == qw).all()
+                assert (e.weight_query(co.query_vector(text), w) == qw).all()
+                w_ids, w_sc, w_cs = co.score_topk(F, seg, qw, scope, k=10, ff=ff)
+                assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist()
+                np.testing.assert_allclose(cs, w_cs, rtol=COS_RTOL, atol=0)
+        w = e.scope_weights([a])
+        text = b"1786 23 4479 313 12 7 1318 21"
+        qw = co.weight_query(co.query_vector(text), w)
+        ids, sc, _, _ = e.search_text(text, [a], 10, ranges=[(500, 9_000), (20_000, 30_000)], weights=w)
+        keys = np.concatenate([co.score_topk_keys(F, seg, qw, [a], k=10, row_lo=lo, row_hi=hi) for lo, hi in [(500, 9_000), (20_000, 30_000)]])
+        from rag_foundation_b200 import unpack_keys
+        w_ids, w_sc, _ = unpack_keys(co.merge_topk(keys, 10))
+        assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist()

@@ -201,3 +201,46 @@ def test_merge_topk_equals_global(zb):
     parts = [co.score_topk_keys(F, seg, q, [0], row_lo=lo, row_hi=hi) for lo, hi in [(0, 1000), (1000, 1001), (1001, 4000)]]
     assert co.merge_topk(np.concatenate(parts)).tolist() == whole.tolist()
     assert rf1.merge_topk(parts) == [int(x) for x in whole]
+
+
+# ---- RF-1w (IDF-weighted variant) ----------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rf1w_golden(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "rf1w_golden.json")))
+
+
+def test_rf1w_weight_cases(rf1w_golden):
+    for n, df, want in rf1w_golden["weight_cases"]:
+        assert int(rf1.idf_weights([df], n)[0]) == want
+        assert int(co.idf_weights(np.full(256, df, np.uint64), n)[0]) == want
+    assert rf1w_golden["saturation"] == [0, 31, 124, 127, 127]
+    sat = co.weight_query(np.array([0, 1, 4, 5, 127] + [0] * 251, np.int8), np.full(256, 31, np.uint8))
+    assert sat[:5].tolist() == [0, 31, 124, 127, 127]
+
+
+def test_rf1w_synthetic_golden_both_oracles(rf1w_golden, zb):
+    g = rf1w_golden["synthetic"]
+    F = co.synth_rows(g["seed"], 0, g["rows"], zb)
+    seg = np.zeros(g["rows"], np.uint32)
+    seg[g["store1"][0]:g["store1"][1]] = 1
+    seg[g["tombstones"]] = rf1.TOMBSTONE
+    for case in g["cases"]:
+        for mod in (rf1, co):
+            df, n = mod.bucket_df(F, seg, case["scope"])
+            assert n == case["n"] and df.tolist() == case["df"]
+            w = mod.idf_weights(df, n)
+            assert w.tolist() == case["w"]
+        for qc in case["queries"]:
+            qw = co.weight_query(co.synth_query(g["seed"], qc["qi"], zb), w)
+            assert (qw == _dense(qc["qw_sparse"])).all()
+            ids, sc, _ = co.score_topk(F, seg, qw, case["scope"])
+            assert ids.tolist() == qc["ids"] and sc.tolist() == qc["scores"]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 2 ** 40), st.integers(0, 2 ** 40))
+def test_rf1w_weights_python_equals_c_and_are_monotone(n, df):
+    df = min(df, n)
+    a = int(rf1.idf_weights([df], n)[0])
+    assert a == int(co.idf_weights(np.full(256, df, np.uint64), n)[0]) and 4 <= a <= 31
+    assert int(rf1.idf_weights([df // 2], n)[0]) >= a      # rarer bucket, weight never smaller

@@ -51,8 +51,13 @@ def _worker(rank, world, port, n_total, seed, out_dir):
             out = np.stack([co.merge_topk(g[:, i, :], k) for i in range(g.shape[1])])
             return torch.from_numpy(out.view(np.int64))
 
-        s = ShardedSearcher(local_search, merge)
+        def local_df(scope):
+            df, n = co.bucket_df(F, seg, scope)
+            return torch.from_numpy(np.concatenate([df, [n]]).astype(np.int64))
+
+        s = ShardedSearcher(local_search, merge, local_df=local_df, weights_fn=co.idf_weights)
         assert s.world == world and s.rank == rank
+        np.save(os.path.join(out_dir, f"w_{rank}.npy"), s.scope_weights([0]))
         q = torch.from_numpy(np.stack([co.synth_query(seed, i, zb) for i in range(5)]))
         keys = s.search_keys(q, [0], 10)
         ids, sc, valid = unpack_keys_torch(keys)
@@ -73,7 +78,9 @@ def test_two_rank_sharded_search_equals_single_index(tmp_path):
     zb = rf1.zipf_bucket_table()
     F = co.synth_rows(seed, 0, n_total, zb)
     seg = np.zeros(n_total, np.uint32)
+    w_all = co.idf_weights(*co.bucket_df(F, seg, [0]))   # RF-1w: all-reduced statistic == whole-corpus statistic
     for r in range(world):
+        assert (np.load(tmp_path / f"w_{r}.npy") == w_all).all()
         ids = np.load(tmp_path / f"ids_{r}.npy")
         sc = np.load(tmp_path / f"sc_{r}.npy")
         for i in range(5):
