@@ -146,6 +146,12 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
 int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
                           uint32_t n_segs, uint32_t k, uint64_t *out_keys_dev, void *stream);
 
+/* rf_search_keys_device with one scope PER QUERY (CSR, as rf_search): the store-sharded multi-GPU
+ * path (whole stores per rank, SURVEY.md 8e / configs[4]) gives every rank the full query batch and
+ * the part of each query's scope it owns -- possibly empty, then that query's keys are all 0. */
+int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                 const uint32_t *seg_off, uint32_t k, uint64_t *out_keys_dev, void *stream);
+
 /* Fused variant of the sharded search: local scan + top-k EXCHANGE in one pass over NVLink peer
  * memory, no collective launch.  Every rank passes the same exchange description: keys_ptrs[r] /
  * flag_ptrs[r] are this process's mappings of rank r's gather buffer ([4][world][nq_cap][k] u64)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_text_in": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_keys_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
+    "rf_search_keys_device_scoped": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp]),
     "rf_search_keys_device_fused": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "rf_featurize_query": (_i32, [_vp, _vp, _sz, _vp]),

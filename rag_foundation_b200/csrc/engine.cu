@@ -148,6 +148,8 @@ struct SearchCtx {
 struct DevicePlan {
     uint64_t epoch = ~0ull;
     DeviceBuf blob, partial, tickets;
+    PinnedBuf h_blob;                 // per-call plans (rf_search_keys_device_scoped): staging + "copy done" event
+    cudaEvent_t h_blob_free = nullptr;
     DeviceBuf gemm_lists, gemm_keys_a, gemm_floors;   // batched tensor-core path scratch
     uint32_t n_ext = 0, max_tiles = 0;
     uint32_t launches = 0;
@@ -726,6 +728,8 @@ int rf_engine_destroy(rf_engine *e) {
     for (auto &kv : e->dev_plans) {
         kv.second->blob.release(); kv.second->partial.release(); kv.second->tickets.release();
         kv.second->gemm_lists.release(); kv.second->gemm_keys_a.release(); kv.second->gemm_floors.release();
+        kv.second->h_blob.release();
+        if (kv.second->h_blob_free) cudaEventDestroy(kv.second->h_blob_free);
         delete kv.second;
     }
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
@@ -1426,6 +1430,53 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
         }
         RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
     }
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    e->searches.fetch_add(nq, std::memory_order_relaxed);
+    return RF_OK;
+}
+
+int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                 const uint32_t *seg_off, uint32_t k, uint64_t *out_keys_dev, void *stream) {
+    if (!e || !q_dev || !seg_off || !out_keys_dev) return fail(RF_EINVAL, "null argument");
+    if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
+    if (nq == 0) return RF_OK;
+    if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PlanBlob b;
+    int rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b);
+    if (rc) return rc;
+    DevicePlan *dp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->plan_mu);
+        DevicePlan *&slot = e->dev_plans[{std::vector<uint32_t>(RF_SCOPE_MAX + 1, 0u), stream}];   // longer than any scope: this stream's per-call plans
+        if (!slot) slot = new DevicePlan();
+        dp = slot;
+    }
+    const uint32_t X = pick_blocks(e, nq, b.max_tiles);
+    const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
+    const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
+    if (b.bytes.size() > dp->blob.cap || need_partial > dp->partial.cap || need_sync > dp->tickets.cap) {
+        RF_CUDA(cudaStreamSynchronize(s));
+        RF_CUDA(dp->blob.reserve(b.bytes.size()));
+        RF_CUDA(dp->partial.reserve(need_partial));
+        if (need_sync > dp->tickets.cap) {
+            RF_CUDA(dp->tickets.reserve(need_sync));
+            RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
+        }
+    }
+    if (!dp->h_blob_free) RF_CUDA(cudaEventCreateWithFlags(&dp->h_blob_free, cudaEventDisableTiming));
+    else RF_CUDA(cudaEventSynchronize(dp->h_blob_free));      // the previous call's upload has left the staging buffer
+    RF_CUDA(dp->h_blob.reserve(b.bytes.size()));
+    memcpy(dp->h_blob.p, b.bytes.data(), b.bytes.size());
+    RF_CUDA(cudaMemcpyAsync(dp->blob.p, dp->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
+    RF_CUDA(cudaEventRecord(dp->h_blob_free, s));
+    ScanArgs a{};
+    fill_args(e, a, static_cast<const uint8_t *>(dp->blob.p), b, q_dev, k, false);
+    a.partial = static_cast<uint64_t *>(dp->partial.p);
+    set_sync_bufs(a, dp->tickets, dp->launches++);
+    a.out_keys = out_keys_dev;
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     return RF_OK;

@@ -274,6 +274,13 @@ class Engine:
         check(self._L.rf_search_keys_device(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k),
                                             int(out_keys_ptr), int(stream) or None))
 
+    def search_keys_device_scoped(self, q_ptr: int, nq: int, scopes, k: int, out_keys_ptr: int, stream: int = 0) -> None:
+        """Device-resident search with one scope per query (`scopes`: list of lists, or a CSR tuple)."""
+        segs, off = scopes if isinstance(scopes, tuple) else scopes_to_csr(scopes)
+        if len(off) != nq + 1:
+            raise ValueError("one scope per query")
+        check(self._L.rf_search_keys_device_scoped(self.handle, q_ptr, nq, _ptr(segs), _ptr(off), k, out_keys_ptr, stream))
+
     def search_keys_device_fused(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int, stream: int,
                                  rank: int, world: int, nq_cap: int, seq: int, keys_ptrs: np.ndarray, flag_ptrs: np.ndarray,
                                  timeout_flag_ptr: int) -> None:

@@ -118,6 +118,92 @@ class ShardedSearcher:
         return unpack_keys_torch(self.search_keys(q, scope, k))
 
 
+class StoreShardedSearcher:
+    """Whole stores per rank (multi-tenant corpora, BASELINE.json configs[4]): global
+    store number g lives on rank g % world, so a query scoped to one store is scored by exactly one
+    GPU and the corpus needs no data-path collective.  Every rank receives the query batch, scores
+    the part of each scope it owns in ONE launch (`rf_search_keys_device_scoped`; a query with
+    nothing local costs an empty block), and the nq x k packed keys are all-gathered and merged so
+    every rank holds the answer -- the same exchange as the chunk-sharded path, which also makes a
+    scope that spans ranks (a user's stores on several GPUs) exact.
+
+    Chunk ids must be unique across ranks: build each rank's Engine with a distinct `id_base`
+    (`id_base_for`).  Stores are numbered in creation order; every rank calls `open_store` with the
+    same names in the same order (SPMD), only the owner creates the segment."""
+
+    def __init__(self, local_search: Callable[[torch.Tensor, Sequence[Sequence[int]], int], torch.Tensor],
+                 merge: Callable[[torch.Tensor, int], torch.Tensor], open_local: Callable[[str], int],
+                 group: Optional[dist.ProcessGroup] = None):
+        self.local_search = local_search
+        self.merge = merge
+        self.open_local = open_local
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.by_name: dict = {}          # store name -> global store number
+        self.local_seg: dict = {}        # global store number -> this rank's engine segment (owned stores only)
+        self._gather_buf: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def id_base_for(rank: int, world: int) -> int:
+        """Disjoint chunk-id ranges per rank (ids are 32-bit, 0xFFFFFFFF is reserved)."""
+        return rank * ((1 << 32) // max(1, world))
+
+    @classmethod
+    def for_engine(cls, engine, group: Optional[dist.ProcessGroup] = None) -> "StoreShardedSearcher":
+        def local_search(q: torch.Tensor, scopes, k: int) -> torch.Tensor:
+            assert q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
+            out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            engine.search_keys_device_scoped(q.data_ptr(), q.shape[0], scopes, k, out.data_ptr(),
+                                             torch.cuda.current_stream(q.device).cuda_stream)
+            return out
+
+        def merge(gathered: torch.Tensor, k: int) -> torch.Tensor:
+            n_lists, nq, _ = gathered.shape
+            out = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+            engine.merge_topk_device(gathered.data_ptr(), n_lists, nq, k, out.data_ptr(),
+                                     torch.cuda.current_stream(gathered.device).cuda_stream)
+            return out
+
+        return cls(local_search, merge, engine.open_store, group)
+
+    def owner(self, store: int) -> int:
+        return store % self.world
+
+    def open_store(self, name: str) -> int:
+        """-> global store number (idempotent).  Collective in the SPMD sense: same calls on every rank."""
+        g = self.by_name.get(name)
+        if g is None:
+            g = self.by_name[name] = len(self.by_name)
+            if self.owner(g) == self.rank:
+                self.local_seg[g] = self.open_local(name)
+        return g
+
+    def local_scopes(self, scopes: Sequence[Sequence[int]]):
+        """Per query: the engine segments of the scope's stores this rank owns (possibly none)."""
+        return [[self.local_seg[g] for g in dict.fromkeys(sc) if g in self.local_seg] for sc in scopes]
+
+    def prepare(self, scopes: Sequence[Sequence[int]]):
+        """Resolve a batch's scopes to this rank's CSR once (a serving loop reuses it across calls)."""
+        from .engine import scopes_to_csr
+        return scopes_to_csr(self.local_scopes(scopes))
+
+    def search_keys(self, q: torch.Tensor, scopes, k: int = 10) -> torch.Tensor:
+        """q int8 [nq, 256] (replicated); scopes: global store numbers per query, or the result of
+        `prepare` -> packed keys int64 [nq, k] on every rank."""
+        local = self.local_search(q, scopes if isinstance(scopes, tuple) else self.local_scopes(scopes), k)
+        if self.world == 1:
+            return local
+        shape = (self.world, local.shape[0], k)
+        if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != local.device:
+            self._gather_buf = torch.empty(shape, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(self._gather_buf.view(shape[0] * shape[1], k), local.contiguous(), group=self.group)
+        return self.merge(self._gather_buf, k)
+
+    def search(self, q: torch.Tensor, scopes: Sequence[Sequence[int]], k: int = 10):
+        return unpack_keys_torch(self.search_keys(q, scopes, k))
+
+
 class FusedShardedSearcher:
     """Sharded search with the exchange fused into the scan kernel: its finishing block stores the
     rank's top-k straight into every rank's gather buffer over NVLink (symmetric memory from

@@ -752,3 +752,62 @@ def test_weighted_text_search_matches_oracle(co, zb, rf1):
         from rag_foundation_b200 import unpack_keys
         w_ids, w_sc, _ = unpack_keys(co.merge_topk(keys, 10))
         assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist()
+
+
+# ------------------------------------------------------------------ whole stores per rank (configs[4], multi-GPU by store)
+def test_device_scoped_search_and_store_sharded_two_engines(co, zb):
+    """rf_search_keys_device_scoped (one scope per query, device-resident) against the oracle, then
+    two engines as two ranks of a StoreShardedSearcher (stores g % 2), merged with the CUDA merge
+    kernel: equals the brute-force ranking over all stores, also for scopes that span both."""
+    import torch
+    from rag_foundation_b200.sharded import StoreShardedSearcher, unpack_keys_torch
+    n_stores, per = 7, 3000
+    world = 2
+    engines, searchers, held = [], [], []
+    try:
+        for r in range(world):
+            e = _engine(n_stores * per, id_base=StoreShardedSearcher.id_base_for(r, world)); engines.append(e)
+            s = StoreShardedSearcher.for_engine(e)
+            s.world, s.rank = world, r              # single process standing in for two ranks
+            searchers.append(s); held.append([])
+        for g in range(n_stores):
+            for r, s in enumerate(searchers):
+                assert s.open_store(f"fileSearchStores/s{g}") == g
+                if s.owner(g) == r:
+                    rows = co.synth_rows(14, g * per, per, zb)
+                    engines[r].ingest_features(s.local_seg[g], g + 1, rows)
+                    held[r].append((g, rows))
+        scopes = [[0], [1], [6], [0, 1], [1, 2, 3, 4, 5], [3, 3], [], [2, 4, 6], [5]] * 3
+        nq = len(scopes)
+        Q = np.stack([co.synth_query(14, i, zb) for i in range(nq)])
+        qd = torch.from_numpy(Q).cuda()
+        local = []
+        for r, s in enumerate(searchers):
+            keys = s.local_search(qd, s.local_scopes(scopes), 10)
+            torch.cuda.synchronize()
+            # the rank's own answer == oracle over its rows with its local segments
+            F = np.concatenate([rows for _, rows in held[r]])
+            sg = np.concatenate([np.full(per, s.local_seg[g], np.uint32) for g, _ in held[r]])
+            got = keys.cpu().numpy().view(np.uint64)
+            for i, sc in enumerate(s.local_scopes(scopes)):
+                want = co.score_topk_keys(F, sg, Q[i], sc, k=10, id_base=engines[r].id_base) if sc else np.zeros(10, np.uint64)
+                assert got[i].tolist() == want.tolist(), (r, i)
+            local.append(keys)
+        merged = searchers[0].merge(torch.stack(local).contiguous(), 10)
+        torch.cuda.synchronize()
+        ids, sc, valid = unpack_keys_torch(merged.cpu())
+        F = co.synth_rows(14, 0, n_stores * per, zb)
+        store = np.repeat(np.arange(n_stores), per)
+        gid = np.zeros(n_stores * per, np.int64)
+        for g in range(n_stores):
+            gid[g * per:(g + 1) * per] = StoreShardedSearcher.id_base_for(g % world, world) + (g // world) * per + np.arange(per)
+        for i, scope in enumerate(scopes):
+            s_all = F.astype(np.int64) @ Q[i].astype(np.int64)
+            rows = np.nonzero(np.isin(store, scope))[0]
+            order = rows[np.lexsort((gid[rows], -s_all[rows]))][:10]
+            m = len(order)
+            assert ids[i][:m].tolist() == gid[order].tolist() and sc[i][:m].tolist() == s_all[order].tolist(), scope
+            assert not valid[i][m:].any()
+    finally:
+        for e in engines:
+            e.close()
