@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librf_b200.so")
-SOURCES = ["engine.cu", "score_topk.cu", "score_topk_gemm.cu", "featurize.cu", "synth.cu"]
-HEADERS = ["rf_device.cuh", "rf_internal.h", os.path.join("..", "..", "include", "rf_b200.h")]
+SOURCES = ["engine.cu", "score_topk.cu", "score_topk_gemm.cu", "score_topk_gemm_pair.cu", "featurize.cu", "synth.cu"]
+HEADERS = ["rf_device.cuh", "rf_gemm_device.cuh", "rf_internal.h", os.path.join("..", "..", "include", "rf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall", "-shared"]
 

@@ -198,6 +198,7 @@ struct rf_engine {
     std::atomic<uint64_t> launches{0};
     uint32_t blocks_override = 0;
     bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
+    bool gemm_pair = true;           // RF_GEMM_PAIR=0 keeps batches of more than 256 queries on the single-CTA kernel
     uint32_t gemm_min_queries = 64;
     uint32_t gemm_sample = 65536;    // rows of the first (floor-finding) pass
     uint32_t gemm_slices_a = 0;      // 0 = as many as fit
@@ -557,21 +558,32 @@ uint32_t fnv1a32(const char *s, size_t n) {
 int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
                 uint32_t k, uint64_t *out_keys_dev, cudaStream_t s) {
     const uint32_t rows = hi - lo;
-    const uint32_t q_groups = (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);
-    const uint32_t slices_full = std::max(1u, static_cast<uint32_t>(e->sm_count) / q_groups);
-    uint32_t sample = std::min(rows / 4, e->gemm_sample) / rf::kGemmTileRows * rf::kGemmTileRows;
-    uint32_t n_a = std::max(1u, std::min(slices_full, sample / rf::kGemmTileRows));
+    // More than 256 queries: CTA pairs (tcgen05 cta_group::2, 256-row tiles, full tensor-pipe rate);
+    // smaller batches stay on the single-CTA kernel, whose spare accumulators take alternate tiles.
+    const bool pair = e->gemm_pair && nq > 256 && e->sm_count >= 2;
+    const uint32_t tile_rows = pair ? rf::kGemmPairTileRows : rf::kGemmTileRows;
+    const uint32_t q_groups = (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);          // 512 queries per block or pair
+    const uint32_t units = pair ? static_cast<uint32_t>(e->sm_count) / 2 : static_cast<uint32_t>(e->sm_count);
+    const uint32_t slices_full = std::max(1u, units / q_groups);
+    uint32_t sample = std::min(rows / 4, e->gemm_sample) / tile_rows * tile_rows;
+    uint32_t n_a = std::max(1u, std::min(slices_full, sample / tile_rows));
     if (e->gemm_slices_a) n_a = std::max(1u, std::min(n_a, e->gemm_slices_a));
-    const uint32_t n_b = std::max(1u, std::min(slices_full, (rows + rf::kGemmTileRows - 1) / rf::kGemmTileRows));
+    const uint32_t n_b = std::max(1u, std::min(slices_full, (rows + tile_rows - 1) / tile_rows));
     const uint32_t kl = rf::kGemmListK;
+    const uint32_t lps = pair ? static_cast<uint32_t>(rf::kGemmPairLists) : rf::gemm_lists_per_slice(nq);
     const size_t keys_bytes = static_cast<size_t>(nq) * kl * 8;
-    if (dp->gemm_lists.cap < rf::gemm_lists_bytes(std::max(n_a, n_b), nq) + keys_bytes || dp->gemm_keys_a.cap < keys_bytes ||
+    const size_t lists_bytes = pair ? rf::gemm_pair_lists_bytes(std::max(n_a, n_b), nq) : rf::gemm_lists_bytes(std::max(n_a, n_b), nq);
+    if (dp->gemm_lists.cap < lists_bytes + keys_bytes || dp->gemm_keys_a.cap < keys_bytes ||
         dp->gemm_floors.cap < static_cast<size_t>(nq) * 8) {
         RF_CUDA(cudaStreamSynchronize(s));
-        RF_CUDA(dp->gemm_lists.reserve(rf::gemm_lists_bytes(std::max(n_a, n_b), nq) + keys_bytes));
+        RF_CUDA(dp->gemm_lists.reserve(lists_bytes + keys_bytes));
         RF_CUDA(dp->gemm_keys_a.reserve(keys_bytes));
         RF_CUDA(dp->gemm_floors.reserve(static_cast<size_t>(nq) * 8));
     }
+    auto launch = [&](const rf::GemmArgs &g, uint32_t n_slices) {
+        return pair ? rf::launch_score_topk_gemm_pair(g, q_dev, e->F, e->cfg.capacity_rows, n_slices, s)
+                    : rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_slices, s);
+    };
     uint64_t *lists = static_cast<uint64_t *>(dp->gemm_lists.p);
     uint64_t *keys_a = static_cast<uint64_t *>(dp->gemm_keys_a.p);
     uint64_t *floors = static_cast<uint64_t *>(dp->gemm_floors.p);
@@ -583,15 +595,14 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.nq = nq;
     g.id_base = static_cast<uint32_t>(e->cfg.id_base);
     g.out_lists = lists;
-    g.lists_per_slice = rf::gemm_lists_per_slice(nq);
+    g.lists_per_slice = pair ? 0u : rf::gemm_lists_per_slice(nq);
     g.debug = nullptr;
     // pass A: group maxima over a sample -> per-query floors (a lower bound of the k-th best score)
     g.floors = nullptr;
     g.group_max_mode = 1;
     g.row_lo = lo;
     g.row_hi = lo + sample;
-    RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_a, s));
-    const uint32_t lps = rf::gemm_lists_per_slice(nq);
+    RF_CUDA(launch(g, n_a));
     RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s));
     RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
     // pass B: every row (the sample included: pass A kept maxima, not chunks), floors from pass A
@@ -600,7 +611,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.row_lo = lo;
     g.row_hi = hi;
     g.debug = e->debug_ts;   // RF_SCAN_DEBUG=1: cycle counters of the second pass
-    RF_CUDA(rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_b, s));
+    RF_CUDA(launch(g, n_b));
     RF_CUDA(rf::launch_merge_lists(lists, n_b * lps, nq, kl, k, out_keys_dev, s));
     e->launches.fetch_add(5, std::memory_order_relaxed);
     return RF_OK;
@@ -660,6 +671,7 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
+    if (const char *s = getenv("RF_GEMM_PAIR")) e->gemm_pair = atoi(s) != 0;
     if (const char *s = getenv("RF_GEMM_SAMPLE")) e->gemm_sample = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM_SLICES_A")) e->gemm_slices_a = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM_MIN_QUERIES")) e->gemm_min_queries = static_cast<uint32_t>(atoi(s));

@@ -35,18 +35,18 @@
 #include <cuda.h>
 
 #include "rf_device.cuh"
+#include "rf_gemm_device.cuh"
 #include "rf_internal.h"
 
 namespace rf {
 
 namespace {
 
-constexpr int kGemmK = kGemmListK;          // list length kept per (thread, query)
+using namespace gemm;
+
 constexpr int kMT = kGemmMT;                // M-tiles (of 128 queries) resident per block
 constexpr int kBN = kGemmTileRows;          // chunk rows per B tile / MMA N
 constexpr int kStagesB = 3;
-constexpr int kKBlockBytes = 128;           // one SW128 swizzle row: 128 int8 of K
-constexpr int kTileKBlock = 128 * kKBlockBytes;   // 16 KB: 128 rows x 128 B
 constexpr int kEpiWarpsPerTile = 4;          // one warp per TMEM lane quarter
 constexpr int kEpiWarps = kMT * kEpiWarpsPerTile;   // 16: one group of four warps per accumulator
 constexpr int kGemmThreads = (2 + kEpiWarps) * 32;  // 576
@@ -58,83 +58,6 @@ struct GemmSmem {
     uint64_t full[kStagesB], empty[kStagesB];
     uint64_t tmem_full[kMT], tmem_empty[kMT];
     uint32_t tmem_base;
-};
-
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
-    const uint64_t addr = (smem_u32(smem) & 0x3FFFFu) >> 4;
-    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-template <bool kAccumulate>
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// v[j] for a warp-uniform j: a 32-way uniform switch over registers (a single-column TMEM reload
-// would queue behind the other warps' 4 KB accumulator loads).
-__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
-    switch (j) {
-#define RF_PICK(i) case i: return v[i];
-        RF_PICK(0) RF_PICK(1) RF_PICK(2) RF_PICK(3) RF_PICK(4) RF_PICK(5) RF_PICK(6) RF_PICK(7)
-        RF_PICK(8) RF_PICK(9) RF_PICK(10) RF_PICK(11) RF_PICK(12) RF_PICK(13) RF_PICK(14) RF_PICK(15)
-        RF_PICK(16) RF_PICK(17) RF_PICK(18) RF_PICK(19) RF_PICK(20) RF_PICK(21) RF_PICK(22) RF_PICK(23)
-        RF_PICK(24) RF_PICK(25) RF_PICK(26) RF_PICK(27) RF_PICK(28) RF_PICK(29) RF_PICK(30)
-#undef RF_PICK
-        default: return v[31];
-    }
-}
-
-// Sorted (descending) top-kGemmK list in registers.
-struct RegList {
-    uint64_t e[kGemmK];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < kGemmK; ++i) e[i] = 0ull;
-    }
-    // x > e[kGemmK-1] is the caller's business; a compare-exchange chain bubbles x into place
-    __device__ __forceinline__ void insert(uint64_t x) {
-        e[kGemmK - 1] = x;
-#pragma unroll
-        for (int i = kGemmK - 1; i > 0; --i) {
-            const uint64_t hi = e[i] > e[i - 1] ? e[i] : e[i - 1];
-            const uint64_t lo = e[i] > e[i - 1] ? e[i - 1] : e[i];
-            e[i - 1] = hi;
-            e[i] = lo;
-        }
-    }
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -247,6 +170,7 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t row_in_tile = lq * 32 + lane;       // query row within the M-tile
         const uint32_t q = q_base + m * 128 + row_in_tile;
         const uint32_t n_scope = a.n_scope;
+        const uint32_t sc0 = a.scope[0], sc1 = a.scope[1], sc2 = a.scope[2], sc3 = a.scope[3];
         RegList list;
         list.clear();
         uint64_t thr = (a.floors && q < a.nq) ? a.floors[q] : 0ull;
@@ -271,10 +195,12 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int h = 0; h < 4; ++h) {
                     const uint32_t row = row0 + h * 32 + lane;
                     const uint32_t sg = seg_next[h];                 // loaded one tile ahead
-                    bool ok = false;
-                    if (row < a.row_hi && sg != kTombstone)
-                        for (uint32_t x = 0; x < n_scope; ++x) ok |= (sg == a.scope[x]);
-                    ok_mask[h] = __ballot_sync(kFull, ok);
+                    // first four scope words from registers (unused entries hold the tombstone value):
+                    // an indexed parameter load per comparison is a dependent constant-cache round trip
+                    bool ok = (sg == sc0) | (sg == sc1) | (sg == sc2) | (sg == sc3);
+                    if (n_scope > 4)
+                        for (uint32_t x = 4; x < n_scope; ++x) ok |= (sg == a.scope[x]);
+                    ok_mask[h] = __ballot_sync(kFull, ok && row < a.row_hi && sg != kTombstone);
                 }
                 if (t + reps < n_tiles) {
 #pragma unroll
@@ -310,9 +236,7 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                         continue;
                     }
-                    int mx = static_cast<int>(v[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = max(mx, static_cast<int>(v[j]));
+                    const int mx = max32(v);
                     const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
                     // scores are >= 0 and < 2^31, so the unsigned compare is exact
                     if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= thr_s)) {
@@ -366,32 +290,6 @@ __global__ void floors_from_keys_kernel(const uint64_t *__restrict__ keys, uint3
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     // score word only: the low word of a group-maximum key is a group tag, not a chunk id
     if (q < nq) floors[q] = k <= k_src ? (keys[static_cast<size_t>(q) * k_src + (k - 1)] & 0xFFFFFFFF00000000ull) : 0ull;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// [rows, 256] int8 row-major -> boxes of 128 rows x 128 bytes, 128-byte swizzle
-bool make_map(CUtensorMap *map, const void *base, uint64_t rows) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {256, rows};
-    cuuint64_t strides[1] = {256};
-    cuuint32_t box[2] = {128, 128};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace

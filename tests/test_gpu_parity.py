@@ -476,7 +476,8 @@ def test_gemm_path_parity(co, zb, n_rows, nq, k):
             assert keys[i].tolist() == want.tolist(), i
 
 
-def test_gemm_path_mask_and_dense_queries(co, zb):
+@pytest.mark.parametrize("nq", [256, 600])      # single-CTA kernel / CTA-pair kernel
+def test_gemm_path_mask_and_dense_queries(co, zb, nq):
     """Tombstoned rows inside the extent, a second store after it, and dense high-magnitude queries
     (many candidates, many ties)."""
     rng = np.random.default_rng(4)
@@ -489,11 +490,12 @@ def test_gemm_path_mask_and_dense_queries(co, zb):
         e.tombstone_doc(2)
         F = np.concatenate(parts)
         seg = np.concatenate([np.full(n // 2, a), np.full(n // 2, 0xFFFFFFFF), np.full(n // 2, a), np.full(n // 2, b)]).astype(np.uint32)
-        Q = rng.integers(0, 4, (256, 256)).astype(np.int8)
+        Q = rng.integers(0, 4, (nq, 256)).astype(np.int8)
         Q[:8] = 127                                   # saturating queries: huge scores
         Q[8:16] = 0                                   # all-zero queries: every score ties at 0
+        Q[nq - 3:] = 127
         keys = _device_batch(e, Q, [a], 10)
-        for i in list(range(0, 256, 9)) + [0, 8, 255]:
+        for i in list(range(0, nq, 9)) + [0, 8, nq - 1]:
             want = co.score_topk_keys(F, seg, Q[i], [a], k=10)
             assert keys[i].tolist() == want.tolist(), i
 
