@@ -603,8 +603,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.row_lo = lo;
     g.row_hi = lo + sample;
     RF_CUDA(launch(g, n_a));
-    RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s));
-    RF_CUDA(rf::launch_floors_from_keys(keys_a, nq, kl, k, floors, s));
+    RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s, floors, k));   // floors[q] = k-th best group maximum
     // pass B: every row (the sample included: pass A kept maxima, not chunks), floors from pass A
     g.floors = floors;
     g.group_max_mode = 0;
@@ -613,7 +612,7 @@ int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, 
     g.debug = e->debug_ts;   // RF_SCAN_DEBUG=1: cycle counters of the second pass
     RF_CUDA(launch(g, n_b));
     RF_CUDA(rf::launch_merge_lists(lists, n_b * lps, nq, kl, k, out_keys_dev, s));
-    e->launches.fetch_add(5, std::memory_order_relaxed);
+    e->launches.fetch_add(4, std::memory_order_relaxed);
     return RF_OK;
 }
 

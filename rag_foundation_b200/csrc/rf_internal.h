@@ -136,14 +136,13 @@ cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const
 // CTA-pair variant (score_topk_gemm_pair.cu, tcgen05 cta_group::2): 256-row chunk tiles, 512 queries per pair,
 // kGemmPairLists lists per (slice, query)
 constexpr int kGemmPairTileRows = 256;
-constexpr int kGemmPairLists = 4;
+constexpr int kGemmPairLists = 1;   // the four column-block lists of a CTA are merged in shared memory before they are written
 size_t gemm_pair_lists_bytes(uint32_t n_slices, uint32_t nq);
 cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
                                         cudaStream_t s);
-cudaError_t launch_floors_from_keys(const uint64_t *keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *floors, cudaStream_t s);
 // keys: [n_lists, nq, k_in] sorted lists -> out [nq, k_out] (k_out <= k_in <= 32, n_lists <= 1024)
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
-                               cudaStream_t s);
+                               cudaStream_t s, uint64_t *floors = nullptr, uint32_t k_floor = 0);
 
 cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint8_t *zipf_bucket_dev,
                               int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,

@@ -601,7 +601,8 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
 // 32 lists (level-1 tournaments run in parallel), warp 0 plays the final over the group winners.
 constexpr int kMergeWarps = 8;
 __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t nq,
-                                                                       uint32_t k_in, uint32_t k_out, uint64_t *__restrict__ out) {
+                                                                       uint32_t k_in, uint32_t k_out, uint64_t *__restrict__ out,
+                                                                       uint64_t *__restrict__ floors, uint32_t k_floor) {
     extern __shared__ __align__(16) uint8_t merge_smem[];   // kMergeWarps areas of 32*k_in keys + level 2 of 32*k_in keys
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t qi = blockIdx.x;
@@ -624,6 +625,9 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
     if (warp != 0) return;
     const uint64_t w = n_groups == 1 ? level2[lane < kin ? lane : 0] : warp_tournament(level2, n_groups, kin, kin, lane);
     if (lane < static_cast<int>(k_out)) out[static_cast<size_t>(qi) * k_out + lane] = (lane < kin) ? w : 0ull;
+    // optional: the k_floor-th best score as a lower-bound key for a following pass (score word only:
+    // the low word of a group-maximum key is a group tag, not a chunk id)
+    if (floors && lane == static_cast<int>(k_floor) - 1) floors[qi] = lane < kin ? (w & 0xFFFFFFFF00000000ull) : 0ull;
 }
 
 // Packed keys -> the result arrays a host caller gets (same arithmetic as finish_query: RF-1 step 8
@@ -712,12 +716,13 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
 }
 
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
-                               cudaStream_t s) {
+                               cudaStream_t s, uint64_t *floors, uint32_t k_floor) {
     if (n_lists == 0 || n_lists > 1024 || k_in == 0 || k_in > RF_TOPK_MAX || k_out > k_in) return cudaErrorInvalidValue;
     const size_t smem = (static_cast<size_t>(kMergeWarps) + 1) * 32 * k_in * 8;   // <= 72 KB at k_in = 32
     if (cudaError_t e = ensure_dynamic_smem(merge_lists_kernel, static_cast<int>((kMergeWarps + 1) * 32 * RF_TOPK_MAX * 8)); e != cudaSuccess)
         return e;
-    merge_lists_kernel<<<nq, kMergeWarps * 32, smem, s>>>(keys, n_lists, nq, k_in, k_out, out);
+    if (floors && (k_floor == 0 || k_floor > k_out)) return cudaErrorInvalidValue;
+    merge_lists_kernel<<<nq, kMergeWarps * 32, smem, s>>>(keys, n_lists, nq, k_in, k_out, out, floors, k_floor);
     return cudaGetLastError();
 }
 

@@ -285,13 +285,6 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-// floors[q] = (k-th best score of query q in `keys` ([nq, k_src] sorted lists)) << 32, for the next pass.
-__global__ void floors_from_keys_kernel(const uint64_t *__restrict__ keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *__restrict__ floors) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    // score word only: the low word of a group-maximum key is a group tag, not a chunk id
-    if (q < nq) floors[q] = k <= k_src ? (keys[static_cast<size_t>(q) * k_src + (k - 1)] & 0xFFFFFFFF00000000ull) : 0ull;
-}
-
 }  // namespace
 
 uint32_t gemm_lists_per_slice(uint32_t nq) {
@@ -308,11 +301,6 @@ cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const
     if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_kernel, smem); e != cudaSuccess) return e;
     dim3 grid(n_slices, (a.nq + kMT * 128 - 1) / (kMT * 128), 1);
     score_topk_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_floors_from_keys(const uint64_t *keys, uint32_t nq, uint32_t k_src, uint32_t k, uint64_t *floors, cudaStream_t s) {
-    floors_from_keys_kernel<<<(nq + 127) / 128, 128, 0, s>>>(keys, nq, k_src, k, floors);
     return cudaGetLastError();
 }
 

@@ -25,7 +25,8 @@
 // quarter w % 4 (its 32 queries) x 64 of the 256 columns in two tcgen05.ld.32x32b.x32; a thread
 // owns one query per M-group and keeps two sorted top-10 lists in registers.  The tenant mask, the
 // candidate path, the floor (group-maximum) pass and the list merge are those of score_topk_gemm.cu;
-// a pair writes 4 lists (one per 64-column block) per query and slice.
+// the four column-block lists of a query are merged in shared memory at the end, so a pair writes one
+// list per query and slice.
 #include <algorithm>
 
 #include <cuda.h>
@@ -45,7 +46,7 @@ constexpr int kPStages = 4;                 // 32 KB per stage per CTA
 constexpr int kPGroups = 2;                 // M-groups (of 256 queries) per pair = accumulators per CTA
 constexpr int kPEpiWarps = 16;
 constexpr int kPThreads = (2 + kPEpiWarps) * 32;   // 576: TMA producer, MMA issuer, 16 epilogue warps
-constexpr int kPColBlocks = kGemmPairLists;  // 4 blocks of 64 accumulator columns, one epilogue warp each per lane quarter
+constexpr int kPColBlocks = 4;              // blocks of 64 accumulator columns, one epilogue warp each per lane quarter
 
 struct PairSmem {
     alignas(1024) uint8_t q[kPGroups][2][kTileKBlock];     // 64 KB: this CTA's 128 queries of each M-group
@@ -318,28 +319,53 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
             d[4] = clock64() - e_start; d[5] = w_tfull; 
         }
-        // one list per (slice, column block, query)
-        if (live0) {
-            uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q0) * kGemmK;
+        // ---- the four column-block lists of a query -> one list, through the (now idle) feature ring:
+        // every tile's MMAs have retired (the last "accumulator ready" was awaited above), so neither
+        // the tensor core nor the TMA unit touches the ring any more
+        uint64_t *stage = reinterpret_cast<uint64_t *>(&sm.b[0][0][0]);           // [g][cb][128 rows][k]: 80 KB of the 128 KB ring
+        const uint32_t row_in_cta = lq * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < kGemmK; ++i) dst[i] = list0.e[i];
+        for (int i = 0; i < kGemmK; ++i) {
+            stage[((0 * kPColBlocks + cb) * 128 + row_in_cta) * kGemmK + i] = list0.e[i];
+            stage[((1 * kPColBlocks + cb) * 128 + row_in_cta) * kGemmK + i] = list1.e[i];
         }
-        if (live1) {
-            uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q0 + 256) * kGemmK;
-#pragma unroll
-            for (int i = 0; i < kGemmK; ++i) dst[i] = list1.e[i];
-        }
-    }
-    if (n_tiles == 0 && warp >= 2) {
-        // a slice without tiles still owes its (empty) lists
-        const uint32_t lq = warp & 3, cb = static_cast<uint32_t>(warp - 2) >> 2;
-        const uint32_t q0 = q_base + rank * 128 + lq * 32 + lane;
-        for (int g = 0; g < kPGroups; ++g) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kPEpiWarps * 32) : "memory");       // the 16 epilogue warps only
+        if (cb < kPGroups) {
+            // warps with cb = g merge M-group g: a 4-way merge of sorted lists, heads in registers
+            const uint32_t g = cb;
             const uint32_t q = q0 + 256 * g;
             if (q < a.nq) {
-                uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q) * kGemmK;
-                for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
+                const uint64_t *src = stage + (static_cast<size_t>(g) * kPColBlocks * 128 + row_in_cta) * kGemmK;
+                uint32_t pos[kPColBlocks];
+                uint64_t head[kPColBlocks];
+#pragma unroll
+                for (int c = 0; c < kPColBlocks; ++c) { pos[c] = 0; head[c] = src[static_cast<size_t>(c) * 128 * kGemmK]; }
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+#pragma unroll
+                for (int i = 0; i < kGemmK; ++i) {
+                    uint64_t best = head[0];
+                    int bc = 0;
+#pragma unroll
+                    for (int c = 1; c < kPColBlocks; ++c)
+                        if (head[c] > best) { best = head[c]; bc = c; }
+                    dst[i] = best;                                                 // 0 once every list has run dry
+#pragma unroll
+                    for (int c = 0; c < kPColBlocks; ++c)
+                        if (c == bc) {
+                            ++pos[c];
+                            head[c] = pos[c] < static_cast<uint32_t>(kGemmK) ? src[static_cast<size_t>(c) * 128 * kGemmK + pos[c]] : 0ull;
+                        }
+                }
             }
+        }
+    }
+    if (n_tiles == 0 && warp >= 2 && warp < 2 + 4 * kPGroups) {
+        // a slice without tiles still owes its (empty) lists
+        const uint32_t lq = warp & 3, g = static_cast<uint32_t>(warp - 2) >> 2;
+        const uint32_t q = q_base + rank * 128 + lq * 32 + lane + 256 * g;
+        if (q < a.nq) {
+            uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+            for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
         }
     }
     tc_fence_before();
