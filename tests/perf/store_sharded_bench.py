@@ -5,7 +5,7 @@ every rank.  Each rank scores the queries whose store it owns in one launch; one
 packed keys + merge kernel gives every rank the answers.  Strong scaling: the corpus and the batch
 are fixed, per-rank work shrinks with G.
 
-  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29533 tools/store_sharded_bench.py
+  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29533 tests/perf/store_sharded_bench.py
 
 One JSON line from rank 0 (CUDA events, max over ranks, >= 3 warm-ups); results are checked against
 the C oracle on a sample of queries (regenerating the scoped store from its counters)."""
@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import c_oracle as co, rf1  # noqa: E402  (checker only)
 from rag_foundation_b200 import Engine  # noqa: E402

@@ -68,13 +68,15 @@ def test_no_gpu_means_loud_failure_not_fallback():
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "rag_foundation_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in src and "from oracle" not in src, f
-                assert "librf1_oracle" not in src, f
+    """oracle/ is test infrastructure: the package and the development tools never touch it
+    (measurement scripts that need it as a checker live under tests/perf/)."""
+    for top in ("rag_foundation_b200", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in src and "from oracle" not in src, f
+                    assert "librf1_oracle" not in src, f
 
 
 def test_rf1w_host_functions_match_the_oracle():
