@@ -60,6 +60,8 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
+// kDebug: in-kernel cycle counters (RF_SCAN_DEBUG=1); the production instantiation has no clock reads in its loops
+template <bool kDebug>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t gemm_smem_raw[];
@@ -121,19 +123,19 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             constexpr uint32_t kKBlockStep = kTileKBlock >> 4;                   // descriptor units (16 B) per K-block
             mbar_wait(&sm.q_full, 0);
             long long w_full = 0, w_empty = 0;
-            const long long c_start = clock64();
+            const long long c_start = kDebug ? clock64() : 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kStagesB;
-                long long c0 = clock64();
+                long long c0 = kDebug ? clock64() : 0;
                 mbar_wait(&sm.full[s], (t / kStagesB) & 1);
-                w_full += clock64() - c0;
+                if (kDebug) w_full += clock64() - c0;
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t m = 0; m < m_tiles; ++m) {
                     const uint32_t acc = m + m_tiles * (t % reps);      // accumulator (and epilogue group) of this unit
-                    c0 = clock64();
+                    if (kDebug) c0 = clock64();
                     if (t >= reps) mbar_wait(&sm.tmem_empty[acc], ((t / reps) - 1) & 1);   // epilogue drained this accumulator
-                    w_empty += clock64() - c0;
+                    if (kDebug) w_empty += clock64() - c0;
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t q_lo = q_lo0 + m * 2 * kKBlockStep;
@@ -154,7 +156,7 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 if (elect_one()) umma_commit(&sm.empty[s]);   // the stage is free once every MMA that reads it has retired
                 __syncwarp();
             }
-            if (a.debug && lane == 0) {
+            if (kDebug && a.debug && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[0] = clock64() - c_start; d[1] = w_full; d[2] = w_empty; d[3] = n_tiles;
             }
@@ -176,7 +178,7 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         uint64_t thr = (a.floors && q < a.nq) ? a.floors[q] : 0ull;
         const bool live = q < a.nq;                        // padding rows never produce candidates
         long long w_tfull = 0, w_cand = 0, n_cand = 0;
-        const long long e_start = clock64();
+        const long long e_start = kDebug ? clock64() : 0;
         if (g < m_tiles * reps) {
             uint32_t seg_next[4];
 #pragma unroll
@@ -209,9 +211,9 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         seg_next[h] = row < a.row_hi ? __ldg(a.seg + row) : kTombstone;
                     }
                 }
-                long long c0 = clock64();
+                long long c0 = kDebug ? clock64() : 0;
                 mbar_wait(&sm.tmem_full[g], (t / reps) & 1);
-                w_tfull += clock64() - c0;
+                if (kDebug) w_tfull += clock64() - c0;
                 tc_fence_after();
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
@@ -240,8 +242,8 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
                     // scores are >= 0 and < 2^31, so the unsigned compare is exact
                     if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= thr_s)) {
-                        const long long cc = clock64();
-                        ++n_cand;
+                        const long long cc = kDebug ? clock64() : 0;
+                        if (kDebug) ++n_cand;
                         uint32_t cand = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
@@ -261,14 +263,14 @@ score_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                                 }
                             }
                         }
-                        w_cand += clock64() - cc;
+                        if (kDebug) w_cand += clock64() - cc;
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tmem_empty[g]);
             }
-            if (a.debug && warp == 2 && lane == 0) {
+            if (kDebug && a.debug && warp == 2 && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[4] = clock64() - e_start; d[5] = w_tfull; d[6] = w_cand; d[7] = n_cand;
             }
@@ -298,9 +300,14 @@ cudaError_t launch_score_topk_gemm(const GemmArgs &a, const int8_t *q_dev, const
     CUtensorMap map_q, map_f;
     if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
     const int smem = static_cast<int>(sizeof(GemmSmem)) + 1024;
-    if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_kernel, smem); e != cudaSuccess) return e;
     dim3 grid(n_slices, (a.nq + kMT * 128 - 1) / (kMT * 128), 1);
-    score_topk_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
+    if (a.debug) {
+        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_kernel<true>, smem); e != cudaSuccess) return e;
+        score_topk_gemm_kernel<true><<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
+    } else {
+        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_kernel<false>, smem); e != cudaSuccess) return e;
+        score_topk_gemm_kernel<false><<<grid, kGemmThreads, smem, s>>>(map_q, map_f, a);
+    }
     return cudaGetLastError();
 }
 

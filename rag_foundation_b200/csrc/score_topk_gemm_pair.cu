@@ -144,6 +144,9 @@ __device__ __forceinline__ void take_group(const uint32_t (&v)[32], uint32_t okm
     }
 }
 
+// kDebug: in-kernel cycle counters (RF_SCAN_DEBUG=1, tools/gemm_timeline.py); the production instantiation
+// carries no clock reads in its loops (they cost 5 % of the batch time)
+template <bool kDebug>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t pair_smem_raw[];
@@ -207,18 +210,18 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             constexpr uint32_t kKBlockStep = kTileKBlock >> 4;                   // descriptor units (16 B) per K-block
             mbar_wait(&sm.q_full, 0);
             long long w_full = 0, w_empty = 0;
-            const long long c_start = clock64();
+            const long long c_start = kDebug ? clock64() : 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kPStages;
-                long long c0 = clock64();
+                long long c0 = kDebug ? clock64() : 0;
                 mbar_wait(&sm.full[s], (t / kPStages) & 1);
-                w_full += clock64() - c0;
+                if (kDebug) w_full += clock64() - c0;
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t g = 0; g < m_groups; ++g) {
-                    c0 = clock64();
+                    if (kDebug) c0 = clock64();
                     if (t >= 1) mbar_wait(&sm.tmem_empty[g], (t - 1) & 1);      // both CTAs' epilogues drained accumulator g
-                    w_empty += clock64() - c0;
+                    if (kDebug) w_empty += clock64() - c0;
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t q_lo = q_lo0 + g * 2 * kKBlockStep;
@@ -239,7 +242,7 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 if (elect_one()) umma2_commit_both(&sm.empty[s]);   // both CTAs' halves of the stage are free once these MMAs retire
                 __syncwarp();
             }
-            if (a.debug && lane == 0) {
+            if (kDebug && a.debug && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[0] = clock64() - c_start; d[1] = w_full; d[2] = w_empty; d[3] = n_tiles;
             }
@@ -260,7 +263,7 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         const uint32_t leader_empty0 = map_to_cta(&sm.tmem_empty[0], 0), leader_empty1 = map_to_cta(&sm.tmem_empty[1], 0);
         const bool gmm = a.group_max_mode != 0;
         long long w_tfull = 0;
-        const long long e_start = clock64();
+        const long long e_start = kDebug ? clock64() : 0;
         // The scope test runs once per tile and column half: keep the first four scope words in
         // registers (read with immediate offsets from the parameter bank; unused entries hold the
         // tombstone value) -- an indexed parameter load per comparison costs a dependent constant-cache
@@ -299,9 +302,9 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
 #pragma unroll
             for (int g = 0; g < kPGroups; ++g) {
                 if (static_cast<uint32_t>(g) >= m_groups) break;
-                const long long c0 = clock64();
+                const long long c0 = kDebug ? clock64() : 0;
                 mbar_wait(&sm.tmem_full[g], t & 1);
-                w_tfull += clock64() - c0;
+                if (kDebug) w_tfull += clock64() - c0;
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((lq * 32u) << 16) + g * kPN + cb * 64;
                 uint32_t v[32];
@@ -315,7 +318,7 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 take_group(v, ok_mask[1], g ? live1 : live0, gmm, a.id_base + row0 + 32, g ? list1 : list0, g ? thr1 : thr0);
             }
         }
-        if (a.debug && warp == 2 && lane == 0) {
+        if (kDebug && a.debug && warp == 2 && lane == 0) {
             unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
             d[4] = clock64() - e_start; d[5] = w_tfull; 
         }
@@ -383,9 +386,14 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
     CUtensorMap map_q, map_f;
     if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
     const int smem = static_cast<int>(sizeof(PairSmem)) + 1024;
-    if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel, smem); e != cudaSuccess) return e;
     dim3 grid(2 * n_slices, (a.nq + kPGroups * 256 - 1) / (kPGroups * 256), 1);   // x: CTA pairs (cluster dims 2 x 1 x 1)
-    score_topk_gemm_pair_kernel<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+    if (a.debug) {
+        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel<true>, smem); e != cudaSuccess) return e;
+        score_topk_gemm_pair_kernel<true><<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+    } else {
+        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel<false>, smem); e != cudaSuccess) return e;
+        score_topk_gemm_pair_kernel<false><<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+    }
     return cudaGetLastError();
 }
 
