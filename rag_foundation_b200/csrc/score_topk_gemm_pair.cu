@@ -28,6 +28,7 @@
 // the four column-block lists of a query are merged in shared memory at the end, so a pair writes one
 // list per query and slice.
 #include <algorithm>
+#include <cstddef>
 
 #include <cuda.h>
 
@@ -100,6 +101,33 @@ __device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t da, uint64_t 
 // arrive on the barrier at this shared offset in BOTH CTAs once every MMA issued so far has retired
 __device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
+// Barrier operations on 32-bit shared-window addresses computed once per thread: the shared structure
+// sits behind a manually aligned pointer, so the compiler converts generic -> shared again at every
+// use (two special-register reads and a dozen instructions per mbarrier wait inside the hot loops).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta_a(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void umma2_commit_both_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"(static_cast<uint16_t>(3))
                  : "memory");
 }
@@ -181,20 +209,35 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    // shared-window addresses of the barriers (one conversion per thread)
+    uint32_t sm_a;
+    {
+        // derived from the shared array itself (a symbol the compiler knows to be in shared memory; the
+        // window base is far more aligned than 1024 B), and pinned in a register by an opaque move so it
+        // is not re-derived from the generic pointer at each use
+        const uint32_t raw_a = smem_u32(pair_smem_raw);
+        const uint32_t aligned = (raw_a + 1023u) & ~1023u;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sm_a) : "r"(aligned));
+    }
+    const uint32_t a_q_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, q_full));
+    const uint32_t a_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, full));
+    const uint32_t a_empty = sm_a + static_cast<uint32_t>(offsetof(PairSmem, empty));
+    const uint32_t a_tmem_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, tmem_full));
+    const uint32_t a_tmem_empty = sm_a + static_cast<uint32_t>(offsetof(PairSmem, tmem_empty));
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own rows, bytes counted on the leader's barriers =====
         if (lane == 0 && n_tiles) {
-            const uint32_t leader_q_full = map_to_cta(&sm.q_full, 0);
+            const uint32_t leader_q_full = map_to_cta_a(a_q_full, 0);
             remote_arrive_expect_tx(leader_q_full, m_groups * 2 * kTileKBlock);
             for (uint32_t g = 0; g < m_groups; ++g)
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d_pair(sm.q[g][kb], &map_q, kb * kKBlockBytes, static_cast<int>(q_base + g * 256 + rank * 128), leader_q_full);
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kPStages;
-                if (t >= kPStages) mbar_wait(&sm.empty[s], ((t / kPStages) - 1) & 1);
+                if (t >= kPStages) mbar_wait_a(a_empty + 8 * s, ((t / kPStages) - 1) & 1);
                 const uint32_t row0 = a.row_lo + (t_lo + t) * kPN + rank * 128;
-                const uint32_t leader_full = map_to_cta(&sm.full[s], 0);
+                const uint32_t leader_full = map_to_cta_a(a_full + 8 * s, 0);
                 remote_arrive_expect_tx(leader_full, 2 * kTileKBlock);
                 for (int kb = 0; kb < 2; ++kb) tma_load_2d_pair(sm.b[s][kb], &map_f, kb * kKBlockBytes, static_cast<int>(row0), leader_full);
             }
@@ -208,19 +251,19 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             const uint32_t q_lo0 = ((smem_u32(&sm.q[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(&sm.b[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
             constexpr uint32_t kKBlockStep = kTileKBlock >> 4;                   // descriptor units (16 B) per K-block
-            mbar_wait(&sm.q_full, 0);
+            mbar_wait_a(a_q_full, 0);
             long long w_full = 0, w_empty = 0;
             const long long c_start = kDebug ? clock64() : 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kPStages;
                 long long c0 = kDebug ? clock64() : 0;
-                mbar_wait(&sm.full[s], (t / kPStages) & 1);
+                mbar_wait_a(a_full + 8 * s, (t / kPStages) & 1);
                 if (kDebug) w_full += clock64() - c0;
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t g = 0; g < m_groups; ++g) {
                     if (kDebug) c0 = clock64();
-                    if (t >= 1) mbar_wait(&sm.tmem_empty[g], (t - 1) & 1);      // both CTAs' epilogues drained accumulator g
+                    if (t >= 1) mbar_wait_a(a_tmem_empty + 8 * g, (t - 1) & 1);      // both CTAs' epilogues drained accumulator g
                     if (kDebug) w_empty += clock64() - c0;
                     tc_fence_after();
                     if (elect_one()) {
@@ -235,11 +278,11 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                                 else umma2_i8<false>(tmem + g * kPN, da, db, idesc);
                             }
                         }
-                        umma2_commit_both(&sm.tmem_full[g]);
+                        umma2_commit_both_a(a_tmem_full + 8 * g);
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma2_commit_both(&sm.empty[s]);   // both CTAs' halves of the stage are free once these MMAs retire
+                if (elect_one()) umma2_commit_both_a(a_empty + 8 * s);   // both CTAs' halves of the stage are free once these MMAs retire
                 __syncwarp();
             }
             if (kDebug && a.debug && lane == 0) {
@@ -260,7 +303,7 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         list1.clear();
         uint64_t thr0 = (a.floors && live0) ? a.floors[q0] : 0ull;
         uint64_t thr1 = (a.floors && live1) ? a.floors[q0 + 256] : 0ull;
-        const uint32_t leader_empty0 = map_to_cta(&sm.tmem_empty[0], 0), leader_empty1 = map_to_cta(&sm.tmem_empty[1], 0);
+        const uint32_t leader_empty0 = map_to_cta_a(a_tmem_empty, 0), leader_empty1 = map_to_cta_a(a_tmem_empty + 8, 0);
         const bool gmm = a.group_max_mode != 0;
         long long w_tfull = 0;
         const long long e_start = kDebug ? clock64() : 0;
@@ -303,7 +346,7 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             for (int g = 0; g < kPGroups; ++g) {
                 if (static_cast<uint32_t>(g) >= m_groups) break;
                 const long long c0 = kDebug ? clock64() : 0;
-                mbar_wait(&sm.tmem_full[g], t & 1);
+                mbar_wait_a(a_tmem_full + 8 * g, t & 1);
                 if (kDebug) w_tfull += clock64() - c0;
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((lq * 32u) << 16) + g * kPN + cb * 64;
