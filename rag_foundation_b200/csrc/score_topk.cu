@@ -287,15 +287,43 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
     const int n_lists = static_cast<int>(gridDim.x);       // engine keeps this <= 1024
     const int n_groups = (n_lists + 31) / 32;
     constexpr int l1_warps = MergeScratch<kWarps>::kL1Warps;
-    for (int g = warp; g < n_groups && warp < l1_warps; g += l1_warps) {
-        const int lists_here = min(32, n_lists - g * 32);
-        const uint64_t *src = part + static_cast<size_t>(g) * 32 * k;
-        uint64_t *area = ms.warp_area[warp];
-        for (int i = lane; i < lists_here * k; i += 32) area[i] = __ldcg(src + i);
-        __syncwarp();
-        const uint64_t w = warp_tournament(area, lists_here, k, k, lane);
-        if (lane < k) ms.level2[g * k + lane] = w;
-        __syncwarp();
+    const int total_keys = n_lists * k;
+    if (total_keys <= l1_warps * kWarpArea) {
+        // All partial lists fit the level-1 scratch: the whole block copies them in ONE sweep (every
+        // thread has its loads in flight together -- this is the tail of a lone query's latency), then
+        // the warps play the level-1 tournaments out of shared memory.
+        uint64_t *flat = &ms.warp_area[0][0];               // list l at flat[l * k]
+        constexpr int kThreads = kWarps * 32;
+        for (int base = static_cast<int>(threadIdx.x); base < total_keys; base += kThreads * 8) {
+            uint64_t t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kThreads;
+                t[u] = idx < total_keys ? __ldcg(part + idx) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kThreads;
+                if (idx < total_keys) flat[idx] = t[u];
+            }
+        }
+        __syncthreads();
+        for (int g = warp; g < n_groups; g += n_warps) {
+            const int lists_here = min(32, n_lists - g * 32);
+            const uint64_t w = warp_tournament(flat + static_cast<size_t>(g) * 32 * k, lists_here, k, k, lane);
+            if (lane < k) ms.level2[g * k + lane] = w;
+        }
+    } else {
+        for (int g = warp; g < n_groups && warp < l1_warps; g += l1_warps) {
+            const int lists_here = min(32, n_lists - g * 32);
+            const uint64_t *src = part + static_cast<size_t>(g) * 32 * k;
+            uint64_t *area = ms.warp_area[warp];
+            for (int i = lane; i < lists_here * k; i += 32) area[i] = __ldcg(src + i);
+            __syncwarp();
+            const uint64_t w = warp_tournament(area, lists_here, k, k, lane);
+            if (lane < k) ms.level2[g * k + lane] = w;
+            __syncwarp();
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) stamp(a, 6);
