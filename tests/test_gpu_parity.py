@@ -813,3 +813,33 @@ def test_device_scoped_search_and_store_sharded_two_engines(co, zb):
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 17, 32])
+def test_other_k_values_single_batch_and_device_paths(co, zb, k):
+    """k from 1 to RF_TOPK_MAX: host single query, host batch, device-resident keys and the merge kernel
+    (k = 32 with the default grid takes the final merge's fallback path, the others the one-sweep path)."""
+    import torch
+    n = 150_000
+    with _engine(n + 10, id_base=3) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=17, start_counter=0, n_rows=n)
+        F, ff = co.synth_rows(17, 0, n, zb, with_ff=True)
+        seg = np.full(n, s, np.uint32)
+        Q = np.stack([co.synth_query(17, i, zb) for i in range(5)])
+        ids, sc, cs, cnt = e.search(Q[:1], [[s]], k=k)
+        _check(co, (ids[0], sc[0], cs[0], cnt[0]), F, seg, Q[0], [s], k, 3, ff)
+        ids, sc, cs, cnt = e.search(Q, [[s]] * 5, k=k)
+        for i in range(5):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), F, seg, Q[i], [s], k, 3, ff)
+        keys = _device_batch(e, Q, [s], k)
+        for i in range(5):
+            assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], [s], k=k, id_base=3).tolist()
+        # merge kernel: three copies of the lists with disjoint halves zeroed must merge back
+        parts = np.stack([np.where((np.arange(k)[None, :] % 3) == r, keys, 0) for r in range(3)]).astype(np.uint64)
+        parts = -np.sort(-parts.view(np.int64), axis=2)          # each list sorted descending, zero padded (keys < 2^63)
+        gathered = torch.from_numpy(np.ascontiguousarray(parts)).cuda()
+        out = torch.zeros((5, k), dtype=torch.int64, device="cuda")
+        e.merge_topk_device(gathered.data_ptr(), 3, 5, k, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy().view(np.uint64) == keys).all()
