@@ -382,6 +382,23 @@ def test_ingest_large_document(co, rf1):
         assert n > 6000
 
 
+def test_ingest_maximum_upload_size(co, rf1):
+    """The reference caps uploads at 25 MB (backend/app/config.py:118): one document of that size,
+    rows / norms / byte spans bit-exact, then the arena is full for anything more."""
+    data = rf1.synth_text(3, 6_910_000)[:25 * 1024 * 1024]
+    assert len(data) == 25 * 1024 * 1024
+    wF, wff, wsp, ntok = co.featurize_doc(data)
+    with _engine(len(wF)) as e:
+        s = e.open_store("fileSearchStores/a")
+        first, n, spans = e.ingest_text(s, 1, data)
+        assert first == 0 and n == len(wF) and (spans == wsp).all()
+        F, sg, ff = e.read_rows(0, n)
+        assert (F == wF).all() and (ff == wff).all() and (sg == s).all()
+        with pytest.raises(RuntimeError) as ei:
+            e.ingest_text(s, 2, b"one more chunk")
+        assert "arena full" in str(ei.value)
+
+
 def test_search_text_equals_search_of_oracle_vector(co, golden):
     g = golden["sample_report"]
     with _engine(1024) as e:
