@@ -671,7 +671,7 @@ def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
     the batched GEMM search, an unpack kernel, one download -- same ids / scores / cosines as the
     oracle, and a mixed-scope batch of the same size still goes through the scan kernel."""
     n, nq = 120_000, 200
-    with _engine(n + 5000) as e:
+    with _engine(n + 8000) as e:
         a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
         e.ingest_synthetic(a, 0, seed=23, start_counter=0, n_rows=n)
         e.ingest_synthetic(b, 0, seed=24, start_counter=0, n_rows=5000)
@@ -691,6 +691,16 @@ def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
         assert e.stats()["kernel_launches"] - l0 == 1
         for i in range(0, nq, 11):
             _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], scopes[i], 10, 0, ffall)
+        # same scope for every query but two stores (two extents): the device route again, on the scan
+        # kernel with one shared plan (the tensor-core kernels want one contiguous extent), then the unpack kernel
+        e.ingest_features(a, 9, F[:3000])                                  # store a now has a second extent after b's rows
+        Fall2 = np.concatenate([Fall, F[:3000]]); ff2 = np.concatenate([ffall, ff[:3000]])
+        seg2 = np.concatenate([seg, np.full(3000, a, np.uint32)])
+        l0 = e.stats()["kernel_launches"]
+        ids, sc, cs, cnt = e.search(Q[:80], [[a]] * 80, k=10)
+        assert e.stats()["kernel_launches"] - l0 == 2
+        for i in range(0, 80, 9):
+            _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall2, seg2, Q[i], [a], 10, 0, ff2)
 
 
 # ------------------------------------------------------------------ RF-1w (IDF-weighted variant)
