@@ -25,8 +25,10 @@
 // quarter w % 4 (its 32 queries) x 64 of the 256 columns in two tcgen05.ld.32x32b.x32; a thread
 // owns one query per M-group and keeps two sorted top-10 lists in registers.  The tenant mask, the
 // candidate path, the floor (group-maximum) pass and the list merge are those of score_topk_gemm.cu;
-// a pair writes 4 lists (one per 64-column block) per query and slice.
+// the four column-block lists of a query are merged in shared memory at the end, so a pair writes one
+// list per query and slice.
 #include <algorithm>
+#include <cstddef>
 
 #include <cuda.h>
 
@@ -45,7 +47,7 @@ constexpr int kPStages = 4;                 // 32 KB per stage per CTA
 constexpr int kPGroups = 2;                 // M-groups (of 256 queries) per pair = accumulators per CTA
 constexpr int kPEpiWarps = 16;
 constexpr int kPThreads = (2 + kPEpiWarps) * 32;   // 576: TMA producer, MMA issuer, 16 epilogue warps
-constexpr int kPColBlocks = kGemmPairLists;  // 4 blocks of 64 accumulator columns, one epilogue warp each per lane quarter
+constexpr int kPColBlocks = 4;              // blocks of 64 accumulator columns, one epilogue warp each per lane quarter
 
 struct PairSmem {
     alignas(1024) uint8_t q[kPGroups][2][kTileKBlock];     // 64 KB: this CTA's 128 queries of each M-group
@@ -103,6 +105,33 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
                  : "memory");
 }
 
+// Barrier operations on 32-bit shared-window addresses computed once per thread: the shared structure
+// sits behind a manually aligned pointer, so the compiler converts generic -> shared again at every
+// use (two special-register reads and a dozen instructions per mbarrier wait inside the hot loops).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta_a(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void umma2_commit_both_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
 // One 32-column group of one query's scores -> the query's list.  Same logic as score_topk_gemm.cu.
 __device__ __forceinline__ void take_group(const uint32_t (&v)[32], uint32_t okm, bool live, bool group_max_mode, uint32_t id0,
                                            RegList &list, uint64_t &thr) {
@@ -119,16 +148,36 @@ __device__ __forceinline__ void take_group(const uint32_t (&v)[32], uint32_t okm
         return;
     }
     const int mx = max32(v);
-    if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= entry_score(thr)))      // scores are in [0, 2^31): unsigned compare is exact
-        take_candidates(v, okm, live, id0, list, thr);
+    const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
+    if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= thr_s)) {     // scores are in [0, 2^31): unsigned compare is exact
+        uint32_t cand = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
+        cand &= okm;
+        if (!live) cand = 0;
+        uint32_t uni = __reduce_or_sync(kFull, cand);
+        while (uni) {
+            const int j = __ffs(uni) - 1;
+            uni &= uni - 1;
+            const uint32_t sc = pick32(v, j);        // j is warp-uniform: a jump, not a TMEM reload
+            if ((cand >> j) & 1u) {
+                const uint64_t key = pack_key(static_cast<int32_t>(sc), id0 + j);
+                if (key > thr) {
+                    list.insert(key);
+                    const uint64_t kth = list.e[kGemmK - 1];
+                    if (kth > thr) thr = kth;
+                }
+            }
+        }
+    }
 }
 
-// ---- 16-bit packed epilogue ------------------------------------------------------------------------
-// When every score of the warp's queries fits 16 bits (sum of a query's counts x 127 <= 65535, checked
-// per warp from the queries themselves), the accumulator is read with tcgen05.ld ... .pack::16b: ONE
-// load brings the warp's 64 columns as 32 registers, register i = (column 2i+1) << 16 | (column 2i)
-// (tools/probe/tmem_pack_probe.cu), and the maximum runs on both halves at once (VIMNMX3.U16x2).
-// Half the loads and half the ALU work per score, and the accumulator goes back after one load.
+// ---- 16-bit packed epilogue -------------------------------------------------------------------------
+// When every score of the batch fits 16 bits (sum of a query's counts x 127 <= 65535 for every query:
+// query_bound_kernel below decides it on the device), the accumulator is read with tcgen05.ld ... .pack::16b:
+// ONE load brings a warp's 64 columns as 32 registers, register i = (column 2i+1) << 16 | (column 2i)
+// (tools/probe/tmem_pack_probe.cu), the accumulator goes back right after that load, and the maxima run on
+// both halves at once (VIMNMX3.U16x2): half the loads and half the ALU work per score.
 __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
@@ -140,35 +189,43 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[3
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// per-half maximum of 32 packed registers: low half = max over even columns, high half = over odd columns
-__device__ __forceinline__ uint32_t max32_u16x2(const uint32_t (&v)[32]) {
-    uint32_t m[11];
+// per-half maxima: low half over the even columns, high half over the odd ones; m[i] = registers 3i .. 3i+2
+__device__ __forceinline__ uint32_t max32_u16x2(const uint32_t (&v)[32], uint32_t (&m)[11]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) m[i] = __vimax3_u16x2(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
     m[10] = __vimax3_u16x2(v[30], v[31], 0u);
     const uint32_t a = __vimax3_u16x2(m[0], m[1], m[2]), b = __vimax3_u16x2(m[3], m[4], m[5]), c = __vimax3_u16x2(m[6], m[7], m[8]);
     return __vimax3_u16x2(__vimax3_u16x2(a, b, c), m[9], m[10]);
 }
-// 64 columns of one query: v packed as above; ok_e / ok_o bit i <=> column 2i / 2i+1 is in scope;
-// id0 = chunk id of column 0.
-__device__ __forceinline__ void take_packed(const uint32_t (&v)[32], uint32_t ok_e, uint32_t ok_o, bool live, bool group_max_mode,
-                                            uint32_t id0, RegList &list, uint64_t &thr) {
-    if (group_max_mode) {
-        // two groups per load: the even and the odd columns (disjoint chunk sets, which is all the
-        // floor argument needs); out-of-scope chunks must not raise the bound
+__device__ __forceinline__ uint32_t max_half(uint32_t x) { return max(x & 0xFFFFu, x >> 16); }
+// candidate bits of three packed registers (warp-uniform triple index -> compile-time register numbers)
+#define RF_CAND(j)                                            \
+    ce |= ((v[j] & 0xFFFFu) >= thr_s ? 1u : 0u) << (j);      \
+    co |= ((v[j] >> 16) >= thr_s ? 1u : 0u) << (j);
+#define RF_TRIPLE(i) \
+    case i: RF_CAND(3 * (i)) RF_CAND(3 * (i) + 1) RF_CAND(3 * (i) + 2) break;
+// 64 columns of one query: v packed as above; ok_e / ok_o bit i <=> column 2i / 2i+1 is in scope; id0 = chunk
+// id of column 0.  thr of a padding row is all ones.
+template <bool kGroupMax, bool kDbg = false>
+__device__ __forceinline__ void take_packed(const uint32_t (&v)[32], uint32_t ok_e, uint32_t ok_o, uint32_t id0, RegList &list,
+                                            uint64_t &thr, long long *dbg = nullptr) {
+    uint32_t parts[11];
+    if (kGroupMax) {
+        // two groups per load: the even and the odd columns (disjoint chunk sets, which is all the floor
+        // argument needs); out-of-scope chunks must not raise the bound
         uint32_t m;
         if ((ok_e & ok_o) == 0xFFFFFFFFu) {
-            m = max32_u16x2(v);
+            m = max32_u16x2(v, parts);
         } else {
             uint32_t w[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) w[i] = v[i] & (((ok_e >> i) & 1u) * 0xFFFFu + ((ok_o >> i) & 1u) * 0xFFFF0000u);
-            m = max32_u16x2(w);
+            m = max32_u16x2(w, parts);
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const uint64_t key = pack_key(static_cast<int32_t>(half ? m >> 16 : m & 0xFFFFu), id0 + half);   // low word only makes groups distinct
-            if (live && (half ? ok_o : ok_e) != 0u && key > thr) {
+            if ((half ? ok_o : ok_e) != 0u && key > thr) {
                 list.insert(key);
                 const uint64_t kth = list.e[kGemmK - 1];
                 if (kth > thr) thr = kth;
@@ -176,19 +233,28 @@ __device__ __forceinline__ void take_packed(const uint32_t (&v)[32], uint32_t ok
         }
         return;
     }
-    const uint32_t m = max32_u16x2(v);
-    const uint32_t mx = max(m & 0xFFFFu, m >> 16);
-    if (__any_sync(kFull, live && mx >= entry_score(thr))) {       // a threshold above 0xFFFF cannot be reached: the test fails
-        const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
-        uint32_t ce = 0, co = 0;
+    const uint32_t m = max32_u16x2(v, parts);
+    const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);      // > 0xFFFF (padding row, or unreachable): the test fails
+    if (__any_sync(kFull, max_half(m) >= thr_s)) {
+        const long long dbg0 = kDbg ? clock64() : 0;
+        // which register triples hold a candidate in some lane: 11 tests on the partial maxima, then only those
+        // triples are compared element by element (warp-uniform walk)
+        uint32_t t1 = 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            ce |= ((v[i] & 0xFFFFu) >= thr_s ? 1u : 0u) << i;
-            co |= ((v[i] >> 16) >= thr_s ? 1u : 0u) << i;
+        for (int i = 0; i < 11; ++i) t1 |= (max_half(parts[i]) >= thr_s ? 1u : 0u) << i;
+        uint32_t uni_t = __reduce_or_sync(kFull, t1);
+        uint32_t ce = 0, co = 0;
+        while (uni_t) {
+            const int tr = __ffs(uni_t) - 1;
+            uni_t &= uni_t - 1;
+            switch (tr) {
+                RF_TRIPLE(0) RF_TRIPLE(1) RF_TRIPLE(2) RF_TRIPLE(3) RF_TRIPLE(4) RF_TRIPLE(5)
+                RF_TRIPLE(6) RF_TRIPLE(7) RF_TRIPLE(8) RF_TRIPLE(9)
+                default: RF_CAND(30) RF_CAND(31) break;
+            }
         }
         ce &= ok_e;
         co &= ok_o;
-        if (!live) ce = co = 0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const uint32_t mine = half ? co : ce;
@@ -196,7 +262,7 @@ __device__ __forceinline__ void take_packed(const uint32_t (&v)[32], uint32_t ok
             while (uni) {
                 const int i = __ffs(uni) - 1;
                 uni &= uni - 1;
-                const uint32_t x = pick32(v, i);
+                const uint32_t x = pick32(v, i);                 // i is warp-uniform: a jump, not a TMEM reload
                 if ((mine >> i) & 1u) {
                     const uint64_t key = pack_key(static_cast<int32_t>(half ? x >> 16 : x & 0xFFFFu), id0 + 2 * i + half);
                     if (key > thr) {
@@ -207,27 +273,35 @@ __device__ __forceinline__ void take_packed(const uint32_t (&v)[32], uint32_t ok
                 }
             }
         }
+        if (kDbg) { dbg[0] += clock64() - dbg0; dbg[1] += 1; }
     }
 }
-// sum of a query's features (they are counts) and whether any is negative; q: 256 int8
-__device__ __forceinline__ bool query_fits_16bit(const int8_t *q) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(q);
-    int sum = 0;
-    uint32_t neg = 0;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const uint4 x = __ldg(p + i);
-        sum = __dp4a(static_cast<int>(x.x), 0x01010101, sum);
-        sum = __dp4a(static_cast<int>(x.y), 0x01010101, sum);
-        sum = __dp4a(static_cast<int>(x.z), 0x01010101, sum);
-        sum = __dp4a(static_cast<int>(x.w), 0x01010101, sum);
-        neg |= (x.x | x.y | x.z | x.w) & 0x80808080u;
-    }
-    return neg == 0u && sum * 127 <= 0xFFFF;     // every score is a sum of q[d] * F[c, d] with 0 <= F <= 127
+#undef RF_TRIPLE
+#undef RF_CAND
+
+// *flag |= 1 when some query's score bound does not fit 16 bits (or a query has a negative feature)
+__global__ void __launch_bounds__(256) query_bound_kernel(const int8_t *__restrict__ q, uint32_t nq, uint32_t *__restrict__ flag) {
+    const uint32_t qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const int2 x = *reinterpret_cast<const int2 *>(q + static_cast<size_t>(qi) * 256 + lane * 8);
+    int sum = __dp4a(x.x, 0x01010101, __dp4a(x.y, 0x01010101, 0));
+    const bool neg = ((static_cast<uint32_t>(x.x) | static_cast<uint32_t>(x.y)) & 0x80808080u) != 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    const bool bad = __any_sync(kFull, neg) || sum * 127 > 0xFFFF;   // every score is a sum of q[d] * F[c, d], 0 <= F <= 127
+    if (bad && lane == 0) atomicOr(flag, 1u);
 }
 
+// kDebug: in-kernel cycle counters (RF_SCAN_DEBUG=1, tools/gemm_timeline.py); the production instantiation
+// carries no clock reads in its loops (they cost 5 % of the batch time)
+// kPacked: the 16-bit packed epilogue.  Both instantiations are launched for a search; the one that does not
+// match the batch's bound flag (a.pack_flag, written by query_bound_kernel) returns at once.
+template <bool kDebug, bool kPacked>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
+    if (a.pack_flag && ((*a.pack_flag == 0u) != kPacked)) return;      // uniform over the whole grid
+    if (!a.pack_flag && kPacked) return;
     extern __shared__ __align__(1024) uint8_t pair_smem_raw[];
     // the dynamic window starts at the same offset in both CTAs, so aligned addresses agree too
     PairSmem &sm = *reinterpret_cast<PairSmem *>((reinterpret_cast<uintptr_t>(pair_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -260,20 +334,35 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    // shared-window addresses of the barriers (one conversion per thread)
+    uint32_t sm_a;
+    {
+        // derived from the shared array itself (a symbol the compiler knows to be in shared memory; the
+        // window base is far more aligned than 1024 B), and pinned in a register by an opaque move so it
+        // is not re-derived from the generic pointer at each use
+        const uint32_t raw_a = smem_u32(pair_smem_raw);
+        const uint32_t aligned = (raw_a + 1023u) & ~1023u;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sm_a) : "r"(aligned));
+    }
+    const uint32_t a_q_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, q_full));
+    const uint32_t a_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, full));
+    const uint32_t a_empty = sm_a + static_cast<uint32_t>(offsetof(PairSmem, empty));
+    const uint32_t a_tmem_full = sm_a + static_cast<uint32_t>(offsetof(PairSmem, tmem_full));
+    const uint32_t a_tmem_empty = sm_a + static_cast<uint32_t>(offsetof(PairSmem, tmem_empty));
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own rows, bytes counted on the leader's barriers =====
         if (lane == 0 && n_tiles) {
-            const uint32_t leader_q_full = map_to_cta(&sm.q_full, 0);
+            const uint32_t leader_q_full = map_to_cta_a(a_q_full, 0);
             remote_arrive_expect_tx(leader_q_full, m_groups * 2 * kTileKBlock);
             for (uint32_t g = 0; g < m_groups; ++g)
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d_pair(sm.q[g][kb], &map_q, kb * kKBlockBytes, static_cast<int>(q_base + g * 256 + rank * 128), leader_q_full);
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kPStages;
-                if (t >= kPStages) mbar_wait(&sm.empty[s], ((t / kPStages) - 1) & 1);
+                if (t >= kPStages) mbar_wait_a(a_empty + 8 * s, ((t / kPStages) - 1) & 1);
                 const uint32_t row0 = a.row_lo + (t_lo + t) * kPN + rank * 128;
-                const uint32_t leader_full = map_to_cta(&sm.full[s], 0);
+                const uint32_t leader_full = map_to_cta_a(a_full + 8 * s, 0);
                 remote_arrive_expect_tx(leader_full, 2 * kTileKBlock);
                 for (int kb = 0; kb < 2; ++kb) tma_load_2d_pair(sm.b[s][kb], &map_f, kb * kKBlockBytes, static_cast<int>(row0), leader_full);
             }
@@ -287,20 +376,20 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             const uint32_t q_lo0 = ((smem_u32(&sm.q[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(&sm.b[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
             constexpr uint32_t kKBlockStep = kTileKBlock >> 4;                   // descriptor units (16 B) per K-block
-            mbar_wait(&sm.q_full, 0);
+            mbar_wait_a(a_q_full, 0);
             long long w_full = 0, w_empty = 0;
-            const long long c_start = clock64();
+            const long long c_start = kDebug ? clock64() : 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t s = t % kPStages;
-                long long c0 = clock64();
-                mbar_wait(&sm.full[s], (t / kPStages) & 1);
-                w_full += clock64() - c0;
+                long long c0 = kDebug ? clock64() : 0;
+                mbar_wait_a(a_full + 8 * s, (t / kPStages) & 1);
+                if (kDebug) w_full += clock64() - c0;
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * 2 * kKBlockStep;
                 for (uint32_t g = 0; g < m_groups; ++g) {
-                    c0 = clock64();
-                    if (t >= 1) mbar_wait(&sm.tmem_empty[g], (t - 1) & 1);      // both CTAs' epilogues drained accumulator g
-                    w_empty += clock64() - c0;
+                    if (kDebug) c0 = clock64();
+                    if (t >= 1) mbar_wait_a(a_tmem_empty + 8 * g, (t - 1) & 1);      // both CTAs' epilogues drained accumulator g
+                    if (kDebug) w_empty += clock64() - c0;
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t q_lo = q_lo0 + g * 2 * kKBlockStep;
@@ -314,14 +403,14 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                                 else umma2_i8<false>(tmem + g * kPN, da, db, idesc);
                             }
                         }
-                        umma2_commit_both(&sm.tmem_full[g]);
+                        umma2_commit_both_a(a_tmem_full + 8 * g);
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma2_commit_both(&sm.empty[s]);   // both CTAs' halves of the stage are free once these MMAs retire
+                if (elect_one()) umma2_commit_both_a(a_empty + 8 * s);   // both CTAs' halves of the stage are free once these MMAs retire
                 __syncwarp();
             }
-            if (a.debug && lane == 0) {
+            if (kDebug && a.debug && lane == 0) {
                 unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
                 d[0] = clock64() - c_start; d[1] = w_full; d[2] = w_empty; d[3] = n_tiles;
             }
@@ -339,10 +428,11 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         list1.clear();
         uint64_t thr0 = (a.floors && live0) ? a.floors[q0] : 0ull;
         uint64_t thr1 = (a.floors && live1) ? a.floors[q0 + 256] : 0ull;
-        const uint32_t leader_empty0 = map_to_cta(&sm.tmem_empty[0], 0), leader_empty1 = map_to_cta(&sm.tmem_empty[1], 0);
+        const uint32_t leader_empty0 = map_to_cta_a(a_tmem_empty, 0), leader_empty1 = map_to_cta_a(a_tmem_empty + 8, 0);
         const bool gmm = a.group_max_mode != 0;
         long long w_tfull = 0;
-        const long long e_start = clock64();
+        long long dbgc[3] = {0, 0, 0};
+        const long long e_start = kDebug ? clock64() : 0;
         // The scope test runs once per tile and column half: keep the first four scope words in
         // registers (read with immediate offsets from the parameter bank; unused entries hold the
         // tombstone value) -- an indexed parameter load per comparison costs a dependent constant-cache
@@ -356,21 +446,22 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 for (uint32_t x = 4; x < n_scope; ++x) ok |= (sg == a.scope[x]);
             return ok && sg != kTombstone;
         };
-        // 16-bit packed reads when every score of this warp's 64 queries provably fits (warp-uniform;
-        // all four column-block warps of a lane quarter see the same queries and decide alike)
-        const bool packed = a.allow_packed &&
-                            __all_sync(kFull, (!live0 || query_fits_16bit(a.q + static_cast<size_t>(q0) * 256)) &&
-                                                  (!live1 || query_fits_16bit(a.q + static_cast<size_t>(q0 + 256) * 256)));
-        // tenant words of this warp's 64 columns, loaded one tile ahead: lane l holds columns l and
-        // 32 + l (plain reads) or 2 l and 2 l + 1 (packed reads: even / odd column masks)
-        const uint32_t c_a = packed ? 2 * lane : lane, c_b = packed ? 2 * lane + 1 : 32 + lane;
+        // tenant words of this warp's 64 columns, loaded one tile ahead: lane l holds columns l and 32 + l
+        // (plain reads: two 32-column masks) or 2 l and 2 l + 1 (packed reads: even- and odd-column masks)
+        const uint32_t c_a = kPacked ? 2 * lane : lane, c_b = kPacked ? 2 * lane + 1 : 32 + lane;
         uint32_t seg_next[2];
         {
             const uint32_t row = a.row_lo + t_lo * kPN + cb * 64;
             seg_next[0] = row + c_a < row_hi ? __ldg(seg_words + row + c_a) : kTombstone;
             seg_next[1] = row + c_b < row_hi ? __ldg(seg_words + row + c_b) : kTombstone;
         }
+        if (kPacked) {       // padding rows never produce candidates: an unreachable threshold instead of a flag
+            if (!live0) thr0 = ~0ull;
+            if (!live1) thr1 = ~0ull;
+        }
+        long long w_mask = 0, w_arr = 0, w_ldx = 0;
         for (uint32_t t = 0; t < n_tiles; ++t) {
+            const long long cm = kDebug ? clock64() : 0;
             const uint32_t row0 = a.row_lo + (t_lo + t) * kPN + cb * 64;   // chunk row of this warp's first column
             uint32_t ok_mask[2];
             ok_mask[0] = __ballot_sync(kFull, row0 + c_a < row_hi && in_scope(seg_next[0]));
@@ -380,26 +471,36 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 seg_next[0] = row + c_a < row_hi ? __ldg(seg_words + row + c_a) : kTombstone;
                 seg_next[1] = row + c_b < row_hi ? __ldg(seg_words + row + c_b) : kTombstone;
             }
+            if (kDebug) w_mask += clock64() - cm;
 #pragma unroll
             for (int g = 0; g < kPGroups; ++g) {
                 if (static_cast<uint32_t>(g) >= m_groups) break;
-                const long long c0 = clock64();
-                mbar_wait(&sm.tmem_full[g], t & 1);
-                w_tfull += clock64() - c0;
+                const long long c0 = kDebug ? clock64() : 0;
+                mbar_wait_a(a_tmem_full + 8 * g, t & 1);
+                if (kDebug) w_tfull += clock64() - c0;
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((lq * 32u) << 16) + g * kPN + cb * 64;
                 uint32_t v[32];
-                if (packed) {
+                if (kPacked) {
+                    const long long cl = kDebug ? clock64() : 0;
                     tmem_ld32_pack16(taddr, v);
+                    const long long ca = kDebug ? clock64() : 0;
                     // the accumulator's only read is in registers: hand it back before working on the values
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) remote_arrive(g ? leader_empty1 : leader_empty0);
-                    take_packed(v, ok_mask[0], ok_mask[1], g ? live1 : live0, gmm, a.id_base + row0, g ? list1 : list0, g ? thr1 : thr0);
+                    if (kDebug) { w_ldx += ca - cl; w_arr += clock64() - ca; }
+                    if (gmm) take_packed<true>(v, ok_mask[0], ok_mask[1], a.id_base + row0, g ? list1 : list0, g ? thr1 : thr0);
+                    else {
+                        const long long k1 = kDebug ? clock64() : 0;
+                        take_packed<false, kDebug>(v, ok_mask[0], ok_mask[1], a.id_base + row0, g ? list1 : list0, g ? thr1 : thr0, dbgc);
+                        if (kDebug) dbgc[2] += clock64() - k1;
+                    }
                 } else {
                     tmem_ld32(taddr, v);
                     take_group(v, ok_mask[0], g ? live1 : live0, gmm, a.id_base + row0, g ? list1 : list0, g ? thr1 : thr0);
                     tmem_ld32(taddr + 32, v);
+                    // the accumulator's last read is in registers: hand it back before working on the values
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) remote_arrive(g ? leader_empty1 : leader_empty0);
@@ -407,32 +508,57 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 }
             }
         }
-        if (a.debug && warp == 2 && lane == 0) {
+        if (kDebug && a.debug && warp == 2 && lane == 0) {
             unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
-            d[4] = clock64() - e_start; d[5] = w_tfull; d[6] = packed ? 1 : 0;
+            d[4] = clock64() - e_start; d[5] = w_tfull; d[6] = w_mask; d[7] = w_arr; d[1] = rank ? dbgc[2] : d[1]; d[2] = rank ? w_ldx : d[2];
         }
-        // one list per (slice, column block, query)
-        if (live0) {
-            uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q0) * kGemmK;
+        // ---- the four column-block lists of a query -> one list, through the (now idle) feature ring:
+        // every tile's MMAs have retired (the last "accumulator ready" was awaited above), so neither
+        // the tensor core nor the TMA unit touches the ring any more
+        uint64_t *stage = reinterpret_cast<uint64_t *>(&sm.b[0][0][0]);           // [g][cb][128 rows][k]: 80 KB of the 128 KB ring
+        const uint32_t row_in_cta = lq * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < kGemmK; ++i) dst[i] = list0.e[i];
+        for (int i = 0; i < kGemmK; ++i) {
+            stage[((0 * kPColBlocks + cb) * 128 + row_in_cta) * kGemmK + i] = list0.e[i];
+            stage[((1 * kPColBlocks + cb) * 128 + row_in_cta) * kGemmK + i] = list1.e[i];
         }
-        if (live1) {
-            uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q0 + 256) * kGemmK;
-#pragma unroll
-            for (int i = 0; i < kGemmK; ++i) dst[i] = list1.e[i];
-        }
-    }
-    if (n_tiles == 0 && warp >= 2) {
-        // a slice without tiles still owes its (empty) lists
-        const uint32_t lq = warp & 3, cb = static_cast<uint32_t>(warp - 2) >> 2;
-        const uint32_t q0 = q_base + rank * 128 + lq * 32 + lane;
-        for (int g = 0; g < kPGroups; ++g) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kPEpiWarps * 32) : "memory");       // the 16 epilogue warps only
+        if (cb < kPGroups) {
+            // warps with cb = g merge M-group g: a 4-way merge of sorted lists, heads in registers
+            const uint32_t g = cb;
             const uint32_t q = q0 + 256 * g;
             if (q < a.nq) {
-                uint64_t *dst = a.out_lists + ((static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q) * kGemmK;
-                for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
+                const uint64_t *src = stage + (static_cast<size_t>(g) * kPColBlocks * 128 + row_in_cta) * kGemmK;
+                uint32_t pos[kPColBlocks];
+                uint64_t head[kPColBlocks];
+#pragma unroll
+                for (int c = 0; c < kPColBlocks; ++c) { pos[c] = 0; head[c] = src[static_cast<size_t>(c) * 128 * kGemmK]; }
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+#pragma unroll
+                for (int i = 0; i < kGemmK; ++i) {
+                    uint64_t best = head[0];
+                    int bc = 0;
+#pragma unroll
+                    for (int c = 1; c < kPColBlocks; ++c)
+                        if (head[c] > best) { best = head[c]; bc = c; }
+                    dst[i] = best;                                                 // 0 once every list has run dry
+#pragma unroll
+                    for (int c = 0; c < kPColBlocks; ++c)
+                        if (c == bc) {
+                            ++pos[c];
+                            head[c] = pos[c] < static_cast<uint32_t>(kGemmK) ? src[static_cast<size_t>(c) * 128 * kGemmK + pos[c]] : 0ull;
+                        }
+                }
             }
+        }
+    }
+    if (n_tiles == 0 && warp >= 2 && warp < 2 + 4 * kPGroups) {
+        // a slice without tiles still owes its (empty) lists
+        const uint32_t lq = warp & 3, g = static_cast<uint32_t>(warp - 2) >> 2;
+        const uint32_t q = q_base + rank * 128 + lq * 32 + lane + 256 * g;
+        if (q < a.nq) {
+            uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+            for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
         }
     }
     tc_fence_before();
@@ -450,9 +576,24 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
     CUtensorMap map_q, map_f;
     if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
     const int smem = static_cast<int>(sizeof(PairSmem)) + 1024;
-    if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel, smem); e != cudaSuccess) return e;
     dim3 grid(2 * n_slices, (a.nq + kPGroups * 256 - 1) / (kPGroups * 256), 1);   // x: CTA pairs (cluster dims 2 x 1 x 1)
-    score_topk_gemm_pair_kernel<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (cudaError_t e = ensure_dynamic_smem(kernel, smem); e != cudaSuccess) return e;
+        kernel<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+        return cudaGetLastError();
+    };
+    // both epilogue variants are enqueued; the one that does not match the batch's bound flag returns at once
+    if (cudaError_t e = a.debug ? go(score_topk_gemm_pair_kernel<true, false>) : go(score_topk_gemm_pair_kernel<false, false>); e != cudaSuccess)
+        return e;
+    if (a.pack_flag)
+        if (cudaError_t e = a.debug ? go(score_topk_gemm_pair_kernel<true, true>) : go(score_topk_gemm_pair_kernel<false, true>); e != cudaSuccess)
+            return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_query_bound(const int8_t *q_dev, uint32_t nq, uint32_t *flag, cudaStream_t s) {
+    if (cudaError_t e = cudaMemsetAsync(flag, 0, 4, s); e != cudaSuccess) return e;
+    query_bound_kernel<<<(nq + 7) / 8, 256, 0, s>>>(q_dev, nq, flag);
     return cudaGetLastError();
 }
 
