@@ -119,8 +119,8 @@ int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uin
  * (CSR, at most RF_SCOPE_MAX each).  Outputs are HOST buffers, nq x k, rows padded with id
  * UINT64_MAX / score 0 / cos 0 beyond out_counts[i].  out_cos / out_counts may be NULL.
  * Blocks until the results are in the caller's buffers.  One launch of the scan kernel (grid.y =
- * queries); a batch of >= 64 queries that all carry the same scope is scored by the tensor-core
- * kernels instead (same results). */
+ * queries); a batch whose queries all carry the same scope is scored by the tensor-core kernels
+ * instead when that is cheaper than one scan per query (same results). */
 int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs,
               const uint32_t *seg_off, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
               float *out_cos, uint32_t *out_counts);

@@ -199,7 +199,7 @@ struct rf_engine {
     uint32_t blocks_override = 0;
     bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
     bool gemm_pair = true;           // RF_GEMM_PAIR=0 keeps batches of more than 256 queries on the single-CTA kernel
-    uint32_t gemm_min_queries = 64;
+    uint32_t gemm_min_queries = 0;   // 0: cost model (gemm_pays); RF_GEMM_MIN_QUERIES=n forces "n queries or more"
     uint32_t gemm_sample = 65536;    // rows of the first (floor-finding) pass
     uint32_t gemm_slices_a = 0;      // 0 = as many as fit
     int scan_variant = rf::kScanVariantTma6x12;
@@ -555,6 +555,15 @@ uint32_t fnv1a32(const char *s, size_t n) {
 // extent gives every query a floor (the k-th largest per-group maximum of the sample is a valid
 // lower bound of its final k-th best score), the second pass scores every row with the
 // candidate path rare, and a tournament merge combines the per-slice lists.  All on stream `s`.
+// Does the batched tensor-core path beat nq passes of the scan kernel over `rows` rows?  Measured on a
+// B200 (tools/small_batch_probe.py): scan ~ 6 + 3.65e-5 * nq * rows us, tensor-core path ~ 33 + 4.6e-5 * rows us
+// (floor pass + two merges are its fixed cost) -- e.g. 8 queries x 1 M rows: 291 vs 79 us; 3 x 200 k: 24 vs 45 us.
+bool gemm_pays(const rf_engine *e, uint32_t nq, uint32_t rows, uint32_t k, double extra_us = 0.0) {
+    if (!e->gemm_enabled || k > static_cast<uint32_t>(rf::kGemmListK) || rows < 32768 || nq < 2) return false;
+    if (e->gemm_min_queries) return nq >= e->gemm_min_queries;
+    return 6.0 + 3.65e-5 * nq * rows > 33.0 + extra_us + 4.6e-5 * rows;
+}
+
 int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
                 uint32_t k, uint64_t *out_keys_dev, cudaStream_t s) {
     const uint32_t rows = hi - lo;
@@ -1086,15 +1095,24 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
     if (nq == 0) return RF_OK;
     if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
     const auto t0 = std::chrono::steady_clock::now();
-    // A large batch whose queries all have the same scope takes the device-resident route (and
-    // with it the tensor-core path when it qualifies): one H2D of the queries, the batched search,
-    // an unpack kernel, one D2H of the results.
-    if (nq >= e->gemm_min_queries && e->gemm_enabled) {
+    // A batch whose queries all have the same scope takes the device-resident route when the
+    // tensor-core path pays for it (or the batch is large: one shared plan instead of nq): one H2D of
+    // the queries, the batched search, an unpack kernel, one D2H of the results.
+    if (nq >= 2 && e->gemm_enabled) {
         const uint32_t n0 = seg_off[1] - seg_off[0];
         bool same = n0 <= RF_SCOPE_MAX;
         for (uint32_t i = 1; same && i < nq; ++i) {
             same = seg_off[i + 1] - seg_off[i] == n0;
             for (uint32_t j = 0; same && j < n0; ++j) same = store_segs[seg_off[i] + j] == store_segs[seg_off[0] + j];
+        }
+        if (same) {
+            std::vector<Extent> ext;
+            {
+                std::shared_lock<std::shared_mutex> lk(e->meta_mu);
+                gather_extents(e, store_segs + seg_off[0], n0, ext);
+            }
+            // 20 us: the route's own copies, unpack kernel and stream synchronisation
+            same = nq >= 64 || (ext.size() == 1 && gemm_pays(e, nq, ext[0].hi - ext[0].lo, k, 20.0));
         }
         if (same) {
             SearchCtx *c = ctx_acquire(e);
@@ -1392,10 +1410,10 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
         // ---- batched tensor-core path: many queries, one contiguous extent, k <= 10 ----
         {
             const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
-            if (!px && e->gemm_enabled && nq >= e->gemm_min_queries && k <= static_cast<uint32_t>(rf::kGemmListK) && hp->n_ext == 1) {
+            if (!px && hp->n_ext == 1) {
                 const uint32_t lo = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo);
                 const uint32_t hi = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi);
-                if (hi - lo >= 32768) {
+                if (gemm_pays(e, nq, hi - lo, k)) {
                     const int rc2 = search_gemm(e, dp, q_dev, nq, hp, lo, hi, k, out_keys_dev, s);
                     if (rc2 == RF_OK) e->searches.fetch_add(nq, std::memory_order_relaxed);
                     return rc2;

@@ -870,3 +870,36 @@ def test_other_k_values_single_batch_and_device_paths(co, zb, k):
         e.merge_topk_device(gathered.data_ptr(), 3, 5, k, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert (out.cpu().numpy().view(np.uint64) == keys).all()
+
+
+def test_small_batches_take_the_tensor_core_path_when_it_pays(co, zb):
+    """A handful of queries over a large store: the cost model routes 3+ queries x 500 k rows (host and
+    device-resident calls) to the batched kernel -- same keys, ids, scores and cosines as the oracle --
+    and leaves 2 queries, or a small store, on the scan kernel."""
+    n = 500_000
+    with _engine(n + 50_000) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        e.ingest_synthetic(a, 0, seed=27, start_counter=0, n_rows=n)
+        e.ingest_synthetic(b, 0, seed=28, start_counter=0, n_rows=40_000)
+        F, ff = co.synth_rows(27, 0, n, zb, with_ff=True)
+        Fb, ffb = co.synth_rows(28, 0, 40_000, zb, with_ff=True)
+        Fall = np.concatenate([F, Fb]); ffall = np.concatenate([ff, ffb])
+        seg = np.concatenate([np.full(n, a), np.full(40_000, b)]).astype(np.uint32)
+        Q = np.stack([co.synth_query(27, i, zb) for i in range(63)])
+        for nq, gemm in [(2, False), (3, True), (5, True), (8, True), (17, True), (63, True)]:
+            l0 = e.stats()["kernel_launches"]
+            keys = _device_batch(e, Q[:nq], [a], 10)
+            assert (e.stats()["kernel_launches"] - l0 == 4) == gemm, nq
+            for i in range(nq):
+                assert keys[i].tolist() == co.score_topk_keys(Fall, seg, Q[i], [a], k=10).tolist(), (nq, i)
+            l0 = e.stats()["kernel_launches"]
+            ids, sc, cs, cnt = e.search(Q[:nq], [[a]] * nq, k=10)
+            # the host call adds its own copies + unpack kernel (20 us in the model): 3 x 500 k stays on the scan kernel
+            assert (e.stats()["kernel_launches"] - l0 == 5) == (gemm and nq >= 5), nq
+            for i in range(nq):
+                _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], [a], 10, 0, ffall)
+        l0 = e.stats()["kernel_launches"]
+        keys = _device_batch(e, Q[:8], [b], 10)                 # 40 k rows: eight scans are cheaper than the fixed cost
+        assert e.stats()["kernel_launches"] - l0 == 1
+        for i in range(8):
+            assert keys[i].tolist() == co.score_topk_keys(Fall, seg, Q[i], [b], k=10).tolist()
