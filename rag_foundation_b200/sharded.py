@@ -211,6 +211,11 @@ class FusedShardedSearcher:
     compute and collective in ONE kernel, no NCCL launch on the data path.  Same results as
     ShardedSearcher (the packed key is a total order)."""
 
+    # Batches of this many queries or more go through the collective path instead: its local search may
+    # take the tensor-core kernels (one pass over the shard for the whole batch), which the fused scan
+    # kernel -- one pass per query -- cannot match (8 queries over a 12.5 M-chunk shard: ~1 ms vs ~3.8 ms).
+    BATCH_THRESHOLD = 4
+
     def __init__(self, engine, nq_cap: int = 64, k: int = 10, group: Optional[dist.ProcessGroup] = None):
         import numpy as np
         import torch.distributed._symmetric_memory as symm_mem
@@ -233,13 +238,16 @@ class FusedShardedSearcher:
         self._flag_ptrs = np.asarray([int(p) for p in self._hf.buffer_ptrs], dtype=np.uint64)
         self._timeout = torch.zeros(1, dtype=torch.int32, device=dev)
         self._seq = 0
+        self._batched = ShardedSearcher.for_engine(engine, self.group)
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)          # every rank has zeroed its flags before anyone publishes
 
     def search_keys(self, q: torch.Tensor, scope: Sequence[int], k: Optional[int] = None,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         k = k or self.k
-        assert k == self.k and q.shape[0] <= self.nq_cap and q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
+        if q.shape[0] >= self.BATCH_THRESHOLD or q.shape[0] > self.nq_cap or k != self.k:
+            return self._batched.search_keys(q, scope, k, out=out)
+        assert q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
         if out is None:
             out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
         self._seq += 1

@@ -31,7 +31,7 @@ fused = FusedShardedSearcher(eng, nq_cap=8, k=10)
 Q = torch.from_numpy(bench.make_queries(64)).to(dev)
 bad = 0
 for it in range(200):
-    nq = 1 + it % 4
+    nq = 1 + it % 8          # 4 and more: FusedShardedSearcher hands the batch to the collective path
     q = Q[(it * 3) % 60:(it * 3) % 60 + nq].contiguous()
     a = nccl.search_keys(q, [seg], 10)
     b = fused.search_keys(q, [seg], 10)
@@ -61,6 +61,9 @@ if res["mismatching_calls"] == 0 and res["timeouts"] == 0:
     res["nccl_ms_per_query"] = timeit(lambda i: nccl.search_keys(Q[i % 64:i % 64 + 1], [seg], 10))
     res["fused_ms_per_query"] = timeit(lambda i: fused.search_keys(Q[i % 64:i % 64 + 1], [seg], 10))
     res["local_scan_only_ms"] = timeit(lambda i: nccl.local_search(Q[i % 64:i % 64 + 1], [seg], 10))
+    res["batch8_ms"] = timeit(lambda i: fused.search_keys(Q[i % 56:i % 56 + 8], [seg], 10), n=50)
+    fused.BATCH_THRESHOLD = 99
+    res["batch8_fused_scan_ms"] = timeit(lambda i: fused.search_keys(Q[i % 56:i % 56 + 8], [seg], 10), n=50)
 if rank == 0:
     print(json.dumps(res))
 eng.close()
