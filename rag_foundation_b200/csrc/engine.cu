@@ -558,10 +558,23 @@ uint32_t fnv1a32(const char *s, size_t n) {
 // Does the batched tensor-core path beat nq passes of the scan kernel over `rows` rows?  Measured on a
 // B200 (tools/small_batch_probe.py): scan ~ 6 + 3.65e-5 * nq * rows us, tensor-core path ~ 33 + 4.6e-5 * rows us
 // (floor pass + two merges are its fixed cost) -- e.g. 8 queries x 1 M rows: 291 vs 79 us; 3 x 200 k: 24 vs 45 us.
-bool gemm_pays(const rf_engine *e, uint32_t nq, uint32_t rows, uint32_t k, double extra_us = 0.0) {
-    if (!e->gemm_enabled || k > static_cast<uint32_t>(rf::kGemmListK) || rows < 32768 || nq < 2) return false;
-    if (e->gemm_min_queries) return nq >= e->gemm_min_queries;
-    return 6.0 + 3.65e-5 * nq * rows > 33.0 + extra_us + 4.6e-5 * rows;
+// `rows`: rows of the scope (what the scan kernel reads per query); `span`: rows of the contiguous range
+// the tensor-core kernels would score (a scope with several extents is scored over its bounding range,
+// the per-row tenant mask drops the foreign rows in between); large batches are compute-bound:
+// 1024 queries x 1 M rows take 0.248 ms.
+bool gemm_pays(const rf_engine *e, uint32_t nq, uint64_t rows, uint64_t span, uint32_t k, double extra_us = 0.0) {
+    if (!e->gemm_enabled || k > static_cast<uint32_t>(rf::kGemmListK) || span < 32768 || nq < 2) return false;
+    if (e->gemm_min_queries) return nq >= e->gemm_min_queries && rows * 2 >= span;
+    const double scan_us = 6.0 + 3.65e-5 * nq * static_cast<double>(rows);
+    const double gemm_us = 33.0 + extra_us + std::max(4.6e-5, 2.1e-7 * nq) * static_cast<double>(span);
+    return scan_us > gemm_us;
+}
+// rows of a sorted, disjoint extent list and the length of its bounding range
+void extent_rows(const uint32_t *lo, const uint32_t *hi, uint32_t n, uint64_t &rows, uint32_t &span_lo, uint32_t &span_hi) {
+    rows = 0;
+    span_lo = n ? lo[0] : 0;
+    span_hi = n ? hi[n - 1] : 0;
+    for (uint32_t i = 0; i < n; ++i) rows += hi[i] - lo[i];
 }
 
 int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
@@ -1112,7 +1125,9 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
                 gather_extents(e, store_segs + seg_off[0], n0, ext);
             }
             // 20 us: the route's own copies, unpack kernel and stream synchronisation
-            same = nq >= 64 || (ext.size() == 1 && gemm_pays(e, nq, ext[0].hi - ext[0].lo, k, 20.0));
+            uint64_t rows = 0;
+            for (const Extent &x : ext) rows += x.hi - x.lo;
+            same = nq >= 64 || (!ext.empty() && gemm_pays(e, nq, rows, ext.back().hi - ext.front().lo, k, 20.0));
         }
         if (same) {
             SearchCtx *c = ctx_acquire(e);
@@ -1407,13 +1422,15 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
             dp->epoch = now;
             dp->max_tiles = b.max_tiles;
         }
-        // ---- batched tensor-core path: many queries, one contiguous extent, k <= 10 ----
+        // ---- batched tensor-core path: k <= 10, when it beats nq scans (gemm_pays) ----
         {
             const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
-            if (!px && hp->n_ext == 1) {
-                const uint32_t lo = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo);
-                const uint32_t hi = *reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi);
-                if (gemm_pays(e, nq, hi - lo, k)) {
+            if (!px && hp->n_ext >= 1) {
+                uint64_t rows;
+                uint32_t lo, hi;
+                extent_rows(reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo) + hp->ext_off,
+                            reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi) + hp->ext_off, hp->n_ext, rows, lo, hi);
+                if (gemm_pays(e, nq, rows, hi - lo, k)) {
                     const int rc2 = search_gemm(e, dp, q_dev, nq, hp, lo, hi, k, out_keys_dev, s);
                     if (rc2 == RF_OK) e->searches.fetch_add(nq, std::memory_order_relaxed);
                     return rc2;

@@ -691,14 +691,14 @@ def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
         assert e.stats()["kernel_launches"] - l0 == 1
         for i in range(0, nq, 11):
             _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], scopes[i], 10, 0, ffall)
-        # same scope for every query but two stores (two extents): the device route again, on the scan
-        # kernel with one shared plan (the tensor-core kernels want one contiguous extent), then the unpack kernel
+        # same scope for every query, but the store now has two extents with another store's rows in between
         e.ingest_features(a, 9, F[:3000])                                  # store a now has a second extent after b's rows
         Fall2 = np.concatenate([Fall, F[:3000]]); ff2 = np.concatenate([ffall, ff[:3000]])
         seg2 = np.concatenate([seg, np.full(3000, a, np.uint32)])
         l0 = e.stats()["kernel_launches"]
         ids, sc, cs, cnt = e.search(Q[:80], [[a]] * 80, k=10)
-        assert e.stats()["kernel_launches"] - l0 == 2
+        # two extents: scored over their bounding range by the tensor-core kernel, store b's rows in between masked out
+        assert e.stats()["kernel_launches"] - l0 == 5
         for i in range(0, 80, 9):
             _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall2, seg2, Q[i], [a], 10, 0, ff2)
 
@@ -903,3 +903,29 @@ def test_small_batches_take_the_tensor_core_path_when_it_pays(co, zb):
         assert e.stats()["kernel_launches"] - l0 == 1
         for i in range(8):
             assert keys[i].tolist() == co.score_topk_keys(Fall, seg, Q[i], [b], k=10).tolist()
+
+
+def test_interleaved_stores_batch_over_the_bounding_range(co, zb):
+    """Two stores ingested alternately (every store has many extents): a same-scope batch is scored by
+    the tensor-core kernel over the scope's bounding range, the other store's rows (half of the range)
+    and a tombstoned document dropped by the per-row mask; a sparse scope stays on the scan kernel."""
+    per, docs = 20_000, 12
+    with _engine(per * docs + 1000) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b"); c = e.open_store("fileSearchStores/c")
+        parts, segs = [], []
+        for d in range(docs):
+            rows = co.synth_rows(29, d * per, per, zb)
+            st = a if d % 2 == 0 else b
+            e.ingest_features(st, d + 1, rows)
+            parts.append(rows); segs.append(np.full(per, st, np.uint32))
+        e.ingest_features(c, 99, parts[0][:1000])
+        e.tombstone_doc(5)                                      # one of store a's documents
+        segs[4][:] = 0xFFFFFFFF
+        F = np.concatenate(parts + [parts[0][:1000]]); seg = np.concatenate(segs + [np.full(1000, c, np.uint32)])
+        Q = np.stack([co.synth_query(29, i, zb) for i in range(32)])
+        for scope, gemm in (([a], True), ([a, b], True), ([c], False)):
+            l0 = e.stats()["kernel_launches"]
+            keys = _device_batch(e, Q, scope, 10)
+            assert (e.stats()["kernel_launches"] - l0 == 4) == gemm, scope
+            for i in range(0, 32, 3):
+                assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], scope, k=10).tolist(), (scope, i)
