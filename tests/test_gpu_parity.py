@@ -929,3 +929,66 @@ def test_interleaved_stores_batch_over_the_bounding_range(co, zb):
             assert (e.stats()["kernel_launches"] - l0 == 4) == gemm, scope
             for i in range(0, 32, 3):
                 assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], scope, k=10).tolist(), (scope, i)
+
+
+@pytest.mark.timeout(300)
+def test_searches_stay_consistent_while_ingest_and_deletes_run(co, zb):
+    """Readers (single queries, text queries, weighted queries, batches) on 6 threads while a writer
+    appends documents to a second store, tombstones some and drops a store.  What a reader sees depends
+    on timing, so the check is by invariants: every hit belongs to a scoped store at read time or
+    earlier (never the other tenant's), ids ascend within equal scores, scores equal a re-scoring of the
+    returned rows, and the store nobody writes to always returns its oracle answer."""
+    import threading
+    n = 120_000
+    with _engine(n + 200_000, n_contexts=6) as e:
+        fixed = e.open_store("fileSearchStores/fixed"); live = e.open_store("fileSearchStores/live")
+        gone = e.open_store("fileSearchStores/gone")
+        e.ingest_synthetic(fixed, 0, seed=31, start_counter=0, n_rows=n)
+        F = co.synth_rows(31, 0, n, zb)
+        Q = np.stack([co.synth_query(31, i, zb) for i in range(8)])
+        want = [co.score_topk(F, np.full(n, fixed, np.uint32), Q[i], [fixed])[0].tolist() for i in range(8)]
+        doc_rows = co.synth_rows(32, 0, 4000, zb)
+        e.ingest_features(gone, 500, doc_rows)
+        stop = threading.Event()
+        errs = []
+
+        def writer():
+            try:
+                for d in range(40):
+                    e.ingest_features(live, 1000 + d, doc_rows[(d % 4) * 1000:(d % 4) * 1000 + 1000])
+                    if d % 5 == 4:
+                        e.tombstone_doc(1000 + d - 2)
+                    if d == 20:
+                        e.drop_store(gone)
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+            finally:
+                stop.set()
+
+        def reader(i):
+            try:
+                it = 0
+                while not stop.is_set() or it < 3:
+                    it += 1
+                    ids, sc, cs, cnt = e.search(Q[i][None, :], [[fixed]], k=10)
+                    assert ids[0].tolist() == want[i]
+                    ids, sc, cs, cnt = e.search(Q[:4], [[live], [fixed, live], [gone], [live, gone]], k=10)
+                    for j in range(4):
+                        m = int(cnt[j])
+                        got_ids, got_sc = ids[j][:m].astype(np.int64), sc[j][:m].astype(np.int64)
+                        assert all((got_sc[x] > got_sc[x + 1]) or (got_sc[x] == got_sc[x + 1] and got_ids[x] < got_ids[x + 1]) for x in range(m - 1))
+                        if m:
+                            rows, sg, _ = e.read_rows(0, e.stats()["n_rows"])
+                            assert (rows[got_ids].astype(np.int32) @ Q[j].astype(np.int32) == got_sc).all()
+                            allowed = {0: {live}, 1: {fixed, live}, 2: {gone}, 3: {live, gone}}[j] | {0xFFFFFFFF}   # a hit may have been deleted since
+                            assert set(sg[got_ids].tolist()) <= allowed, (j, set(sg[got_ids].tolist()))
+                    w = e.scope_weights([fixed, live])
+                    ids2, _, _, _ = e.search_text(b"1786 23 4479 313 12 7 1318 21", [fixed, live], 10, weights=w)
+                    assert len(ids2) == 10
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+
+        ts = [threading.Thread(target=writer)] + [threading.Thread(target=reader, args=(i,)) for i in range(5)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs[:2]
+        assert e.lookup_store("fileSearchStores/gone") is None
