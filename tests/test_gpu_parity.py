@@ -691,6 +691,9 @@ def test_host_batch_same_scope_takes_the_tensor_core_route(co, zb):
         assert e.stats()["kernel_launches"] - l0 == 1
         for i in range(0, nq, 11):
             _check(co, (ids[i], sc[i], cs[i], cnt[i]), Fall, seg, Q[i], scopes[i], 10, 0, ffall)
+        for scope in ([77], []):                                           # unknown store / empty scope, large same-scope batch
+            ids, sc, cs, cnt = e.search(Q[:70], [scope] * 70, k=10)
+            assert (cnt == 0).all() and (ids == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and (sc == 0).all()
         # same scope for every query, but the store now has two extents with another store's rows in between
         e.ingest_features(a, 9, F[:3000])                                  # store a now has a second extent after b's rows
         Fall2 = np.concatenate([Fall, F[:3000]]); ff2 = np.concatenate([ffall, ff[:3000]])
