@@ -43,29 +43,72 @@ __device__ __forceinline__ bool kept_start(const uint8_t *s) {
 }
 
 // Stage one 4 KB block of lowered text (+1 byte before, +4 after; zero = separator outside).
-__device__ __forceinline__ void stage_block(const uint8_t *__restrict__ text, size_t n, size_t base, uint8_t *s_txt) {
-    for (int i = threadIdx.x; i < static_cast<int>(kFeatBlockBytes) + 5; i += kFeatThreads) {
-        const long long g = static_cast<long long>(base) + i - 1;
-        const uint8_t b = (g >= 0 && static_cast<size_t>(g) < n) ? text[g] : 0;
-        s_txt[i] = lower_byte(b);
+// Shared copy of a 4 KB text block, lower-cased: s_txt[1 + i] = text[base + i]; s_txt[0] is the byte before the
+// block and s_txt[4097 .. 4100] the four after it (0 outside the document).  s_txt + 1 is 16-byte aligned:
+// the block is exactly one 16-byte global load and one 16-byte shared store per thread.
+constexpr int kStageBytes = 16 + static_cast<int>(kFeatBlockBytes) + 16;
+__device__ __forceinline__ uint8_t *stage_origin(uint8_t *s_raw) { return s_raw + 15; }
+
+// four packed ASCII bytes -> lower case (bytes >= 0x80 are left alone)
+__device__ __forceinline__ uint32_t lower4(uint32_t x) {
+    const uint32_t lo7 = x & 0x7F7F7F7Fu;
+    const uint32_t ge_A = lo7 + 0x3F3F3F3Fu;           // bit 7 of a byte set <=> byte >= 'A' (0x41)
+    const uint32_t ge_bracket = lo7 + 0x25252525u;     // bit 7 set <=> byte >= '[' (0x5B)
+    const uint32_t upper = ge_A & ~ge_bracket & ~x & 0x80808080u;
+    return x | (upper >> 2);                            // + 0x20
+}
+
+__device__ __forceinline__ void stage_block(const uint8_t *__restrict__ text, size_t n, size_t base, uint8_t *s_raw) {
+    static_assert(kFeatBlockBytes == kFeatThreads * 16, "one 16-byte load per thread");
+    const size_t at = base + static_cast<size_t>(threadIdx.x) * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (at < n) {
+        v = *reinterpret_cast<const uint4 *>(text + at);       // the text buffer is padded by 64 bytes
+        if (at + 16 > n) {                                      // last bytes of the document: clear what lies beyond it
+            const uint32_t keep = static_cast<uint32_t>(n - at);        // 1 .. 15
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int valid = static_cast<int>(keep) - 4 * i;       // bytes of this word inside the document
+                w[i] = valid >= 4 ? w[i] : valid <= 0 ? 0u : (w[i] & ((1u << (8 * valid)) - 1u));
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        v = make_uint4(lower4(v.x), lower4(v.y), lower4(v.z), lower4(v.w));
+    }
+    *reinterpret_cast<uint4 *>(s_raw + 16 + threadIdx.x * 16) = v;
+    uint8_t *s_txt = stage_origin(s_raw);
+    if (threadIdx.x == 0) s_txt[0] = base > 0 ? lower_byte(text[base - 1]) : 0;
+    if (threadIdx.x >= 1 && threadIdx.x <= 4) {
+        const size_t g = base + kFeatBlockBytes + (threadIdx.x - 1);
+        s_txt[1 + kFeatBlockBytes + (threadIdx.x - 1)] = g < n ? lower_byte(text[g]) : 0;
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_txt) {
-    const uint8_t *s = s_txt + 1 + threadIdx.x * kBytesPerThread;
+// bit j <=> a kept token starts at the thread's byte j: the 16 bytes come back as one 16-byte shared load,
+// the byte before and the four after as two more, and the rule runs on registers
+__device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_raw) {
+    const uint8_t *mine = s_raw + 16 + threadIdx.x * 16;
+    const uint4 v = *reinterpret_cast<const uint4 *>(mine);
+    const uint32_t next = *reinterpret_cast<const uint32_t *>(mine + 16);
+    uint8_t w[21];
+    w[0] = mine[-1];
+    const uint32_t words[5] = {v.x, v.y, v.z, v.w, next};
+#pragma unroll
+    for (int i = 0; i < 20; ++i) w[1 + i] = static_cast<uint8_t>(words[i >> 2] >> (8 * (i & 3)));
     uint32_t flags = 0;
 #pragma unroll
-    for (int j = 0; j < kBytesPerThread; ++j) flags |= (kept_start(s + j) ? 1u : 0u) << j;
+    for (int j = 0; j < kBytesPerThread; ++j) flags |= (kept_start(w + 1 + j) ? 1u : 0u) << j;
     return flags;
 }
 
 __global__ void __launch_bounds__(kFeatThreads) count_tokens_kernel(const uint8_t *__restrict__ text, size_t n,
                                                                     uint32_t *__restrict__ block_counts) {
-    __shared__ uint8_t s_txt[kFeatBlockBytes + 8];
+    __shared__ __align__(16) uint8_t s_raw[kStageBytes];
     __shared__ uint32_t s_warp[kFeatThreads / 32];
-    stage_block(text, n, static_cast<size_t>(blockIdx.x) * kFeatBlockBytes, s_txt);
-    uint32_t c = __popc(thread_flags(s_txt));
+    stage_block(text, n, static_cast<size_t>(blockIdx.x) * kFeatBlockBytes, s_raw);
+    uint32_t c = __popc(thread_flags(s_raw));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
     if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
@@ -124,11 +167,12 @@ __global__ void __launch_bounds__(kFeatThreads) emit_tokens_kernel(const uint8_t
                                                                    uint8_t *__restrict__ tok_bucket,
                                                                    uint32_t *__restrict__ tok_start,
                                                                    uint32_t *__restrict__ tok_end) {
-    __shared__ uint8_t s_txt[kFeatBlockBytes + 8];
+    __shared__ __align__(16) uint8_t s_raw[kStageBytes];
     __shared__ uint32_t s_warp[kFeatThreads / 32];
     const size_t base = static_cast<size_t>(blockIdx.x) * kFeatBlockBytes;
-    stage_block(text, n, base, s_txt);
-    const uint32_t flags = thread_flags(s_txt);
+    stage_block(text, n, base, s_raw);
+    const uint8_t *s_txt = stage_origin(s_raw);
+    const uint32_t flags = thread_flags(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t c = __popc(flags);
     uint32_t inc = c;
