@@ -60,6 +60,7 @@ typedef struct rf_stats {
     uint64_t hbm_bytes;       /* device bytes held by the engine              */
     uint64_t searches;        /* queries answered                             */
     uint64_t kernel_launches; /* kernels launched by this engine since create */
+    uint64_t free_rows;       /* rows below n_rows given back by deletes, waiting to be reused */
 } rf_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -98,13 +99,19 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
                         uint64_t start_counter, uint64_t n_rows, const uint16_t *zipf_vocab,
                         uint64_t *first_chunk);
 
-/* GeminiRag.delete_document_from_store (gemini_rag.py:354-424, 699-702). */
+/* GeminiRag.delete_document_from_store (gemini_rag.py:354-424, 699-702).  The rows are masked at once
+ * and given back to the arena: a later ingest that fits a freed run reuses those rows (and their chunk
+ * ids), so a delete-heavy tenant does not exhaust capacity_rows.  rf_store_drop does the same for every
+ * row of the store. */
 int rf_doc_tombstone(rf_engine *e, uint64_t doc_id);
 
 /* ---- durability: the HBM index is volatile and the reference deletes uploads
  * after ingest (services/ingestion.py:341), so the engine can write / read a snapshot file:
- * header {magic "RFB2SNP1", dim, n_rows, id_base, n_stores, n_docs}, store table (name, dropped,
- * extents), document table (id, store, extents), then int8 rows, uint32 segment words, int32 norms.
+ * header {magic "RFB2SNP2", dim, version, n_rows, id_base, n_stores, n_docs, n_free}, store table (name,
+ * dropped, extents), document table (id, store, extents), free list, then int8 rows, uint32 segment
+ * words, int32 norms, and a trailer {magic, 64-bit checksum of everything before it}.  Save writes
+ * "<path>.tmp", fsyncs and renames it over <path> (a failed save never damages the previous file);
+ * load verifies the checksum and every extent before it publishes anything.
  * rf_snapshot_load needs a freshly created engine (no rows, no stores) with capacity >= n_rows and
  * the same id_base. */
 int rf_snapshot_save(rf_engine *e, const char *path);
@@ -147,6 +154,15 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
  * ((uint64(score) << 32) | (0xFFFFFFFF - global_id)), 0 = no result.  All queries share one scope. */
 int rf_search_keys_device(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
                           uint32_t n_segs, uint32_t k, uint64_t *out_keys_dev, void *stream);
+
+/* Overlap promise for the device-resident searches on `stream` (default: off).  With allow != 0 their scan
+ * kernels are launched with programmatic stream serialisation: a search's scan phase may start while the
+ * previous kernel on the stream is still in its merge tail (back-to-back queries then stream at the full
+ * HBM rate).  The kernel reads its query vectors BEFORE it waits for that predecessor, so the caller
+ * promises that no KERNEL enqueued on `stream` between two searches writes q_dev (copies are fine; a
+ * resident query batch is the intended use).  Without the promise every search is a fully serialised
+ * launch. */
+int rf_stream_set_overlap(rf_engine *e, void *stream, int allow);
 
 /* rf_search_keys_device with one scope PER QUERY (CSR, as rf_search): the store-sharded multi-GPU
  * path (whole stores per rank, SURVEY.md 8e / configs[4]) gives every rank the full query batch and

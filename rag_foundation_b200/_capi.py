@@ -33,7 +33,7 @@ class rf_peer_exchange(C.Structure):
 class rf_stats(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("capacity_rows", C.c_uint64), ("n_stores", C.c_uint64),
                 ("n_docs", C.c_uint64), ("hbm_bytes", C.c_uint64), ("searches", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("free_rows", C.c_uint64)]
 
 
 # name -> (restype, argtypes); the test-suite checks every one of these is exported
@@ -60,6 +60,7 @@ SIGNATURES = {
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_text_in": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_keys_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
+    "rf_stream_set_overlap": (_i32, [_vp, _vp, _i32]),
     "rf_search_keys_device_scoped": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp]),
     "rf_search_keys_device_fused": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),

@@ -18,12 +18,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#include <unistd.h>
 
 #include "rf_internal.h"
 
@@ -55,6 +58,18 @@ void extents_append(std::vector<Extent> &v, uint32_t lo, uint32_t hi) {
     if (lo >= hi) return;
     if (!v.empty() && v.back().hi == lo) v.back().hi = hi;
     else v.push_back({lo, hi});
+}
+
+// Remove rows [lo, hi) from an extent list (any order, disjoint).
+void extents_subtract(std::vector<Extent> &v, uint32_t lo, uint32_t hi) {
+    std::vector<Extent> out;
+    out.reserve(v.size() + 1);
+    for (const Extent &x : v) {
+        if (x.hi <= lo || x.lo >= hi) { out.push_back(x); continue; }
+        if (x.lo < lo) out.push_back({x.lo, lo});
+        if (x.hi > hi) out.push_back({hi, x.hi});
+    }
+    v.swap(out);
 }
 
 struct Store {
@@ -144,16 +159,27 @@ struct SearchCtx {
     uint32_t seq = 0;        // completion sequence number written by the kernel into m_out
 };
 
-// A scan plan resident on the device for rf_search_keys_device (cached per scope + stream).
-struct DevicePlan {
-    uint64_t epoch = ~0ull;
+// Scratch of the device-resident searches on one caller stream (rf_search_keys_device*): per STREAM, not
+// per scope -- a single-scope plan rides in the kernel parameters (rf::kInlineExt extents), so nothing
+// scope-keyed lives on the device and a service with 10 k tenants holds no more than kMaxStreamStates
+// of these.  Least recently used states are released when the table is full.
+struct StreamState {
+    std::mutex mu;                    // one search at a time prepares a launch on this stream
+    uint64_t last_use = 0;
+    bool overlap = false;             // rf_stream_set_overlap: scan launches may overlap their predecessor's tail
     DeviceBuf blob, partial, tickets;
-    PinnedBuf h_blob;                 // per-call plans (rf_search_keys_device_scoped): staging + "copy done" event
+    PinnedBuf h_blob;                 // per-query plans (rf_search_keys_device_scoped): staging + "copy done" event
     cudaEvent_t h_blob_free = nullptr;
     DeviceBuf gemm_lists, gemm_keys_a, gemm_floors;   // batched tensor-core path scratch
-    uint32_t n_ext = 0, max_tiles = 0;
     uint32_t launches = 0;
+    void release() {
+        blob.release(); partial.release(); tickets.release(); h_blob.release();
+        gemm_lists.release(); gemm_keys_a.release(); gemm_floors.release();
+        if (h_blob_free) cudaEventDestroy(h_blob_free);
+        h_blob_free = nullptr;
+    }
 };
+constexpr size_t kMaxStreamStates = 64;
 
 struct PlanBlob {  // host staging of everything one launch needs besides F/seg/ff
     std::vector<uint8_t> bytes;
@@ -182,7 +208,9 @@ struct rf_engine {
     std::mutex df_mu;                // RF-1w statistics cache: scope -> (generation, df[256] + n)
     std::map<std::vector<uint32_t>, std::pair<uint64_t, std::vector<uint64_t>>> df_cache;
 
-    std::mutex ingest_mu;            // one ingest at a time (shared scratch + append cursor)
+    std::mutex ingest_mu;            // one ingest at a time (shared scratch + append cursor + free list)
+    std::vector<Extent> free_ext;    // rows of deleted documents / dropped stores, sorted, coalesced: reused first-fit
+    uint64_t free_rows = 0;
     cudaStream_t ingest_stream = nullptr;
     DeviceBuf sc_text, sc_counts, sc_bucket, sc_start, sc_end, sc_ntok, sc_spans;
 
@@ -191,8 +219,9 @@ struct rf_engine {
     std::vector<SearchCtx *> free_ctx;
     std::vector<SearchCtx *> all_ctx;
 
-    std::mutex plan_mu;
-    std::map<std::pair<std::vector<uint32_t>, void *>, DevicePlan *> dev_plans;
+    std::mutex plan_mu;              // guards the table only; a launch holds its StreamState's own mutex
+    std::unordered_map<void *, std::shared_ptr<StreamState>> stream_states;
+    uint64_t stream_tick = 0;
 
     std::atomic<uint64_t> searches{0};
     std::atomic<uint64_t> launches{0};
@@ -480,7 +509,7 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
         h_flag[0] = 0;
         a.done_flag = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->m_out.d) + flag_off);
         a.done_seq = ++c->seq ? c->seq : ++c->seq;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
         e->launches.fetch_add(1, std::memory_order_relaxed);
         t1 = lap(1, t0);
         // Spin on the completion word; fall back to the stream's status so a failed launch can
@@ -496,7 +525,7 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
         h = static_cast<const uint8_t *>(c->m_out.h);
     } else {
         a.done_flag = nullptr;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
         e->launches.fetch_add(1, std::memory_order_relaxed);
         RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
                                 cudaMemcpyDeviceToHost, c->stream));
@@ -517,31 +546,80 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
     return RF_OK;
 }
 
-// Reserve the next `n` rows (caller holds ingest_mu).  Published later by publish_rows.
-int reserve_rows(rf_engine *e, uint64_t n, uint64_t *first) {
+// Reserve `n` contiguous rows (caller holds ingest_mu): first fit among the rows that deletes gave back,
+// else the tail of the arena.  *reused tells the caller the rows lie inside the published range, where a
+// concurrent scan of a bounding range may read them: it must then write features first and the segment
+// words (which un-mask the rows) in a second, later pass.  Published by publish_rows.
+int reserve_rows(rf_engine *e, uint64_t n, uint64_t *first, bool *reused) {
+    *reused = false;
+    if (n) {
+        for (size_t i = 0; i < e->free_ext.size(); ++i) {
+            Extent &x = e->free_ext[i];
+            if (static_cast<uint64_t>(x.hi - x.lo) < n) continue;
+            *first = x.lo;
+            x.lo += static_cast<uint32_t>(n);
+            if (x.lo == x.hi) e->free_ext.erase(e->free_ext.begin() + static_cast<ptrdiff_t>(i));
+            e->free_rows -= n;
+            *reused = true;
+            return RF_OK;
+        }
+    }
     if (e->n_rows + n > e->cfg.capacity_rows)
-        return fail(RF_ECAPACITY, "arena full: %llu + %llu rows > capacity %llu", (unsigned long long)e->n_rows,
-                    (unsigned long long)n, (unsigned long long)e->cfg.capacity_rows);
+        return fail(RF_ECAPACITY, "arena full: %llu + %llu rows > capacity %llu (%llu freed rows, none in a run of %llu)",
+                    (unsigned long long)e->n_rows, (unsigned long long)n, (unsigned long long)e->cfg.capacity_rows,
+                    (unsigned long long)e->free_rows, (unsigned long long)n);
     *first = e->n_rows;
     return RF_OK;
 }
 
-void publish_rows(rf_engine *e, uint32_t store_seg, uint64_t doc_id, bool track_doc, uint64_t first, uint64_t n) {
+// Give reserved-but-unpublished rows back (an ingest failed after reserve_rows).
+void unreserve_rows(rf_engine *e, uint64_t first, uint64_t n, bool reused);
+
+// Rows [lo, hi) are masked (their segment words are tombstones) and belong to no store or document any
+// more: add them to the free list (caller holds ingest_mu).
+void free_list_add(rf_engine *e, uint32_t lo, uint32_t hi) {
+    if (lo >= hi) return;
+    auto it = std::lower_bound(e->free_ext.begin(), e->free_ext.end(), lo, [](const Extent &x, uint32_t v) { return x.lo < v; });
+    it = e->free_ext.insert(it, Extent{lo, hi});
+    e->free_rows += hi - lo;
+    if (it + 1 != e->free_ext.end() && (it + 1)->lo <= it->hi) {
+        it->hi = std::max(it->hi, (it + 1)->hi);
+        it = e->free_ext.erase(it + 1) - 1;
+    }
+    if (it != e->free_ext.begin() && (it - 1)->hi >= it->lo) {
+        (it - 1)->hi = std::max((it - 1)->hi, it->hi);
+        e->free_ext.erase(it);
+    }
+}
+
+void unreserve_rows(rf_engine *e, uint64_t first, uint64_t n, bool reused) {
+    if (reused) free_list_add(e, static_cast<uint32_t>(first), static_cast<uint32_t>(first + n));
+}
+
+// Returns RF_ENOTFOUND when the store was dropped while the ingest ran (its rows are then given back).
+int publish_rows(rf_engine *e, uint32_t store_seg, uint64_t doc_id, bool track_doc, uint64_t first, uint64_t n) {
     std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+    if (store_seg >= e->stores.size() || e->stores[store_seg].dropped) return fail(RF_ENOTFOUND, "unknown store segment %u", store_seg);
     extents_append(e->stores[store_seg].ext, static_cast<uint32_t>(first), static_cast<uint32_t>(first + n));
     if (track_doc) {
         Doc &d = e->docs[doc_id];
         d.store = store_seg;
         extents_append(d.ext, static_cast<uint32_t>(first), static_cast<uint32_t>(first + n));
     }
-    e->n_rows = first + n;
+    e->n_rows = std::max<uint64_t>(e->n_rows, first + n);
     e->epoch.fetch_add(1);
+    return RF_OK;
 }
 
 int check_store(rf_engine *e, uint32_t seg) {
     std::shared_lock<std::shared_mutex> lk(e->meta_mu);
     if (seg >= e->stores.size() || e->stores[seg].dropped) return fail(RF_ENOTFOUND, "unknown store segment %u", seg);
     return RF_OK;
+}
+
+std::shared_ptr<StreamState> stream_state_touch(rf_engine *e, const std::shared_ptr<StreamState> &st) {
+    st->last_use = ++e->stream_tick;
+    return st;
 }
 
 uint32_t fnv1a32(const char *s, size_t n) {
@@ -577,7 +655,7 @@ void extent_rows(const uint32_t *lo, const uint32_t *hi, uint32_t n, uint64_t &r
     for (uint32_t i = 0; i < n; ++i) rows += hi[i] - lo[i];
 }
 
-int search_gemm(rf_engine *e, DevicePlan *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
+int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq, const ScanPlan *plan, uint32_t lo, uint32_t hi,
                 uint32_t k, uint64_t *out_keys_dev, cudaStream_t s) {
     const uint32_t rows = hi - lo;
     // More than 256 queries: CTA pairs (tcgen05 cta_group::2, 256-row tiles, full tensor-pipe rate);
@@ -758,13 +836,8 @@ int rf_engine_destroy(rf_engine *e) {
         c->d_in.release(); c->d_out.release(); c->d_partial.release(); c->d_tickets.release();
         delete c;
     }
-    for (auto &kv : e->dev_plans) {
-        kv.second->blob.release(); kv.second->partial.release(); kv.second->tickets.release();
-        kv.second->gemm_lists.release(); kv.second->gemm_keys_a.release(); kv.second->gemm_floors.release();
-        kv.second->h_blob.release();
-        if (kv.second->h_blob_free) cudaEventDestroy(kv.second->h_blob_free);
-        delete kv.second;
-    }
+    for (auto &kv : e->stream_states) kv.second->release();
+    e->stream_states.clear();
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
     e->sc_text.release(); e->sc_counts.release(); e->sc_bucket.release(); e->sc_start.release();
     e->sc_end.release(); e->sc_ntok.release(); e->sc_spans.release();
@@ -800,6 +873,7 @@ int rf_engine_stats(rf_engine *e, rf_stats *out) {
     out->hbm_bytes = e->hbm_bytes;
     out->searches = e->searches.load();
     out->kernel_launches = e->launches.load();
+    out->free_rows = e->free_rows;   // (read without ingest_mu: a statistic)
     return RF_OK;
 }
 
@@ -832,6 +906,7 @@ static int tombstone_extents(rf_engine *e, const std::vector<Extent> &ext) {
         RF_CUDA(cudaMemsetAsync(e->seg + x.lo, 0xFF, static_cast<size_t>(x.hi - x.lo) * 4, e->ingest_stream));
     RF_CUDA(cudaStreamSynchronize(e->ingest_stream));
     e->tomb_gen.fetch_add(1);
+    for (const Extent &x : ext) free_list_add(e, x.lo, x.hi);   // masked now: the rows can be written again
     return RF_OK;
 }
 
@@ -861,7 +936,12 @@ int rf_doc_tombstone(rf_engine *e, uint64_t doc_id) {
         auto it = e->docs.find(doc_id);
         if (it == e->docs.end()) return fail(RF_ENOTFOUND, "unknown document %llu", (unsigned long long)doc_id);
         ext.swap(it->second.ext);
+        const uint32_t st = it->second.store;
         e->docs.erase(it);
+        // the rows leave the store's extents too: once masked they may be handed to another store's document
+        if (st < e->stores.size())
+            for (const Extent &x : ext) extents_subtract(e->stores[st].ext, x.lo, x.hi);
+        e->epoch.fetch_add(1);
     }
     return tombstone_extents(e, ext);
 }
@@ -894,19 +974,34 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     RF_CUDA(cudaStreamSynchronize(s));
     const uint32_t nc = n_tokens == 0 ? 0 : 1 + ((n_tokens > 128 ? n_tokens - 128 : 0) + 111) / 112;
     uint64_t first = 0;
-    if ((rc = reserve_rows(e, nc, &first))) return rc;
+    bool reused = false;
+    if ((rc = reserve_rows(e, nc, &first, &reused))) return rc;
     if (nc) {
         RF_CUDA(e->sc_spans.reserve(static_cast<size_t>(nc) * 16));
         int64_t *d_spans = static_cast<int64_t *>(e->sc_spans.p);
-        RF_CUDA(rf::launch_rows_from_tokens(w, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, e->seg + first, store_seg,
-                                            d_spans, s));
+        // rows taken from the free list lie inside ranges a concurrent search may be scanning (masked):
+        // features and norms first, the segment words that un-mask them only after those are complete
+        RF_CUDA(rf::launch_rows_from_tokens(w, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, reused ? nullptr : e->seg + first,
+                                            store_seg, d_spans, s));
         ++launches;
         const uint32_t ns = spans ? std::min(nc, max_spans) : 0;
         if (ns) RF_CUDA(cudaMemcpyAsync(spans, d_spans, static_cast<size_t>(ns) * 16, cudaMemcpyDeviceToHost, s));
         RF_CUDA(cudaStreamSynchronize(s));
+        if (reused) {
+            RF_CUDA(rf::launch_fill_u32(e->seg + first, nc, store_seg, s));
+            ++launches;
+            RF_CUDA(cudaStreamSynchronize(s));
+        }
     }
     e->launches.fetch_add(launches);
-    publish_rows(e, store_seg, doc_id, true, first, nc);
+    if ((rc = publish_rows(e, store_seg, doc_id, true, first, nc))) {   // the store was dropped meanwhile
+        if (nc) {
+            cudaMemsetAsync(e->seg + first, 0xFF, static_cast<size_t>(nc) * 4, s);
+            cudaStreamSynchronize(s);
+            unreserve_rows(e, first, nc, reused);
+        }
+        return rc;
+    }
     if (first_chunk) *first_chunk = e->cfg.id_base + first;
     if (n_chunks) *n_chunks = nc;
     return RF_OK;
@@ -920,16 +1015,29 @@ int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const 
     std::lock_guard<std::mutex> ing(e->ingest_mu);
     RF_CUDA(cudaSetDevice(e->cfg.device));
     uint64_t first = 0;
-    if ((rc = reserve_rows(e, n_rows, &first))) return rc;
+    bool reused = false;
+    if ((rc = reserve_rows(e, n_rows, &first, &reused))) return rc;
     cudaStream_t s = e->ingest_stream;
     if (n_rows) {
         RF_CUDA(cudaMemcpyAsync(e->F + first * RF_DIM, rows, n_rows * RF_DIM,
                                 rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-        RF_CUDA(rf::launch_row_meta(e->F + first * RF_DIM, n_rows, e->ff + first, e->seg + first, store_seg, s));
+        RF_CUDA(rf::launch_row_meta(e->F + first * RF_DIM, n_rows, e->ff + first, reused ? nullptr : e->seg + first, store_seg, s));
         e->launches.fetch_add(1);
         RF_CUDA(cudaStreamSynchronize(s));
+        if (reused) {   // see rf_ingest_text
+            RF_CUDA(rf::launch_fill_u32(e->seg + first, n_rows, store_seg, s));
+            e->launches.fetch_add(1);
+            RF_CUDA(cudaStreamSynchronize(s));
+        }
     }
-    publish_rows(e, store_seg, doc_id, true, first, n_rows);
+    if ((rc = publish_rows(e, store_seg, doc_id, true, first, n_rows))) {
+        if (n_rows) {
+            cudaMemsetAsync(e->seg + first, 0xFF, static_cast<size_t>(n_rows) * 4, s);
+            cudaStreamSynchronize(s);
+            unreserve_rows(e, first, n_rows, reused);
+        }
+        return rc;
+    }
     if (first_chunk) *first_chunk = e->cfg.id_base + first;
     return RF_OK;
 }
@@ -955,9 +1063,11 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
         RF_CUDA(cudaMalloc(&e->zipf_bucket, 65536));
         RF_CUDA(cudaMemcpy(e->zipf_bucket, zb.data(), 65536, cudaMemcpyHostToDevice));
     }
-    uint64_t first = 0;
-    int rc = reserve_rows(e, n_rows, &first);
-    if (rc) return rc;
+    // the generator appends at the tail only (row content is tied to its counter; a measurement input)
+    if (e->n_rows + n_rows > e->cfg.capacity_rows)
+        return fail(RF_ECAPACITY, "arena full: %llu + %llu rows > capacity %llu", (unsigned long long)e->n_rows,
+                    (unsigned long long)n_rows, (unsigned long long)e->cfg.capacity_rows);
+    const uint64_t first = e->n_rows;
     RF_CUDA(rf::launch_synth_rows(seed, start_counter, n_rows, e->zipf_bucket, e->F + first * RF_DIM, e->ff + first,
                                   e->seg + first, first_seg, rows_per_store, s));
     e->launches.fetch_add(1);
@@ -977,18 +1087,68 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
 }
 
 namespace {
+// Snapshot file, version 2: header, store table, document table, free list, the three row arrays, and a
+// trailer {magic "RFB2END2", checksum} -- a 64-bit multiply-xorshift hash of every byte before it, so a
+// truncated or corrupted file is refused at load.  Written to "<path>.tmp", flushed, fsync'ed and renamed
+// over <path>: a crash or a full disk mid-save leaves the previous snapshot intact.
 struct SnapHeader {
     char magic[8];
-    uint32_t dim, reserved;
-    uint64_t n_rows, id_base, n_stores, n_docs;
+    uint32_t dim, version;
+    uint64_t n_rows, id_base, n_stores, n_docs, n_free;
 };
-bool put(FILE *f, const void *p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
-bool get(FILE *f, void *p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+struct SnapTrailer {
+    char magic[8];
+    uint64_t checksum;
+};
+struct Hasher {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    void feed(const void *p, size_t n) {
+        const uint8_t *b = static_cast<const uint8_t *>(p);
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            memcpy(&w, b + i, 8);
+            h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
+            h ^= h >> 29;
+        }
+        if (i < n) {
+            uint64_t w = 0;
+            memcpy(&w, b + i, n - i);
+            h = (h ^ w ^ (static_cast<uint64_t>(n - i) << 56)) * 0x94D049BB133111EBull;
+            h ^= h >> 31;
+        }
+    }
+};
+struct SnapWriter {
+    FILE *f = nullptr;
+    Hasher hs;
+    bool ok = true;
+    void put(const void *p, size_t n) {
+        if (!ok || n == 0) return;
+        ok = fwrite(p, 1, n, f) == n;
+        hs.feed(p, n);
+    }
+};
+struct SnapReader {
+    FILE *f = nullptr;
+    Hasher hs;
+    bool get(void *p, size_t n) {
+        if (n == 0) return true;
+        if (fread(p, 1, n, f) != n) return false;
+        hs.feed(p, n);
+        return true;
+    }
+};
 struct FileCloser {
     FILE *f;
     ~FileCloser() { if (f) fclose(f); }
 };
 constexpr size_t kSnapChunk = 64u << 20;
+bool extents_valid(const std::vector<Extent> &v, uint64_t n_rows) {
+    for (const Extent &x : v)
+        if (x.lo > x.hi || x.hi > n_rows) return false;
+    return true;
+}
 }  // namespace
 
 int rf_snapshot_save(rf_engine *e, const char *path) {
@@ -996,36 +1156,56 @@ int rf_snapshot_save(rf_engine *e, const char *path) {
     std::lock_guard<std::mutex> ing(e->ingest_mu);          // no appends / tombstones while we copy
     std::shared_lock<std::shared_mutex> lk(e->meta_mu);
     RF_CUDA(cudaSetDevice(e->cfg.device));
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(RF_EINVAL, "cannot open %s for writing", path);
-    FileCloser fc{f};
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(RF_EINVAL, "cannot open %s for writing", tmp.c_str());
+    SnapWriter w;
+    w.f = f;
+    auto abandon = [&](const char *what) {
+        fclose(f);
+        unlink(tmp.c_str());
+        return fail(RF_EINVAL, "%s %s failed; the previous snapshot (if any) is untouched", what, tmp.c_str());
+    };
     SnapHeader h{};
-    memcpy(h.magic, "RFB2SNP1", 8);
+    memcpy(h.magic, "RFB2SNP2", 8);
     h.dim = RF_DIM;
+    h.version = 2;
     h.n_rows = e->n_rows;
     h.id_base = e->cfg.id_base;
     h.n_stores = e->stores.size();
     h.n_docs = e->docs.size();
-    bool ok = put(f, &h, sizeof h);
+    h.n_free = e->free_ext.size();
+    w.put(&h, sizeof h);
     for (const Store &s : e->stores) {
         const uint32_t len = static_cast<uint32_t>(s.name.size()), dropped = s.dropped ? 1u : 0u, n_ext = static_cast<uint32_t>(s.ext.size());
-        ok = ok && put(f, &len, 4) && put(f, s.name.data(), len) && put(f, &dropped, 4) && put(f, &n_ext, 4) && put(f, s.ext.data(), n_ext * sizeof(Extent));
+        w.put(&len, 4); w.put(s.name.data(), len); w.put(&dropped, 4); w.put(&n_ext, 4); w.put(s.ext.data(), n_ext * sizeof(Extent));
     }
     for (const auto &kv : e->docs) {
         const uint32_t n_ext = static_cast<uint32_t>(kv.second.ext.size());
-        ok = ok && put(f, &kv.first, 8) && put(f, &kv.second.store, 4) && put(f, &n_ext, 4) && put(f, kv.second.ext.data(), n_ext * sizeof(Extent));
+        w.put(&kv.first, 8); w.put(&kv.second.store, 4); w.put(&n_ext, 4); w.put(kv.second.ext.data(), n_ext * sizeof(Extent));
     }
-    if (!ok) return fail(RF_EINVAL, "write to %s failed", path);
+    w.put(e->free_ext.data(), e->free_ext.size() * sizeof(Extent));
+    if (!w.ok) return abandon("write to");
     std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(e->n_rows * RF_DIM, 1)));
     const struct { const void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
     for (const auto &arr : arrays) {
         const size_t total = e->n_rows * arr.elt;
         for (size_t off = 0; off < total; off += buf.size()) {
             const size_t n = std::min(buf.size(), total - off);
-            RF_CUDA(cudaMemcpy(buf.data(), static_cast<const uint8_t *>(arr.base) + off, n, cudaMemcpyDeviceToHost));
-            if (!put(f, buf.data(), n)) return fail(RF_EINVAL, "write to %s failed", path);
+            if (cudaMemcpy(buf.data(), static_cast<const uint8_t *>(arr.base) + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaGetLastError();
+                return abandon("device read for");
+            }
+            w.put(buf.data(), n);
+            if (!w.ok) return abandon("write to");
         }
     }
+    SnapTrailer t{};
+    memcpy(t.magic, "RFB2END2", 8);
+    t.checksum = w.hs.h;
+    if (fwrite(&t, 1, sizeof t, f) != sizeof t || fflush(f) != 0 || fsync(fileno(f)) != 0) return abandon("flush of");
+    if (fclose(f) != 0) { unlink(tmp.c_str()); return fail(RF_EINVAL, "close of %s failed", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { unlink(tmp.c_str()); return fail(RF_EINVAL, "rename of %s over %s failed", tmp.c_str(), path); }
     return RF_OK;
 }
 
@@ -1038,51 +1218,69 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) return fail(RF_ENOTFOUND, "cannot open %s", path);
     FileCloser fc{f};
+    SnapReader r;
+    r.f = f;
     SnapHeader h{};
-    if (!get(f, &h, sizeof h) || memcmp(h.magic, "RFB2SNP1", 8) != 0 || h.dim != RF_DIM) return fail(RF_EINVAL, "%s is not an RF-1 snapshot", path);
+    if (!r.get(&h, sizeof h) || memcmp(h.magic, "RFB2SNP2", 8) != 0 || h.dim != RF_DIM || h.version != 2)
+        return fail(RF_EINVAL, "%s is not an RF-1 snapshot (version 2)", path);
     if (h.n_rows > e->cfg.capacity_rows) return fail(RF_ECAPACITY, "snapshot holds %llu rows, engine capacity is %llu", (unsigned long long)h.n_rows, (unsigned long long)e->cfg.capacity_rows);
     if (h.id_base != e->cfg.id_base) return fail(RF_EINVAL, "snapshot id_base %llu != engine id_base %llu", (unsigned long long)h.id_base, (unsigned long long)e->cfg.id_base);
+    if (h.n_stores > (1ull << 32) || h.n_docs > (1ull << 40) || h.n_free > h.n_rows + 1) return fail(RF_EINVAL, "%s: implausible table sizes", path);
     std::vector<Store> stores(h.n_stores);
     bool ok = true;
     for (Store &s : stores) {
         uint32_t len = 0, dropped = 0, n_ext = 0;
-        ok = ok && get(f, &len, 4) && len < (1u << 20);
+        ok = ok && r.get(&len, 4) && len < (1u << 20);
         if (!ok) break;
         s.name.resize(len);
-        ok = get(f, &s.name[0], len) && get(f, &dropped, 4) && get(f, &n_ext, 4) && n_ext <= h.n_rows + 1;
+        ok = r.get(&s.name[0], len) && r.get(&dropped, 4) && r.get(&n_ext, 4) && n_ext <= h.n_rows + 1;
         if (!ok) break;
         s.dropped = dropped != 0;
         s.ext.resize(n_ext);
-        ok = get(f, s.ext.data(), n_ext * sizeof(Extent));
+        ok = r.get(s.ext.data(), n_ext * sizeof(Extent)) && extents_valid(s.ext, h.n_rows);
     }
     std::unordered_map<uint64_t, Doc> docs;
     for (uint64_t i = 0; ok && i < h.n_docs; ++i) {
         uint64_t id = 0;
         uint32_t store = 0, n_ext = 0;
-        ok = get(f, &id, 8) && get(f, &store, 4) && get(f, &n_ext, 4) && n_ext <= h.n_rows + 1;
+        ok = r.get(&id, 8) && r.get(&store, 4) && r.get(&n_ext, 4) && n_ext <= h.n_rows + 1 && store < h.n_stores;
         if (!ok) break;
         Doc d;
         d.store = store;
         d.ext.resize(n_ext);
-        ok = get(f, d.ext.data(), n_ext * sizeof(Extent));
+        ok = r.get(d.ext.data(), n_ext * sizeof(Extent)) && extents_valid(d.ext, h.n_rows);
         docs.emplace(id, std::move(d));
     }
-    if (!ok) return fail(RF_EINVAL, "%s is truncated or corrupt", path);
+    std::vector<Extent> free_ext(ok ? h.n_free : 0);
+    ok = ok && r.get(free_ext.data(), free_ext.size() * sizeof(Extent)) && extents_valid(free_ext, h.n_rows);
+    if (!ok) return fail(RF_EINVAL, "%s is truncated or corrupt (tables)", path);
+    // The arrays go straight into the (empty) arena; nothing is published until the checksum has matched,
+    // and a failed load masks whatever it wrote.
+    auto unwind = [&](const char *what) {
+        cudaMemset(e->seg, 0xFF, static_cast<size_t>(h.n_rows) * 4);
+        return fail(RF_EINVAL, "%s is %s; nothing was loaded", path, what);
+    };
     std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(h.n_rows * RF_DIM, 1)));
     const struct { void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
     for (const auto &arr : arrays) {
         const size_t total = h.n_rows * arr.elt;
         for (size_t off = 0; off < total; off += buf.size()) {
             const size_t n = std::min(buf.size(), total - off);
-            if (!get(f, buf.data(), n)) return fail(RF_EINVAL, "%s is truncated", path);
+            if (!r.get(buf.data(), n)) return unwind("truncated");
             RF_CUDA(cudaMemcpy(static_cast<uint8_t *>(arr.base) + off, buf.data(), n, cudaMemcpyHostToDevice));
         }
     }
+    SnapTrailer t{};
+    if (fread(&t, 1, sizeof t, f) != sizeof t || memcmp(t.magic, "RFB2END2", 8) != 0) return unwind("truncated (no trailer)");
+    if (t.checksum != r.hs.h) return unwind("corrupt (checksum mismatch)");
     e->stores.swap(stores);
     e->store_by_name.clear();
     for (uint32_t i = 0; i < e->stores.size(); ++i)
         if (!e->stores[i].dropped) e->store_by_name.emplace(e->stores[i].name, i);
     e->docs.swap(docs);
+    e->free_ext.swap(free_ext);
+    e->free_rows = 0;
+    for (const Extent &x : e->free_ext) e->free_rows += x.hi - x.lo;
     e->n_rows = h.n_rows;
     e->epoch.fetch_add(1);
     return RF_OK;
@@ -1231,21 +1429,20 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
     if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
-    // blob, query text and the query vector share the context's input buffer: one H2D copy
+    // weights, query text and the query vector share the context's input buffer: one H2D copy (the plan
+    // of a single query rides in the kernel parameters)
     const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
-    const size_t blob_pad = (b.bytes.size() + 255) & ~static_cast<size_t>(255);
-    const size_t w_pad = weights ? RF_DIM : 0;   // [blob | weights | text | query vector]
-    const size_t need = blob_pad + w_pad + text_pad + RF_DIM;
+    const size_t w_pad = weights ? RF_DIM : 0;   // [weights | text | query vector]
+    const size_t need = w_pad + text_pad + RF_DIM;
     RF_CUDA(c->h_in.reserve(need));
     RF_CUDA(c->d_in.reserve(need));
     uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
     uint8_t *d = static_cast<uint8_t *>(c->d_in.p);
-    memcpy(h, b.bytes.data(), b.bytes.size());
-    if (weights) memcpy(h + blob_pad, weights, RF_DIM);
-    if (n) memcpy(h + blob_pad + w_pad, utf8, n);
-    RF_CUDA(cudaMemcpyAsync(d, h, blob_pad + w_pad + n, cudaMemcpyHostToDevice, c->stream));
-    int8_t *d_q = reinterpret_cast<int8_t *>(d + blob_pad + w_pad + text_pad);
-    RF_CUDA(rf::launch_featurize_query(d + blob_pad + w_pad, static_cast<uint32_t>(n), weights ? d + blob_pad : nullptr, d_q, c->stream));
+    if (weights) memcpy(h, weights, RF_DIM);
+    if (n) memcpy(h + w_pad, utf8, n);
+    if (w_pad + n) RF_CUDA(cudaMemcpyAsync(d, h, w_pad + n, cudaMemcpyHostToDevice, c->stream));
+    int8_t *d_q = reinterpret_cast<int8_t *>(d + w_pad + text_pad);
+    RF_CUDA(rf::launch_featurize_query(d + w_pad, static_cast<uint32_t>(n), weights ? d : nullptr, d_q, c->stream));
     e->launches.fetch_add(1);
 
     const OutLayout L(1, k);
@@ -1258,8 +1455,9 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     ScanArgs a{};
-    fill_args(e, a, d, b, d_q, k, false);
+    fill_args(e, a, nullptr, b, d_q, k, false);
     maybe_inline_plan(a, b, 1, false);
+    if (!a.inline_plan) return fail(RF_EINVAL, "internal: a single-query plan exceeds %u extents", rf::kInlineExt);
     uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
     a.partial = static_cast<uint64_t *>(c->d_partial.p);
     set_sync_bufs(a, c->d_tickets, c->launches++);
@@ -1268,7 +1466,9 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
-    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, e->scan_variant, c->stream));
+    // the query vector comes from the kernel just before this one on the stream: a fully serialised launch
+    // (an overlapped one may read d_q before featurize_query's writes are visible)
+    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, e->scan_variant, c->stream, false));
     e->launches.fetch_add(1);
     uint8_t *ho = static_cast<uint8_t *>(c->h_out.p);
     RF_CUDA(cudaMemcpyAsync(ho + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
@@ -1393,6 +1593,37 @@ int rf_search_keys_device_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, 
     return search_keys_device_impl(e, q_dev, nq, store_segs, n_segs, k, out_keys_dev, stream, px);
 }
 
+// The per-stream scratch of the device-resident searches (created on first use; when the table is full the
+// least recently used state nobody holds is released -- cudaFree synchronises the device, so kernels that
+// still read its buffers have finished).
+static std::shared_ptr<StreamState> stream_state(rf_engine *e, void *stream) {
+    std::lock_guard<std::mutex> lk(e->plan_mu);
+    std::shared_ptr<StreamState> &slot = e->stream_states[stream];
+    if (!slot) {
+        if (e->stream_states.size() > kMaxStreamStates) {
+            auto victim = e->stream_states.end();
+            for (auto it = e->stream_states.begin(); it != e->stream_states.end(); ++it)
+                if (it->second && it->second.use_count() == 1 && (victim == e->stream_states.end() || it->second->last_use < victim->second->last_use))
+                    victim = it;
+            if (victim != e->stream_states.end()) {
+                victim->second->release();
+                e->stream_states.erase(victim);
+            }
+        }
+        e->stream_states[stream] = std::make_shared<StreamState>();
+        return stream_state_touch(e, e->stream_states[stream]);
+    }
+    return stream_state_touch(e, slot);
+}
+
+int rf_stream_set_overlap(rf_engine *e, void *stream, int allow) {
+    if (!e) return fail(RF_EINVAL, "null argument");
+    std::shared_ptr<StreamState> st = stream_state(e, stream);
+    std::lock_guard<std::mutex> lk(st->mu);
+    st->overlap = allow != 0;
+    return RF_OK;
+}
+
 static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs, uint32_t n_segs,
                                    uint32_t k, uint64_t *out_keys_dev, void *stream, const rf_peer_exchange *px) {
     if (!e || !q_dev || !out_keys_dev) return fail(RF_EINVAL, "null argument");
@@ -1402,80 +1633,67 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
     if (n_segs > RF_SCOPE_MAX) return fail(RF_EINVAL, "scope has %u segments (max %u)", n_segs, RF_SCOPE_MAX);
     RF_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    std::vector<uint32_t> key(store_segs, store_segs + n_segs);
-    DevicePlan *dp = nullptr;
+    // one shared plan, built on the host from the scope's current extents and passed in the kernel
+    // parameters: nothing about a scope is resident on the device between calls
     PlanBlob b;
-    {
-        std::lock_guard<std::mutex> lk(e->plan_mu);
-        DevicePlan *&slot = e->dev_plans[{key, stream}];
-        if (!slot) slot = new DevicePlan();
-        dp = slot;
-        const uint64_t now = e->epoch.load();
-        const uint32_t seg_off[2] = {0, n_segs};
-        int rc = build_blob(e, nullptr, 1, store_segs, seg_off, true, b);  // offsets are deterministic for a scope
-        if (rc) return rc;
-        if (dp->epoch != now) {
-            // synchronous (rare: only when the scope's extents changed since the last call)
-            RF_CUDA(cudaStreamSynchronize(s));
-            RF_CUDA(dp->blob.reserve(b.bytes.size()));
-            RF_CUDA(cudaMemcpy(dp->blob.p, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice));
-            dp->epoch = now;
-            dp->max_tiles = b.max_tiles;
+    const uint32_t seg_off[2] = {0, n_segs};
+    int rc = build_blob(e, nullptr, 1, store_segs, seg_off, true, b);
+    if (rc) return rc;
+    const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
+    std::shared_ptr<StreamState> st = stream_state(e, stream);
+    std::lock_guard<std::mutex> lk(st->mu);
+    // ---- batched tensor-core path: k <= 10, when it beats nq scans (gemm_pays) ----
+    if (!px && hp->n_ext >= 1) {
+        uint64_t rows;
+        uint32_t lo, hi;
+        extent_rows(reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo) + hp->ext_off,
+                    reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi) + hp->ext_off, hp->n_ext, rows, lo, hi);
+        if (gemm_pays(e, nq, rows, hi - lo, k)) {
+            rc = search_gemm(e, st.get(), q_dev, nq, hp, lo, hi, k, out_keys_dev, s);
+            if (rc == RF_OK) e->searches.fetch_add(nq, std::memory_order_relaxed);
+            return rc;
         }
-        // ---- batched tensor-core path: k <= 10, when it beats nq scans (gemm_pays) ----
-        {
-            const ScanPlan *hp = reinterpret_cast<const ScanPlan *>(b.bytes.data() + b.off_plans);
-            if (!px && hp->n_ext >= 1) {
-                uint64_t rows;
-                uint32_t lo, hi;
-                extent_rows(reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_lo) + hp->ext_off,
-                            reinterpret_cast<const uint32_t *>(b.bytes.data() + b.off_hi) + hp->ext_off, hp->n_ext, rows, lo, hi);
-                if (gemm_pays(e, nq, rows, hi - lo, k)) {
-                    const int rc2 = search_gemm(e, dp, q_dev, nq, hp, lo, hi, k, out_keys_dev, s);
-                    if (rc2 == RF_OK) e->searches.fetch_add(nq, std::memory_order_relaxed);
-                    return rc2;
-                }
-            }
-        }
-        const uint32_t X = pick_blocks(e, nq, dp->max_tiles);
-        const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
-        if (need_partial > dp->partial.cap || static_cast<size_t>(nq) * kSyncBytesPerQuery + 8 > dp->tickets.cap) {
-            RF_CUDA(cudaStreamSynchronize(s));
-            RF_CUDA(dp->partial.reserve(need_partial));
-            if (static_cast<size_t>(nq) * kSyncBytesPerQuery + 8 > dp->tickets.cap) {
-                RF_CUDA(dp->tickets.reserve(static_cast<size_t>(nq) * kSyncBytesPerQuery + 8));
-                RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
-            }
-        }
-        ScanArgs a{};
-        fill_args(e, a, static_cast<const uint8_t *>(dp->blob.p), b, q_dev, k, true);
-        maybe_inline_plan(a, b, nq, true);
-        a.partial = static_cast<uint64_t *>(dp->partial.p);
-        set_sync_bufs(a, dp->tickets, dp->launches++);
-        a.out_keys = out_keys_dev;
-        if (px) {
-            // fused exchange: the scan publishes into every rank's gather buffer, the merge waits on flags
-            const size_t slot = px->seq & 3u;   // four buffers: a rank is never more than three calls ahead of a peer's merge
-            const size_t keys_off = slot * px->world * px->nq_cap * static_cast<size_t>(k);
-            const size_t flag_off = slot * px->world * static_cast<size_t>(px->nq_cap);
-            for (uint32_t r = 0; r < px->world; ++r) {
-                a.px_keys[r] = reinterpret_cast<uint64_t *>(px->keys_ptrs[r]) + keys_off;
-                a.px_flags[r] = reinterpret_cast<uint32_t *>(px->flag_ptrs[r]) + flag_off;
-            }
-            a.px_rank = px->rank;
-            a.px_world = px->world;
-            a.px_seq = px->seq;
-            a.px_nq_cap = px->nq_cap;
-            a.px_out = out_keys_dev;
-            a.px_timeout = px->timeout_flag_dev;
-            if (static_cast<size_t>(nq) * k * 8 > dp->gemm_keys_a.cap) {          // the local (pre-merge) list
-                RF_CUDA(cudaStreamSynchronize(s));
-                RF_CUDA(dp->gemm_keys_a.reserve(static_cast<size_t>(nq) * k * 8));
-            }
-            a.out_keys = static_cast<uint64_t *>(dp->gemm_keys_a.p);
-        }
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
     }
+    const uint32_t X = pick_blocks(e, nq, b.max_tiles);
+    const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
+    const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
+    if (need_partial > st->partial.cap || need_sync > st->tickets.cap) {
+        RF_CUDA(cudaStreamSynchronize(s));
+        RF_CUDA(st->partial.reserve(need_partial));
+        if (need_sync > st->tickets.cap) {
+            RF_CUDA(st->tickets.reserve(need_sync));
+            RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
+        }
+    }
+    ScanArgs a{};
+    fill_args(e, a, nullptr, b, q_dev, k, true);
+    maybe_inline_plan(a, b, nq, true);
+    if (!a.inline_plan) return fail(RF_EINVAL, "internal: a single-scope plan exceeds %u extents", rf::kInlineExt);
+    a.partial = static_cast<uint64_t *>(st->partial.p);
+    set_sync_bufs(a, st->tickets, st->launches++);
+    a.out_keys = out_keys_dev;
+    if (px) {
+        // fused exchange: the scan publishes into every rank's gather buffer, the merge waits on flags
+        const size_t slot = px->seq & 3u;   // four buffers: a rank is never more than three calls ahead of a peer's merge
+        const size_t keys_off = slot * px->world * px->nq_cap * static_cast<size_t>(k);
+        const size_t flag_off = slot * px->world * static_cast<size_t>(px->nq_cap);
+        for (uint32_t r = 0; r < px->world; ++r) {
+            a.px_keys[r] = reinterpret_cast<uint64_t *>(px->keys_ptrs[r]) + keys_off;
+            a.px_flags[r] = reinterpret_cast<uint32_t *>(px->flag_ptrs[r]) + flag_off;
+        }
+        a.px_rank = px->rank;
+        a.px_world = px->world;
+        a.px_seq = px->seq;
+        a.px_nq_cap = px->nq_cap;
+        a.px_out = out_keys_dev;
+        a.px_timeout = px->timeout_flag_dev;
+        if (static_cast<size_t>(nq) * k * 8 > st->gemm_keys_a.cap) {          // the local (pre-merge) list
+            RF_CUDA(cudaStreamSynchronize(s));
+            RF_CUDA(st->gemm_keys_a.reserve(static_cast<size_t>(nq) * k * 8));
+        }
+        a.out_keys = static_cast<uint64_t *>(st->gemm_keys_a.p);
+    }
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     return RF_OK;
@@ -1492,37 +1710,33 @@ int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq,
     PlanBlob b;
     int rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b);
     if (rc) return rc;
-    DevicePlan *dp = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(e->plan_mu);
-        DevicePlan *&slot = e->dev_plans[{std::vector<uint32_t>(RF_SCOPE_MAX + 1, 0u), stream}];   // longer than any scope: this stream's per-call plans
-        if (!slot) slot = new DevicePlan();
-        dp = slot;
-    }
+    std::shared_ptr<StreamState> st = stream_state(e, stream);
+    std::lock_guard<std::mutex> lk(st->mu);
     const uint32_t X = pick_blocks(e, nq, b.max_tiles);
     const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
     const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
-    if (b.bytes.size() > dp->blob.cap || need_partial > dp->partial.cap || need_sync > dp->tickets.cap) {
+    if (b.bytes.size() > st->blob.cap || need_partial > st->partial.cap || need_sync > st->tickets.cap) {
         RF_CUDA(cudaStreamSynchronize(s));
-        RF_CUDA(dp->blob.reserve(b.bytes.size()));
-        RF_CUDA(dp->partial.reserve(need_partial));
-        if (need_sync > dp->tickets.cap) {
-            RF_CUDA(dp->tickets.reserve(need_sync));
-            RF_CUDA(cudaMemset(dp->tickets.p, 0, dp->tickets.cap));
+        RF_CUDA(st->blob.reserve(b.bytes.size()));
+        RF_CUDA(st->partial.reserve(need_partial));
+        if (need_sync > st->tickets.cap) {
+            RF_CUDA(st->tickets.reserve(need_sync));
+            RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
         }
     }
-    if (!dp->h_blob_free) RF_CUDA(cudaEventCreateWithFlags(&dp->h_blob_free, cudaEventDisableTiming));
-    else RF_CUDA(cudaEventSynchronize(dp->h_blob_free));      // the previous call's upload has left the staging buffer
-    RF_CUDA(dp->h_blob.reserve(b.bytes.size()));
-    memcpy(dp->h_blob.p, b.bytes.data(), b.bytes.size());
-    RF_CUDA(cudaMemcpyAsync(dp->blob.p, dp->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
-    RF_CUDA(cudaEventRecord(dp->h_blob_free, s));
+    if (!st->h_blob_free) RF_CUDA(cudaEventCreateWithFlags(&st->h_blob_free, cudaEventDisableTiming));
+    else RF_CUDA(cudaEventSynchronize(st->h_blob_free));      // the previous call's upload has left the staging buffer
+    RF_CUDA(st->h_blob.reserve(b.bytes.size()));
+    memcpy(st->h_blob.p, b.bytes.data(), b.bytes.size());
+    RF_CUDA(cudaMemcpyAsync(st->blob.p, st->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
+    RF_CUDA(cudaEventRecord(st->h_blob_free, s));
     ScanArgs a{};
-    fill_args(e, a, static_cast<const uint8_t *>(dp->blob.p), b, q_dev, k, false);
-    a.partial = static_cast<uint64_t *>(dp->partial.p);
-    set_sync_bufs(a, dp->tickets, dp->launches++);
+    fill_args(e, a, static_cast<const uint8_t *>(st->blob.p), b, q_dev, k, false);
+    a.partial = static_cast<uint64_t *>(st->partial.p);
+    set_sync_bufs(a, st->tickets, st->launches++);
     a.out_keys = out_keys_dev;
-    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s));
+    // the plans were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     return RF_OK;

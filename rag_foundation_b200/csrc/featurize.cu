@@ -14,6 +14,8 @@
 //           window's buckets -> one 256-byte int8 row, its sum of squares, store word, byte span
 // A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
 // look-ahead, so stop-word removal needs no second compaction.
+#include <algorithm>
+
 #include "rf_device.cuh"
 #include "rf_internal.h"
 
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
         if (lane == 0) {
             ff[w] = sq;
-            seg[w] = store_seg;
+            if (seg) seg[w] = store_seg;
             if (spans) {
                 spans[2 * static_cast<size_t>(w)] = tok_start[lo];
                 spans[2 * static_cast<size_t>(w) + 1] = tok_end[hi - 1];
@@ -355,12 +357,24 @@ __global__ void __launch_bounds__(256) row_meta_kernel(const int8_t *__restrict_
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
         if (lane == 0) {
             ff[r] = sq;
-            seg[r] = store_seg;
+            if (seg) seg[r] = store_seg;
         }
     }
 }
 
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p, uint64_t n, uint32_t value) {
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        p[i] = value;
+}
+
 }  // namespace
+
+cudaError_t launch_fill_u32(uint32_t *p, uint64_t n, uint32_t value, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 148ull * 8ull));
+    fill_u32_kernel<<<blocks, 256, 0, s>>>(p, n, value);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
                             cudaStream_t s) {

@@ -65,13 +65,14 @@ struct ScanArgs {
     uint32_t id_base;           // global id of row 0
     uint32_t k;
     uint32_t shared_plan;       // 1: every query uses plans[0] (one scope for the whole batch)
-    // Inline copy of plans[0] and its (<= kInlineExt) extents: used when inline_plan != 0, which
-    // requires shared_plan or nq == 1.  Kernel parameters live in the constant bank.
+    // Inline copy of plans[0] and its extents (the engine caps a plan at kInlineExt of them): used when
+    // inline_plan != 0, which requires shared_plan or nq == 1.  Kernel parameters live in the constant
+    // bank, so a single-scope search needs no device-resident plan at all (nothing to cache or evict).
     uint32_t inline_plan;
     ScanPlan plan0;
-    uint32_t inl_lo[8];
-    uint32_t inl_hi[8];
-    uint32_t inl_tile0[9];
+    uint32_t inl_lo[64];
+    uint32_t inl_hi[64];
+    uint32_t inl_tile0[65];
     // Fused top-k exchange over NVLink peer memory (sharded search): when px_world > 1 the block
     // that finishes a query stores its k keys into every rank's gather buffer and then releases
     // a per-(rank, query) flag there; merge_wait_kernel on each rank acquires the flags and merges.
@@ -87,7 +88,7 @@ struct ScanArgs {
     uint32_t dbg_flags;            // diagnostics (RF_SCAN_DBG): 1 = no seg bulk copy, 2 = static round-robin tiles instead of stealing
     unsigned long long *debug_ts;  // diagnostics (RF_SCAN_DEBUG=1): [grid.x][8] globaltimer stamps, else null
 };
-constexpr uint32_t kInlineExt = 8;
+constexpr uint32_t kInlineExt = 64;
 
 // launchers (each returns the cudaError_t of the launch)
 enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, default tma 8x24)
@@ -101,7 +102,13 @@ enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, de
     kScanVariantTma4x8 = 7,     // 64 KB ring: three blocks per SM
     kScanVariantCount = 8
 };
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s);
+// `overlap`: launch with programmatic stream serialisation (the kernel's scan phase may start while the
+// previous kernel in the stream is still in its merge tail).  Everything the kernel reads before its
+// griddepcontrol.wait -- the query vectors and the plan -- must then be complete before the PREVIOUS
+// kernel in the stream started: true for kernel parameters and for buffers written by a copy, not for a
+// query vector another kernel has just produced.
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s,
+                                   bool overlap);
 // packed keys [nq, k] -> ids / scores / cosines / counts (host-visible result layout); q: [nq, 256] device
 cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
                                uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s);
@@ -177,7 +184,9 @@ struct DfArgs {
     uint32_t prefix[kDfMaxExtents + 1]; // rows before extent i; prefix[n_ext] = total
 };
 cudaError_t launch_bucket_df(const DfArgs &a, int sm_count, cudaStream_t s);
-// ff[r] = sum of squares of row r, seg[r] = store_seg, for rows appended as raw features
+// p[0 .. n) = value (segment words of rows that were written while still masked)
+cudaError_t launch_fill_u32(uint32_t *p, uint64_t n, uint32_t value, cudaStream_t s);
+// ff[r] = sum of squares of row r, seg[r] = store_seg (seg may be null), for rows appended as raw features
 cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
                             cudaStream_t s);
 

@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__rest
 }
 
 template <int kConsumers, int kStages>
-cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
+cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s, bool overlap) {
     using Smem = TmaSmem<kConsumers, kStages>;
     auto kern = score_topk_scan_tma_kernel<kConsumers, kStages>;
     if (cudaError_t e = ensure_dynamic_smem(kern, static_cast<int>(sizeof(Smem))); e != cudaSuccess) return e;
@@ -714,7 +714,7 @@ cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = overlap ? 1 : 0;   // without the attribute griddepcontrol.wait returns at once: a fully serialised launch
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
@@ -728,7 +728,8 @@ uint32_t scan_default_blocks_per_query(int sm_count, int variant) {
     return static_cast<uint32_t>(sm_count) * (two ? 2u : 1u);
 }
 
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s) {
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s,
+                                   bool overlap) {
     dim3 grid(blocks_per_query, nq, 1);
     switch (variant) {
         case kScanVariantLdg: {
@@ -738,13 +739,13 @@ cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t bloc
             score_topk_scan_ldg_kernel<<<grid, kLdgWarps * 32, sizeof(MergeScratch<kLdgWarps>), s>>>(a);
             return cudaGetLastError();
         }
-        case kScanVariantTma8x24: return launch_tma<8, 24>(a, grid, s);
-        case kScanVariantTma12x24: return launch_tma<12, 24>(a, grid, s);
-        case kScanVariantTma8x16: return launch_tma<8, 16>(a, grid, s);
-        case kScanVariantTma6x12: return launch_tma<6, 12>(a, grid, s);
-        case kScanVariantTma12x12: return launch_tma<12, 12>(a, grid, s);
-        case kScanVariantTma4x12: return launch_tma<4, 12>(a, grid, s);
-        case kScanVariantTma4x8: return launch_tma<4, 8>(a, grid, s);
+        case kScanVariantTma8x24: return launch_tma<8, 24>(a, grid, s, overlap);
+        case kScanVariantTma12x24: return launch_tma<12, 24>(a, grid, s, overlap);
+        case kScanVariantTma8x16: return launch_tma<8, 16>(a, grid, s, overlap);
+        case kScanVariantTma6x12: return launch_tma<6, 12>(a, grid, s, overlap);
+        case kScanVariantTma12x12: return launch_tma<12, 12>(a, grid, s, overlap);
+        case kScanVariantTma4x12: return launch_tma<4, 12>(a, grid, s, overlap);
+        case kScanVariantTma4x8: return launch_tma<4, 8>(a, grid, s, overlap);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -274,6 +274,12 @@ class Engine:
         check(self._L.rf_search_keys_device(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k),
                                             int(out_keys_ptr), int(stream) or None))
 
+    def set_stream_overlap(self, stream: int, allow: bool = True) -> None:
+        """Promise for the device-resident searches on `stream` (see rf_stream_set_overlap in rf_b200.h): no
+        kernel enqueued between two searches writes their query buffer, so scan launches may overlap the
+        previous kernel's tail (programmatic dependent launch)."""
+        check(self._L.rf_stream_set_overlap(self.handle, int(stream) or None, 1 if allow else 0))
+
     def search_keys_device_scoped(self, q_ptr: int, nq: int, scopes, k: int, out_keys_ptr: int, stream: int = 0) -> None:
         """Device-resident search with one scope per query (`scopes`: list of lists, or a CSR tuple)."""
         segs, off = scopes if isinstance(scopes, tuple) else scopes_to_csr(scopes)
