@@ -132,6 +132,19 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
               const uint32_t *seg_off, uint32_t k, uint64_t *out_ids, int32_t *out_scores,
               float *out_cos, uint32_t *out_counts);
 
+/* The same search in two halves, for a host that wants several searches in flight from one thread (the
+ * engine group launches one per GPU, then collects them): rf_search_begin validates, takes a search
+ * context and enqueues the work; rf_search_end blocks until the results are in the caller's buffers and
+ * ALWAYS returns the context to the pool (also when it fails).  Every successful begin must be followed by
+ * exactly one end.  out_q (RF_DIM, may be NULL) receives the query vector of a text search. */
+typedef struct rf_pending rf_pending;
+int rf_search_begin(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs,
+                    const uint32_t *seg_off, uint32_t k, rf_pending **out);
+int rf_search_text_begin(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
+                         const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k, rf_pending **out);
+int rf_search_end(rf_engine *e, rf_pending *p, uint64_t *out_ids, int32_t *out_scores, float *out_cos,
+                  uint32_t *out_counts, int8_t *out_q);
+
 /* Same, from query text: tokenise + hash on the GPU, then search, no host round trip between.
  * (MockGeminiRag._contents_to_text picks the text, gemini_rag.py:640-654.) */
 int rf_search_text(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs,
@@ -223,6 +236,66 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
                      uint32_t n_segs, const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights,
                      uint32_t k, uint64_t *out_ids, int32_t *out_scores, float *out_cos,
                      uint32_t *out_count, int8_t *out_q /* RF_DIM, may be NULL */);
+
+/* ---- engine group: several GPUs behind ONE index in one process ----------------------------------------
+ * The reference's backend is one object per process behind get_rag_client() (gemini_rag.py:721-725), called
+ * by the chat route (routes/chat.py:499-505) and the ingest worker (services/ingestion.py:45-52); the north
+ * star shards large corpora over the 8 GPUs of a box.  A group owns one engine per listed device and
+ * presents the single-engine calls: store numbers are the same on every device, chunk ids are global
+ * (engine d numbers its rows from id_bases[d]; NULL = d * floor((2^32 - 2) / n_devices)), placement decides
+ * where a document's rows go, and a search runs concurrently on every device that holds rows of the scope,
+ * the per-device top-k lists (k keys each, landing in mapped host memory) being merged on the host under the
+ * RF-1 order -- a total order, so the result equals the single-engine answer bit for bit.  A device may be
+ * listed twice (two engines on one GPU): that is how the single-GPU test-suite covers this code. */
+#define RF_GROUP_MAX 8u
+enum {
+    RF_PLACE_STORE = 0,   /* whole stores per device: store g lives on device g % n (a store-scoped query touches one GPU) */
+    RF_PLACE_SPREAD = 1   /* each document goes to the device holding the fewest rows (one huge store is sharded by chunk) */
+};
+typedef struct rf_group rf_group;
+typedef struct rf_group_config {
+    uint32_t struct_size;     /* sizeof(rf_group_config) */
+    uint32_t n_devices;       /* 1 .. RF_GROUP_MAX */
+    const int32_t *devices;   /* CUDA ordinals [n_devices] */
+    const uint64_t *id_bases; /* [n_devices] or NULL */
+    uint32_t n_contexts;      /* concurrent searches per device; 0 -> 8 */
+    uint32_t placement;       /* RF_PLACE_* */
+    uint64_t capacity_rows;   /* rows reserved PER DEVICE */
+} rf_group_config;
+int rf_group_create(const rf_group_config *cfg, rf_group **out);
+int rf_group_destroy(rf_group *g);
+int rf_group_size(rf_group *g, uint32_t *n_devices);
+int rf_group_engine(rf_group *g, uint32_t index, rf_engine **out);  /* the engine of one device (borrowed) */
+int rf_group_stats(rf_group *g, rf_stats *total, rf_stats *per_device /* [n_devices] or NULL */);
+const char *rf_group_last_error(void);
+/* stores / ingest / deletes: as rf_store_*, rf_ingest_*, rf_doc_tombstone, with group store numbers */
+int rf_group_store_open(rf_group *g, const char *fs_name, uint32_t *store);
+int rf_group_store_lookup(rf_group *g, const char *fs_name, uint32_t *store);
+int rf_group_store_drop(rf_group *g, uint32_t store);
+int rf_group_ingest_text(rf_group *g, uint32_t store, uint64_t doc_id, const uint8_t *utf8, size_t n,
+                         uint64_t *first_chunk, uint32_t *n_chunks, int64_t *spans, uint32_t max_spans);
+int rf_group_ingest_features(rf_group *g, uint32_t store, uint64_t doc_id, const int8_t *rows, uint64_t n_rows,
+                             uint64_t *first_chunk);
+/* RF-1 synthetic corpus.  RF_PLACE_SPREAD: rows_per_store must be 0; the n_rows counters are cut into
+ * n_devices contiguous runs, device d generating run d (with id_bases[d] = start_counter + start of run d
+ * the chunk ids equal those of one engine holding the whole corpus).  RF_PLACE_STORE: store first_store + i
+ * takes rows [i * rows_per_store, ...) on device (first_store + i) % n_devices. */
+int rf_group_ingest_synthetic(rf_group *g, uint32_t first_store, uint64_t rows_per_store, uint64_t seed,
+                              uint64_t start_counter, uint64_t n_rows, const uint16_t *zipf_vocab);
+int rf_group_doc_tombstone(rf_group *g, uint64_t doc_id);
+/* queries: as rf_search / rf_search_text_w (HOST buffers; blocks until the merged results are in them) */
+int rf_group_search(rf_group *g, const int8_t *q, uint32_t nq, const uint32_t *stores, const uint32_t *store_off,
+                    uint32_t k, uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts);
+int rf_group_search_text(rf_group *g, const uint8_t *utf8, size_t n, const uint32_t *stores, uint32_t n_stores,
+                         const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k,
+                         uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_count,
+                         int8_t *out_q /* RF_DIM, may be NULL */);
+/* RF-1w: document frequencies summed over the devices (the statistic is a sum over rows) */
+int rf_group_scope_df(rf_group *g, const uint32_t *stores, uint32_t n_stores, uint64_t *out_df, uint64_t *out_n);
+/* durability: "<path>.dev<d>" per device (rf_snapshot_save) + "<path>.group"; load into an empty group of the
+ * same size and placement */
+int rf_group_snapshot_save(rf_group *g, const char *path);
+int rf_group_snapshot_load(rf_group *g, const char *path);
 
 #ifdef __cplusplus
 }

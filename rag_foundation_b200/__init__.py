@@ -9,6 +9,6 @@ hand-written sm_100a CUDA in librf_b200.so (csrc/), reached through the C-ABI in
 There is no CPU fallback and nothing here imports oracle/.
 """
 from .adapter import B200Rag, UploadResult, get_rag_client  # noqa: F401
-from .engine import Engine, unpack_keys  # noqa: F401
+from .engine import Engine, EngineGroup, unpack_keys  # noqa: F401
 
-__all__ = ["B200Rag", "UploadResult", "get_rag_client", "Engine", "unpack_keys"]
+__all__ = ["B200Rag", "UploadResult", "get_rag_client", "Engine", "EngineGroup", "unpack_keys"]

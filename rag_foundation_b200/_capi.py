@@ -30,6 +30,15 @@ class rf_peer_exchange(C.Structure):
                 ("timeout_flag_dev", C.c_void_p)]
 
 
+class rf_group_config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_devices", C.c_uint32), ("devices", C.c_void_p), ("id_bases", C.c_void_p),
+                ("n_contexts", C.c_uint32), ("placement", C.c_uint32), ("capacity_rows", C.c_uint64)]
+
+
+RF_PLACE_STORE, RF_PLACE_SPREAD = 0, 1
+RF_GROUP_MAX = 8
+
+
 class rf_stats(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("capacity_rows", C.c_uint64), ("n_stores", C.c_uint64),
                 ("n_docs", C.c_uint64), ("hbm_bytes", C.c_uint64), ("searches", C.c_uint64),
@@ -57,6 +66,9 @@ SIGNATURES = {
     "rf_snapshot_load": (_i32, [_vp, C.c_char_p]),
     "rf_rows_read": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp]),
     "rf_search": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "rf_search_begin": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "rf_search_text_begin": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
+    "rf_search_end": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_text_in": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "rf_search_keys_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
@@ -70,6 +82,24 @@ SIGNATURES = {
     "rf_idf_weights": (_i32, [_vp, _u64, _u32, _vp]),
     "rf_weight_query": (_i32, [_vp, _vp, _u32, _vp]),
     "rf_search_text_w": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "rf_group_create": (_i32, [C.POINTER(rf_group_config), C.POINTER(_vp)]),
+    "rf_group_destroy": (_i32, [_vp]),
+    "rf_group_size": (_i32, [_vp, C.POINTER(_u32)]),
+    "rf_group_engine": (_i32, [_vp, _u32, C.POINTER(_vp)]),
+    "rf_group_stats": (_i32, [_vp, C.POINTER(rf_stats), _vp]),
+    "rf_group_last_error": (C.c_char_p, []),
+    "rf_group_store_open": (_i32, [_vp, C.c_char_p, C.POINTER(_u32)]),
+    "rf_group_store_lookup": (_i32, [_vp, C.c_char_p, C.POINTER(_u32)]),
+    "rf_group_store_drop": (_i32, [_vp, _u32]),
+    "rf_group_ingest_text": (_i32, [_vp, _u32, _u64, _vp, _sz, C.POINTER(_u64), C.POINTER(_u32), _vp, _u32]),
+    "rf_group_ingest_features": (_i32, [_vp, _u32, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "rf_group_ingest_synthetic": (_i32, [_vp, _u32, _u64, _u64, _u64, _u64, _vp]),
+    "rf_group_doc_tombstone": (_i32, [_vp, _u64]),
+    "rf_group_search": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "rf_group_search_text": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "rf_group_scope_df": (_i32, [_vp, _vp, _u32, _vp, C.POINTER(_u64)]),
+    "rf_group_snapshot_save": (_i32, [_vp, C.c_char_p]),
+    "rf_group_snapshot_load": (_i32, [_vp, C.c_char_p]),
 }
 
 _lib = None
@@ -98,14 +128,14 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def check(code: int) -> None:
+def check(code: int, group: bool = False) -> None:
     """Map C-ABI error codes onto the exceptions the reference's callers handle:
     RF_EBUSY -> TimeoutError (retryable: gemini_rag.py:22-27, routes/chat.py:1076);
     everything else -> RuntimeError (-> `unexpected_error` frame, routes/chat.py:1130-1143)."""
     if code == RF_OK:
         return
     L = lib()
-    detail = (L.rf_last_error() or b"").decode("utf-8", "replace") or L.rf_strerror(code).decode()
+    detail = ((L.rf_group_last_error() if group else L.rf_last_error()) or b"").decode("utf-8", "replace") or L.rf_strerror(code).decode()
     if code == RF_EBUSY:
         raise TimeoutError(f"librf_b200: {detail}")
     raise RfError(code, detail)

@@ -26,6 +26,7 @@ from typing import Any, Dict, Generator, List, Optional, Sequence, Union
 import numpy as np
 
 from .engine import Engine
+from .metrics import gemini_calls_total, gemini_latency
 
 TOPK_DEFAULT = int(os.environ.get("RAG_TOPK", "10"))
 SNIPPET_MAX_BYTES = 1024
@@ -55,14 +56,20 @@ class _Doc:
 class Registry:
     """Process-global state behind every B200Rag facade: the engine and the chunk sidecar."""
 
+    SIDECAR = "sidecar.msgpack"
+
     def __init__(self, engine: Engine):
         self.engine = engine
         self.lock = threading.RLock()
+        # an upload (engine ingest + registration here) and a snapshot exclude each other, so the
+        # engine file and the sidecar written by save() always describe the same set of documents
+        self.ingest_lock = threading.Lock()
         self.docs: Dict[int, _Doc] = {}
         self.doc_by_file: Dict[str, int] = {}
         self.first_chunks: List[int] = []   # sorted, parallel to first_chunk_doc
         self.first_chunk_doc: List[int] = []
         self.ops: Dict[str, dict] = {}
+        self.deleted_stores: set = set()
         self.next_doc = 1
 
     def chunk_to_doc(self, chunk_id: int) -> Optional[tuple]:
@@ -75,31 +82,72 @@ class Registry:
                 return None
             return d, chunk_id - d.first_chunk
 
+    def add_doc(self, doc: _Doc) -> None:
+        with self.lock:
+            self.docs[doc.doc_id] = doc
+            self.doc_by_file[doc.file_id] = doc.doc_id
+            if doc.n_chunks:
+                i = bisect.bisect_right(self.first_chunks, doc.first_chunk)
+                self.first_chunks.insert(i, doc.first_chunk)
+                self.first_chunk_doc.insert(i, doc.doc_id)
+
+    def forget_doc(self, doc_id: int) -> Optional[_Doc]:
+        """Drop a deleted document entirely -- its bytes, spans, metadata and index entries (the
+        reference's cleanup path, services/cleanup.py:37,66, means the data to be gone; the engine may hand
+        its chunk ids to a later document)."""
+        with self.lock:
+            doc = self.docs.pop(doc_id, None)
+            if doc is None:
+                return None
+            self.doc_by_file.pop(doc.file_id, None)
+            if doc.n_chunks:
+                i = bisect.bisect_left(self.first_chunks, doc.first_chunk)
+                while i < len(self.first_chunks) and self.first_chunks[i] == doc.first_chunk:
+                    if self.first_chunk_doc[i] == doc_id:
+                        del self.first_chunks[i]
+                        del self.first_chunk_doc[i]
+                        break
+                    i += 1
+            return doc
 
     # ---- durability: engine snapshot + the chunk-text sidecar (SURVEY.md 8f-2) ----
     def save(self, directory: str) -> None:
-        import pickle
+        """Engine snapshot(s) + sidecar, both written to a temporary name, fsync'ed and renamed.  The sidecar
+        is msgpack (plain data: nothing executable is read back at load)."""
+        import msgpack
         os.makedirs(directory, exist_ok=True)
-        with self.lock:
+        with self.ingest_lock, self.lock:
             self.engine.save_snapshot(os.path.join(directory, "index.rfsnap"))
-            side = {"docs": self.docs, "doc_by_file": self.doc_by_file, "first_chunks": self.first_chunks,
-                    "first_chunk_doc": self.first_chunk_doc, "ops": self.ops, "next_doc": self.next_doc}
-            tmp = os.path.join(directory, "sidecar.pkl.tmp")
+            docs = [{"doc_id": d.doc_id, "store_name": d.store_name, "display_name": d.display_name, "file_id": d.file_id,
+                     "first_chunk": d.first_chunk, "n_chunks": d.n_chunks,
+                     "spans": np.ascontiguousarray(d.spans, dtype="<i8").tobytes(), "data": d.data,
+                     "custom_metadata": d.custom_metadata, "meta": d.meta} for d in self.docs.values()]
+            side = {"version": 2, "docs": docs, "ops": self.ops, "next_doc": self.next_doc,
+                    "deleted_stores": sorted(self.deleted_stores)}
+            tmp = os.path.join(directory, self.SIDECAR + ".tmp")
             with open(tmp, "wb") as f:
-                pickle.dump(side, f, protocol=pickle.HIGHEST_PROTOCOL)
-            os.replace(tmp, os.path.join(directory, "sidecar.pkl"))
+                f.write(msgpack.packb(side, use_bin_type=True))
+                f.flush()
+                os.fsync(f.fileno())
+            os.replace(tmp, os.path.join(directory, self.SIDECAR))
 
     @classmethod
     def load(cls, engine: Engine, directory: str) -> "Registry":
-        """`engine` must be freshly created (empty).  The sidecar is this process's own pickle."""
-        import pickle
+        """`engine` must be freshly created (empty)."""
+        import msgpack
         engine.load_snapshot(os.path.join(directory, "index.rfsnap"))
         reg = cls(engine)
-        with open(os.path.join(directory, "sidecar.pkl"), "rb") as f:
-            side = pickle.load(f)
-        reg.docs, reg.doc_by_file = side["docs"], side["doc_by_file"]
-        reg.first_chunks, reg.first_chunk_doc = side["first_chunks"], side["first_chunk_doc"]
-        reg.ops, reg.next_doc = side["ops"], side["next_doc"]
+        with open(os.path.join(directory, cls.SIDECAR), "rb") as f:
+            side = msgpack.unpackb(f.read(), raw=False, strict_map_key=False)
+        if side.get("version") != 2:
+            raise ValueError("unknown sidecar version")
+        for d in side["docs"]:
+            spans = np.frombuffer(d["spans"], dtype="<i8").reshape(-1, 2).copy()
+            reg.add_doc(_Doc(int(d["doc_id"]), d["store_name"], d["display_name"], d["file_id"], int(d["first_chunk"]),
+                             int(d["n_chunks"]), spans, bytes(d["data"]), d.get("custom_metadata"), meta=d.get("meta") or {}))
+        reg.ops = dict(side["ops"])
+        reg.next_doc = int(side["next_doc"])
+        reg.deleted_stores = set(side.get("deleted_stores") or [])
         return reg
 
 
@@ -109,13 +157,25 @@ _registry_lock = threading.Lock()
 
 def get_registry() -> Registry:
     """Lazily create the process-global engine from env flags (kept beside, not inside, the
-    reference's Settings -- SURVEY.md §5): RAG_B200_CAPACITY_ROWS, RAG_B200_DEVICE."""
+    reference's Settings -- SURVEY.md §5): RAG_B200_CAPACITY_ROWS, RAG_B200_DEVICE, or RAG_B200_DEVICES=0,1,..
+    for an engine group over several GPUs."""
     global _registry
     with _registry_lock:
         if _registry is None:
             cap = int(os.environ.get("RAG_B200_CAPACITY_ROWS", str(4_000_000)))
-            dev = int(os.environ.get("RAG_B200_DEVICE", "0"))
-            _registry = Registry(Engine(capacity_rows=cap, device=dev, n_contexts=int(os.environ.get("RAG_B200_CONTEXTS", "16"))))
+            n_ctx = int(os.environ.get("RAG_B200_CONTEXTS", "16"))
+            devices = os.environ.get("RAG_B200_DEVICES", "").strip()
+            if devices:
+                # several GPUs behind ONE adapter: an engine per device in this process, stores placed by
+                # RAG_B200_PLACEMENT ("store": whole stores per GPU; "spread": documents round-robin, so one
+                # huge store is sharded by chunk); capacity is per device
+                from .engine import EngineGroup
+                devs = [int(x) for x in devices.split(",") if x.strip() != ""]
+                _registry = Registry(EngineGroup(devs, capacity_rows=cap, n_contexts=n_ctx,
+                                                 placement=os.environ.get("RAG_B200_PLACEMENT", "store")))
+            else:
+                dev = int(os.environ.get("RAG_B200_DEVICE", "0"))
+                _registry = Registry(Engine(capacity_rows=cap, device=dev, n_contexts=n_ctx))
         return _registry
 
 
@@ -184,6 +244,12 @@ def _get_response_name(response: Any, *, context: str) -> str:  # gemini_rag.py:
     return name
 
 
+def stream_lead(grounding: Sequence[dict]) -> str:
+    """Text of the first stream chunk (the mock's is "[mock-mode] " + question, gemini_rag.py:676-683)."""
+    lead = grounding[0]["text"].strip().splitlines()[0][:200] if grounding and grounding[0]["text"].strip() else "no matching passages"
+    return f"[b200-retrieval] {lead}"
+
+
 def build_final_response(grounding: Sequence[dict]) -> Any:
     """Final stream chunk, shaped like MockGeminiRag._mock_response (gemini_rag.py:704-718) but
     with one grounding chunk per retrieved citation, in rank order."""
@@ -227,42 +293,52 @@ class B200Rag:
             return
         reg.engine.drop_store(seg)
         with reg.lock:
-            for d in reg.docs.values():
-                if d.store_name == store_name:
-                    d.deleted = True
+            reg.deleted_stores.add(store_name)
+            for doc_id in [d.doc_id for d in reg.docs.values() if d.store_name == store_name]:
+                reg.forget_doc(doc_id)
 
     # -------- Upload & operations (gemini_rag.py:307-352, 426-460, 614-638) --------
     def upload_file(self, store_name: str, file_path: str, *, display_name: Optional[str] = None,
                     custom_metadata: Optional[List[Dict[str, Union[str, float, int]]]] = None,
                     chunking_config: Optional[Dict] = None) -> UploadResult:
-        reg = self._reg
         with open(file_path, "rb") as f:
             data = f.read()
-        seg = reg.engine.lookup_store(store_name)
-        if seg is None:
-            seg = reg.engine.open_store(store_name)   # stores created before this process started
-        with reg.lock:
-            doc_id = reg.next_doc
-            reg.next_doc += 1
+        return self.upload_bytes(store_name, data, display_name=display_name or os.path.basename(file_path),
+                                 custom_metadata=custom_metadata)
+
+    def upload_bytes(self, store_name: str, data: bytes, *, display_name: str,
+                     custom_metadata: Optional[Any] = None) -> UploadResult:
+        """upload_file once the document bytes are in memory (what the engine daemon receives)."""
+        reg = self._reg
+        start = time.perf_counter()
         op_name = f"operations/b200-{uuid.uuid4().hex}"
-        file_id = f"files/b200-{doc_id:016x}"
         try:
-            first, n_chunks, spans = reg.engine.ingest_text(seg, doc_id, data)
+            seg = reg.engine.lookup_store(store_name)
+            if seg is None:
+                # a store this engine has never seen (created before a restart without a snapshot) is an
+                # error unless RAG_B200_AUTOCREATE_STORES=1; a store that was deleted here always is
+                if store_name in reg.deleted_stores or os.environ.get("RAG_B200_AUTOCREATE_STORES", "0") != "1":
+                    raise ValueError(f"unknown or deleted store {store_name!r}")
+                seg = reg.engine.open_store(store_name)
+            with reg.ingest_lock:
+                with reg.lock:
+                    doc_id = reg.next_doc
+                    reg.next_doc += 1
+                file_id = f"files/b200-{doc_id:016x}"
+                first, n_chunks, spans = reg.engine.ingest_text(seg, doc_id, data)
+                reg.add_doc(_Doc(doc_id, store_name, display_name, file_id, first, n_chunks, spans, data, custom_metadata,
+                                 meta=normalize_custom_metadata(custom_metadata)))
+                with reg.lock:
+                    reg.ops[op_name] = {"done": True, "error": None, "n_chunks": n_chunks, "file_id": file_id}
+            gemini_calls_total.labels("upload", "ok").inc()
+            return UploadResult(operation_name=op_name, file_id=file_id)
         except Exception as exc:
             with reg.lock:
                 reg.ops[op_name] = {"done": True, "error": str(exc)}
+            gemini_calls_total.labels("upload", "error").inc()
             raise
-        doc = _Doc(doc_id, store_name, display_name or os.path.basename(file_path), file_id, first, n_chunks, spans,
-                   data, custom_metadata, meta=normalize_custom_metadata(custom_metadata))
-        with reg.lock:
-            reg.docs[doc_id] = doc
-            reg.doc_by_file[file_id] = doc_id
-            if n_chunks:
-                i = bisect.bisect_right(reg.first_chunks, first)
-                reg.first_chunks.insert(i, first)
-                reg.first_chunk_doc.insert(i, doc_id)
-            reg.ops[op_name] = {"done": True, "error": None, "n_chunks": n_chunks, "file_id": file_id}
-        return UploadResult(operation_name=op_name, file_id=file_id)
+        finally:
+            gemini_latency.labels("upload").observe(time.perf_counter() - start)
 
     def op_status(self, op_name: str | dict) -> dict[str, Any]:
         name = _get_response_name(op_name, context="operation status request")
@@ -281,9 +357,10 @@ class B200Rag:
             doc = reg.docs.get(doc_id) if doc_id is not None else None
             if doc is None or doc.deleted:
                 return
-            doc.deleted = True
+            doc.deleted = True          # no second tombstone from a concurrent delete
         if doc.n_chunks:
-            reg.engine.tombstone_doc(doc.doc_id)
+            reg.engine.tombstone_doc(doc.doc_id)   # masked in the index first, forgotten here after
+        reg.forget_doc(doc.doc_id)
 
     # -------- Query (gemini_rag.py:472-551, 656-694) --------
     def retrieve(self, text: str, store_names: Sequence[str], k: Optional[int] = None,
@@ -327,16 +404,34 @@ class B200Rag:
 
     def ask(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
             system: str | None = None) -> Any:
-        return build_final_response(self.retrieve(contents_to_text(contents), store_names, metadata_filter=metadata_filter))
+        start = time.perf_counter()
+        try:
+            resp = build_final_response(self.retrieve(contents_to_text(contents), store_names, metadata_filter=metadata_filter))
+            gemini_calls_total.labels("generate", "ok").inc()
+            return resp
+        except Exception:
+            gemini_calls_total.labels("generate", "error").inc()
+            raise
+        finally:
+            gemini_latency.labels("generate").observe(time.perf_counter() - start)
 
     def ask_stream(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,
                    system: str | None = None) -> Generator:
-        text = contents_to_text(contents)
-        grounding = self.retrieve(text, store_names, metadata_filter=metadata_filter)   # the GPU work; no lock is held across the yields
-        lead = grounding[0]["text"].strip().splitlines()[0][:200] if grounding else "no matching passages"
-        yield SimpleNamespace(text=f"[b200-retrieval] {lead}", candidates=None,
-                              usage_metadata=SimpleNamespace(prompt_token_count=0, candidates_token_count=0))
-        yield build_final_response(grounding)
+        start = time.perf_counter()
+        try:
+            text = contents_to_text(contents)
+            grounding = self.retrieve(text, store_names, metadata_filter=metadata_filter)   # the GPU work; no lock is held across the yields
+            yield SimpleNamespace(text=stream_lead(grounding), candidates=None,
+                                  usage_metadata=SimpleNamespace(prompt_token_count=0, candidates_token_count=0))
+            yield build_final_response(grounding)
+            gemini_calls_total.labels("generate_stream", "ok").inc()
+        except GeneratorExit:            # the route abandoned the stream (client disconnect, chat.py:562-566)
+            raise
+        except Exception:
+            gemini_calls_total.labels("generate_stream", "error").inc()
+            raise
+        finally:
+            gemini_latency.labels("generate_stream").observe(time.perf_counter() - start)
 
     # -------- Citations (gemini_rag.py:554-599) --------
     @staticmethod
@@ -368,6 +463,16 @@ class B200Rag:
     @staticmethod
     def new_stream_ids() -> tuple[str, str]:
         return str(uuid.uuid4()), str(uuid.uuid4())
+
+
+# Inside the backend process the reference's own implementations of the pure wire helpers are used
+# (nothing to keep in step); the restatements above serve the daemon and the tests, where `app` is absent.
+try:
+    from app.services.gemini_rag import GeminiRag as _RefGeminiRag   # type: ignore
+    B200Rag.extract_citations_from_response = staticmethod(_RefGeminiRag.extract_citations_from_response)
+    B200Rag.new_stream_ids = staticmethod(_RefGeminiRag.new_stream_ids)
+except Exception:   # noqa: BLE001
+    _RefGeminiRag = None
 
 
 def get_rag_client():

@@ -157,6 +157,16 @@ struct SearchCtx {
     DeviceBuf d_in, d_out, d_partial, d_tickets;
     uint32_t launches = 0;   // parity selects the sync set
     uint32_t seq = 0;        // completion sequence number written by the kernel into m_out
+    // the search in flight on this context, between rf_search_begin and rf_search_end
+    struct Pending {
+        bool active = false;
+        bool mapped = false;       // results land in m_out (spin on the completion word) / are copied to h_out (stream sync)
+        uint32_t nq = 0, k = 0;
+        size_t flag_off = 0;
+        uint32_t done_seq = 0;
+        bool has_q = false;        // text searches: the query vector follows the results in h_out
+        std::chrono::steady_clock::time_point t_launched;
+    } pend;
 };
 
 // Scratch of the device-resident searches on one caller stream (rf_search_keys_device*): per STREAM, not
@@ -442,17 +452,11 @@ struct OutLayout {
     }
 };
 
-// One search on a context: (blob upload unless everything rides in the kernel parameters) + scan;
-// the last block writes ids / scores / cosines straight into mapped pinned host memory, so there
-// is no device-to-host copy to enqueue: launch, wait, hand the results to the caller.
-int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_host, uint32_t nq, uint32_t k, bool shared,
-               uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
+// One search on a context, first half: (blob upload unless everything rides in the kernel parameters) +
+// scan launch; the last block writes ids / scores / cosines straight into mapped pinned host memory when
+// the batch is small, so there is no device-to-host copy to enqueue.  search_wait is the second half.
+int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_host, uint32_t nq, uint32_t k, bool shared) {
     const auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](int slot, std::chrono::steady_clock::time_point from) {
-        const auto now = std::chrono::steady_clock::now();
-        if (e->profile) e->prof_ns[slot] += std::chrono::duration_cast<std::chrono::nanoseconds>(now - from).count();
-        return now;
-    };
     const OutLayout L(nq, k);
     const uint32_t X = pick_blocks(e, nq, b.max_tiles);
     const size_t flag_off = (L.total + 15) & ~static_cast<size_t>(15);   // [seq word, finished-query counter]
@@ -501,48 +505,73 @@ int run_search(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_ho
     a.out_scores = reinterpret_cast<int32_t *>(d_out + L.off_scores);
     a.out_cos = reinterpret_cast<float *>(d_out + L.off_cos);
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
-    const uint8_t *h = nullptr;
-    std::chrono::steady_clock::time_point t1;
+    SearchCtx::Pending &pd = c->pend;
+    pd = SearchCtx::Pending{};
+    pd.mapped = mapped;
+    pd.nq = nq;
+    pd.k = k;
+    // The query and the plan come from the kernel parameters or from the copy just enqueued, never from a
+    // preceding kernel: the launch may overlap its predecessor's tail.
     if (mapped) {
         // The flag word sits right after the results in the same mapped allocation.
         volatile uint32_t *h_flag = reinterpret_cast<volatile uint32_t *>(static_cast<uint8_t *>(c->m_out.h) + flag_off);
         h_flag[0] = 0;
         a.done_flag = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->m_out.d) + flag_off);
         a.done_seq = ++c->seq ? c->seq : ++c->seq;
+        pd.flag_off = flag_off;
+        pd.done_seq = a.done_seq;
         RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
-        e->launches.fetch_add(1, std::memory_order_relaxed);
-        t1 = lap(1, t0);
+    } else {
+        a.done_flag = nullptr;
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
+        RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
+                                cudaMemcpyDeviceToHost, c->stream));
+    }
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    pd.active = true;
+    pd.t_launched = std::chrono::steady_clock::now();
+    if (e->profile) e->prof_ns[1] += std::chrono::duration_cast<std::chrono::nanoseconds>(pd.t_launched - t0).count();
+    return RF_OK;
+}
+
+// Second half: wait for the search in flight on `c` and hand its results to the caller.
+int search_wait(rf_engine *e, SearchCtx *c, uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts,
+                int8_t *out_q) {
+    SearchCtx::Pending &pd = c->pend;
+    if (!pd.active) return fail(RF_EINVAL, "no search in flight on this context");
+    pd.active = false;
+    const OutLayout L(pd.nq, pd.k);
+    const uint8_t *h = nullptr;
+    if (pd.mapped) {
         // Spin on the completion word; fall back to the stream's status so a failed launch can
         // never hang the caller.
-        for (uint32_t spins = 0; h_flag[0] != a.done_seq; ++spins) {
+        volatile uint32_t *h_flag = reinterpret_cast<volatile uint32_t *>(static_cast<uint8_t *>(c->m_out.h) + pd.flag_off);
+        for (uint32_t spins = 0; h_flag[0] != pd.done_seq; ++spins) {
             if ((spins & 0x3FFu) == 0x3FFu) {
                 const cudaError_t qe = cudaStreamQuery(c->stream);
                 if (qe == cudaSuccess) break;
                 if (qe != cudaErrorNotReady) return fail(RF_ECUDA, "scan kernel failed: %s", cudaGetErrorString(qe));
             }
         }
-        if (h_flag[0] != a.done_seq) RF_CUDA(cudaStreamSynchronize(c->stream));
+        if (h_flag[0] != pd.done_seq) RF_CUDA(cudaStreamSynchronize(c->stream));
         h = static_cast<const uint8_t *>(c->m_out.h);
     } else {
-        a.done_flag = nullptr;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
-        e->launches.fetch_add(1, std::memory_order_relaxed);
-        RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
-                                cudaMemcpyDeviceToHost, c->stream));
-        t1 = lap(1, t0);
         RF_CUDA(cudaStreamSynchronize(c->stream));
         h = static_cast<const uint8_t *>(c->h_out.p);
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    const auto t2 = lap(2, t1);
-    const size_t n = static_cast<size_t>(nq) * k;
+    const auto t2 = std::chrono::steady_clock::now();
+    const size_t n = static_cast<size_t>(pd.nq) * pd.k;
     memcpy(out_ids, h + L.off_ids, n * 8);
     memcpy(out_scores, h + L.off_scores, n * 4);
     if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
-    if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(nq) * 4);
-    e->searches.fetch_add(nq, std::memory_order_relaxed);
-    lap(3, t2);
-    if (e->profile) e->prof_n += 1;
+    if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(pd.nq) * 4);
+    if (out_q && pd.has_q) memcpy(out_q, h + L.total, RF_DIM);
+    if (e->profile) {
+        e->prof_ns[2] += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - pd.t_launched).count();
+        e->prof_ns[3] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t2).count();
+        e->prof_n += 1;
+    }
     return RF_OK;
 }
 
@@ -1299,12 +1328,12 @@ int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uin
     return RF_OK;
 }
 
-int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off, uint32_t k,
-              uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
-    if (!e || !q || !seg_off || !out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+int rf_search_begin(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off, uint32_t k,
+                    rf_pending **out) {
+    if (!e || !q || !seg_off || !out) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
-    if (nq == 0) return RF_OK;
-    if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    if (nq == 0 || nq > 65535) return fail(RF_EINVAL, "between 1 and 65535 queries per call");
+    *out = nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     // A batch whose queries all have the same scope takes the device-resident route when the
     // tensor-core path pays for it (or the batch is large: one shared plan instead of nq): one H2D of
@@ -1349,13 +1378,13 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
                                            reinterpret_cast<float *>(d_out + L.off_cos), reinterpret_cast<uint32_t *>(d_out + L.off_counts), c->stream));
             e->launches.fetch_add(1, std::memory_order_relaxed);
             RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
-            RF_CUDA(cudaStreamSynchronize(c->stream));
-            const uint8_t *h = static_cast<const uint8_t *>(c->h_out.p);
-            const size_t n = static_cast<size_t>(nq) * k;
-            memcpy(out_ids, h + L.off_ids, n * 8);
-            memcpy(out_scores, h + L.off_scores, n * 4);
-            if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
-            if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(nq) * 4);
+            c->pend = SearchCtx::Pending{};
+            c->pend.nq = nq;
+            c->pend.k = k;
+            c->pend.active = true;
+            c->pend.t_launched = std::chrono::steady_clock::now();
+            g.c = nullptr;     // the caller's rf_search_end releases the context
+            *out = reinterpret_cast<rf_pending *>(c);
             return RF_OK;
         }
     }
@@ -1367,7 +1396,36 @@ int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
     if (e->profile) e->prof_ns[0] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-    return run_search(e, c, b, q, nq, k, false, out_ids, out_scores, out_cos, out_counts);
+    if ((rc = search_launch(e, c, b, q, nq, k, false))) return rc;
+    e->searches.fetch_add(nq, std::memory_order_relaxed);
+    g.c = nullptr;
+    *out = reinterpret_cast<rf_pending *>(c);
+    return RF_OK;
+}
+
+int rf_search_end(rf_engine *e, rf_pending *p, uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts,
+                  int8_t *out_q) {
+    if (!e || !p) return fail(RF_EINVAL, "null argument");
+    SearchCtx *c = reinterpret_cast<SearchCtx *>(p);
+    CtxGuard g{e, c};              // the context goes back to the pool whatever happens below
+    if (!out_ids || !out_scores) {
+        cudaSetDevice(e->cfg.device);
+        cudaStreamSynchronize(c->stream);
+        c->pend.active = false;
+        return fail(RF_EINVAL, "null argument");
+    }
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    return search_wait(e, c, out_ids, out_scores, out_cos, out_counts, out_q);
+}
+
+int rf_search(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off, uint32_t k,
+              uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts) {
+    if (!e || !q || !seg_off || !out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+    if (nq == 0) return (k == 0 || k > RF_TOPK_MAX) ? fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX) : RF_OK;
+    rf_pending *p = nullptr;
+    const int rc = rf_search_begin(e, q, nq, store_segs, seg_off, k, &p);
+    if (rc) return rc;
+    return rf_search_end(e, p, out_ids, out_scores, out_cos, out_counts, nullptr);
 }
 
 int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_q) {
@@ -1403,10 +1461,10 @@ int rf_search_text_in(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_
     return rf_search_text_w(e, utf8, n, store_segs, n_segs, ranges, n_ranges, nullptr, k, out_ids, out_scores, out_cos, out_count, out_q);
 }
 
-int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
-                     const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k, uint64_t *out_ids,
-                     int32_t *out_scores, float *out_cos, uint32_t *out_count, int8_t *out_q) {
-    if (!e || (!utf8 && n) || !out_ids || !out_scores || (!ranges && n_ranges)) return fail(RF_EINVAL, "null argument");
+int rf_search_text_begin(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
+                         const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k, rf_pending **out) {
+    if (!e || (!utf8 && n) || !out || (!ranges && n_ranges)) return fail(RF_EINVAL, "null argument");
+    *out = nullptr;
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (n > (1u << 26)) return fail(RF_EINVAL, "query text too long");
     std::vector<Extent> lim;
@@ -1472,15 +1530,27 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
     e->launches.fetch_add(1);
     uint8_t *ho = static_cast<uint8_t *>(c->h_out.p);
     RF_CUDA(cudaMemcpyAsync(ho + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
-    if (out_q) RF_CUDA(cudaMemcpyAsync(ho + L.total, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
-    RF_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(out_ids, ho + L.off_ids, static_cast<size_t>(k) * 8);
-    memcpy(out_scores, ho + L.off_scores, static_cast<size_t>(k) * 4);
-    if (out_cos) memcpy(out_cos, ho + L.off_cos, static_cast<size_t>(k) * 4);
-    if (out_count) memcpy(out_count, ho + L.off_counts, 4);
-    if (out_q) memcpy(out_q, ho + L.total, RF_DIM);
+    RF_CUDA(cudaMemcpyAsync(ho + L.total, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
+    c->pend = SearchCtx::Pending{};
+    c->pend.nq = 1;
+    c->pend.k = k;
+    c->pend.has_q = true;
+    c->pend.active = true;
+    c->pend.t_launched = std::chrono::steady_clock::now();
     e->searches.fetch_add(1);
+    g.c = nullptr;
+    *out = reinterpret_cast<rf_pending *>(c);
     return RF_OK;
+}
+
+int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t *store_segs, uint32_t n_segs,
+                     const uint64_t *ranges, uint32_t n_ranges, const uint8_t *weights, uint32_t k, uint64_t *out_ids,
+                     int32_t *out_scores, float *out_cos, uint32_t *out_count, int8_t *out_q) {
+    if (!out_ids || !out_scores) return fail(RF_EINVAL, "null argument");
+    rf_pending *p = nullptr;
+    const int rc = rf_search_text_begin(e, utf8, n, store_segs, n_segs, ranges, n_ranges, weights, k, &p);
+    if (rc) return rc;
+    return rf_search_end(e, p, out_ids, out_scores, out_cos, out_count, out_q);
 }
 
 // ---- RF-1w statistics ------------------------------------------------------------------------------

@@ -47,6 +47,39 @@ def scopes_to_csr(scopes: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarr
     return segs, off
 
 
+def _search_text(owner, call, text: bytes, scope: Sequence[int], k: int, ranges, weights):
+    """Shared body of Engine.search_text / EngineGroup.search_text: argument marshalling and the split of a
+    long range list over several launches (the kernel plan holds 64 extents)."""
+    text = bytes(text)
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.uint8)
+        if weights.shape != (RF_DIM,):
+            raise ValueError(f"weights must be uint8 [{RF_DIM}]")
+    rng = None
+    if ranges is not None:
+        rng = np.ascontiguousarray(np.asarray(list(ranges), dtype=np.uint64).reshape(-1, 2))
+        if rng.shape[0] == 0:
+            q0 = owner.featurize_query(text)
+            return (np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32),
+                    q0 if weights is None else owner.weight_query(q0, weights))
+        if rng.shape[0] > owner.RANGES_PER_CALL:   # many matching documents: several launches, merged here
+            parts = [_search_text(owner, call, text, scope, k, rng[i:i + owner.RANGES_PER_CALL], weights)
+                     for i in range(0, rng.shape[0], owner.RANGES_PER_CALL)]
+            ids = np.concatenate([p[0] for p in parts]); sc = np.concatenate([p[1] for p in parts])
+            cs = np.concatenate([p[2] for p in parts])
+            order = np.lexsort((ids, -sc.astype(np.int64)))[:k]   # (score desc, id asc): the RF-1 order
+            return ids[order], sc[order], cs[order], parts[0][3]
+    segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+    ids = np.zeros(k, np.uint64)
+    sc = np.zeros(k, np.int32)
+    cs = np.zeros(k, np.float32)
+    cnt = C.c_uint32()
+    q = np.zeros(RF_DIM, np.int8)
+    call(text, segs, len(scope), rng, weights, k, ids, sc, cs, cnt, q)
+    m = int(cnt.value)
+    return ids[:m], sc[:m], cs[:m], q
+
+
 class Engine:
     """One GPU's share of the chunk index (feature arena in HBM + store extents)."""
 
@@ -200,36 +233,12 @@ class Engine:
         `ranges`: optional sorted, disjoint [(lo, hi), ...] global chunk id ranges to stay inside
         (doc-level metadata filters).  `weights`: optional uint8 [256] RF-1w bucket weights
         (`idf_weights`); the returned q is then the weighted vector."""
-        text = bytes(text)
-        if weights is not None:
-            weights = np.ascontiguousarray(weights, dtype=np.uint8)
-            if weights.shape != (RF_DIM,):
-                raise ValueError(f"weights must be uint8 [{RF_DIM}]")
-        rng = None
-        if ranges is not None:
-            rng = np.ascontiguousarray(np.asarray(list(ranges), dtype=np.uint64).reshape(-1, 2))
-            if rng.shape[0] == 0:
-                q0 = self.featurize_query(text)
-                return (np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.float32),
-                        q0 if weights is None else self.weight_query(q0, weights))
-            if rng.shape[0] > self.RANGES_PER_CALL:   # many matching documents: several launches, merged here
-                parts = [self.search_text(text, scope, k, ranges=rng[i:i + self.RANGES_PER_CALL], weights=weights)
-                         for i in range(0, rng.shape[0], self.RANGES_PER_CALL)]
-                ids = np.concatenate([p[0] for p in parts]); sc = np.concatenate([p[1] for p in parts])
-                cs = np.concatenate([p[2] for p in parts])
-                order = np.lexsort((ids, -sc.astype(np.int64)))[:k]   # (score desc, id asc): the RF-1 order
-                return ids[order], sc[order], cs[order], parts[0][3]
-        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
-        ids = np.zeros(k, np.uint64)
-        sc = np.zeros(k, np.int32)
-        cs = np.zeros(k, np.float32)
-        cnt = C.c_uint32()
-        q = np.zeros(RF_DIM, np.int8)
-        check(self._L.rf_search_text_w(self.handle, text or b"\0", len(text), _ptr(segs), len(scope), _ptr(rng),
+        return _search_text(self, self._search_text_call, text, scope, k, ranges, weights)
+
+    def _search_text_call(self, text, segs, n_segs, rng, weights, k, ids, sc, cs, cnt, q):
+        check(self._L.rf_search_text_w(self.handle, text or b"\0", len(text), _ptr(segs), n_segs, _ptr(rng),
                                        0 if rng is None else rng.shape[0], _ptr(weights), int(k), _ptr(ids), _ptr(sc),
                                        _ptr(cs), C.byref(cnt), _ptr(q)))
-        m = int(cnt.value)
-        return ids[:m], sc[:m], cs[:m], q
 
     def featurize_query(self, text: bytes) -> np.ndarray:
         text = bytes(text)
@@ -301,6 +310,173 @@ class Engine:
     def merge_topk_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, out_keys_ptr: int, stream: int = 0) -> None:
         check(self._L.rf_merge_topk_device(self.handle, int(keys_ptr), int(n_lists), int(nq), int(k), int(out_keys_ptr),
                                            int(stream) or None))
+
+
+class EngineGroup:
+    """Several GPUs behind one index in THIS process (include/rf_b200.h, rf_group_*): the same surface as
+    Engine for everything the adapter uses, so `Registry(EngineGroup([...]))` is a drop-in.  Stores keep one
+    number on every device, chunk ids are global, a search runs on every device that holds rows of the scope
+    and the per-device top-k lists are merged on the host (bit-identical to one engine holding everything).
+    `devices` may repeat an ordinal (two engines on one GPU) -- how the single-GPU test-suite covers it."""
+
+    RANGES_PER_CALL = Engine.RANGES_PER_CALL
+
+    def __init__(self, devices: Sequence[int], capacity_rows: int, n_contexts: int = 8, placement: str = "store",
+                 id_bases: Optional[Sequence[int]] = None):
+        self._L = lib()
+        placements = {"store": _capi.RF_PLACE_STORE, "spread": _capi.RF_PLACE_SPREAD}
+        if placement not in placements:
+            raise ValueError("placement must be 'store' or 'spread'")
+        devs = np.asarray(list(devices), dtype=np.int32)
+        bases = None if id_bases is None else np.asarray(list(id_bases), dtype=np.uint64)
+        if bases is not None and bases.shape != devs.shape:
+            raise ValueError("one id base per device")
+        cfg = _capi.rf_group_config(C.sizeof(_capi.rf_group_config), int(devs.size), _ptr(devs), _ptr(bases), int(n_contexts),
+                                    placements[placement], int(capacity_rows))
+        h = C.c_void_p()
+        check(self._L.rf_group_create(C.byref(cfg), C.byref(h)), group=True)
+        self._h = h
+        self.devices = [int(d) for d in devs]
+        self.placement = placement
+        self.capacity_rows = int(capacity_rows)
+        self._zipf = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.rf_group_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise RuntimeError("engine group is closed")
+        return self._h
+
+    def stats(self, per_device: bool = False):
+        st = _capi.rf_stats()
+        per = (_capi.rf_stats * len(self.devices))()
+        check(self._L.rf_group_stats(self.handle, C.byref(st), C.cast(per, C.c_void_p)), group=True)
+        tot = {f: int(getattr(st, f)) for f, _ in st._fields_}
+        if not per_device:
+            return tot
+        return tot, [{f: int(getattr(p, f)) for f, _ in p._fields_} for p in per]
+
+    # ------------------------------------------------------------------ stores / ingest / deletes
+    def open_store(self, fs_name: str) -> int:
+        s = C.c_uint32()
+        check(self._L.rf_group_store_open(self.handle, fs_name.encode("utf-8"), C.byref(s)), group=True)
+        return int(s.value)
+
+    def lookup_store(self, fs_name: str) -> Optional[int]:
+        s = C.c_uint32()
+        rc = self._L.rf_group_store_lookup(self.handle, fs_name.encode("utf-8"), C.byref(s))
+        if rc == _capi.RF_ENOTFOUND:
+            return None
+        check(rc, group=True)
+        return int(s.value)
+
+    def drop_store(self, store: int) -> None:
+        check(self._L.rf_group_store_drop(self.handle, int(store)), group=True)
+
+    def ingest_text(self, store: int, doc_id: int, data: bytes, want_spans: bool = True):
+        data = bytes(data)
+        first = C.c_uint64()
+        nch = C.c_uint32()
+        max_spans = (len(data) // 2 + 1 + 111) // 112 + 1 if want_spans else 0
+        spans = np.zeros((max(max_spans, 1), 2), np.int64)
+        check(self._L.rf_group_ingest_text(self.handle, int(store), int(doc_id), data or b"\0", len(data), C.byref(first),
+                                           C.byref(nch), _ptr(spans) if want_spans else None, max_spans), group=True)
+        n = int(nch.value)
+        return int(first.value), n, spans[:n].copy()
+
+    def ingest_features(self, store: int, doc_id: int, rows) -> int:
+        rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, RF_DIM)
+        first = C.c_uint64()
+        check(self._L.rf_group_ingest_features(self.handle, int(store), int(doc_id), _ptr(rows), rows.shape[0], C.byref(first)), group=True)
+        return int(first.value)
+
+    def ingest_synthetic(self, first_store: int, rows_per_store: int, seed: int, start_counter: int, n_rows: int) -> None:
+        if self._zipf is None:
+            self._zipf = load_zipf_vocab()
+        check(self._L.rf_group_ingest_synthetic(self.handle, int(first_store), int(rows_per_store), int(seed), int(start_counter),
+                                                int(n_rows), _ptr(self._zipf)), group=True)
+
+    def tombstone_doc(self, doc_id: int) -> None:
+        check(self._L.rf_group_doc_tombstone(self.handle, int(doc_id)), group=True)
+
+    def save_snapshot(self, path: str) -> None:
+        check(self._L.rf_group_snapshot_save(self.handle, os.fsencode(path)), group=True)
+
+    def load_snapshot(self, path: str) -> None:
+        check(self._L.rf_group_snapshot_load(self.handle, os.fsencode(path)), group=True)
+
+    # ------------------------------------------------------------------ query
+    def search(self, q, scopes, k: int = 10):
+        """As Engine.search: q int8 [nq, 256] (host), one list of stores per query or a CSR pair."""
+        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, RF_DIM)
+        nq = q.shape[0]
+        if isinstance(scopes, tuple) and len(scopes) == 2 and isinstance(scopes[0], np.ndarray):
+            segs = np.ascontiguousarray(scopes[0], dtype=np.uint32)
+            off = np.ascontiguousarray(scopes[1], dtype=np.uint32)
+            if off.shape != (nq + 1,) or int(off[-1]) > segs.size:
+                raise ValueError("CSR scopes: off must have nq + 1 entries ending within segs")
+        else:
+            if len(scopes) != nq:
+                raise ValueError("one scope per query")
+            segs, off = scopes_to_csr(scopes)
+        ids = np.empty((nq, k), np.uint64)
+        sc = np.empty((nq, k), np.int32)
+        cs = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        rc = self._L.rf_group_search(self._h, _ptr(q), nq, _ptr(segs), _ptr(off), k, _ptr(ids), _ptr(sc), _ptr(cs), _ptr(cnt))
+        if rc:
+            check(rc, group=True)
+        return ids, sc, cs, cnt
+
+    def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None, weights=None):
+        return _search_text(self, self._search_text_call, text, scope, k, ranges, weights)
+
+    def _search_text_call(self, text, segs, n_segs, rng, weights, k, ids, sc, cs, cnt, q):
+        check(self._L.rf_group_search_text(self.handle, text or b"\0", len(text), _ptr(segs), n_segs, _ptr(rng),
+                                           0 if rng is None else rng.shape[0], _ptr(weights), int(k), _ptr(ids), _ptr(sc),
+                                           _ptr(cs), C.byref(cnt), _ptr(q)), group=True)
+
+    def engine_handle(self, index: int) -> C.c_void_p:
+        h = C.c_void_p()
+        check(self._L.rf_group_engine(self.handle, int(index), C.byref(h)), group=True)
+        return h
+
+    def featurize_query(self, text: bytes) -> np.ndarray:
+        text = bytes(text)
+        q = np.zeros(RF_DIM, np.int8)
+        check(self._L.rf_featurize_query(self.engine_handle(0), text or b"\0", len(text), _ptr(q)))
+        return q
+
+    def scope_df(self, scope: Sequence[int]) -> Tuple[np.ndarray, int]:
+        segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
+        df = np.zeros(RF_DIM, np.uint64)
+        n = C.c_uint64()
+        check(self._L.rf_group_scope_df(self.handle, _ptr(segs), len(scope), _ptr(df), C.byref(n)), group=True)
+        return df, int(n.value)
+
+    idf_weights = Engine.idf_weights
+    weight_query = Engine.weight_query
+
+    def scope_weights(self, scope: Sequence[int]) -> np.ndarray:
+        return self.idf_weights(*self.scope_df(scope))
 
 
 def unpack_keys(keys: np.ndarray):

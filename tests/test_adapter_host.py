@@ -210,3 +210,82 @@ def test_metadata_filter_narrows_to_matching_documents(rag, tmp_path):
     assert rag.retrieve("q", [store], metadata_filter={"team": "nobody"}) == [] and "ranges" not in seen
     list(rag.ask_stream(contents="q", store_names=[store], metadata_filter={"team": ["dev"]}, model="m"))
     assert seen["ranges"] == [(2, 4)]
+
+
+def test_delete_forgets_the_document_and_upload_to_a_deleted_store_fails(rag, tmp_path, monkeypatch):
+    store = rag.create_store("s")
+    p = tmp_path / "d.txt"
+    p.write_text("alpha beta gamma")
+    up = rag.upload_file(store, str(p))
+    reg = rag._reg
+    assert len(reg.docs) == 1 and reg.first_chunks == [0]
+    rag.delete_document_from_store(store, 1, file_id=up.file_id)
+    assert reg.docs == {} and reg.doc_by_file == {} and reg.first_chunks == [] and reg.first_chunk_doc == []
+    reg.engine.hits = [(0, 5)]
+    assert rag.retrieve("alpha", [store]) == []                  # a stale hit on a forgotten chunk is dropped, not mis-attributed
+    # the engine may hand the freed chunk ids to the next document: the lookup must find the NEW one
+    reg.engine.next_row = 0
+    up2 = rag.upload_file(store, str(p), display_name="second.txt")
+    assert rag.retrieve("alpha", [store])[0]["title"] == "second.txt" and up2.file_id != up.file_id
+    rag.delete_store(store)
+    assert reg.docs == {} and store in reg.deleted_stores
+    with pytest.raises(ValueError, match="unknown or deleted store"):
+        rag.upload_file(store, str(p))
+    with pytest.raises(ValueError, match="unknown or deleted store"):
+        rag.upload_file("fileSearchStores/never-created", str(p))
+    monkeypatch.setenv("RAG_B200_AUTOCREATE_STORES", "1")
+    rag.upload_file("fileSearchStores/never-created", str(p))     # explicitly allowed
+    with pytest.raises(ValueError):
+        rag.upload_file(store, str(p))                            # a deleted store stays deleted
+
+
+def test_metrics_series_of_the_reference_are_fed(rag, tmp_path):
+    """backend/app/metrics.py:6-8 -- same series names and operation labels as GeminiRag."""
+    from rag_foundation_b200 import metrics
+    if metrics.SOURCE == "disabled":
+        pytest.skip("prometheus_client is not installed")
+    import sys
+    ref = sys.modules.get("app.metrics")     # loaded when the reference's own test module ran first in this process
+    if ref is not None:
+        from prometheus_client import REGISTRY
+    else:
+        REGISTRY = metrics.REGISTRY
+
+    def val(name, **labels):
+        return REGISTRY.get_sample_value(name, labels) or 0.0
+    before = {k: val("gemini_api_calls_total", operation=k[0], status=k[1])
+              for k in [("upload", "ok"), ("upload", "error"), ("generate_stream", "ok"), ("generate", "ok")]}
+    lat0 = val("gemini_api_latency_seconds_count", operation="generate_stream")
+    store = rag.create_store("s")
+    p = tmp_path / "d.txt"
+    p.write_text("alpha beta")
+    rag.upload_file(store, str(p))
+    with pytest.raises(ValueError):
+        rag.upload_file("fileSearchStores/nope", str(p))
+    list(rag.ask_stream(contents="alpha", store_names=[store], metadata_filter=None, model="m"))
+    rag.ask(contents="alpha", store_names=[store], metadata_filter=None, model="m")
+    after = {k: val("gemini_api_calls_total", operation=k[0], status=k[1]) for k in before}
+    assert all(after[k] == before[k] + 1 for k in before), (before, after)
+    assert val("gemini_api_latency_seconds_count", operation="generate_stream") == lat0 + 1
+
+
+def test_registry_sidecar_round_trip_is_plain_data(rag, tmp_path):
+    store = rag.create_store("s")
+    for i in range(3):
+        p = tmp_path / f"d{i}.txt"
+        p.write_text(" ".join(f"w{j}" for j in range(150 + i)))
+        rag.upload_file(store, str(p), display_name=f"d{i}.txt", custom_metadata=[{"key": "n", "numeric_value": i}])
+    reg = rag._reg
+    reg.engine.save_snapshot = lambda path: open(path, "wb").write(b"snap")
+    reg.save(str(tmp_path / "snap"))
+    raw = open(tmp_path / "snap" / "sidecar.msgpack", "rb").read()
+    import msgpack
+    assert msgpack.unpackb(raw, raw=False)["version"] == 2      # not a pickle
+    eng2 = ScriptedEngine()
+    eng2.load_snapshot = lambda path: None
+    reg2 = ad.Registry.load(eng2, str(tmp_path / "snap"))
+    assert sorted(reg2.docs) == sorted(reg.docs) and reg2.first_chunks == reg.first_chunks and reg2.next_doc == reg.next_doc
+    for k, d in reg.docs.items():
+        d2 = reg2.docs[k]
+        assert (d2.spans == d.spans).all() and d2.data == d.data and d2.meta == d.meta and d2.display_name == d.display_name
+    assert reg2.ops == reg.ops

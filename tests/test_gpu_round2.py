@@ -1,0 +1,430 @@
+"""GPU parity tests added in round 2 (all through the C-ABI): BASELINE configs[2] at its full size, the
+fused NVLink exchange under pytest (two engines, peer pointers within one process), the engine group
+(several engines behind one index), row reuse after deletes, snapshot integrity, and the overlap promise
+of the device-resident searches."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COS_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def co():
+    from oracle import c_oracle
+    return c_oracle
+
+
+@pytest.fixture(scope="module")
+def zb():
+    from oracle import rf1
+    return rf1.zipf_bucket_table()
+
+
+def _engine(cap, **kw):
+    from rag_foundation_b200 import Engine
+    return Engine(capacity_rows=cap, **kw)
+
+
+def _keys(ids, sc):
+    """(ids, scores) -> packed RF-1 keys, 0 where there is no result."""
+    ids = np.asarray(ids, np.uint64)
+    valid = ids != np.uint64(0xFFFFFFFFFFFFFFFF)
+    k = (np.asarray(sc).astype(np.int64).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - (ids & np.uint64(0xFFFFFFFF)))
+    return np.where(valid, k, np.uint64(0))
+
+
+# ------------------------------------------------------------------ configs[2] at BASELINE size
+@pytest.mark.timeout(600)
+def test_config2_full_size_every_query_against_the_oracle(co, zb):
+    """BASELINE configs[2] itself: 1 M chunks x 1024 batched queries on the tensor-core path; EVERY query's
+    top-10 (ids, scores, tie order) is compared with the C oracle, not a sample."""
+    import torch
+    n, nq, k = 1_000_000, 1024, 10
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/cfg2")
+        e.ingest_synthetic(s, 0, seed=0, start_counter=0, n_rows=n)
+        Q = np.stack([co.synth_query(0, i, zb) for i in range(nq)])
+        qd = torch.from_numpy(Q).cuda()
+        out = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+        l0 = e.stats()["kernel_launches"]
+        e.search_keys_device(qd.data_ptr(), nq, [s], k, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert e.stats()["kernel_launches"] - l0 <= 4, "the batch should have taken the tensor-core path"
+        keys = out.cpu().numpy().view(np.uint64)
+        F = co.synth_rows(0, 0, n, zb)
+        seg = np.full(n, s, np.uint32)
+        bad = [i for i in range(nq) if keys[i].tolist() != co.score_topk_keys(F, seg, Q[i], [s], k=k).tolist()]
+        assert bad == [], f"{len(bad)} of {nq} queries differ from the oracle, first {bad[:5]}"
+        # the same batch through the host entry point (rf_search routes it to the same kernels)
+        ids, sc, cs, cnt = e.search(Q, (np.full(nq, s, np.uint32), np.arange(nq + 1, dtype=np.uint32)), k=k)
+        assert (cnt == k).all() and (_keys(ids, sc) == keys).all()
+        # ties at the k-th score: wherever the 10th and 11th best scores are equal the id order decides
+        ties = 0
+        for i in range(0, nq, 64):
+            w = co.score_topk_keys(F, seg, Q[i], [s], k=12)
+            ties += int((w[9] >> np.uint64(32)) == (w[10] >> np.uint64(32)))
+        assert ties > 0, "the sampled queries should include k-th-score ties (the order under test)"
+
+
+# ------------------------------------------------------------------ fused exchange under pytest
+@pytest.mark.timeout(300)
+def test_fused_exchange_two_engines_one_process(co, zb):
+    """rf_search_keys_device_fused with world = 2 inside ONE process: two engines (shards) on the same GPU,
+    the 'peer' pointers are plain device pointers, the two kernels run concurrently on two streams and each
+    finishes by storing into BOTH gather buffers, releasing flags and acquiring the other's.  Result on both
+    'ranks' == the NCCL-path merge == the oracle over the whole corpus."""
+    import torch
+    from rag_foundation_b200.sharded import shard_range
+    n, k, nq_cap = 400_000, 10, 8
+    world = 2
+    engines, streams = [], [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            e = _engine(hi - lo, id_base=lo)
+            engines.append(e)
+            s = e.open_store("fileSearchStores/a")
+            e.ingest_synthetic(s, 0, seed=5, start_counter=lo, n_rows=hi - lo)
+        keys_buf = [torch.zeros(4 * world * nq_cap * k, dtype=torch.int64, device="cuda") for _ in range(world)]
+        flag_buf = [torch.zeros(4 * world * nq_cap, dtype=torch.int32, device="cuda") for _ in range(world)]
+        timeout = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        kp = np.asarray([t.data_ptr() for t in keys_buf], np.uint64)
+        fp = np.asarray([t.data_ptr() for t in flag_buf], np.uint64)
+        F = co.synth_rows(5, 0, n, zb)
+        seg = np.zeros(n, np.uint32)
+        torch.cuda.synchronize()
+        seq = 0
+        for nq in (1, 3, 1, 8, 1, 1, 2):          # > 4 calls: the four-slot buffers wrap around
+            Q = np.stack([co.synth_query(5, 100 * seq + i, zb) for i in range(nq)])
+            qd = torch.from_numpy(Q).cuda()
+            outs = [torch.zeros((nq, k), dtype=torch.int64, device="cuda") for _ in range(world)]
+            torch.cuda.synchronize()
+            seq += 1
+            for r in range(world):
+                engines[r].search_keys_device_fused(qd.data_ptr(), nq, [0], k, outs[r].data_ptr(), streams[r].cuda_stream,
+                                                    r, world, nq_cap, seq, kp, fp, timeout[r].data_ptr())
+            torch.cuda.synchronize()
+            assert not any(int(t.item()) for t in timeout), "a peer's keys never arrived"
+            got = [o.cpu().numpy().view(np.uint64) for o in outs]
+            assert (got[0] == got[1]).all()
+            for i in range(nq):
+                assert got[0][i].tolist() == co.score_topk_keys(F, seg, Q[i], [0], k=k).tolist()
+    finally:
+        for e in engines:
+            e.close()
+
+
+# ------------------------------------------------------------------ engine group
+def _group(devices, cap, **kw):
+    from rag_foundation_b200 import EngineGroup
+    return EngineGroup(devices, capacity_rows=cap, **kw)
+
+
+def _group_devices(n):
+    """n engines: distinct GPUs when the box has them, else all on GPU 0 (the logic under test is the same)."""
+    import torch
+    have = torch.cuda.device_count()
+    return list(range(n)) if have >= n else [0] * n
+
+
+@pytest.mark.parametrize("n_dev", [2, 8])
+def test_group_chunk_sharded_equals_single_engine(co, zb, n_dev):
+    """One store spread over n_dev engines (the 100 M-chunk layout in small): ids, scores, cosines and counts
+    of rf_group_search == one engine holding everything == the oracle; single queries and batches."""
+    n, k = 240_000, 10
+    from rag_foundation_b200.sharded import shard_range
+    bases = [shard_range(n, d, n_dev)[0] for d in range(n_dev)]
+    with _group(_group_devices(n_dev), n // n_dev, placement="spread", id_bases=bases) as g, _engine(n) as e:
+        gs = g.open_store("fileSearchStores/big")
+        es = e.open_store("fileSearchStores/big")
+        g.ingest_synthetic(gs, 0, seed=9, start_counter=0, n_rows=n)
+        e.ingest_synthetic(es, 0, seed=9, start_counter=0, n_rows=n)
+        tot, per = g.stats(per_device=True)
+        assert tot["n_rows"] == n and all(p["n_rows"] == n // n_dev for p in per)
+        F, ff = co.synth_rows(9, 0, n, zb, with_ff=True)
+        seg = np.zeros(n, np.uint32)
+        Q = np.stack([co.synth_query(9, i, zb) for i in range(20)])
+        for i in range(4):
+            a = g.search(Q[i:i + 1], [[gs]], k=k)
+            b = e.search(Q[i:i + 1], [[es]], k=k)
+            for x, y in zip(a, b):
+                assert (x == y).all()
+            w_ids, w_sc, w_cs = co.score_topk(F, seg, Q[i], [0], k=k, ff=ff)
+            assert a[0][0].tolist() == w_ids.tolist() and a[1][0].tolist() == w_sc.tolist()
+            np.testing.assert_allclose(a[2][0], w_cs, rtol=COS_RTOL)
+        a = g.search(Q, [[gs]] * 20, k=k)           # batch: each engine may take the tensor-core route
+        b = e.search(Q, [[es]] * 20, k=k)
+        for x, y in zip(a, b):
+            assert (x == y).all()
+        a = g.search(Q[:3], [[gs]] * 3, k=32)        # k = 32 through the host merge
+        b = e.search(Q[:3], [[es]] * 3, k=32)
+        for x, y in zip(a, b):
+            assert (x == y).all()
+
+
+def test_group_store_placement_multi_tenant_batch(co, zb):
+    """Whole stores per engine: 12 stores over 3 engines, a batch of store-scoped queries (each engine gets
+    only its own queries), scopes that span engines, an unknown store, a dropped store, a deleted document."""
+    rows, n_st, k = 5_000, 12, 10
+    with _group(_group_devices(3), 4 * rows + 64, placement="store") as g:
+        stores = [g.open_store(f"fileSearchStores/t{i}") for i in range(n_st)]
+        assert stores == list(range(n_st))
+        g.ingest_synthetic(0, rows, seed=4, start_counter=0, n_rows=rows * n_st)
+        tot, per = g.stats(per_device=True)
+        assert [p["n_rows"] for p in per] == [4 * rows] * 3
+        F = co.synth_rows(4, 0, rows * n_st, zb)
+        seg = (np.arange(rows * n_st) // rows).astype(np.uint32)
+        # global chunk id of corpus row r: engine d = store % 3 numbers its rows from d * stride
+        stride = 0xFFFFFFFE // 3
+        store_of = np.arange(rows * n_st) // rows
+        gid = (store_of % 3) * stride + (store_of // 3) * rows + np.arange(rows * n_st) % rows
+
+        def want(q, scope):
+            # independent numpy restatement of RF-1 steps 6-7 over the group's chunk ids (a scope that spans
+            # engines ranks score ties by those ids, not by the corpus row)
+            m = np.isin(seg, np.asarray(scope, np.uint32))
+            sc = F[m].astype(np.int32) @ q.astype(np.int32)
+            ids = gid[m]
+            order = np.lexsort((ids, -sc.astype(np.int64)))[:k]
+            return ids[order].tolist(), sc[order].tolist()
+
+        rng = np.random.default_rng(1)
+        nq = 64
+        Q = np.stack([co.synth_query(4, i, zb) for i in range(nq)])
+        scopes = [[int(rng.integers(0, n_st))] for _ in range(nq)]
+        scopes[5] = [1, 2, 9]                         # spans all three engines
+        scopes[6] = [3, 99]                           # an unknown store contributes nothing
+        scopes[7] = []                                # empty scope
+        ids, sc, cs, cnt = g.search(Q, scopes, k=k)
+        for i in range(nq):
+            w_ids, w_sc = want(Q[i], [s for s in scopes[i] if s < n_st])
+            assert int(cnt[i]) == len(w_ids) and sc[i][:cnt[i]].tolist() == w_sc, i
+            assert ids[i][:cnt[i]].tolist() == w_ids, i
+            assert (ids[i][cnt[i]:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+        # text ingest goes to the store's engine; its chunk ids come from that engine's range
+        doc = (" ".join(f"tenant seven report word{i}" for i in range(400))).encode()
+        first, n_chunks, spans = g.ingest_text(7, 1001, doc)
+        assert n_chunks > 0 and (7 % 3) * stride <= first < (7 % 3 + 1) * stride
+        h_ids, h_sc, _, q = g.search_text(b"tenant seven report", [7], k)
+        assert (q == co.query_vector(b"tenant seven report")).all()
+        assert first <= int(h_ids[0]) < first + n_chunks
+        g.tombstone_doc(1001)
+        h2 = g.search_text(b"tenant seven report", [7], k)
+        assert not any(first <= int(x) < first + n_chunks for x in h2[0])
+        g.drop_store(3)
+        assert g.lookup_store("fileSearchStores/t3") is None
+        ids, sc, cs, cnt = g.search(Q[:2], [[3], [3, 4]], k=k)
+        assert int(cnt[0]) == 0 and ids[1][:cnt[1]].tolist() == want(Q[1], [4])[0]
+        # RF-1w statistic = sum over engines
+        df, nn = g.scope_df([1, 2, 9])
+        w_df, w_n = co.bucket_df(F, seg, [1, 2, 9])
+        assert nn == w_n and (df == w_df).all()
+
+
+def test_group_behind_the_adapter_equals_single_engine(tmp_path, co):
+    """B200Rag over an engine group returns the single-engine citations bit for bit (uri aside: chunk ids are
+    global per group): same documents, same questions, tf and idf scoring, metadata filter, delete, snapshot."""
+    from rag_foundation_b200 import B200Rag, Engine, EngineGroup
+    from rag_foundation_b200.adapter import Registry
+    rng = np.random.default_rng(7)
+    vocab = [f"term{i}" for i in range(300)]
+    docs = []
+    for d in range(24):
+        words = rng.choice(vocab, size=int(rng.integers(150, 900)))
+        p = tmp_path / f"doc{d}.txt"
+        p.write_text(" ".join(words))
+        docs.append(p)
+    single = B200Rag(registry=Registry(Engine(capacity_rows=4096)))
+    for placement in ("spread", "store"):
+        group = B200Rag(registry=Registry(EngineGroup(_group_devices(2), capacity_rows=4096, placement=placement)))
+        names = []
+        for rag in (single, group):
+            ss = [rag.create_store("a"), rag.create_store("b")]
+            names.append(ss)
+            for d, p in enumerate(docs):
+                rag.upload_file(ss[d % 2], str(p), display_name=p.name, custom_metadata=[{"key": "team", "string_value": "ops" if d % 3 else "dev"}])
+        for scoring in ("tf", "idf"):
+            single.scoring = group.scoring = scoring
+            for qi in range(12):
+                text = " ".join(rng.choice(vocab, size=6))
+                for scope_pick, mf in ((slice(0, 1), None), (slice(0, 2), None), (slice(0, 2), {"team": "dev"})):
+                    a = single.retrieve(text, names[0][scope_pick], metadata_filter=mf)
+                    b = group.retrieve(text, names[1][scope_pick], metadata_filter=mf)
+                    # chunk ids differ between the two layouts, so rows that TIE on the score may rank (and, at the
+                    # k-th score, be selected) differently: the scores must agree position by position, and the
+                    # citations above the k-th score as sets
+                    sa, sb = [h["score"] for h in a], [h["score"] for h in b]
+                    assert sa == sb, (placement, scoring, text)
+                    cut = sa[-1] if len(sa) == single.top_k else -1
+                    strip = lambda hits: sorted((h["title"], h["text"], h["score"], h["cosine"], h["uri"].split("/")[-1].split("#")[0])   # noqa: E731
+                                                for h in hits if h["score"] > cut)
+                    assert strip(a) == strip(b), (placement, scoring, text)
+        # snapshot round trip of the group registry
+        group._reg.save(str(tmp_path / f"snap-{placement}"))
+        reg2 = Registry.load(EngineGroup(_group_devices(2), capacity_rows=4096, placement=placement), str(tmp_path / f"snap-{placement}"))
+        again = B200Rag(registry=reg2)
+        text = "term1 term2 term3 term4"
+        assert again.retrieve(text, names[1]) == group.retrieve(text, names[1])
+        reg2.engine.close()
+        for rag, ss in ((single, names[0]), (group, names[1])):
+            rag.delete_store(ss[0]); rag.delete_store(ss[1])
+        group._reg.engine.close()
+    single._reg.engine.close()
+
+
+# ------------------------------------------------------------------ deletes give their rows back
+def test_ingest_delete_ingest_at_capacity(co):
+    """A delete-heavy tenant does not exhaust the arena: freed rows (and their chunk ids) are reused, searches
+    stay exact, and a concurrent reader never sees a half-written reused row as a hit of the wrong store."""
+    from rag_foundation_b200._capi import RfError, RF_ECAPACITY
+    text = lambda tag, n: (" ".join(f"{tag}{i % 50} filler{i}" for i in range(n))).encode()   # noqa: E731
+    with _engine(64) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        first1, n1, _ = e.ingest_text(a, 1, text("alpha", 1100))
+        first2, n2, _ = e.ingest_text(b, 2, text("beta", 1100))
+        first3, n3, _ = e.ingest_text(a, 3, text("gamma", 1100))
+        assert n1 == n2 == n3 == 20 and 3 * n1 <= 64 < 4 * n1            # the arena cannot take a 4th document
+        assert e.stats()["free_rows"] == 0
+        stop = threading.Event()
+        wrong = []
+
+        def reader():
+            while not stop.is_set():
+                ids, sc, _, _ = e.search_text(b"beta1 beta2 beta3", [b], 10)
+                wrong.extend(int(x) for x in ids if not (first2 <= int(x) < first2 + n2))
+        th = threading.Thread(target=reader)
+        th.start()
+        try:
+            for rnd in range(12):                     # far more rows than the arena holds, in total
+                e.tombstone_doc(1 if rnd == 0 else 100 + rnd - 1)
+                assert e.stats()["free_rows"] == n1
+                f, n, _ = e.ingest_text(a, 100 + rnd, text(f"r{rnd}x", 1100))
+                assert (f, n) == (first1, n1), "the freed run is reused (same chunk ids)"
+                assert e.stats()["free_rows"] == 0
+                ids, sc, _, q = e.search_text(f"r{rnd}x1 r{rnd}x2".encode(), [a], 10)
+                F, seg, ff = e.read_rows(0, e.stats()["n_rows"])
+                w_ids, w_sc, _ = co.score_topk(F, seg, q, [a], k=10, ff=ff)
+                assert ids.tolist() == w_ids.tolist() and sc.tolist() == w_sc.tolist()
+                assert all(first1 <= int(x) < first1 + n1 or first3 <= int(x) < first3 + n3 for x in ids)
+        finally:
+            stop.set()
+            th.join()
+        assert wrong == []
+        # a document larger than any freed run still fails loudly
+        e.tombstone_doc(111)
+        with pytest.raises(RfError) as err:
+            e.ingest_text(a, 999, text("big", 3300))
+        assert err.value.code == RF_ECAPACITY
+        # dropping a store frees its rows too, and a deleted document's rows leave its store's extents
+        e.drop_store(b)
+        assert e.stats()["free_rows"] == n1 + n2
+        c = e.open_store("fileSearchStores/c")
+        f, n, _ = e.ingest_text(c, 500, text("delta", 2000))          # 36 chunks: only the coalesced run of both freed documents takes it
+        assert f == first1 and n1 < n <= n1 + n2
+        ids, _, _, _ = e.search_text(b"delta1 delta2", [c], 10)
+        assert len(ids) and all(f <= int(x) < f + n for x in ids)
+        ids, _, _, _ = e.search_text(b"delta1 delta2", [a], 10)      # store a no longer reaches the rows it gave back
+        assert all(first3 <= int(x) < first3 + n3 for x in ids)
+
+
+def test_snapshot_is_atomic_and_checksummed(tmp_path, co, zb):
+    from rag_foundation_b200._capi import RfError
+    n = 20_000
+    path = str(tmp_path / "index.rfsnap")
+    with _engine(n + 100) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=2, start_counter=0, n_rows=n)
+        e.ingest_text(s, 1, b"some words to delete later " * 100)
+        e.tombstone_doc(1)
+        e.save_snapshot(path)
+        good = open(path, "rb").read()
+        assert not os.path.exists(path + ".tmp")
+        # a failed save (unwritable temporary) leaves the previous file untouched
+        os.mkdir(path + ".tmp")
+        with pytest.raises(RfError):
+            e.save_snapshot(path)
+        os.rmdir(path + ".tmp")
+        assert open(path, "rb").read() == good
+        q = co.synth_query(2, 0, zb)
+        want = e.search(q[None], [[s]], k=10)
+        free_rows = e.stats()["free_rows"]
+    with _engine(n + 100) as e2:
+        e2.load_snapshot(path)
+        got = e2.search(q[None], [[0]], k=10)
+        for x, y in zip(want, got):
+            assert (x == y).all()
+        assert e2.stats()["free_rows"] == free_rows
+    for what, blob in (("flipped byte", good[:len(good) // 2] + bytes([good[len(good) // 2] ^ 0x40]) + good[len(good) // 2 + 1:]),
+                       ("truncated", good[:-4096]), ("no trailer", good[:-16])):
+        bad = str(tmp_path / "bad.rfsnap")
+        open(bad, "wb").write(blob)
+        with _engine(n + 100) as e3:
+            with pytest.raises(RfError):
+                e3.load_snapshot(bad)
+            assert e3.stats()["n_rows"] == 0 and e3.lookup_store("fileSearchStores/a") is None, what
+            s3 = e3.open_store("fileSearchStores/fresh")          # the engine is still usable and empty
+            assert e3.search(q[None], [[s3]], k=10)[3][0] == 0
+
+
+def test_device_searches_with_and_without_the_overlap_promise(co, zb):
+    """Back-to-back device-resident searches: (a) default = fully serialised launches, the query vector may be
+    produced by a kernel right before each search; (b) with rf_stream_set_overlap the launches overlap (PDL)
+    over a resident query batch.  Both equal the oracle."""
+    import torch
+    n, k = 300_000, 10
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=6, start_counter=0, n_rows=n)
+        F = co.synth_rows(6, 0, n, zb)
+        seg = np.full(n, s, np.uint32)
+        Q = np.stack([co.synth_query(6, i, zb) for i in range(48)])
+        want = [co.score_topk_keys(F, seg, Q[i], [s], k=k).tolist() for i in range(48)]
+        Qd = torch.from_numpy(Q).cuda()
+        stream = torch.cuda.current_stream().cuda_stream
+        # (a) the query is written by a torch kernel immediately before every search, into the SAME buffer
+        qbuf = torch.zeros((1, 256), dtype=torch.int8, device="cuda")
+        out = torch.zeros((48, k), dtype=torch.int64, device="cuda")
+        for rep in range(3):
+            for i in range(48):
+                torch.add(Qd[i:i + 1], 0, out=qbuf)          # a kernel, not a copy
+                e.search_keys_device(qbuf.data_ptr(), 1, [s], k, out[i].data_ptr(), stream)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().view(np.uint64)
+            assert [g.tolist() for g in got] == want
+        # (b) resident batch + promise
+        e.set_stream_overlap(stream, True)
+        out.zero_()
+        for i in range(48):
+            e.search_keys_device(Qd[i:i + 1].data_ptr(), 1, [s], k, out[i].data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert [g.tolist() for g in out.cpu().numpy().view(np.uint64)] == want
+        e.set_stream_overlap(stream, False)
+
+
+def test_many_scopes_hold_no_device_state(co, zb):
+    """Thousands of distinct scopes through the device-resident entry point on one stream: the engine keeps per-STREAM
+    scratch only, so its device footprint does not grow with the number of tenants."""
+    import torch
+    rows, n_st = 64, 2_000
+    with _engine(rows * n_st) as e:
+        for i in range(n_st):
+            e.open_store(f"fileSearchStores/t{i}")
+        e.ingest_synthetic(0, rows, seed=1, start_counter=0, n_rows=rows * n_st)
+        q = torch.from_numpy(co.synth_query(1, 0, zb)[None]).cuda()
+        out = torch.zeros((1, 10), dtype=torch.int64, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        e.search_keys_device(q.data_ptr(), 1, [0], 10, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        for i in range(n_st):
+            e.search_keys_device(q.data_ptr(), 1, [i], 10, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert free0 - torch.cuda.mem_get_info()[0] < (8 << 20), "device memory grew with the number of scopes"
+        F = co.synth_rows(1, (n_st - 1) * rows, rows, zb)
+        want = co.score_topk_keys(F, np.full(rows, n_st - 1, np.uint32), co.synth_query(1, 0, zb), [n_st - 1], k=10, id_base=(n_st - 1) * rows)
+        assert out.cpu().numpy().view(np.uint64)[0].tolist() == want.tolist()

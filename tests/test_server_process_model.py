@@ -18,11 +18,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.timeout(120)
 
 
+KEY = "test-secret-0123456789abcdef"
+
+
 @pytest.fixture()
-def served(tmp_path):
+def served(tmp_path, monkeypatch):
+    monkeypatch.setenv("RAG_B200_AUTHKEY", KEY)
     reg = ad.Registry(ScriptedEngine())
     sock = str(tmp_path / "rag.sock")
-    srv = Server(sock, reg).start()
+    srv = Server(sock, reg, snapshot_dir=str(tmp_path / "snaps")).start()
     yield sock, reg
     srv.close()
 
@@ -62,6 +66,7 @@ def test_second_process_sees_the_same_index(served, tmp_path):
         import os, sys, json
         sys.path.insert(0, {ROOT!r})
         os.environ["RAG_B200_SOCKET"] = {sock!r}
+        os.environ["RAG_B200_AUTHKEY"] = {KEY!r}
         from rag_foundation_b200 import get_rag_client
         rag = get_rag_client()
         up = rag.upload_file({store!r}, {str(p)!r}, display_name="worker.txt")
@@ -77,6 +82,73 @@ def test_second_process_sees_the_same_index(served, tmp_path):
     assert cits[0]["title"] == "worker.txt"
 
 
-def test_daemon_away_is_retryable(tmp_path):
+def test_daemon_away_is_retryable(tmp_path, monkeypatch):
+    monkeypatch.setenv("RAG_B200_AUTHKEY", KEY)
     with pytest.raises(TimeoutError):                          # gemini_rag.py:22-27: TimeoutError is retried upstream
         RemoteB200Rag(str(tmp_path / "nobody.sock")).create_store("x")
+
+
+def test_no_default_secret_and_wrong_secret_is_refused(served, tmp_path, monkeypatch):
+    sock, reg = served
+    monkeypatch.delenv("RAG_B200_AUTHKEY")
+    with pytest.raises(RuntimeError, match="RAG_B200_AUTHKEY"):
+        Server(str(tmp_path / "other.sock"), reg)               # the daemon refuses to start without a secret
+    with pytest.raises(RuntimeError, match="RAG_B200_AUTHKEY"):
+        RemoteB200Rag(sock)
+    monkeypatch.setenv("RAG_B200_AUTHKEY", "another-secret-0123456789")
+    with pytest.raises((PermissionError, TimeoutError)):
+        RemoteB200Rag(sock).list_stores()
+    assert oct(os.stat(sock).st_mode & 0o777) == "0o600"
+
+
+def test_wire_carries_data_only_and_save_stays_in_its_directory(served, tmp_path):
+    """A pickle sent to the socket is never unpickled (frames are msgpack), and `save` takes a plain name."""
+    import pickle
+    import socket as so
+    import struct
+    from rag_foundation_b200 import server as sv
+    sock, reg = served
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+    s = so.socket(so.AF_UNIX, so.SOCK_STREAM)
+    s.connect(sock)
+    sv._handshake_client(s, KEY.encode())
+    body = pickle.dumps(("create_store", (Evil(),), {}))
+    s.sendall(struct.pack(">I", len(body)) + body)
+    try:
+        s.settimeout(5)
+        s.recv(16)
+    except OSError:
+        pass
+    s.close()
+    assert not marker.exists()
+    rag = RemoteB200Rag(sock)
+    for bad in ("../escape", "/etc/passwd", "a/b", ""):
+        with pytest.raises(ValueError):
+            rag._call("save", bad)
+    reg.engine.save_snapshot = lambda path: open(path, "wb").write(b"snap")     # the scripted engine has no snapshot
+    where = rag._call("save", "nightly")
+    assert where == str(tmp_path / "snaps" / "nightly") and os.path.exists(os.path.join(where, "sidecar.msgpack"))
+
+
+def test_upload_is_never_sent_twice(served, tmp_path):
+    """A connection that drops after an upload was sent is NOT retried (the document would be ingested twice);
+    idempotent calls are."""
+    sock, reg = served
+    rag = RemoteB200Rag(sock)
+    store = rag.create_store("demo")
+    p = tmp_path / "doc.txt"
+    p.write_text("one copy only")
+    rag.list_stores()
+    rag._local.conn.close()                                    # the daemon's side sees EOF; our socket object is dead
+    with pytest.raises(TimeoutError):
+        rag.upload_file(store, str(p))
+    assert reg.engine.ingested == []
+    rag._local.conn = None
+    rag.upload_file(store, str(p))
+    rag._local.conn.close()
+    assert rag.list_stores() == []                             # idempotent: reconnects and succeeds
+    assert len(reg.engine.ingested) == 1
