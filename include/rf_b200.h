@@ -237,6 +237,12 @@ int rf_search_text_w(rf_engine *e, const uint8_t *utf8, size_t n, const uint32_t
                      uint32_t k, uint64_t *out_ids, int32_t *out_scores, float *out_cos,
                      uint32_t *out_count, int8_t *out_q /* RF_DIM, may be NULL */);
 
+/* ---- measurement aid: the achievable dense int8 rate of the tensor pipe on `device` (a kernel that only
+ * issues tcgen05.mma.cta_group::2.kind::i8 256 x 256 x 32, the scoring GEMM's shape), timed with CUDA events:
+ * the roofline denominator of the batched scoring path (configs[2]).  n_batches of 8 MMAs per
+ * CTA pair (>= 8; 4000 takes a few ms).  *ops_per_s counts 2 * M * N * K per MMA. */
+int rf_probe_int8_peak(int device, uint32_t n_batches, double *ops_per_s, double *ms /* may be NULL */);
+
 /* ---- engine group: several GPUs behind ONE index in one process ----------------------------------------
  * The reference's backend is one object per process behind get_rag_client() (gemini_rag.py:721-725), called
  * by the chat route (routes/chat.py:499-505) and the ingest worker (services/ingestion.py:45-52); the north

@@ -82,6 +82,7 @@ SIGNATURES = {
     "rf_idf_weights": (_i32, [_vp, _u64, _u32, _vp]),
     "rf_weight_query": (_i32, [_vp, _vp, _u32, _vp]),
     "rf_search_text_w": (_i32, [_vp, _vp, _sz, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "rf_probe_int8_peak": (_i32, [_i32, _u32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rf_group_create": (_i32, [C.POINTER(rf_group_config), C.POINTER(_vp)]),
     "rf_group_destroy": (_i32, [_vp]),
     "rf_group_size": (_i32, [_vp, C.POINTER(_u32)]),

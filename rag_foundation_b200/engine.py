@@ -479,6 +479,13 @@ class EngineGroup:
         return self.idf_weights(*self.scope_df(scope))
 
 
+def probe_int8_peak(device: int = 0, n_batches: int = 4000) -> Tuple[float, float]:
+    """-> (int8 ops/s, ms): the tensor pipe's achievable dense int8 rate on `device` (rf_probe_int8_peak)."""
+    ops, ms = C.c_double(), C.c_double()
+    check(lib().rf_probe_int8_peak(int(device), int(n_batches), C.byref(ops), C.byref(ms)))
+    return float(ops.value), float(ms.value)
+
+
 def unpack_keys(keys: np.ndarray):
     """Packed RF-1 keys -> (ids uint64, scores int32, valid bool)."""
     keys = np.asarray(keys, dtype=np.uint64)

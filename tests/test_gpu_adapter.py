@@ -121,42 +121,105 @@ def test_snapshot_round_trip(tmp_path, golden_dir):
             e.close()
 
 
-@pytest.mark.timeout(180)
-def test_daemon_with_real_engine_and_concurrent_clients(tmp_path, golden_dir):
-    """SURVEY 8f-1 on the GPU: one daemon owns the engine, several client threads (the reference
-    runs one daemon thread per stream, routes/chat.py:520) query it at once."""
-    import threading
-    from rag_foundation_b200 import Engine
-    from rag_foundation_b200 import adapter as ad
-    from rag_foundation_b200.server import RemoteB200Rag, Server
+def _run_client(code, env, timeout=120):
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
+
+@pytest.mark.timeout(300)
+def test_daemon_process_ingest_process_query_process(tmp_path, golden_dir):
+    """SURVEY 8f-1 on the GPU with REAL processes, the reference's layout (backend/Dockerfile:42: 4 API workers;
+    worker.py:122-126: one ARQ ingest worker): the engine daemon is its own process and owns the HBM index, a
+    second process (the 'worker') creates a store and uploads, a third (an 'API worker') asks -- all through
+    get_rag_client() with RAG_B200_SOCKET set -- and this process hammers it from 8 threads meanwhile.  The
+    daemon then snapshots, is killed, and a fresh daemon serves the same answers from the snapshot."""
+    import signal
+    import subprocess
+    import sys
+    import textwrap
+    import threading
+    import time
+    from rag_foundation_b200.server import RemoteB200Rag
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     g = json.load(open(os.path.join(golden_dir, "rf1_golden.json")))
     wire = json.load(open(os.path.join(golden_dir, "config1_wire.json")))
-    reg = ad.Registry(Engine(capacity_rows=4096, n_contexts=4))
-    srv = Server(str(tmp_path / "rag.sock"), reg).start()
-    try:
-        rag = RemoteB200Rag(str(tmp_path / "rag.sock"))
-        store = rag.create_store("demo")
-        p = tmp_path / "sample-report.md"
-        p.write_bytes(g["sample_report"]["text"].encode("utf-8"))
-        rag.upload_file(store, str(p), display_name="sample-report.md")
-        local = ad.B200Rag(registry=reg).retrieve(wire["demo_query"], [store])
-        assert local and local[0]["title"] == "sample-report.md"
-        errs = []
+    sock = str(tmp_path / "rag.sock")
+    env = dict(os.environ, RAG_B200_SOCKET=sock, RAG_B200_AUTHKEY="cross-process-secret-0123456789", RAG_B200_CAPACITY_ROWS="8192",
+               RAG_B200_SNAPSHOT_DIR=str(tmp_path / "snaps"), PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    doc = tmp_path / "sample-report.md"
+    doc.write_bytes(g["sample_report"]["text"].encode("utf-8"))
 
-        def client():
-            try:
-                r = RemoteB200Rag(str(tmp_path / "rag.sock"))
-                for _ in range(20):
-                    assert r.retrieve(wire["demo_query"], [store]) == local
-            except Exception as ex:   # noqa: BLE001
-                errs.append(ex)
-        ts = [threading.Thread(target=client) for _ in range(8)]
-        [t.start() for t in ts]; [t.join() for t in ts]
-        assert not errs, errs[:1]
+    def start_daemon(extra=""):
+        code = f"import sys; sys.path.insert(0, {root!r})\n{extra}\nfrom rag_foundation_b200.server import serve; serve()"
+        p = subprocess.Popen([sys.executable, "-c", code], env=env, stderr=subprocess.PIPE, text=True)
+        for _ in range(600):
+            if os.path.exists(sock):
+                return p
+            if p.poll() is not None:
+                raise AssertionError("daemon died: " + p.stderr.read()[-2000:])
+            time.sleep(0.1)
+        p.kill()
+        raise AssertionError("daemon did not come up")
+
+    daemon = start_daemon()
+    try:
+        worker = textwrap.dedent(f"""
+            import json
+            from rag_foundation_b200 import get_rag_client
+            rag = get_rag_client()
+            store = rag.create_store("demo")
+            up = rag.upload_file(store, {str(doc)!r}, display_name="sample-report.md")
+            print(json.dumps({{"cls": type(rag).__name__, "store": store, "done": rag.op_status(up.operation_name)["done"], "file": up.file_id}}))
+        """)
+        w = _run_client(worker, env)
+        assert w["cls"] == "RemoteB200Rag" and w["done"] is True
+        api = textwrap.dedent(f"""
+            import json
+            from rag_foundation_b200 import get_rag_client
+            rag = get_rag_client()
+            chunks = list(rag.ask_stream(contents=[{{"role": "user", "parts": [{{"text": {wire["demo_query"]!r}}}]}}],
+                                         store_names=[{w["store"]!r}], metadata_filter=None, model="m"))
+            cits = rag.extract_citations_from_response(chunks[1])
+            print(json.dumps({{"n": len(chunks), "cits": cits}}))
+        """)
+        a = _run_client(api, env)
+        assert a["n"] == 2 and a["cits"] and a["cits"][0]["title"] == "sample-report.md" and a["cits"][0]["store"] == w["store"]
+        os.environ["RAG_B200_AUTHKEY"] = env["RAG_B200_AUTHKEY"]
+        try:
+            local = RemoteB200Rag(sock).retrieve(wire["demo_query"], [w["store"]])
+            assert [c["uri"] for c in a["cits"]] == [h["uri"] for h in local]
+            errs = []
+
+            def client():
+                try:
+                    r = RemoteB200Rag(sock)
+                    for _ in range(20):
+                        assert r.retrieve(wire["demo_query"], [w["store"]]) == local
+                except Exception as ex:   # noqa: BLE001
+                    errs.append(ex)
+            ts = [threading.Thread(target=client) for _ in range(8)]
+            [t.start() for t in ts]; [t.join() for t in ts]
+            assert not errs, errs[:1]
+            stats = RemoteB200Rag(sock)._call("stats")
+            assert stats["n_rows"] >= 1 and stats["searches"] >= 160
+            where = RemoteB200Rag(sock)._call("save", "nightly")
+            daemon.send_signal(signal.SIGKILL)
+            daemon.wait(30)
+            os.unlink(sock)
+            # a fresh daemon process restores the snapshot before it starts serving
+            daemon = start_daemon(extra=("from rag_foundation_b200 import adapter as ad, Engine\n"
+                                         f"ad.set_registry(ad.Registry.load(Engine(capacity_rows=8192), {where!r}))"))
+            assert RemoteB200Rag(sock).retrieve(wire["demo_query"], [w["store"]]) == local
+        finally:
+            os.environ.pop("RAG_B200_AUTHKEY", None)
     finally:
-        srv.close()
-        reg.engine.close()
+        if daemon.poll() is None:
+            daemon.kill()
+            daemon.wait(30)
 
 
 def test_idf_scoring_through_the_adapter_and_quality_eval(tmp_path):

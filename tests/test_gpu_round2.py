@@ -97,6 +97,17 @@ def test_fused_exchange_two_engines_one_process(co, zb):
         fp = np.asarray([t.data_ptr() for t in flag_buf], np.uint64)
         F = co.synth_rows(5, 0, n, zb)
         seg = np.zeros(n, np.uint32)
+        # Warm-up (world = 1: no exchange) so every engine's per-stream scratch exists: a device allocation
+        # issued between the two launches below would keep them from running concurrently (CUDA's implicit
+        # synchronisation rules) -- and here, unlike one process per GPU, each kernel NEEDS the other to run.
+        warm = torch.zeros((nq_cap, 256), dtype=torch.int8, device="cuda")
+        sink = torch.zeros((nq_cap, k), dtype=torch.int64, device="cuda")
+        for r in range(world):
+            engines[r].search_keys_device_fused(warm.data_ptr(), nq_cap, [0], k, sink.data_ptr(), streams[r].cuda_stream,
+                                                0, 1, nq_cap, 1, kp[r:r + 1], fp[r:r + 1], timeout[r].data_ptr())
+        torch.cuda.synchronize()
+        for t in flag_buf:
+            t.zero_()
         torch.cuda.synchronize()
         seq = 0
         for nq in (1, 3, 1, 8, 1, 1, 2):          # > 4 calls: the four-slot buffers wrap around
@@ -267,7 +278,7 @@ def test_group_behind_the_adapter_equals_single_engine(tmp_path, co):
         # snapshot round trip of the group registry
         group._reg.save(str(tmp_path / f"snap-{placement}"))
         reg2 = Registry.load(EngineGroup(_group_devices(2), capacity_rows=4096, placement=placement), str(tmp_path / f"snap-{placement}"))
-        again = B200Rag(registry=reg2)
+        again = B200Rag(registry=reg2, scoring=group.scoring)
         text = "term1 term2 term3 term4"
         assert again.retrieve(text, names[1]) == group.retrieve(text, names[1])
         reg2.engine.close()
