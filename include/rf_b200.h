@@ -87,6 +87,15 @@ int rf_store_drop(rf_engine *e, uint32_t store_seg);                         /* 
  * gemini_rag.py:631-638). */
 int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint8_t *utf8, size_t n,
                    uint64_t *first_chunk, uint32_t *n_chunks, int64_t *spans, uint32_t max_spans);
+/* `utf8` may live anywhere; the engine looks (cudaPointerGetAttributes) and takes the matching route:
+ *   pageable host memory -- staged through the engine's own ring of pinned slots by helper threads, so host
+ *                           memcpy, PCIe transfer and the tokenise kernels overlap chunk by chunk;
+ *   pinned host memory   -- (rf_host_alloc, or registered by the caller) DMA straight from it, same pipeline;
+ *   device memory        -- no transfer at all.
+ * rf_host_alloc / rf_host_free hand out pinned buffers for hosts that want to read an upload straight into
+ * DMA-able memory (the reference's worker reads a temp file, services/ingestion.py:45-52, uploads.py:245-261). */
+int rf_host_alloc(size_t n, void **out);
+int rf_host_free(void *p);
 
 /* Append pre-computed int8 rows (host or device pointer, n_rows x RF_DIM). */
 int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const int8_t *rows,

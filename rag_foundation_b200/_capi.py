@@ -59,6 +59,8 @@ SIGNATURES = {
     "rf_store_lookup": (_i32, [_vp, C.c_char_p, C.POINTER(_u32)]),
     "rf_store_drop": (_i32, [_vp, _u32]),
     "rf_ingest_text": (_i32, [_vp, _u32, _u64, _vp, _sz, C.POINTER(_u64), C.POINTER(_u32), _vp, _u32]),
+    "rf_host_alloc": (_i32, [_sz, C.POINTER(_vp)]),
+    "rf_host_free": (_i32, [_vp]),
     "rf_ingest_features": (_i32, [_vp, _u32, _u64, _vp, _u64, _i32, C.POINTER(_u64)]),
     "rf_ingest_synthetic": (_i32, [_vp, _u32, _u64, _u64, _u64, _u64, _vp, C.POINTER(_u64)]),
     "rf_doc_tombstone": (_i32, [_vp, _u64]),

@@ -23,6 +23,7 @@
 #include <new>
 #include <shared_mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -150,6 +151,9 @@ struct MappedBuf {   // pinned host memory the GPU writes results into directly 
     }
 };
 
+struct CopyPool;
+void copy_pool_destroy(CopyPool *p);
+
 struct SearchCtx {
     cudaStream_t stream = nullptr;
     MappedBuf m_out;
@@ -197,6 +201,81 @@ struct PlanBlob {  // host staging of everything one launch needs besides F/seg/
     uint32_t max_tiles = 0;
 };
 
+// ---- staging of documents that arrive in pageable host memory ------------------------------------------
+// A copy from pageable memory makes the driver stage through its own small pinned buffers (~10 GB/s).
+// The engine stages itself: the document is cut into chunks, helper threads (and the ingesting thread,
+// whenever it has nothing to enqueue) memcpy chunks into a ring of pinned slots, and the ingesting thread
+// enqueues each chunk's DMA -- and the tokeniser launch of the chunk before it -- as soon as the slot is
+// full, in order.  Host memcpy, PCIe transfer and the tokenise kernels overlap.
+constexpr size_t kStageChunk = 2u << 20;
+constexpr uint32_t kStageSlots = 8;
+constexpr size_t kStageMinBytes = 1u << 20;     // smaller documents take one copy, no helpers
+
+struct CopyPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+    uint64_t job_gen = 0;
+    // the job in flight (valid while job_live)
+    const uint8_t *src = nullptr;
+    uint8_t *ring = nullptr;
+    size_t n = 0;
+    uint32_t n_chunks = 0;
+    cudaEvent_t *ev = nullptr;
+    std::atomic<uint32_t> next{0};        // next chunk to claim
+    std::atomic<uint32_t> issued{0};      // chunks whose DMA has been enqueued (and its slot event recorded)
+    std::atomic<uint32_t> helpers_in{0};  // helpers currently inside the job
+    std::atomic<bool> job_live{false};
+    std::vector<std::atomic<uint8_t>> staged;
+
+    // Claim and stage one chunk; false when none is left.
+    bool stage_one() {
+        const uint32_t c = next.fetch_add(1, std::memory_order_relaxed);
+        if (c >= n_chunks) return false;
+        if (c >= kStageSlots) {   // the slot's previous tenant must have left for the device
+            while (issued.load(std::memory_order_acquire) + kStageSlots <= c) std::this_thread::yield();
+            cudaEventSynchronize(ev[c % kStageSlots]);
+        }
+        const size_t off = static_cast<size_t>(c) * kStageChunk;
+        memcpy(ring + (c % kStageSlots) * kStageChunk, src + off, std::min(kStageChunk, n - off));
+        staged[c].store(1, std::memory_order_release);
+        return true;
+    }
+    void helper() {
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || job_gen != seen; });
+                if (stop) return;
+                seen = job_gen;
+                if (!job_live.load()) continue;
+                helpers_in.fetch_add(1);
+            }
+            while (job_live.load(std::memory_order_acquire) && stage_one()) {}
+            helpers_in.fetch_sub(1);
+        }
+    }
+};
+
+CopyPool *copy_pool_create(unsigned n_threads) {
+    CopyPool *p = new (std::nothrow) CopyPool();
+    if (!p) return nullptr;
+    for (unsigned i = 0; i < n_threads; ++i) p->threads.emplace_back([p] { p->helper(); });
+    return p;
+}
+void copy_pool_destroy(CopyPool *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv.notify_all();
+    for (std::thread &t : p->threads) t.join();
+    delete p;
+}
+
 }  // namespace
 
 struct rf_engine {
@@ -222,7 +301,12 @@ struct rf_engine {
     std::vector<Extent> free_ext;    // rows of deleted documents / dropped stores, sorted, coalesced: reused first-fit
     uint64_t free_rows = 0;
     cudaStream_t ingest_stream = nullptr;
-    DeviceBuf sc_text, sc_counts, sc_bucket, sc_start, sc_end, sc_ntok, sc_spans;
+    DeviceBuf sc_text, sc_state, sc_bucket, sc_cstart, sc_end, sc_ctl, sc_spans, sc_deferred;
+    PinnedBuf sc_stage;              // staging ring for documents in pageable host memory (kStageSlots chunks)
+    PinnedBuf sc_ctl_host;           // control words read back per document
+    cudaEvent_t stage_ev[8] = {};    // "this slot's copy has left the staging buffer"
+    struct CopyPool *copy_pool = nullptr;   // helper threads that fill the staging ring (created on the first large document)
+    std::atomic<uint64_t> ingest_bytes{0}, ingest_ns{0};
 
     std::mutex ctx_mu;
     std::condition_variable ctx_cv;
@@ -868,8 +952,12 @@ int rf_engine_destroy(rf_engine *e) {
     for (auto &kv : e->stream_states) kv.second->release();
     e->stream_states.clear();
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
-    e->sc_text.release(); e->sc_counts.release(); e->sc_bucket.release(); e->sc_start.release();
-    e->sc_end.release(); e->sc_ntok.release(); e->sc_spans.release();
+    copy_pool_destroy(e->copy_pool);
+    e->sc_text.release(); e->sc_state.release(); e->sc_bucket.release(); e->sc_cstart.release();
+    e->sc_end.release(); e->sc_ctl.release(); e->sc_spans.release(); e->sc_deferred.release();
+    e->sc_stage.release(); e->sc_ctl_host.release();
+    for (cudaEvent_t ev : e->stage_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e->debug_ts) cudaFree(e->debug_ts);
     if (e->zipf_bucket) cudaFree(e->zipf_bucket);
     if (e->F) cudaFree(e->F);
@@ -975,6 +1063,109 @@ int rf_doc_tombstone(rf_engine *e, uint64_t doc_id) {
     return tombstone_extents(e, ext);
 }
 
+// Text of one document -> device (e->sc_text) with the tokeniser launched behind it, chunk by chunk.
+// Caller holds ingest_mu.  On return every tokenise launch is enqueued on the ingest stream.
+static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::TokenizeArgs &t) {
+    cudaStream_t s = e->ingest_stream;
+    const uint32_t n_blocks = t.n_blocks;
+    int launches = 0;
+    // where does the text live?  (a plain malloc'ed buffer reports "unregistered")
+    cudaPointerAttributes attr{};
+    cudaMemoryType where = cudaMemoryTypeUnregistered;
+    if (n && cudaPointerGetAttributes(&attr, utf8) == cudaSuccess) where = attr.type;
+    else cudaGetLastError();
+    uint8_t *d_text = static_cast<uint8_t *>(e->sc_text.p);
+    auto blocks_upto = [&](size_t bytes) { return static_cast<uint32_t>((bytes + rf::kFeatBlockBytes - 1) / rf::kFeatBlockBytes); };
+    if (n == 0) return RF_OK;
+    if (where == cudaMemoryTypeDevice || where == cudaMemoryTypeManaged) {
+        // already in HBM: one device copy into the padded, aligned scratch, one launch
+        RF_CUDA(cudaMemcpyAsync(d_text, utf8, n, cudaMemcpyDeviceToDevice, s));
+        t.avail_end = n;
+        RF_CUDA(rf::launch_tokenize(t, n_blocks, s));
+        e->launches.fetch_add(1);
+        return RF_OK;
+    }
+    const bool pinned_src = where == cudaMemoryTypeHost;
+    if (n < kStageMinBytes) {
+        const uint8_t *src = utf8;
+        if (!pinned_src) {
+            RF_CUDA(e->sc_stage.reserve(kStageChunk * kStageSlots));
+            memcpy(e->sc_stage.p, utf8, n);
+            src = static_cast<const uint8_t *>(e->sc_stage.p);
+        }
+        RF_CUDA(cudaMemcpyAsync(d_text, src, n, cudaMemcpyHostToDevice, s));
+        t.avail_end = n;
+        RF_CUDA(rf::launch_tokenize(t, n_blocks, s));
+        e->launches.fetch_add(1);
+        return RF_OK;
+    }
+    // ---- chunked: DMA of chunk c, then the tokeniser over the blocks of chunk c - 1 (whose look-ahead
+    // bytes -- a block's 4-byte halo, a token running on -- are in chunk c)
+    const uint32_t n_chunks = static_cast<uint32_t>((n + kStageChunk - 1) / kStageChunk);
+    CopyPool *pool = nullptr;
+    if (!pinned_src) {
+        RF_CUDA(e->sc_stage.reserve(kStageChunk * kStageSlots));
+        for (cudaEvent_t &ev : e->stage_ev)
+            if (!ev) RF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (!e->copy_pool) {
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            e->copy_pool = copy_pool_create(std::min(3u, hw > 1 ? hw - 1 : 0u));
+            if (!e->copy_pool) return fail(RF_ENOMEM, "host allocation failed");
+        }
+        pool = e->copy_pool;
+        pool->src = utf8;
+        pool->ring = static_cast<uint8_t *>(e->sc_stage.p);
+        pool->n = n;
+        pool->n_chunks = n_chunks;
+        pool->ev = e->stage_ev;
+        pool->next.store(0);
+        pool->issued.store(0);
+        if (pool->staged.size() < n_chunks) pool->staged = std::vector<std::atomic<uint8_t>>(n_chunks);
+        for (uint32_t c = 0; c < n_chunks; ++c) pool->staged[c].store(0, std::memory_order_relaxed);
+        pool->job_live.store(true, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(pool->mu);
+            ++pool->job_gen;
+        }
+        pool->cv.notify_all();
+    }
+    int rc = RF_OK;
+    uint32_t blocks_done = 0;
+    for (uint32_t c = 0; c < n_chunks && rc == RF_OK; ++c) {
+        const size_t off = static_cast<size_t>(c) * kStageChunk, len = std::min(kStageChunk, n - off);
+        const uint8_t *src = utf8 + off;
+        if (pool) {
+            // fill slots ourselves while the one we need is not ready (the helpers may still be waking up)
+            while (!pool->staged[c].load(std::memory_order_acquire))
+                if (!pool->stage_one()) std::this_thread::yield();
+            src = pool->ring + (c % kStageSlots) * kStageChunk;
+        }
+        cudaError_t ce = cudaMemcpyAsync(d_text + off, src, len, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess && pool) {
+            ce = cudaEventRecord(e->stage_ev[c % kStageSlots], s);
+            pool->issued.store(c + 1, std::memory_order_release);
+        }
+        if (ce == cudaSuccess && c >= 1) {
+            t.avail_end = off + len;
+            const uint32_t upto = blocks_upto(off);        // blocks that START before this chunk
+            ce = rf::launch_tokenize(t, upto - blocks_done, s);
+            blocks_done = upto;
+            ++launches;
+        }
+        if (ce != cudaSuccess) rc = fail(RF_ECUDA, "ingest pipeline failed: %s", cudaGetErrorString(ce));
+    }
+    if (pool) {
+        pool->issued.store(n_chunks + kStageSlots, std::memory_order_release);   // release any helper still waiting for a slot
+        pool->job_live.store(false, std::memory_order_release);
+        while (pool->helpers_in.load(std::memory_order_acquire)) std::this_thread::yield();
+    }
+    if (rc) return rc;
+    t.avail_end = n;
+    RF_CUDA(rf::launch_tokenize(t, n_blocks - blocks_done, s));
+    e->launches.fetch_add(launches + 1);
+    return RF_OK;
+}
+
 int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint8_t *utf8, size_t n, uint64_t *first_chunk,
                    uint32_t *n_chunks, int64_t *spans, uint32_t max_spans) {
     if (!e || (!utf8 && n)) return fail(RF_EINVAL, "null argument");
@@ -982,25 +1173,44 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     int rc = check_store(e, store_seg);
     if (rc) return rc;
     std::lock_guard<std::mutex> ing(e->ingest_mu);
+    const auto t_start = std::chrono::steady_clock::now();
     RF_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = e->ingest_stream;
     const uint32_t n_blocks = static_cast<uint32_t>((n + rf::kFeatBlockBytes - 1) / rf::kFeatBlockBytes);
     const size_t max_tokens = n / 2 + 1;
     RF_CUDA(e->sc_text.reserve(n + 64));
-    RF_CUDA(e->sc_counts.reserve((static_cast<size_t>(n_blocks) + 1) * 4));
+    RF_CUDA(e->sc_state.reserve((static_cast<size_t>(n_blocks) + 1) * 8));
     RF_CUDA(e->sc_bucket.reserve(max_tokens));
-    RF_CUDA(e->sc_start.reserve(max_tokens * 4));
     RF_CUDA(e->sc_end.reserve(max_tokens * 4));
-    RF_CUDA(e->sc_ntok.reserve(4));
-    rf::FeaturizeWork w{static_cast<uint8_t *>(e->sc_text.p), static_cast<uint32_t *>(e->sc_counts.p),
-                        static_cast<uint8_t *>(e->sc_bucket.p), static_cast<uint32_t *>(e->sc_start.p),
-                        static_cast<uint32_t *>(e->sc_end.p), static_cast<uint32_t *>(e->sc_ntok.p)};
-    if (n) RF_CUDA(cudaMemcpyAsync(w.text, utf8, n, cudaMemcpyHostToDevice, s));
-    int launches = 0;
-    RF_CUDA(rf::launch_tokenize(w, n, s, &launches));
-    uint32_t n_tokens = 0;
-    RF_CUDA(cudaMemcpyAsync(&n_tokens, w.n_tokens, 4, cudaMemcpyDeviceToHost, s));
+    RF_CUDA(e->sc_cstart.reserve((max_tokens / 112 + 2) * 4));
+    RF_CUDA(e->sc_ctl.reserve(rf::kCtlWords * 4));
+    RF_CUDA(e->sc_deferred.reserve(2 * rf::kMaxDeferred * 4));
+    RF_CUDA(e->sc_ctl_host.reserve(rf::kCtlWords * 4));
+    rf::TokenizeArgs t{};
+    t.text = static_cast<const uint8_t *>(e->sc_text.p);
+    t.n = n;
+    t.avail_end = n;
+    t.n_blocks = n_blocks;
+    t.state = static_cast<uint64_t *>(e->sc_state.p);
+    t.ctl = static_cast<uint32_t *>(e->sc_ctl.p);
+    t.tok_bucket = static_cast<uint8_t *>(e->sc_bucket.p);
+    t.tok_end = static_cast<uint32_t *>(e->sc_end.p);
+    t.chunk_start = static_cast<uint32_t *>(e->sc_cstart.p);
+    t.deferred = static_cast<uint32_t *>(e->sc_deferred.p);
+    RF_CUDA(cudaMemsetAsync(t.ctl, 0, rf::kCtlWords * 4, s));
+    if (n_blocks) RF_CUDA(cudaMemsetAsync(t.state, 0, static_cast<size_t>(n_blocks) * 8, s));
+    if ((rc = copy_and_tokenize(e, utf8, n, t))) return rc;
+    volatile uint32_t *h_ctl = static_cast<volatile uint32_t *>(e->sc_ctl_host.p);
+    RF_CUDA(cudaMemcpyAsync(e->sc_ctl_host.p, t.ctl, rf::kCtlWords * 4, cudaMemcpyDeviceToHost, s));
     RF_CUDA(cudaStreamSynchronize(s));
+    const uint32_t n_tokens = h_ctl[rf::kCtlTokens], n_deferred = h_ctl[rf::kCtlDeferred];
+    int launches = 0;
+    if (n_deferred) {   // tokens longer than a whole copy chunk: hash them now that every byte is here
+        if (n_deferred > rf::kMaxDeferred) return fail(RF_EINVAL, "internal: %u parked tokens (max %u)", n_deferred, rf::kMaxDeferred);
+        t.avail_end = n;
+        RF_CUDA(rf::launch_hash_deferred(t, n_deferred, s));
+        ++launches;
+    }
     const uint32_t nc = n_tokens == 0 ? 0 : 1 + ((n_tokens > 128 ? n_tokens - 128 : 0) + 111) / 112;
     uint64_t first = 0;
     bool reused = false;
@@ -1010,7 +1220,7 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
         int64_t *d_spans = static_cast<int64_t *>(e->sc_spans.p);
         // rows taken from the free list lie inside ranges a concurrent search may be scanning (masked):
         // features and norms first, the segment words that un-mask them only after those are complete
-        RF_CUDA(rf::launch_rows_from_tokens(w, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, reused ? nullptr : e->seg + first,
+        RF_CUDA(rf::launch_rows_from_tokens(t, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, reused ? nullptr : e->seg + first,
                                             store_seg, d_spans, s));
         ++launches;
         const uint32_t ns = spans ? std::min(nc, max_spans) : 0;
@@ -1033,6 +1243,27 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     }
     if (first_chunk) *first_chunk = e->cfg.id_base + first;
     if (n_chunks) *n_chunks = nc;
+    e->ingest_bytes.fetch_add(n, std::memory_order_relaxed);
+    e->ingest_ns.fetch_add(static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count()),
+                           std::memory_order_relaxed);
+    return RF_OK;
+}
+
+int rf_host_alloc(size_t n, void **out) {
+    if (!out || n == 0) return fail(RF_EINVAL, "null argument");
+    const cudaError_t ce = cudaHostAlloc(out, n, cudaHostAllocPortable);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RF_ENOMEM, "cudaHostAlloc of %zu bytes failed: %s", n, cudaGetErrorString(ce));
+    }
+    return RF_OK;
+}
+
+int rf_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RF_EINVAL, "not a buffer from rf_host_alloc");
+    }
     return RF_OK;
 }
 

@@ -5,13 +5,12 @@
 // ARQ worker at backend/app/services/ingestion.py:45-52.  The tokeniser rule restates
 // scripts/benchmark/metrics.py:6,13-19 at byte level.
 //
-// Byte/integer work, bound by the H2D copy of the text (PCIe) and then HBM:
-//   pass A  count kept-token starts per 4 KB block          (reads text once)
-//   pass B  exclusive scan of the block counts               (one block, <= 6400 entries for 25 MB)
-//   pass C  recompute flags, in-block scan, hash each kept token (FNV-1a 32) and emit
-//           (bucket, byte start, byte end) at its global token ordinal
-//   rows    one warp per chunk window [112 w, 112 w + 128): shared-memory histogram of the
-//           window's buckets -> one 256-byte int8 row, its sum of squares, store word, byte span
+// Byte/integer work, bound by the H2D copy of the text (PCIe), which the engine overlaps with it:
+//   tokenise  ONE pass per copied chunk of text: 4 KB blocks flag their kept-token starts, learn how many
+//             tokens precede them by a decoupled look-back, hash each token (FNV-1a 32) and emit
+//             (bucket, byte end [, byte start of a window's first token]) at its global token ordinal
+//   rows      one warp per chunk window [112 w, 112 w + 128): shared-memory histogram of the
+//             window's buckets -> one 256-byte int8 row, its sum of squares, store word, byte span
 // A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
 // look-ahead, so stop-word removal needs no second compaction.
 #include <algorithm>
@@ -105,74 +104,37 @@ __device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_raw) {
     return flags;
 }
 
-__global__ void __launch_bounds__(kFeatThreads) count_tokens_kernel(const uint8_t *__restrict__ text, size_t n,
-                                                                    uint32_t *__restrict__ block_counts) {
-    __shared__ __align__(16) uint8_t s_raw[kStageBytes];
-    __shared__ uint32_t s_warp[kFeatThreads / 32];
-    stage_block(text, n, static_cast<size_t>(blockIdx.x) * kFeatBlockBytes, s_raw);
-    uint32_t c = __popc(thread_flags(s_raw));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
-    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kFeatThreads / 32; ++w) t += s_warp[w];
-        block_counts[blockIdx.x] = t;
-    }
+// ---- single-pass tokeniser --------------------------------------------------------------------------------
+// One block per 4 KB of text: stage + lower-case it, flag the kept-token starts, and place the block's
+// tokens at their GLOBAL ordinals in the same pass -- the exclusive token count of everything before the
+// block comes from a decoupled look-back over a per-block status array (aggregate published as soon as
+// the block has counted, inclusive prefix once it has looked back), so the text is read once and there is
+// no separate count / scan pass.  Blocks take their number from a ticket, so a block's predecessors have
+// always started.  The text may still be arriving: a launch covers the blocks of one copied chunk and
+// bytes are valid up to `avail_end`; a token that runs past it (only possible for a token longer than a
+// whole chunk) is parked in a short list and hashed by hash_deferred_kernel once every byte is there.
+// Per kept token: bucket (1 B) and end offset (4 B) at its ordinal; the start offset only for the tokens
+// that open a chunk window (ordinal % 112 == 0).
+constexpr uint64_t kStAggregate = 1ull << 32, kStInclusive = 2ull << 32;
+
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// In-place exclusive scan of counts[0..n), total to counts[n] and *n_tokens.  One block.
-__global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t *__restrict__ counts, uint32_t n,
-                                                           uint32_t *__restrict__ n_tokens) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0;
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, w, o);
-                if (lane >= o) w += t;
-            }
-            s_warp[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t warp_off = warp ? s_warp[warp - 1] : 0;
-        const uint32_t carry = s_carry;
-        if (i < n) counts[i] = carry + warp_off + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + s_warp[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        counts[n] = s_carry;
-        *n_tokens = s_carry;
-    }
-}
-
-__global__ void __launch_bounds__(kFeatThreads) emit_tokens_kernel(const uint8_t *__restrict__ text, size_t n,
-                                                                   const uint32_t *__restrict__ block_off,
-                                                                   uint8_t *__restrict__ tok_bucket,
-                                                                   uint32_t *__restrict__ tok_start,
-                                                                   uint32_t *__restrict__ tok_end) {
+__global__ void __launch_bounds__(kFeatThreads) tokenize_kernel(const TokenizeArgs a) {
     __shared__ __align__(16) uint8_t s_raw[kStageBytes];
     __shared__ uint32_t s_warp[kFeatThreads / 32];
-    const size_t base = static_cast<size_t>(blockIdx.x) * kFeatBlockBytes;
-    stage_block(text, n, base, s_raw);
+    __shared__ uint32_t s_block, s_ex;
+    if (threadIdx.x == 0) s_block = atomicAdd(a.ctl + kCtlTicket, 1u);
+    __syncthreads();
+    const uint32_t B = s_block;
+    const size_t base = static_cast<size_t>(B) * kFeatBlockBytes;
+    stage_block(a.text, a.n, base, s_raw);
     const uint8_t *s_txt = stage_origin(s_raw);
     const uint32_t flags = thread_flags(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -185,9 +147,38 @@ __global__ void __launch_bounds__(kFeatThreads) emit_tokens_kernel(const uint8_t
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t warp_off = 0;
-    for (int w = 0; w < warp; ++w) warp_off += s_warp[w];
-    uint32_t ord = block_off[blockIdx.x] + warp_off + inc - c;
+    uint32_t warp_off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kFeatThreads / 32; ++w) {
+        if (w < warp) warp_off += s_warp[w];
+        total += s_warp[w];
+    }
+    if (warp == 0) {
+        // ---- decoupled look-back (warp 0): 32 predecessors per step, nearest first
+        if (lane == 0) st_release_u64(a.state + B, (B == 0 ? kStInclusive : kStAggregate) | total);
+        uint32_t ex = 0;
+        for (int64_t j = static_cast<int64_t>(B) - 1; j >= 0; j -= 32) {
+            const int64_t idx = j - lane;
+            uint64_t v = kStInclusive;                        // before the first block: an inclusive prefix of 0
+            if (idx >= 0) {
+                do { v = ld_acquire_u64(a.state + idx); } while ((v >> 32) == 0);
+            }
+            const unsigned incl = __ballot_sync(kFull, (v >> 32) == 2);
+            const int stop = incl ? __ffs(incl) - 1 : 31;    // nearest predecessor that already knows its prefix
+            uint32_t part = lane <= stop ? static_cast<uint32_t>(v) : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+            ex += part;
+            if (incl) break;
+        }
+        if (lane == 0) {
+            if (B) st_release_u64(a.state + B, kStInclusive | (ex + total));
+            s_ex = ex;
+            if (B + 1 == a.n_blocks) a.ctl[kCtlTokens] = ex + total;
+        }
+    }
+    __syncthreads();
+    uint32_t ord = s_ex + warp_off + inc - c;
 
     uint32_t f = flags;
     while (f) {
@@ -196,26 +187,52 @@ __global__ void __launch_bounds__(kFeatThreads) emit_tokens_kernel(const uint8_t
         const size_t start = base + static_cast<size_t>(threadIdx.x) * kBytesPerThread + j;
         uint32_t h = 0x811C9DC5u;
         size_t p = start;
-        // tokens are short; bytes past this block come from L2 (the block just streamed them in)
-        while (p < n) {
+        // tokens are short; bytes past this block come from L2 (the copy just streamed them in)
+        while (p < a.avail_end) {
             const uint8_t cb = (p - base) < static_cast<size_t>(kFeatBlockBytes) + 4 ? s_txt[p - base + 1]
-                                                                                    : lower_byte(text[p]);
+                                                                                    : lower_byte(a.text[p]);
             if (!token_byte(cb)) break;
             h ^= cb;
             h *= 0x01000193u;
             ++p;
         }
-        tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
-        tok_start[ord] = static_cast<uint32_t>(start);
-        tok_end[ord] = static_cast<uint32_t>(p);
+        if (ord % kChunkStride == 0) a.chunk_start[ord / kChunkStride] = static_cast<uint32_t>(start);
+        if (p == a.avail_end && a.avail_end < a.n) {
+            // ran out of copied bytes mid-token: finish it later (hash_deferred_kernel)
+            const uint32_t slot = atomicAdd(a.ctl + kCtlDeferred, 1u);
+            if (slot < kMaxDeferred) {
+                a.deferred[2 * slot] = ord;
+                a.deferred[2 * slot + 1] = static_cast<uint32_t>(start);
+            }
+        } else {
+            a.tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
+            a.tok_end[ord] = static_cast<uint32_t>(p);
+        }
         ++ord;
     }
+}
+
+__global__ void __launch_bounds__(64) hash_deferred_kernel(const TokenizeArgs a, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t ord = a.deferred[2 * i];
+    size_t p = a.deferred[2 * i + 1];
+    uint32_t h = 0x811C9DC5u;
+    while (p < a.n) {
+        const uint8_t cb = lower_byte(a.text[p]);
+        if (!token_byte(cb)) break;
+        h ^= cb;
+        h *= 0x01000193u;
+        ++p;
+    }
+    a.tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
+    a.tok_end[ord] = static_cast<uint32_t>(p);
 }
 
 constexpr int kRowWarps = 8;
 
 __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
-    const uint8_t *__restrict__ tok_bucket, const uint32_t *__restrict__ tok_start,
+    const uint8_t *__restrict__ tok_bucket, const uint32_t *__restrict__ chunk_start,
     const uint32_t *__restrict__ tok_end, uint32_t n_tokens, uint32_t n_chunks, int8_t *__restrict__ F,
     int32_t *__restrict__ ff, uint32_t *__restrict__ seg, uint32_t store_seg, int64_t *__restrict__ spans) {
     __shared__ uint32_t hist[kRowWarps][kDim];
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
             ff[w] = sq;
             if (seg) seg[w] = store_seg;
             if (spans) {
-                spans[2 * static_cast<size_t>(w)] = tok_start[lo];
+                spans[2 * static_cast<size_t>(w)] = chunk_start[w];
                 spans[2 * static_cast<size_t>(w) + 1] = tok_end[hi - 1];
             }
         }
@@ -385,23 +402,24 @@ cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint3
     return cudaGetLastError();
 }
 
-cudaError_t launch_tokenize(const FeaturizeWork &w, size_t n_bytes, cudaStream_t s, int *launches) {
-    const uint32_t n_blocks = static_cast<uint32_t>((n_bytes + kFeatBlockBytes - 1) / kFeatBlockBytes);
-    if (n_blocks) count_tokens_kernel<<<n_blocks, kFeatThreads, 0, s>>>(w.text, n_bytes, w.block_counts);
-    scan_counts_kernel<<<1, 1024, 0, s>>>(w.block_counts, n_blocks, w.n_tokens);
-    if (n_blocks)
-        emit_tokens_kernel<<<n_blocks, kFeatThreads, 0, s>>>(w.text, n_bytes, w.block_counts, w.tok_bucket, w.tok_start,
-                                                          w.tok_end);
-    if (launches) *launches += n_blocks ? 3 : 1;
+cudaError_t launch_tokenize(const TokenizeArgs &a, uint32_t n_blocks_here, cudaStream_t s) {
+    if (n_blocks_here == 0) return cudaSuccess;
+    tokenize_kernel<<<n_blocks_here, kFeatThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F, int32_t *ff,
+cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    hash_deferred_kernel<<<(count + 63) / 64, 64, 0, s>>>(a, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F, int32_t *ff,
                                     uint32_t *seg, uint32_t store_seg, int64_t *spans_dev, cudaStream_t s) {
     if (n_chunks == 0) return cudaSuccess;
     uint32_t blocks = (n_chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
-    rows_from_tokens_kernel<<<blocks, kRowWarps * 32, 0, s>>>(w.tok_bucket, w.tok_start, w.tok_end, n_tokens, n_chunks, F, ff,
+    rows_from_tokens_kernel<<<blocks, kRowWarps * 32, 0, s>>>(w.tok_bucket, w.chunk_start, w.tok_end, n_tokens, n_chunks, F, ff,
                                                              seg, store_seg, spans_dev);
     return cudaGetLastError();
 }

@@ -156,17 +156,25 @@ cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_
                               cudaStream_t s);
 
 // featurisation (featurize.cu)
-struct FeaturizeWork {       // device scratch for one document
-    uint8_t *text;           // [cap_bytes + 64] padded copy of the document
-    uint32_t *block_counts;  // [n_blocks + 1]
-    uint8_t *tok_bucket;     // [cap_tokens]
-    uint32_t *tok_start;     // [cap_tokens]
-    uint32_t *tok_end;       // [cap_tokens]
-    uint32_t *n_tokens;      // [1]
-};
 constexpr uint32_t kFeatBlockBytes = 4096;
-cudaError_t launch_tokenize(const FeaturizeWork &w, size_t n_bytes, cudaStream_t s, int *launches);
-cudaError_t launch_rows_from_tokens(const FeaturizeWork &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
+constexpr uint32_t kMaxDeferred = 64;    // tokens longer than a whole copy chunk, finished after the last copy
+enum : uint32_t { kCtlTicket = 0, kCtlTokens = 1, kCtlDeferred = 2, kCtlWords = 4 };   // control words (zeroed per document)
+struct TokenizeArgs {        // device scratch for one document
+    const uint8_t *text;     // [>= n + 64] padded device copy of the document, 16-byte aligned
+    size_t n;                // document bytes
+    size_t avail_end;        // bytes [0, avail_end) have arrived (== n for the last / only launch)
+    uint32_t n_blocks;       // 4 KB blocks of the whole document
+    uint64_t *state;         // [n_blocks] look-back status words (zeroed per document)
+    uint32_t *ctl;           // [kCtlWords]
+    uint8_t *tok_bucket;     // [cap_tokens]
+    uint32_t *tok_end;       // [cap_tokens]
+    uint32_t *chunk_start;   // [cap_tokens / 112 + 2] byte offset of the first token of each chunk window
+    uint32_t *deferred;      // [2 * kMaxDeferred] (ordinal, start) of parked tokens
+};
+// the next n_blocks_here blocks of the document (block numbers come from the ticket in ctl)
+cudaError_t launch_tokenize(const TokenizeArgs &a, uint32_t n_blocks_here, cudaStream_t s);
+cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStream_t s);
+cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
                                     int32_t *ff, uint32_t *seg, uint32_t store_seg, int64_t *spans_dev,
                                     cudaStream_t s);
 // weights: [256] u8 device (RF-1w) or null (plain RF-1)

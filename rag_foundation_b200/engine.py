@@ -160,6 +160,14 @@ class Engine:
         n = int(nch.value)
         return int(first.value), n, spans[:n].copy()
 
+    def ingest_text_ptr(self, seg: int, doc_id: int, ptr: int, n: int):
+        """ingest_text from a raw pointer -- pinned host memory (`PinnedBuffer`) or device memory; the engine
+        detects which.  -> (first_chunk_id, n_chunks)."""
+        first = C.c_uint64()
+        nch = C.c_uint32()
+        check(self._L.rf_ingest_text(self.handle, int(seg), int(doc_id), int(ptr), int(n), C.byref(first), C.byref(nch), None, 0))
+        return int(first.value), int(nch.value)
+
     def ingest_features(self, seg: int, doc_id: int, rows, n_rows: Optional[int] = None, on_device: bool = False) -> int:
         first = C.c_uint64()
         if on_device:
@@ -310,6 +318,32 @@ class Engine:
     def merge_topk_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, out_keys_ptr: int, stream: int = 0) -> None:
         check(self._L.rf_merge_topk_device(self.handle, int(keys_ptr), int(n_lists), int(nq), int(k), int(out_keys_ptr),
                                            int(stream) or None))
+
+
+class PinnedBuffer:
+    """Page-locked host memory from rf_host_alloc, exposed as a numpy uint8 array (`.array`): read an upload
+    straight into it (`file.readinto(buf.array)`) and hand `buf.ptr` to `Engine.ingest_text_ptr` -- the DMA then
+    runs from the caller's own buffer, no staging copy."""
+
+    def __init__(self, n: int):
+        self._L = lib()
+        p = C.c_void_p()
+        check(self._L.rf_host_alloc(int(n), C.byref(p)))
+        self.ptr = int(p.value)
+        self.n = int(n)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.n).from_address(self.ptr))
+
+    def close(self) -> None:
+        p, self.ptr = getattr(self, "ptr", 0), 0
+        if p:
+            self.array = None
+            self._L.rf_host_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class EngineGroup:

@@ -439,3 +439,79 @@ def test_many_scopes_hold_no_device_state(co, zb):
         F = co.synth_rows(1, (n_st - 1) * rows, rows, zb)
         want = co.score_topk_keys(F, np.full(rows, n_st - 1, np.uint32), co.synth_query(1, 0, zb), [n_st - 1], k=10, id_base=(n_st - 1) * rows)
         assert out.cpu().numpy().view(np.uint64)[0].tolist() == want.tolist()
+
+
+# ------------------------------------------------------------------ staged, chunk-pipelined ingest
+def _check_ingest(e, seg, doc_id, data, co, ptr=None):
+    if ptr is None:
+        first, n, spans = e.ingest_text(seg, doc_id, data)
+    else:
+        first, n = e.ingest_text_ptr(seg, doc_id, ptr, len(data))
+        spans = None
+    wF, wff, wsp, _ = co.featurize_doc(data)
+    assert n == len(wF), (n, len(wF))
+    F, sg, ff = e.read_rows(first - e.id_base, n)
+    assert (F == wF).all() and (ff == wff).all() and (sg == seg).all()
+    if spans is not None:
+        assert (spans == wsp).all()
+    return first, n
+
+
+@pytest.mark.timeout(600)
+def test_pipelined_ingest_sources_and_chunk_boundaries(co):
+    """Documents larger than one 2 MB copy chunk go through the staging ring (helper threads + chunk-by-chunk
+    DMA + one tokeniser launch per chunk with a decoupled look-back across all of them): rows, norms and spans
+    equal the oracle for pageable, pinned (rf_host_alloc) and device-resident sources; tokens that straddle a
+    chunk boundary, stop words at the boundary, and tokens LONGER than a whole chunk (hashed after the last
+    copy) included."""
+    import torch
+    from rag_foundation_b200.engine import PinnedBuffer
+    rng = np.random.default_rng(11)
+    CH = 2 << 20
+    words = [b"alpha", b"the", b"Beta9", b"a", b"an", b"gamma", b"x", b"\xc3\xa9t\xc3\xa9", b"Zeta_zeta", b"0042"]
+
+    def running_text(n):
+        parts, size = [], 0
+        while size < n:
+            w = words[int(rng.integers(0, len(words)))]
+            parts.append(w)
+            size += len(w) + 1
+        return b" ".join(parts)[:n]
+
+    docs = {
+        "5 MB running text": running_text(5 * CH // 2 + 12345),
+        "token across the first chunk boundary": running_text(CH - 3) + b"straddlingtoken" + b" " + running_text(CH),
+        "stop word ends exactly at the boundary": running_text(CH - 4)[:CH - 4] + b" the" + b" next words here " + running_text(CH // 2),
+        "stop-word prefix continues into the next chunk": running_text(CH - 2)[:CH - 2] + b" t" + b"heory of chunks " + running_text(CH // 2),
+        "a 5 MB token": b"lead in " + b"q" * (5 * CH // 2) + b" tail words follow " + running_text(100_000),
+        "document is one giant token": b"z" * (3 * CH + 17),
+        "exactly two chunks": running_text(2 * CH),
+        "one byte over a chunk": running_text(CH + 1),
+    }
+    with _engine(400_000) as e:
+        s = e.open_store("fileSearchStores/ingest")
+        doc_id = 1
+        for name, data in docs.items():
+            _check_ingest(e, s, doc_id, data, co)
+            doc_id += 1
+            pb = PinnedBuffer(len(data))
+            pb.array[:] = np.frombuffer(data, np.uint8)
+            _check_ingest(e, s, doc_id, data, co, ptr=pb.ptr)
+            pb.close()
+            doc_id += 1
+            dd = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+            off = 1 if len(data) > 4 else 0                      # a device pointer need not be aligned
+            torch.cuda.synchronize()
+            _check_ingest(e, s, doc_id, data[off:], co, ptr=dd.data_ptr() + off)
+            doc_id += 1
+        # concurrent uploads from several threads (the ARQ worker runs up to 10, worker.py:125) serialise cleanly
+        errs = []
+
+        def up(i):
+            try:
+                _check_ingest(e, s, 1000 + i, docs["5 MB running text"][i * 1000:], co)
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+        ths = [threading.Thread(target=up, args=(i,)) for i in range(4)]
+        [t.start() for t in ths]; [t.join() for t in ths]
+        assert not errs, errs[:1]
