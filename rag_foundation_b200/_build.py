@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "librf_b200.so")
 SOURCES = ["engine.cu", "group.cu", "score_topk.cu", "score_topk_gemm.cu", "score_topk_gemm_pair.cu", "featurize.cu", "synth.cu",
-           "peak_probe.cu"]
+           "peak_probe.cu", "hostcopy.cpp"]
 HEADERS = ["rf_device.cuh", "rf_gemm_device.cuh", "rf_internal.h", os.path.join("..", "..", "include", "rf_b200.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = [*ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall"]

@@ -202,14 +202,15 @@ struct PlanBlob {  // host staging of everything one launch needs besides F/seg/
 };
 
 // ---- staging of documents that arrive in pageable host memory ------------------------------------------
-// A copy from pageable memory makes the driver stage through its own small pinned buffers (~10 GB/s).
+// A copy from pageable memory makes the driver stage through its own small pinned buffers (~10-15 GB/s).
 // The engine stages itself: the document is cut into chunks, helper threads (and the ingesting thread,
-// whenever it has nothing to enqueue) memcpy chunks into a ring of pinned slots, and the ingesting thread
-// enqueues each chunk's DMA -- and the tokeniser launch of the chunk before it -- as soon as the slot is
-// full, in order.  Host memcpy, PCIe transfer and the tokenise kernels overlap.
-constexpr size_t kStageChunk = 2u << 20;
-constexpr uint32_t kStageSlots = 8;
-constexpr size_t kStageMinBytes = 1u << 20;     // smaller documents take one copy, no helpers
+// whenever it has nothing to enqueue) memcpy chunks into a pinned buffer, and the ingesting thread enqueues
+// each chunk's DMA -- and the tokeniser launch of the chunk before it -- as soon as the chunk is there, in
+// order.  Host memcpy, PCIe transfer and the tokenise kernels overlap.  The helpers make no CUDA call and
+// wait for nothing: the buffer holds a whole window of the document (32 MB; the upload cap is 25 MB), so no
+// slot is ever reused while its copy is in flight.
+constexpr size_t kStageWindowBytes = 32u << 20;   // pinned staging buffer per engine: one window of a document (the upload cap is 25 MB)
+constexpr size_t kStageMinBytes = 1u << 20;       // smaller documents take one copy, no helpers
 
 struct CopyPool {
     std::vector<std::thread> threads;
@@ -217,30 +218,41 @@ struct CopyPool {
     std::condition_variable cv;
     bool stop = false;
     uint64_t job_gen = 0;
-    // the job in flight (valid while job_live)
+    // the job in flight (valid while job_live): stage src[0, n) into dst[0, n), chunk by chunk, in order
     const uint8_t *src = nullptr;
-    uint8_t *ring = nullptr;
-    size_t n = 0;
+    uint8_t *dst = nullptr;
+    size_t n = 0, chunk = 0;
     uint32_t n_chunks = 0;
-    cudaEvent_t *ev = nullptr;
     std::atomic<uint32_t> next{0};        // next chunk to claim
-    std::atomic<uint32_t> issued{0};      // chunks whose DMA has been enqueued (and its slot event recorded)
     std::atomic<uint32_t> helpers_in{0};  // helpers currently inside the job
     std::atomic<bool> job_live{false};
     std::vector<std::atomic<uint8_t>> staged;
 
-    // Claim and stage one chunk; false when none is left.
+    // Claim and stage one chunk (pure host work: no CUDA call, nothing to wait for); false when none is left.
     bool stage_one() {
         const uint32_t c = next.fetch_add(1, std::memory_order_relaxed);
         if (c >= n_chunks) return false;
-        if (c >= kStageSlots) {   // the slot's previous tenant must have left for the device
-            while (issued.load(std::memory_order_acquire) + kStageSlots <= c) std::this_thread::yield();
-            cudaEventSynchronize(ev[c % kStageSlots]);
-        }
-        const size_t off = static_cast<size_t>(c) * kStageChunk;
-        memcpy(ring + (c % kStageSlots) * kStageChunk, src + off, std::min(kStageChunk, n - off));
+        const size_t off = static_cast<size_t>(c) * chunk;
+        rf::stage_copy(dst + off, src + off, std::min(chunk, n - off));
         staged[c].store(1, std::memory_order_release);
         return true;
+    }
+    void begin(const uint8_t *s, uint8_t *d, size_t bytes, size_t chunk_bytes) {
+        src = s; dst = d; n = bytes; chunk = chunk_bytes;
+        n_chunks = static_cast<uint32_t>((bytes + chunk_bytes - 1) / chunk_bytes);
+        next.store(0);
+        if (staged.size() < n_chunks) staged = std::vector<std::atomic<uint8_t>>(n_chunks);
+        for (uint32_t c = 0; c < n_chunks; ++c) staged[c].store(0, std::memory_order_relaxed);
+        job_live.store(true, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ++job_gen;
+        }
+        cv.notify_all();
+    }
+    void end() {
+        job_live.store(false, std::memory_order_release);
+        while (helpers_in.load(std::memory_order_acquire)) std::this_thread::yield();
     }
     void helper() {
         uint64_t seen = 0;
@@ -301,10 +313,14 @@ struct rf_engine {
     std::vector<Extent> free_ext;    // rows of deleted documents / dropped stores, sorted, coalesced: reused first-fit
     uint64_t free_rows = 0;
     cudaStream_t ingest_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // the document's DMA runs here, back to back, while the tokeniser works on ingest_stream
+    cudaEvent_t copy_ev[16] = {};            // "chunk c has arrived" (reused round-robin; waited on by ingest_stream in order)
+    cudaEvent_t ingest_idle = nullptr;       // the previous document's kernels have finished with the text scratch
     DeviceBuf sc_text, sc_state, sc_bucket, sc_cstart, sc_end, sc_ctl, sc_spans, sc_deferred;
-    PinnedBuf sc_stage;              // staging ring for documents in pageable host memory (kStageSlots chunks)
+    PinnedBuf sc_stage;              // staging ring for documents in pageable host memory
+    size_t stage_chunk = 2u << 20;   // bytes per copy chunk (RF_STAGE_CHUNK_KB) and helper threads (RF_STAGE_THREADS)
+    uint32_t stage_threads = 1;      // (on the measured hosts aggregate memcpy bandwidth stops scaling at two threads)
     PinnedBuf sc_ctl_host;           // control words read back per document
-    cudaEvent_t stage_ev[8] = {};    // "this slot's copy has left the staging buffer"
     struct CopyPool *copy_pool = nullptr;   // helper threads that fill the staging ring (created on the first large document)
     std::atomic<uint64_t> ingest_bytes{0}, ingest_ns{0};
 
@@ -882,6 +898,11 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     if (e->cfg.n_contexts == 0) e->cfg.n_contexts = 8;
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
+    if (const char *s = getenv("RF_STAGE_THREADS")) e->stage_threads = static_cast<uint32_t>(std::max(0, std::min(32, atoi(s))));
+    if (const char *s = getenv("RF_STAGE_CHUNK_KB")) {
+        const int kb = atoi(s);
+        if (kb >= 64 && kb <= 8192 && (kb & (kb - 1)) == 0) e->stage_chunk = static_cast<size_t>(kb) << 10;
+    }
     if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
     if (const char *s = getenv("RF_GEMM_PAIR")) e->gemm_pair = atoi(s) != 0;
     if (const char *s = getenv("RF_GEMM_SAMPLE")) e->gemm_sample = static_cast<uint32_t>(atoi(s));
@@ -914,7 +935,9 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     }
     e->hbm_bytes = cap * (RF_DIM + 8);
     // unwritten rows read as tombstones
-    if ((ce = cudaMemset(e->seg, 0xFF, cap * 4)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((ce = cudaMemset(e->seg, 0xFF, cap * 4)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ingest_idle, cudaEventDisableTiming)) != cudaSuccess) {
         const int rc = fail(RF_ECUDA, "engine init failed: %s", cudaGetErrorString(ce));
         rf_engine_destroy(e);
         return rc;
@@ -952,12 +975,14 @@ int rf_engine_destroy(rf_engine *e) {
     for (auto &kv : e->stream_states) kv.second->release();
     e->stream_states.clear();
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ingest_idle) cudaEventDestroy(e->ingest_idle);
+    for (cudaEvent_t ev : e->copy_ev)
+        if (ev) cudaEventDestroy(ev);
     copy_pool_destroy(e->copy_pool);
     e->sc_text.release(); e->sc_state.release(); e->sc_bucket.release(); e->sc_cstart.release();
     e->sc_end.release(); e->sc_ctl.release(); e->sc_spans.release(); e->sc_deferred.release();
     e->sc_stage.release(); e->sc_ctl_host.release();
-    for (cudaEvent_t ev : e->stage_ev)
-        if (ev) cudaEventDestroy(ev);
     if (e->debug_ts) cudaFree(e->debug_ts);
     if (e->zipf_bucket) cudaFree(e->zipf_bucket);
     if (e->F) cudaFree(e->F);
@@ -1089,8 +1114,8 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
     if (n < kStageMinBytes) {
         const uint8_t *src = utf8;
         if (!pinned_src) {
-            RF_CUDA(e->sc_stage.reserve(kStageChunk * kStageSlots));
-            memcpy(e->sc_stage.p, utf8, n);
+            RF_CUDA(e->sc_stage.reserve(kStageWindowBytes));
+            rf::stage_copy(e->sc_stage.p, utf8, n);
             src = static_cast<const uint8_t *>(e->sc_stage.p);
         }
         RF_CUDA(cudaMemcpyAsync(d_text, src, n, cudaMemcpyHostToDevice, s));
@@ -1101,63 +1126,57 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
     }
     // ---- chunked: DMA of chunk c, then the tokeniser over the blocks of chunk c - 1 (whose look-ahead
     // bytes -- a block's 4-byte halo, a token running on -- are in chunk c)
-    const uint32_t n_chunks = static_cast<uint32_t>((n + kStageChunk - 1) / kStageChunk);
+    const size_t chunk = e->stage_chunk;
     CopyPool *pool = nullptr;
     if (!pinned_src) {
-        RF_CUDA(e->sc_stage.reserve(kStageChunk * kStageSlots));
-        for (cudaEvent_t &ev : e->stage_ev)
-            if (!ev) RF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        RF_CUDA(e->sc_stage.reserve(kStageWindowBytes));
         if (!e->copy_pool) {
             const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-            e->copy_pool = copy_pool_create(std::min(3u, hw > 1 ? hw - 1 : 0u));
+            e->copy_pool = copy_pool_create(std::min(e->stage_threads, hw > 1 ? hw - 1 : 0u));
             if (!e->copy_pool) return fail(RF_ENOMEM, "host allocation failed");
         }
         pool = e->copy_pool;
-        pool->src = utf8;
-        pool->ring = static_cast<uint8_t *>(e->sc_stage.p);
-        pool->n = n;
-        pool->n_chunks = n_chunks;
-        pool->ev = e->stage_ev;
-        pool->next.store(0);
-        pool->issued.store(0);
-        if (pool->staged.size() < n_chunks) pool->staged = std::vector<std::atomic<uint8_t>>(n_chunks);
-        for (uint32_t c = 0; c < n_chunks; ++c) pool->staged[c].store(0, std::memory_order_relaxed);
-        pool->job_live.store(true, std::memory_order_release);
-        {
-            std::lock_guard<std::mutex> lk(pool->mu);
-            ++pool->job_gen;
-        }
-        pool->cv.notify_all();
     }
+    // Copies go to their own stream so the DMA engine never waits for a tokenise kernel: chunk c's arrival is
+    // an event the compute stream waits on before it tokenises chunk c - 1.  The memsets of the control words
+    // (compute stream, already enqueued) and the copies touch different buffers; the copy stream only has to
+    // wait until the PREVIOUS document's kernels are done with the text scratch (they are: every ingest ends
+    // with a synchronise of the compute stream).
+    cudaStream_t cs = e->copy_stream;
+    for (cudaEvent_t &ev : e->copy_ev)
+        if (!ev) RF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     int rc = RF_OK;
-    uint32_t blocks_done = 0;
-    for (uint32_t c = 0; c < n_chunks && rc == RF_OK; ++c) {
-        const size_t off = static_cast<size_t>(c) * kStageChunk, len = std::min(kStageChunk, n - off);
-        const uint8_t *src = utf8 + off;
+    uint32_t blocks_done = 0, g = 0;      // g: chunks enqueued so far (over all windows)
+    for (size_t w_off = 0; w_off < n && rc == RF_OK; w_off += kStageWindowBytes) {
+        const size_t w_len = std::min(kStageWindowBytes, n - w_off);
+        const uint32_t n_chunks = static_cast<uint32_t>((w_len + chunk - 1) / chunk);
         if (pool) {
-            // fill slots ourselves while the one we need is not ready (the helpers may still be waking up)
-            while (!pool->staged[c].load(std::memory_order_acquire))
-                if (!pool->stage_one()) std::this_thread::yield();
-            src = pool->ring + (c % kStageSlots) * kStageChunk;
+            if (w_off) RF_CUDA(cudaStreamSynchronize(cs));    // the previous window's copies have left the staging buffer
+            pool->begin(utf8 + w_off, static_cast<uint8_t *>(e->sc_stage.p), w_len, chunk);
         }
-        cudaError_t ce = cudaMemcpyAsync(d_text + off, src, len, cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess && pool) {
-            ce = cudaEventRecord(e->stage_ev[c % kStageSlots], s);
-            pool->issued.store(c + 1, std::memory_order_release);
+        for (uint32_t c = 0; c < n_chunks && rc == RF_OK; ++c) {
+            const size_t off = static_cast<size_t>(c) * chunk, len = std::min(chunk, w_len - off);
+            const uint8_t *src = utf8 + w_off + off;
+            if (pool) {
+                // stage chunks ourselves while the one we need is not there yet (the helpers may still be waking up)
+                while (!pool->staged[c].load(std::memory_order_acquire)) pool->stage_one();
+                src = static_cast<const uint8_t *>(e->sc_stage.p) + off;
+            }
+            // (an event may be re-recorded freely: a stream wait binds to the record that preceded it)
+            cudaError_t ce = cudaMemcpyAsync(d_text + w_off + off, src, len, cudaMemcpyHostToDevice, cs);
+            if (ce == cudaSuccess) ce = cudaEventRecord(e->copy_ev[g % 16], cs);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, e->copy_ev[g % 16], 0);
+            ++g;
+            if (ce == cudaSuccess && w_off + off > 0) {
+                t.avail_end = w_off + off + len;
+                const uint32_t upto = blocks_upto(w_off + off);        // blocks that START before this chunk
+                ce = rf::launch_tokenize(t, upto - blocks_done, s);
+                blocks_done = upto;
+                ++launches;
+            }
+            if (ce != cudaSuccess) rc = fail(RF_ECUDA, "ingest pipeline failed: %s", cudaGetErrorString(ce));
         }
-        if (ce == cudaSuccess && c >= 1) {
-            t.avail_end = off + len;
-            const uint32_t upto = blocks_upto(off);        // blocks that START before this chunk
-            ce = rf::launch_tokenize(t, upto - blocks_done, s);
-            blocks_done = upto;
-            ++launches;
-        }
-        if (ce != cudaSuccess) rc = fail(RF_ECUDA, "ingest pipeline failed: %s", cudaGetErrorString(ce));
-    }
-    if (pool) {
-        pool->issued.store(n_chunks + kStageSlots, std::memory_order_release);   // release any helper still waiting for a slot
-        pool->job_live.store(false, std::memory_order_release);
-        while (pool->helpers_in.load(std::memory_order_acquire)) std::this_thread::yield();
+        if (pool) pool->end();
     }
     if (rc) return rc;
     t.avail_end = n;

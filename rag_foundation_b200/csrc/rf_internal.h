@@ -155,6 +155,9 @@ cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_
                               int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,
                               cudaStream_t s);
 
+// host memcpy into a pinned staging buffer with non-temporal stores (hostcopy.cpp)
+void stage_copy(void *dst, const void *src, size_t n);
+
 // featurisation (featurize.cu)
 constexpr uint32_t kFeatBlockBytes = 4096;
 constexpr uint32_t kMaxDeferred = 64;    // tokens longer than a whole copy chunk, finished after the last copy
