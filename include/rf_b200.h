@@ -216,6 +216,15 @@ int rf_search_keys_device_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, 
                                 uint32_t n_segs, uint32_t k, const rf_peer_exchange *px,
                                 uint64_t *out_keys_dev, void *stream);
 
+/* The store-sharded form of the fused exchange (whole stores per rank, configs[4]): one scope per query as in
+ * rf_search_keys_device_scoped, `px` as above with nq_cap >= nq.  Every rank runs every query over the part of
+ * its scope it owns (mostly nothing); the scan kernel stores each query's k keys into every rank's gather
+ * buffer and releases the flag, and a second small kernel behind it on the stream acquires the `world` flags
+ * of each query and merges into out_keys_dev [nq, k] -- two launches, no collective, no host round trip. */
+int rf_search_keys_device_scoped_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                       const uint32_t *seg_off, uint32_t k, const rf_peer_exchange *px,
+                                       uint64_t *out_keys_dev, void *stream);
+
 /* k-way merge after the all-gather of the sharded path: keys_dev is n_lists x nq x k packed keys
  * (device), out_keys_dev nq x k.  Enqueued on `stream`, no synchronisation. */
 int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "rf_stream_set_overlap": (_i32, [_vp, _vp, _i32]),
     "rf_search_keys_device_scoped": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp]),
     "rf_search_keys_device_fused": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
+    "rf_search_keys_device_scoped_fused": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, C.POINTER(rf_peer_exchange), _vp, _vp]),
     "rf_merge_topk_device": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "rf_featurize_query": (_i32, [_vp, _vp, _sz, _vp]),
     "rf_scope_df": (_i32, [_vp, _vp, _u32, _vp, C.POINTER(_u64)]),

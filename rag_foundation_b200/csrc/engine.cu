@@ -85,6 +85,7 @@ struct Doc {
 };
 
 constexpr uint32_t kMaxExtPerQuery = 64;   // more are coalesced (the row mask keeps it exact)
+constexpr uint32_t kTableMinQueries = 4;   // batches of this many differently-scoped queries read their plans from the store table
 constexpr uint32_t kTilesPerBlockTarget = 160;   // ~1.3 MB streamed per block: start-up and merge stay under 10 %
 
 struct DeviceBuf {
@@ -194,6 +195,19 @@ struct StreamState {
     }
 };
 constexpr size_t kMaxStreamStates = 64;
+
+// Device-resident copy of every store's extents (rf::StoreEntry + flat lo / hi arrays), rebuilt when the
+// extents change (engine epoch).  Batches of store-scoped queries read their plans from it in the kernel, so
+// the host neither builds nor uploads a plan per query.  Readers hold `mu` shared from the moment they take the
+// pointers until their launch is enqueued; a rebuild holds it exclusively (and frees the old buffers with
+// cudaFree, which waits for every kernel already enqueued).
+struct StoreTable {
+    std::shared_mutex mu;
+    uint64_t epoch = ~0ull;
+    DeviceBuf entries, lo, hi;
+    std::vector<uint32_t> h_next, h_tiles;     // host mirror: extents / tiles per store (grid sizing, the 64-extent check)
+    uint32_t n_stores = 0;
+};
 
 struct PlanBlob {  // host staging of everything one launch needs besides F/seg/ff
     std::vector<uint8_t> bytes;
@@ -329,6 +343,7 @@ struct rf_engine {
     std::vector<SearchCtx *> free_ctx;
     std::vector<SearchCtx *> all_ctx;
 
+    StoreTable tbl;
     std::mutex plan_mu;              // guards the table only; a launch holds its StreamState's own mutex
     std::unordered_map<void *, std::shared_ptr<StreamState>> stream_states;
     uint64_t stream_tick = 0;
@@ -336,6 +351,7 @@ struct rf_engine {
     std::atomic<uint64_t> searches{0};
     std::atomic<uint64_t> launches{0};
     uint32_t blocks_override = 0;
+    bool table_enabled = true;       // RF_STORE_TABLE=0: host-built plans for every batch (A/B comparison)
     bool gemm_enabled = true;        // RF_GEMM=0 forces the scan kernel for batched device searches
     bool gemm_pair = true;           // RF_GEMM_PAIR=0 keeps batches of more than 256 queries on the single-CTA kernel
     uint32_t gemm_min_queries = 0;   // 0: cost model (gemm_pays); RF_GEMM_MIN_QUERIES=n forces "n queries or more"
@@ -457,6 +473,95 @@ int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store
     return RF_OK;
 }
 
+// Take the store table for reading (rebuilding it first if the extents changed since it was built).
+int table_acquire(rf_engine *e, std::shared_lock<std::shared_mutex> &lk) {
+    StoreTable &t = e->tbl;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        lk = std::shared_lock<std::shared_mutex>(t.mu);
+        if (t.epoch == e->epoch.load()) return RF_OK;
+        lk.unlock();
+        std::unique_lock<std::shared_mutex> ul(t.mu);
+        if (t.epoch == e->epoch.load()) continue;
+        std::vector<rf::StoreEntry> ent;
+        std::vector<uint32_t> lo, hi;
+        std::vector<Extent> ext;
+        uint64_t now;
+        {
+            std::shared_lock<std::shared_mutex> ml(e->meta_mu);
+            now = e->epoch.load();       // extents cannot change while meta_mu is held
+            ent.resize(e->stores.size());
+            t.h_next.assign(e->stores.size(), 0);
+            t.h_tiles.assign(e->stores.size(), 0);
+            for (uint32_t sg = 0; sg < e->stores.size(); ++sg) {
+                const Store &st = e->stores[sg];
+                rf::StoreEntry &en = ent[sg];
+                en = rf::StoreEntry{static_cast<uint32_t>(lo.size()), 0, 0, 0};
+                if (st.dropped || st.ext.empty()) continue;
+                const std::vector<Extent> *src = &st.ext;
+                if (st.ext.size() > kMaxExtPerQuery) {   // coalesce across the smallest gaps (the row mask keeps it exact)
+                    gather_extents(e, &sg, 1, ext);
+                    src = &ext;
+                }
+                for (const Extent &x : *src) {
+                    lo.push_back(x.lo);
+                    hi.push_back(x.hi);
+                    en.total_tiles += (x.hi - x.lo + rf::kScanTileRows - 1) / rf::kScanTileRows;
+                }
+                en.n_ext = static_cast<uint32_t>(src->size());
+                t.h_next[sg] = en.n_ext;
+                t.h_tiles[sg] = en.total_tiles;
+            }
+        }
+        if (lo.empty()) { lo.push_back(0); hi.push_back(0); }
+        if (ent.empty()) ent.push_back(rf::StoreEntry{0, 0, 0, 0});
+        RF_CUDA(cudaSetDevice(e->cfg.device));
+        RF_CUDA(t.entries.reserve(ent.size() * sizeof(rf::StoreEntry) * 2));     // (headroom: fewer re-allocations as stores are added)
+        RF_CUDA(t.lo.reserve(lo.size() * 4 * 2));
+        RF_CUDA(t.hi.reserve(hi.size() * 4 * 2));
+        RF_CUDA(cudaDeviceSynchronize());        // kernels that read the previous contents have finished
+        RF_CUDA(cudaMemcpy(t.entries.p, ent.data(), ent.size() * sizeof(rf::StoreEntry), cudaMemcpyHostToDevice));
+        RF_CUDA(cudaMemcpy(t.lo.p, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+        RF_CUDA(cudaMemcpy(t.hi.p, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+        t.n_stores = static_cast<uint32_t>(t.h_next.size());
+        t.epoch = now;
+    }
+    return fail(RF_EBUSY, "store table kept changing under a search");
+}
+
+// Can this batch take its plans from the store table?  (Every scope within RF_SCOPE_MAX stores and
+// rf::kInlineExt extents in all.)  Also the largest tile count of any query, for the grid.  Caller holds the table.
+bool table_batch_ok(const rf_engine *e, uint32_t nq, const uint32_t *store_segs, const uint32_t *seg_off, uint32_t *max_tiles) {
+    const StoreTable &t = e->tbl;
+    uint32_t mt = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint32_t s0 = seg_off[i], s1 = seg_off[i + 1];
+        if (s1 < s0 || s1 - s0 > RF_SCOPE_MAX) return false;
+        uint32_t ext = 0, tiles = 0;
+        for (uint32_t j = s0; j < s1; ++j) {
+            const uint32_t sg = store_segs[j];
+            if (sg >= t.n_stores) continue;
+            bool dup = false;
+            for (uint32_t x = s0; x < j; ++x) dup |= (store_segs[x] == sg);
+            if (dup) continue;
+            ext += t.h_next[sg];
+            tiles += t.h_tiles[sg];
+        }
+        if (ext > rf::kInlineExt) return false;
+        mt = std::max(mt, tiles);
+    }
+    *max_tiles = mt;
+    return true;
+}
+
+void fill_table_args(const rf_engine *e, ScanArgs &a, const uint8_t *d_blob, size_t off_segoff, size_t off_segs) {
+    a.st_tbl = static_cast<const rf::StoreEntry *>(e->tbl.entries.p);
+    a.st_lo = static_cast<const uint32_t *>(e->tbl.lo.p);
+    a.st_hi = static_cast<const uint32_t *>(e->tbl.hi.p);
+    a.st_n_stores = e->tbl.n_stores;
+    a.q_seg_off = reinterpret_cast<const uint32_t *>(d_blob + off_segoff);
+    a.q_segs = reinterpret_cast<const uint32_t *>(d_blob + off_segs);
+}
+
 uint32_t pick_blocks(rf_engine *e, uint32_t nq, uint32_t max_tiles) {
     if (e->blocks_override) return std::max(1u, std::min(std::min(e->blocks_override, 1024u), std::max(max_tiles, 1u)));
     const uint32_t wave = rf::scan_default_blocks_per_query(e->sm_count, e->scan_variant);
@@ -555,10 +660,17 @@ struct OutLayout {
 // One search on a context, first half: (blob upload unless everything rides in the kernel parameters) +
 // scan launch; the last block writes ids / scores / cosines straight into mapped pinned host memory when
 // the batch is small, so there is no device-to-host copy to enqueue.  search_wait is the second half.
-int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_host, uint32_t nq, uint32_t k, bool shared) {
+// `tq` non-null: the plans come from the store table (caller holds it): only the queries and their scope lists
+// travel to the device, `b` is unused.
+struct TableQuery {
+    const uint32_t *segs, *off;
+    uint32_t max_tiles;
+};
+int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q_host, uint32_t nq, uint32_t k, bool shared,
+                  const TableQuery *tq = nullptr) {
     const auto t0 = std::chrono::steady_clock::now();
     const OutLayout L(nq, k);
-    const uint32_t X = pick_blocks(e, nq, b.max_tiles);
+    const uint32_t X = pick_blocks(e, nq, tq ? tq->max_tiles : b.max_tiles);
     const size_t flag_off = (L.total + 15) & ~static_cast<size_t>(15);   // [seq word, finished-query counter]
     if (flag_off + 16 > c->m_out.cap) {
         RF_CUDA(c->m_out.reserve(flag_off + 16));
@@ -572,14 +684,38 @@ int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q
         RF_CUDA(cudaMemsetAsync(c->d_tickets.p, 0, c->d_tickets.cap, c->stream));
     }
     ScanArgs a{};
-    fill_args(e, a, nullptr, b, nullptr, k, shared);
-    maybe_inline_plan(a, b, nq, shared);
-    const bool inline_q = nq == 1;
+    const bool inline_q = nq == 1 && !tq;
+    if (tq) {
+        // [queries | scope offsets | scope stores] in one H2D copy
+        auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
+        const size_t n_segs = tq->off[nq];
+        const size_t off_off = align(static_cast<size_t>(nq) * RF_DIM), off_segs = align(off_off + (static_cast<size_t>(nq) + 1) * 4);
+        const size_t total = align(off_segs + std::max<size_t>(n_segs, 1) * 4);
+        RF_CUDA(c->h_in.reserve(total));
+        RF_CUDA(c->d_in.reserve(total));
+        uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
+        memcpy(h, q_host, static_cast<size_t>(nq) * RF_DIM);
+        memcpy(h + off_off, tq->off, (static_cast<size_t>(nq) + 1) * 4);
+        if (n_segs) memcpy(h + off_segs, tq->segs, n_segs * 4);
+        RF_CUDA(cudaMemcpyAsync(c->d_in.p, h, total, cudaMemcpyHostToDevice, c->stream));
+        a.F = e->F;
+        a.seg = e->seg;
+        a.ff = e->ff;
+        a.q = static_cast<const int8_t *>(c->d_in.p);
+        a.id_base = static_cast<uint32_t>(e->cfg.id_base);
+        a.k = k;
+        a.debug_ts = e->debug_ts;
+        a.dbg_flags = e->dbg_flags;
+        fill_table_args(e, a, static_cast<const uint8_t *>(c->d_in.p), off_off, off_segs);
+    } else {
+        fill_args(e, a, nullptr, b, nullptr, k, shared);
+        maybe_inline_plan(a, b, nq, shared);
+    }
     if (inline_q) {
         memcpy(a.q_inline, q_host, RF_DIM);
         a.q = nullptr;
     }
-    if (!(inline_q && a.inline_plan)) {   // queries and/or plans travel as one H2D copy
+    if (!tq && !(inline_q && a.inline_plan)) {   // queries and/or plans travel as one H2D copy
         RF_CUDA(c->h_in.reserve(b.bytes.size()));
         RF_CUDA(c->d_in.reserve(b.bytes.size()));
         memcpy(c->h_in.p, b.bytes.data(), b.bytes.size());
@@ -904,6 +1040,7 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
         if (kb >= 64 && kb <= 8192 && (kb & (kb - 1)) == 0) e->stage_chunk = static_cast<size_t>(kb) << 10;
     }
     if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
+    if (const char *s = getenv("RF_STORE_TABLE")) e->table_enabled = atoi(s) != 0;
     if (const char *s = getenv("RF_GEMM_PAIR")) e->gemm_pair = atoi(s) != 0;
     if (const char *s = getenv("RF_GEMM_SAMPLE")) e->gemm_sample = static_cast<uint32_t>(atoi(s));
     if (const char *s = getenv("RF_GEMM_SLICES_A")) e->gemm_slices_a = static_cast<uint32_t>(atoi(s));
@@ -974,6 +1111,7 @@ int rf_engine_destroy(rf_engine *e) {
     }
     for (auto &kv : e->stream_states) kv.second->release();
     e->stream_states.clear();
+    e->tbl.entries.release(); e->tbl.lo.release(); e->tbl.hi.release();
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ingest_idle) cudaEventDestroy(e->ingest_idle);
@@ -1639,14 +1777,24 @@ int rf_search_begin(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *
         }
     }
     PlanBlob b;
-    int rc = build_blob(e, q, nq, store_segs, seg_off, false, b);
-    if (rc) return rc;
+    int rc = RF_OK;
+    // Several queries with their own scopes: the kernel reads each query's extents from the device-resident
+    // store table, so the host builds no plan per query (unless a scope has more extents than a plan holds).
+    std::shared_lock<std::shared_mutex> tbl_lock;
+    TableQuery tq{store_segs, seg_off, 0};
+    bool use_table = false;
+    if (nq >= kTableMinQueries && e->table_enabled) {
+        if ((rc = table_acquire(e, tbl_lock))) return rc;
+        use_table = table_batch_ok(e, nq, store_segs, seg_off, &tq.max_tiles);
+        if (!use_table) tbl_lock.unlock();
+    }
+    if (!use_table && (rc = build_blob(e, q, nq, store_segs, seg_off, false, b))) return rc;
     SearchCtx *c = ctx_acquire(e);
     if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
     if (e->profile) e->prof_ns[0] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-    if ((rc = search_launch(e, c, b, q, nq, k, false))) return rc;
+    if ((rc = search_launch(e, c, b, q, nq, k, false, use_table ? &tq : nullptr))) return rc;
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     g.c = nullptr;
     *out = reinterpret_cast<rf_pending *>(c);
@@ -2019,26 +2167,49 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
     return RF_OK;
 }
 
-int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
-                                 const uint32_t *seg_off, uint32_t k, uint64_t *out_keys_dev, void *stream) {
+static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                          const uint32_t *seg_off, uint32_t k, uint64_t *out_keys_dev, void *stream,
+                                          const rf_peer_exchange *px) {
     if (!e || !q_dev || !seg_off || !out_keys_dev) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
     if (nq == 0) return RF_OK;
     if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
     RF_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // plans: from the device-resident store table when every scope fits a plan, else built here per query
+    std::shared_lock<std::shared_mutex> tbl_lock;
+    bool use_table = false;
+    uint32_t max_tiles = 0;
+    int rc = RF_OK;
+    if (e->table_enabled) {
+        if ((rc = table_acquire(e, tbl_lock))) return rc;
+        use_table = table_batch_ok(e, nq, store_segs, seg_off, &max_tiles);
+        if (!use_table) tbl_lock.unlock();
+    }
     PlanBlob b;
-    int rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b);
-    if (rc) return rc;
+    size_t off_off = 0, off_segs = 0;
+    if (use_table) {
+        auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
+        const size_t n_segs = seg_off[nq];
+        off_segs = align((static_cast<size_t>(nq) + 1) * 4);
+        b.bytes.resize(align(off_segs + std::max<size_t>(n_segs, 1) * 4));
+        memcpy(b.bytes.data() + off_off, seg_off, (static_cast<size_t>(nq) + 1) * 4);
+        if (n_segs) memcpy(b.bytes.data() + off_segs, store_segs, n_segs * 4);
+        b.max_tiles = max_tiles;
+    } else if ((rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b))) {
+        return rc;
+    }
     std::shared_ptr<StreamState> st = stream_state(e, stream);
     std::lock_guard<std::mutex> lk(st->mu);
     const uint32_t X = pick_blocks(e, nq, b.max_tiles);
     const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
     const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
-    if (b.bytes.size() > st->blob.cap || need_partial > st->partial.cap || need_sync > st->tickets.cap) {
+    const size_t need_local = px ? static_cast<size_t>(nq) * k * 8 : 0;
+    if (b.bytes.size() > st->blob.cap || need_partial > st->partial.cap || need_sync > st->tickets.cap || need_local > st->gemm_keys_a.cap) {
         RF_CUDA(cudaStreamSynchronize(s));
         RF_CUDA(st->blob.reserve(b.bytes.size()));
         RF_CUDA(st->partial.reserve(need_partial));
+        RF_CUDA(st->gemm_keys_a.reserve(need_local));
         if (need_sync > st->tickets.cap) {
             RF_CUDA(st->tickets.reserve(need_sync));
             RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
@@ -2051,15 +2222,75 @@ int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq,
     RF_CUDA(cudaMemcpyAsync(st->blob.p, st->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
     RF_CUDA(cudaEventRecord(st->h_blob_free, s));
     ScanArgs a{};
-    fill_args(e, a, static_cast<const uint8_t *>(st->blob.p), b, q_dev, k, false);
+    if (use_table) {
+        a.F = e->F;
+        a.seg = e->seg;
+        a.ff = e->ff;
+        a.q = q_dev;
+        a.id_base = static_cast<uint32_t>(e->cfg.id_base);
+        a.k = k;
+        a.debug_ts = e->debug_ts;
+        a.dbg_flags = e->dbg_flags;
+        fill_table_args(e, a, static_cast<const uint8_t *>(st->blob.p), off_off, off_segs);
+    } else {
+        fill_args(e, a, static_cast<const uint8_t *>(st->blob.p), b, q_dev, k, false);
+    }
     a.partial = static_cast<uint64_t *>(st->partial.p);
     set_sync_bufs(a, st->tickets, st->launches++);
     a.out_keys = out_keys_dev;
-    // the plans were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
+    uint64_t *gather_local = nullptr;
+    uint32_t *flags_local = nullptr;
+    if (px) {
+        // Store-sharded exchange: a query's rows live on one rank (or a few), every rank runs every query, most
+        // of them over nothing.  A block that WAITED for its peers here would hold an SM slot the peers' own
+        // scans may need (hundreds of such blocks per launch), so the scan only publishes -- keys into every
+        // rank's gather buffer, then a release flag -- and a second, tiny kernel behind it acquires the flags
+        // and merges (one warp per query).
+        const size_t slot = px->seq & 3u;
+        const size_t keys_off = slot * px->world * px->nq_cap * static_cast<size_t>(k);
+        const size_t flag_off = slot * px->world * static_cast<size_t>(px->nq_cap);
+        for (uint32_t r = 0; r < px->world; ++r) {
+            a.px_keys[r] = reinterpret_cast<uint64_t *>(px->keys_ptrs[r]) + keys_off;
+            a.px_flags[r] = reinterpret_cast<uint32_t *>(px->flag_ptrs[r]) + flag_off;
+        }
+        a.px_rank = px->rank;
+        a.px_world = px->world;
+        a.px_seq = px->seq;
+        a.px_nq_cap = px->nq_cap;
+        a.px_out = out_keys_dev;
+        a.px_timeout = px->timeout_flag_dev;
+        a.px_publish_only = 1;
+        a.out_keys = static_cast<uint64_t *>(st->gemm_keys_a.p);    // the local (pre-merge) lists
+        gather_local = a.px_keys[px->rank];
+        flags_local = a.px_flags[px->rank];
+    }
+    // the plans / scope lists were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
     RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
-    e->launches.fetch_add(1, std::memory_order_relaxed);
+    uint32_t launched = 1;
+    if (px && px->world > 1) {
+        RF_CUDA(rf::launch_merge_wait(gather_local, flags_local, px->world, px->nq_cap, nq, k, px->seq, out_keys_dev, px->timeout_flag_dev, s));
+        ++launched;
+    } else if (px) {
+        RF_CUDA(cudaMemcpyAsync(out_keys_dev, a.out_keys, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    e->launches.fetch_add(launched, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     return RF_OK;
+}
+
+int rf_search_keys_device_scoped(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                 const uint32_t *seg_off, uint32_t k, uint64_t *out_keys_dev, void *stream) {
+    return search_keys_device_scoped_impl(e, q_dev, nq, store_segs, seg_off, k, out_keys_dev, stream, nullptr);
+}
+
+int rf_search_keys_device_scoped_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
+                                       const uint32_t *seg_off, uint32_t k, const rf_peer_exchange *px, uint64_t *out_keys_dev,
+                                       void *stream) {
+    if (!px || px->struct_size != sizeof(rf_peer_exchange)) return fail(RF_EINVAL, "bad rf_peer_exchange");
+    if (px->world == 0 || px->world > 8 || px->rank >= px->world) return fail(RF_EINVAL, "world must be in [1, 8] and rank < world");
+    if (!px->keys_ptrs || !px->flag_ptrs || !px->timeout_flag_dev) return fail(RF_EINVAL, "null exchange buffer");
+    if (nq > px->nq_cap || k != px->k || px->seq == 0) return fail(RF_EINVAL, "exchange buffers are sized for nq <= %u, k == %u, seq > 0", px->nq_cap, px->k);
+    return search_keys_device_scoped_impl(e, q_dev, nq, store_segs, seg_off, k, out_keys_dev, stream, px);
 }
 
 int rf_merge_topk_device(rf_engine *e, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k,

@@ -21,6 +21,9 @@
 //     no collective.  (The SPMD device-resident path -- one process per GPU, results staying in HBM --
 //     exchanges inside the scan kernel instead: rf_search_keys_device_fused.)
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -28,6 +31,7 @@
 #include <new>
 #include <shared_mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -47,6 +51,64 @@ int gfail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+
+// One launcher thread per device: the calling thread hands every participating device its "begin" (query
+// upload + kernel launch, a few microseconds of driver calls each) and they run side by side instead of one
+// after the other -- with 8 GPUs and a batch that keeps each of them busy for only ~50 us, launching in turn
+// would cost more than the scan.  A launcher spins for a short while after its last task (a serving loop keeps
+// it hot) and sleeps otherwise; a caller that finds the launchers asleep launches in turn itself and wakes
+// them for the next call.
+struct Launcher {
+    std::thread th;
+    std::mutex owner;                    // one caller at a time, from post to collect
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint32_t> state{0};      // 0 idle, 1 task posted, 2 task done
+    std::atomic<bool> asleep{true};
+    std::atomic<bool> kick{false};       // "wake up and stay hot for a while": a caller expects to come back soon
+    bool stop = false;
+    void (*fn)(void *) = nullptr;
+    void *arg = nullptr;
+
+    void run() {
+        using clock = std::chrono::steady_clock;
+        auto last = clock::now();
+        while (true) {
+            if (state.load(std::memory_order_acquire) == 1) {
+                fn(arg);
+                state.store(2, std::memory_order_release);
+                last = clock::now();
+                continue;
+            }
+            if (clock::now() - last < std::chrono::microseconds(300)) continue;     // stay hot between back-to-back calls
+            std::unique_lock<std::mutex> lk(mu);
+            asleep.store(true, std::memory_order_release);
+            cv.wait(lk, [&] { return stop || kick.load(std::memory_order_acquire) || state.load(std::memory_order_acquire) == 1; });
+            kick.store(false, std::memory_order_release);
+            asleep.store(false, std::memory_order_release);
+            if (stop) return;
+            last = clock::now();
+        }
+    }
+    void wake() {
+        std::lock_guard<std::mutex> lk(mu);
+        kick.store(true, std::memory_order_release);
+        cv.notify_one();
+    }
+    void post(void (*f)(void *), void *a) {
+        fn = f;
+        arg = a;
+        state.store(1, std::memory_order_release);
+        if (asleep.load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> lk(mu);
+            cv.notify_one();
+        }
+    }
+    void collect() {
+        while (state.load(std::memory_order_acquire) != 2) {}
+        state.store(0, std::memory_order_release);
+    }
+};
 
 struct Hit {
     uint64_t id;
@@ -72,6 +134,7 @@ struct rf_group {
     std::vector<std::vector<uint64_t>> rows_on;        // [device][store]: rows ever placed there (never decremented: conservative)
     std::vector<uint64_t> dev_rows;                    // rows placed per device (placement balance)
     std::unordered_map<uint64_t, uint32_t> doc_dev;    // document -> device
+    std::vector<Launcher *> launchers;                 // one per device (groups of two or more)
 };
 
 namespace {
@@ -154,12 +217,28 @@ int rf_group_create(const rf_group_config *cfg, rf_group **out) {
         }
     g->rows_on.assign(G, {});
     g->dev_rows.assign(G, 0);
+    if (G >= 2 && !getenv("RF_GROUP_SERIAL"))
+        for (uint32_t d = 0; d < G; ++d) {
+            Launcher *l = new (std::nothrow) Launcher();
+            if (!l) break;
+            l->th = std::thread([l] { l->run(); });
+            g->launchers.push_back(l);
+        }
     *out = g;
     return RF_OK;
 }
 
 int rf_group_destroy(rf_group *g) {
     if (!g) return RF_OK;
+    for (Launcher *l : g->launchers) {
+        {
+            std::lock_guard<std::mutex> lk(l->mu);
+            l->stop = true;
+        }
+        l->cv.notify_one();
+        l->th.join();
+        delete l;
+    }
     for (rf_engine *e : g->eng) rf_engine_destroy(e);
     delete g;
     return RF_OK;
@@ -392,27 +471,73 @@ int rf_group_search(rf_group *g, const int8_t *q, uint32_t nq, const uint32_t *s
     };
     std::vector<PerDev> pd(G);
     int rc = RF_OK;
-    // ---- launch on every device that holds rows of some query's scope (concurrent on the GPUs)
-    for (uint32_t d = 0; d < G && rc == RF_OK; ++d) {
-        if (!(any & (1u << d))) continue;
-        PerDev &w = pd[d];
+    // ---- launch on every device that holds rows of some query's scope (concurrent on the GPUs).  Each device
+    // gets only the queries that have rows there: its share of the query rows, compacted, and their scopes.
+    struct Begin {
+        rf_group *g; PerDev *w; uint32_t d, nq, k;
+        const int8_t *q; const uint32_t *stores, *store_off; const uint32_t *qmask;
+        int rc;
+        char err[256];
+    };
+    auto begin_fn = [](void *p) {
+        Begin &b = *static_cast<Begin *>(p);
+        PerDev &w = *b.w;
         w.off.push_back(0);
-        for (uint32_t i = 0; i < nq; ++i) {
-            if (!(qmask[i] & (1u << d))) continue;
+        for (uint32_t i = 0; i < b.nq; ++i) {
+            if (!(b.qmask[i] & (1u << b.d))) continue;
             w.qidx.push_back(i);
-            w.segs.insert(w.segs.end(), stores + store_off[i], stores + store_off[i + 1]);
+            w.segs.insert(w.segs.end(), b.stores + b.store_off[i], b.stores + b.store_off[i + 1]);
             w.off.push_back(static_cast<uint32_t>(w.segs.size()));
         }
         const uint32_t n_here = static_cast<uint32_t>(w.qidx.size());
-        const int8_t *qd = q;
-        if (n_here != nq) {                       // compact this device's queries
+        const int8_t *qd = b.q;
+        if (n_here != b.nq) {                       // compact this device's queries
             w.qrows.resize(static_cast<size_t>(n_here) * RF_DIM);
-            for (uint32_t j = 0; j < n_here; ++j) memcpy(w.qrows.data() + static_cast<size_t>(j) * RF_DIM, q + static_cast<size_t>(w.qidx[j]) * RF_DIM, RF_DIM);
+            for (uint32_t j = 0; j < n_here; ++j) memcpy(w.qrows.data() + static_cast<size_t>(j) * RF_DIM, b.q + static_cast<size_t>(w.qidx[j]) * RF_DIM, RF_DIM);
             qd = w.qrows.data();
         }
         if (w.segs.empty()) w.segs.push_back(0);
-        rc = rf_search_begin(g->eng[d], qd, n_here, w.segs.data(), w.off.data(), k, &w.p);
+        b.rc = rf_search_begin(b.g->eng[b.d], qd, n_here, w.segs.data(), w.off.data(), b.k, &w.p);
+        if (b.rc) snprintf(b.err, sizeof b.err, "%s", rf_last_error());      // (the error text is thread-local to the launcher)
+    };
+    std::vector<Begin> begins(G);
+    uint32_t n_part = 0;
+    for (uint32_t d = 0; d < G; ++d) {
+        begins[d] = Begin{g, &pd[d], d, nq, k, q, stores, store_off, qmask.data(), RF_OK, {0}};
+        n_part += (any >> d) & 1u;
     }
+    // side by side on the launcher threads when they are awake (or the batch is big enough to be worth waking
+    // them); in turn on this thread otherwise
+    bool parallel = n_part >= 2 && !g->launchers.empty();
+    if (parallel && nq < 8)
+        for (uint32_t d = 0; d < G && parallel; ++d)
+            if ((any >> d) & 1u) parallel = !g->launchers[d]->asleep.load(std::memory_order_acquire);
+    if (parallel) {
+        for (uint32_t d = 0; d < G; ++d)
+            if ((any >> d) & 1u) {
+                g->launchers[d]->owner.lock();
+                g->launchers[d]->post(begin_fn, &begins[d]);
+            }
+        for (uint32_t d = 0; d < G; ++d)
+            if ((any >> d) & 1u) {
+                g->launchers[d]->collect();
+                g->launchers[d]->owner.unlock();
+            }
+    } else {
+        for (uint32_t d = 0; d < G; ++d)
+            if ((any >> d) & 1u) {
+                begin_fn(&begins[d]);
+                if (begins[d].rc) break;
+            }
+        if (n_part >= 2)      // a serving loop's next call finds the launchers awake
+            for (uint32_t d = 0; d < G && !g->launchers.empty(); ++d)
+                if (((any >> d) & 1u) && g->launchers[d]->asleep.load(std::memory_order_acquire)) g->launchers[d]->wake();
+    }
+    for (uint32_t d = 0; d < G; ++d)
+        if (begins[d].rc && rc == RF_OK) {
+            rc = begins[d].rc;
+            snprintf(g_gerr, sizeof g_gerr, "device %u: %s", d, begins[d].err[0] ? begins[d].err : rf_last_error());
+        }
     // ---- collect (every begun search must be ended, also after a failure) and merge on the host
     const size_t nk = static_cast<size_t>(nq) * k;
     std::vector<Hit> best(nk), tmp(k), src(k);

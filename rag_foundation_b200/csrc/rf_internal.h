@@ -44,6 +44,16 @@ struct ScanPlan {
     uint32_t scope[RF_SCOPE_MAX];
 };
 
+// Device-resident store table (one entry per store segment, rebuilt by the engine when extents change):
+// a batch of store-scoped queries then needs only its scope lists on the device -- the kernel gathers each
+// query's extents from the table itself, and the host builds no per-query plan.
+struct StoreEntry {
+    uint32_t ext_off;       // first extent of the store in the table's flat lo / hi arrays
+    uint32_t n_ext;         // 0 for an empty or dropped store (at most kInlineExt: more are coalesced)
+    uint32_t total_tiles;   // sum over extents of ceil(rows / 32)
+    uint32_t reserved;
+};
+
 struct ScanArgs {
     const int8_t *F;            // [rows, 256] int8, row-major, 256-byte rows
     const uint32_t *seg;        // [rows] store segment word (0xFFFFFFFF = tombstone)
@@ -62,6 +72,12 @@ struct ScanArgs {
     int32_t *out_scores;        // [nq, k] or null
     float *out_cos;             // [nq, k] or null
     uint32_t *out_counts;       // [nq] or null
+    // plans from the store table (st_tbl != null; plans / ext_* are then unused): query qi's scope is
+    // q_segs[q_seg_off[qi] .. q_seg_off[qi + 1]) (at most RF_SCOPE_MAX stores, at most kInlineExt extents in all)
+    const StoreEntry *st_tbl;
+    const uint32_t *st_lo, *st_hi;
+    const uint32_t *q_seg_off, *q_segs;
+    uint32_t st_n_stores;
     uint32_t id_base;           // global id of row 0
     uint32_t k;
     uint32_t shared_plan;       // 1: every query uses plans[0] (one scope for the whole batch)
@@ -79,6 +95,8 @@ struct ScanArgs {
     uint64_t *px_keys[8];          // rank r's gather buffer [world][px_nq_cap][k] (peer-mapped pointers)
     uint32_t *px_flags[8];         // rank r's flags [world][px_nq_cap]
     uint32_t px_rank, px_world, px_seq, px_nq_cap;
+    uint32_t px_publish_only;      // 1: store + release only; launch_merge_wait acquires and merges (large batches: a block
+                                   //    that waits for peers must not hold an SM slot the scan still needs)
     uint64_t *px_out;              // [nq, k] merged result of all ranks (this rank's copy)
     uint32_t *px_timeout;          // set to 1 if a peer's keys did not arrive within the wait bound
     uint32_t *done_flag;           // mapped host word: set to done_seq after the results are visible to the host (or null)
@@ -115,6 +133,10 @@ cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int3
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,
                               uint64_t *out_keys, cudaStream_t s);
 uint32_t scan_default_blocks_per_query(int sm_count, int variant);
+// Second half of the publish-only exchange: one warp per query acquires the `world` flags of its query in this
+// rank's buffer (bounded wait -> zeroed result + *timeout = 1) and merges the `world` lists into out [nq, k].
+cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k,
+                              uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s);
 
 // ---- batched GEMM path (score_topk_gemm.cu) ----------------------------------------------------
 constexpr int kGemmListK = 10;      // top-k kept per (thread, query) in registers; searches with k <= 10 qualify

@@ -110,7 +110,61 @@ struct BlockPlan {
     uint32_t n_ext, n_scope, t_lo, t_hi, total_tiles;
 };
 
+// Plan of query qi gathered from the device-resident store table: the extents of every store in the query's
+// scope, concatenated (stores own disjoint rows, so the order does not matter: tiles are located through the
+// prefix array).  Warp 0 does it; ends with __syncthreads().
+__device__ __forceinline__ void stage_plan_from_table(const ScanArgs &a, int qi, BlockPlan &bp) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const uint32_t s0 = a.q_seg_off[qi], s1 = a.q_seg_off[qi + 1];
+        const uint32_t n_scope = min(s1 - s0, static_cast<uint32_t>(RF_SCOPE_MAX));
+        if (lane < RF_SCOPE_MAX) bp.scope[lane] = lane < static_cast<int>(n_scope) ? a.q_segs[s0 + lane] : kTombstone;
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < n_scope; ++j) {
+            const uint32_t sg = a.q_segs[s0 + j];
+            bool dup = false;
+            for (uint32_t i = 0; i < j; ++i) dup |= (a.q_segs[s0 + i] == sg);
+            if (dup || sg >= a.st_n_stores) continue;
+            const StoreEntry en = a.st_tbl[sg];
+            const uint32_t take = min(en.n_ext, static_cast<uint32_t>(kMaxExtSmem) - cnt);
+            for (uint32_t i = lane; i < take; i += 32) {
+                bp.lo[cnt + i] = a.st_lo[en.ext_off + i];
+                bp.hi[cnt + i] = a.st_hi[en.ext_off + i];
+            }
+            cnt += take;
+        }
+        __syncwarp();
+        // exclusive prefix of the tile counts over <= 64 extents: two per lane
+        const uint32_t ta = lane < static_cast<int>(cnt) ? (bp.hi[lane] - bp.lo[lane] + kTileRows - 1) / kTileRows : 0u;
+        const uint32_t tb = lane + 32 < static_cast<int>(cnt) ? (bp.hi[lane + 32] - bp.lo[lane + 32] + kTileRows - 1) / kTileRows : 0u;
+        uint32_t ia = ta, ib = tb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t xa = __shfl_up_sync(kFull, ia, o), xb = __shfl_up_sync(kFull, ib, o);
+            if (lane >= o) { ia += xa; ib += xb; }
+        }
+        const uint32_t total_a = __shfl_sync(kFull, ia, 31), total = total_a + __shfl_sync(kFull, ib, 31);
+        bp.tile0[lane] = ia - ta;
+        bp.tile0[lane + 32] = total_a + ib - tb;
+        if (lane == 0) {
+            bp.tile0[kMaxExtSmem] = total;
+            bp.n_ext = cnt;
+            bp.total_tiles = total;
+            bp.n_scope = n_scope;
+            bp.t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total) * blockIdx.x / gridDim.x);
+            bp.t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total) * (blockIdx.x + 1) / gridDim.x);
+        }
+        __syncwarp();
+        if (lane == 0 && cnt < static_cast<uint32_t>(kMaxExtSmem)) bp.tile0[cnt] = total;   // the sentinel the tile cursor stops at
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void stage_plan(const ScanArgs &a, int qi, BlockPlan &bp) {
+    if (a.st_tbl) {
+        stage_plan_from_table(a, qi, bp);
+        return;
+    }
     if (a.inline_plan) {
         // single query / shared scope with few extents: the plan rides in the kernel parameters
         // (constant bank), so no dependent global loads stand before the first feature load
@@ -375,6 +429,8 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
             uint32_t *flag = a.px_flags[lane] + static_cast<size_t>(a.px_rank) * a.px_nq_cap + qi;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.px_seq) : "memory");
         }
+        if (a.px_publish_only) goto px_done;     // merge_wait_kernel (next in the stream) acquires and merges
+        {
         bool arrived = true;
         if (lane < static_cast<int>(a.px_world)) {
             const uint32_t *flag = a.px_flags[a.px_rank] + static_cast<size_t>(lane) * a.px_nq_cap + qi;
@@ -397,7 +453,9 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         const uint64_t merged = warp_tournament(lists, static_cast<int>(a.px_world), k, k, lane);
         if (lane < k) a.px_out[static_cast<size_t>(qi) * k + lane] = arrived ? merged : 0ull;
         if (!arrived && lane == 0) atomicExch(a.px_timeout, 1u);
+        }
     }
+px_done:
     if (lane == 0) {
         if (a.out_counts) a.out_counts[qi] = __popc(found);
         a.tickets[qi] = 0;  // ready for the next launch that uses this sync set
@@ -664,6 +722,38 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
     if (floors && lane == static_cast<int>(k_floor) - 1) floors[qi] = lane < kin ? (w & 0xFFFFFFFF00000000ull) : 0ull;
 }
 
+// Second half of the publish-only exchange (store-sharded batches): one warp per query.  Lane r acquires rank
+// r's flag for the query in this rank's buffer, then the warp plays the tournament over the `world` lists.
+__global__ void __launch_bounds__(128) merge_wait_kernel(const uint64_t *__restrict__ gather, const uint32_t *__restrict__ flags,
+                                                         uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k, uint32_t seq,
+                                                         uint64_t *__restrict__ out, uint32_t *__restrict__ timeout) {
+    __shared__ uint64_t lists[4][8 * kListCap];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t qi = blockIdx.x * 4 + w;
+    if (qi >= nq) return;
+    bool arrived = true;
+    if (lane < static_cast<int>(world)) {
+        const uint32_t *flag = flags + static_cast<size_t>(lane) * nq_cap + qi;
+        const long long t0 = clock64();
+        uint32_t v;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == seq) break;
+            if (clock64() - t0 > (4ll << 30)) { arrived = false; break; }   // ~2 s: fail loudly, never hang
+        }
+    }
+    arrived = __all_sync(kFull, arrived);
+    const int kk = static_cast<int>(k);
+    for (int i = lane; i < static_cast<int>(world) * kk; i += 32) {
+        const int r = i / kk, j = i % kk;
+        lists[w][i] = __ldcg(gather + (static_cast<size_t>(r) * nq_cap + qi) * kk + j);
+    }
+    __syncwarp();
+    const uint64_t merged = warp_tournament(lists[w], static_cast<int>(world), kk, kk, lane);
+    if (lane < kk) out[static_cast<size_t>(qi) * kk + lane] = arrived ? merged : 0ull;
+    if (!arrived && lane == 0) atomicExch(timeout, 1u);
+}
+
 // Packed keys -> the result arrays a host caller gets (same arithmetic as finish_query: RF-1 step 8
 // for the cosine).  One warp per query.
 __global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__restrict__ keys, const int8_t *__restrict__ q,
@@ -764,6 +854,13 @@ cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t 
 cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
                                uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s) {
     unpack_keys_kernel<<<(nq + 3) / 4, 128, 0, s>>>(keys, q, ff, id_base, nq, k, out_ids, out_scores, out_cos, out_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k,
+                              uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s) {
+    if (world == 0 || world > 8 || k == 0 || k > RF_TOPK_MAX || nq == 0) return cudaErrorInvalidValue;
+    merge_wait_kernel<<<(nq + 3) / 4, 128, 0, s>>>(gather, flags, world, nq_cap, nq, k, seq, out, timeout);
     return cudaGetLastError();
 }
 

@@ -315,6 +315,19 @@ class Engine:
         check(self._L.rf_search_keys_device_fused(self.handle, int(q_ptr), int(nq), _ptr(segs), len(scope), int(k), C.byref(px),
                                                   int(out_keys_ptr), int(stream) or None))
 
+    def search_keys_device_scoped_fused(self, q_ptr: int, nq: int, scopes, k: int, out_keys_ptr: int, stream: int,
+                                        rank: int, world: int, nq_cap: int, seq: int, keys_ptrs: np.ndarray, flag_ptrs: np.ndarray,
+                                        timeout_flag_ptr: int) -> None:
+        """Store-sharded batch with the exchange in the kernels (rf_search_keys_device_scoped_fused): one scope
+        per query (`scopes`: list of lists or a CSR tuple of THIS rank's segments, possibly empty per query)."""
+        segs, off = scopes if isinstance(scopes, tuple) else scopes_to_csr(scopes)
+        if len(off) != nq + 1:
+            raise ValueError("one scope per query")
+        px = _capi.rf_peer_exchange(C.sizeof(_capi.rf_peer_exchange), int(rank), int(world), int(nq_cap), int(k), int(seq),
+                                    keys_ptrs.ctypes.data, flag_ptrs.ctypes.data, int(timeout_flag_ptr))
+        check(self._L.rf_search_keys_device_scoped_fused(self.handle, int(q_ptr), int(nq), _ptr(segs), _ptr(off), int(k), C.byref(px),
+                                                         int(out_keys_ptr), int(stream) or None))
+
     def merge_topk_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, out_keys_ptr: int, stream: int = 0) -> None:
         check(self._L.rf_merge_topk_device(self.handle, int(keys_ptr), int(n_lists), int(nq), int(k), int(out_keys_ptr),
                                            int(stream) or None))

@@ -204,6 +204,55 @@ class StoreShardedSearcher:
         return unpack_keys_torch(self.search_keys(q, scopes, k))
 
 
+class FusedStoreShardedSearcher(StoreShardedSearcher):
+    """StoreShardedSearcher with the exchange inside the kernels (rf_search_keys_device_scoped_fused): each rank's
+    scan stores every query's k keys into every rank's gather buffer over NVLink (symmetric memory) and releases
+    a flag; a one-warp-per-query kernel behind it acquires the flags and merges.  Two launches per batch on each
+    rank, no NCCL collective on the data path; the per-query plans come from the engine's device-resident store
+    table, so the host sends only the scope lists.  Same results as the all-gather path."""
+
+    def __init__(self, engine, nq_cap: int = 1024, k: int = 10, group: Optional[dist.ProcessGroup] = None):
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm_mem
+        base = StoreShardedSearcher.for_engine(engine, group)
+        super().__init__(base.local_search, base.merge, base.open_local, group)
+        self.engine = engine
+        self.k, self.nq_cap = k, nq_cap
+        pg = group or dist.group.WORLD
+        if self.world > 8:
+            raise ValueError("the fused exchange serves the GPUs of one box (world <= 8)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._keys = symm_mem.empty((4 * self.world * nq_cap * k,), dtype=torch.int64, device=dev)
+        self._flags = symm_mem.empty((4 * self.world * nq_cap,), dtype=torch.int32, device=dev)
+        self._keys.zero_()
+        self._flags.zero_()
+        self._hk = symm_mem.rendezvous(self._keys, pg)
+        self._hf = symm_mem.rendezvous(self._flags, pg)
+        self._keys_ptrs = np.asarray([int(p) for p in self._hk.buffer_ptrs], dtype=np.uint64)
+        self._flag_ptrs = np.asarray([int(p) for p in self._hf.buffer_ptrs], dtype=np.uint64)
+        self._timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._seq = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(pg)          # every rank has zeroed its flags before anyone publishes
+
+    def search_keys(self, q: torch.Tensor, scopes, k: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        k = k or self.k
+        if q.shape[0] > self.nq_cap or k != self.k:
+            return super().search_keys(q, scopes, k)
+        assert q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
+        if out is None:
+            out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        self._seq += 1
+        local = scopes if isinstance(scopes, tuple) else self.prepare(scopes)
+        self.engine.search_keys_device_scoped_fused(q.data_ptr(), q.shape[0], local, k, out.data_ptr(),
+                                                    torch.cuda.current_stream(q.device).cuda_stream, self.rank, self.world,
+                                                    self.nq_cap, self._seq, self._keys_ptrs, self._flag_ptrs, self._timeout.data_ptr())
+        return out
+
+    def timed_out(self) -> bool:
+        return bool(self._timeout.item())
+
+
 class FusedShardedSearcher:
     """Sharded search with the exchange fused into the scan kernel: its finishing block stores the
     rank's top-k straight into every rank's gather buffer over NVLink (symmetric memory from

@@ -515,3 +515,154 @@ def test_pipelined_ingest_sources_and_chunk_boundaries(co):
         ths = [threading.Thread(target=up, args=(i,)) for i in range(4)]
         [t.start() for t in ths]; [t.join() for t in ths]
         assert not errs, errs[:1]
+
+
+# ------------------------------------------------------------------ store table + store-sharded fused exchange
+def test_store_table_batches_equal_host_built_plans(co, zb):
+    """Batches of differently-scoped queries read their plans from the device-resident store table: same answers
+    as host-built plans (RF_STORE_TABLE=0) and the oracle -- interleaved ingests (many extents per store), scopes
+    of several stores, duplicates and unknown stores in a scope, a store with more extents than a plan holds
+    (falls back), deletes and drops between batches (the table is rebuilt)."""
+    import subprocess
+    import sys
+    import torch
+    rows = 700
+    n_st = 40
+    with _engine(rows * n_st * 3 + 4096) as e:
+        stores = [e.open_store(f"fileSearchStores/t{i}") for i in range(n_st)]
+        parts, segs = [], []
+        doc = 0
+        for rnd in range(3):                       # interleaved: every store ends up with three extents
+            for s in stores:
+                blk = co.synth_rows(40 + rnd, s * rows, rows, zb)
+                doc += 1
+                e.ingest_features(s, doc, blk)
+                parts.append(blk); segs.append(np.full(rows, s, np.uint32))
+        for i in range(70):                        # one store with more extents than a plan holds
+            for s in (stores[3], stores[4]):
+                blk = co.synth_rows(50, (i * 2 + s) * 16, 16, zb)
+                doc += 1
+                e.ingest_features(s, doc, blk)
+                parts.append(blk); segs.append(np.full(16, s, np.uint32))
+        F = np.concatenate(parts); seg = np.concatenate(segs)
+        rng = np.random.default_rng(3)
+        nq = 96
+        Q = np.stack([co.synth_query(41, i, zb) for i in range(nq)])
+
+        def scopes_for(with_big):
+            sc = []
+            for i in range(nq):
+                n = int(rng.integers(1, 5))
+                pick = [int(x) for x in rng.choice([s for s in stores if with_big or s not in (3, 4)], size=n, replace=False)]
+                if i % 7 == 0:
+                    pick.append(pick[0])           # duplicate
+                if i % 11 == 0:
+                    pick.append(9999)              # unknown store
+                sc.append(pick)
+            return sc
+
+        def check(scopes):
+            l0 = e.stats()["kernel_launches"]
+            ids, sc, cs, cnt = e.search(Q, scopes, k=10)
+            assert e.stats()["kernel_launches"] - l0 == 1
+            qd = torch.from_numpy(Q).cuda()
+            out = torch.zeros((nq, 10), dtype=torch.int64, device="cuda")
+            e.search_keys_device_scoped(qd.data_ptr(), nq, scopes, 10, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert (_keys(ids, sc) == out.cpu().numpy().view(np.uint64)).all()
+            Fh, segh, ffh = e.read_rows(0, e.stats()["n_rows"])
+            for i in range(nq):
+                w_ids, w_sc, _ = co.score_topk(Fh, segh, Q[i], [s for s in scopes[i] if s < n_st], k=10, ff=ffh)
+                m = len(w_ids)
+                assert int(cnt[i]) == m and ids[i][:m].tolist() == w_ids.tolist() and sc[i][:m].tolist() == w_sc.tolist(), i
+        check(scopes_for(False))                   # every scope fits: the table path
+        check(scopes_for(True))                    # some scopes exceed 64 extents: the whole batch falls back, same answers
+        e.tombstone_doc(5); e.tombstone_doc(45); e.drop_store(stores[7])
+        check(scopes_for(False))                   # the table was rebuilt after the deletes
+        first = e.ingest_features(stores[9], 9000, co.synth_rows(60, 0, 300, zb))
+        sc9 = [[9]] * nq
+        ids, sc, _, cnt = e.search(Q, sc9, k=10)
+        Fh, segh, ffh = e.read_rows(0, e.stats()["n_rows"])
+        w_ids, w_sc, _ = co.score_topk(Fh, segh, Q[0], [9], k=10, ff=ffh)
+        assert ids[0].tolist() == w_ids.tolist() and first >= 0
+    # A/B: the same first batch with host-built plans (the table disabled) gives the same keys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from oracle import c_oracle as co, rf1\n"
+            "from rag_foundation_b200 import Engine\n"
+            "zb = rf1.zipf_bucket_table()\n"
+            "e = Engine(capacity_rows=20000)\n"
+            "ss = [e.open_store('s%%d' %% i) for i in range(8)]\n"
+            "e.ingest_synthetic(0, 2000, seed=1, start_counter=0, n_rows=16000)\n"
+            "Q = np.stack([co.synth_query(1, i, zb) for i in range(32)])\n"
+            "ids, sc, _, _ = e.search(Q, [[i %% 8, (i * 3) %% 8] for i in range(32)], k=10)\n"
+            "print(ids.tobytes().hex()[:64], int(ids.astype(np.int64).sum()), int(sc.sum()))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = [subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, RF_STORE_TABLE=v)) for v in ("1", "0")]
+    assert all(o.returncode == 0 for o in outs), outs[0].stderr[-1500:] + outs[1].stderr[-1500:]
+    assert outs[0].stdout == outs[1].stdout and outs[0].stdout.strip()
+
+
+@pytest.mark.timeout(300)
+def test_store_sharded_fused_exchange_two_engines_one_process(co, zb):
+    """rf_search_keys_device_scoped_fused, world = 2 in one process (two engines on one GPU, whole stores per
+    'rank'): a 256-query batch, most queries owned by one rank, some scopes spanning both; the publish-only scan
+    + merge_wait pair on each rank returns the single-index answer on BOTH ranks."""
+    import torch
+    from rag_foundation_b200.engine import scopes_to_csr
+    rows, n_st, k, nq, nq_cap, world = 3000, 16, 10, 256, 256, 2
+    engines, streams = [], [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for r in range(world):
+            e = _engine(rows * n_st // world + 64, id_base=r * (1 << 30))
+            engines.append(e)
+            for g in range(n_st):
+                e.open_store(f"fileSearchStores/t{g}")            # same numbering on both ranks; rows only on the owner
+            for g in range(r, n_st, world):
+                e.ingest_synthetic(g, 0, seed=70, start_counter=g * rows, n_rows=rows)
+        F = co.synth_rows(70, 0, rows * n_st, zb)
+        seg = (np.arange(rows * n_st) // rows).astype(np.uint32)
+        store_of = np.arange(rows * n_st) // rows
+        gid = (store_of % world) * (1 << 30) + (store_of // world) * rows + np.arange(rows * n_st) % rows
+        rng = np.random.default_rng(9)
+        Q = np.stack([co.synth_query(70, i, zb) for i in range(nq)])
+        scopes = [[int(rng.integers(0, n_st))] for _ in range(nq)]
+        for i in range(0, nq, 9):
+            scopes[i] = [int(x) for x in rng.choice(n_st, size=3, replace=False)]      # spans both ranks
+        scopes[1] = []
+        csr = scopes_to_csr(scopes)
+        keys_buf = [torch.zeros(4 * world * nq_cap * k, dtype=torch.int64, device="cuda") for _ in range(world)]
+        flag_buf = [torch.zeros(4 * world * nq_cap, dtype=torch.int32, device="cuda") for _ in range(world)]
+        timeout = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        kp = np.asarray([t.data_ptr() for t in keys_buf], np.uint64)
+        fp = np.asarray([t.data_ptr() for t in flag_buf], np.uint64)
+        qd = torch.from_numpy(Q).cuda()
+        outs = [torch.zeros((nq, k), dtype=torch.int64, device="cuda") for _ in range(world)]
+        # warm-up without an exchange so the per-stream scratch exists (see the chunk-sharded fused test)
+        for r in range(world):
+            engines[r].search_keys_device_scoped_fused(qd.data_ptr(), nq, csr, k, outs[r].data_ptr(), streams[r].cuda_stream,
+                                                       0, 1, nq_cap, 1, kp[r:r + 1], fp[r:r + 1], timeout[r].data_ptr())
+        torch.cuda.synchronize()
+        for t in flag_buf:
+            t.zero_()
+        torch.cuda.synchronize()
+        for seq in range(1, 7):
+            for o in outs:
+                o.zero_()
+            torch.cuda.synchronize()
+            for r in range(world):
+                engines[r].search_keys_device_scoped_fused(qd.data_ptr(), nq, csr, k, outs[r].data_ptr(), streams[r].cuda_stream,
+                                                           r, world, nq_cap, seq, kp, fp, timeout[r].data_ptr())
+            torch.cuda.synchronize()
+            assert not any(int(t.item()) for t in timeout)
+            got = [o.cpu().numpy().view(np.uint64) for o in outs]
+            assert (got[0] == got[1]).all()
+        for i in range(nq):
+            m = np.isin(seg, np.asarray(scopes[i], np.uint32))
+            sc = F[m].astype(np.int32) @ Q[i].astype(np.int32)
+            ids = gid[m]
+            order = np.lexsort((ids, -sc.astype(np.int64)))[:k]
+            want = (sc[order].astype(np.int64).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - ids[order].astype(np.uint64))
+            assert got[0][i][:len(want)].tolist() == want.tolist() and (got[0][i][len(want):] == 0).all(), i
+    finally:
+        for e in engines:
+            e.close()
