@@ -381,6 +381,68 @@ def leg_cfg4(torch, dev, hbm_peak, n_stores, per_store, sample_parity: bool, dev
     return out
 
 
+def leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, n_stores, per_store, sample_parity: bool):
+    """configs[4] sharded by whole stores, one process per GPU (all ranks call this): every rank holds the stores
+    g with g % world == rank, receives the whole 1024-query batch (device-resident), scans what it owns and
+    exchanges inside the kernels (publish-only scan + merge_wait over NVLink peer memory).  CUDA events, max
+    over ranks."""
+    from rag_foundation_b200 import Engine
+    from rag_foundation_b200.sharded import FusedStoreShardedSearcher, StoreShardedSearcher
+    nq = 1024
+    rng = np.random.default_rng(5)
+    Q = make_queries(nq, seed=SEED + 4)
+    scopes = [[int(rng.integers(0, n_stores))] for _ in range(nq)]
+    owned = (n_stores + world - 1 - rank) // world
+    base = StoreShardedSearcher.id_base_for(rank, world)
+    eng = Engine(capacity_rows=owned * per_store, device=dev.index or 0, id_base=base)
+    try:
+        srch = FusedStoreShardedSearcher(eng, nq_cap=nq, k=K)
+        for g in range(n_stores):
+            srch.open_store(f"fileSearchStores/mt{g}")
+        for g in range(rank, n_stores, world):
+            eng.ingest_synthetic(srch.local_seg[g], 0, seed=SEED + 4, start_counter=g * per_store, n_rows=per_store)
+        qd = torch.from_numpy(Q).to(dev)
+        local = srch.prepare(scopes)
+        out = torch.zeros((nq, K), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        torch.cuda.synchronize(dev)
+        eng.set_stream_overlap(stream.cuda_stream, True)
+        srch.search_keys(qd, local, K, out=out)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        keys = out.cpu().numpy().view(np.uint64)
+        bad = None
+        if rank == 0 and sample_parity:
+            ids = np.where(keys != 0, np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF)), np.uint64(0xFFFFFFFFFFFFFFFF))
+            sc = (keys >> np.uint64(32)).astype(np.int64).astype(np.int32)
+            stride = (1 << 32) // world
+            bad = cfg4_parity(ids, sc, Q, scopes, per_store, lambda st: (st % world) * stride + (st // world) * per_store)
+        for _ in range(3):
+            srch.search_keys(qd, local, K, out=out)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            srch.search_keys(qd, local, K, out=out)
+        e1.record(stream)
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        timed_out = srch.timed_out()
+        again = out.cpu().numpy().view(np.uint64)
+        alg = nq * per_store * BYTES_PER_CHUNK
+        return {"spmd_ms_per_batch": ms, "spmd_qps": nq / (ms * 1e-3), "spmd_parity_mismatches": bad, "spmd_stable": bool((again == keys).all()) and not timed_out,
+                "spmd_exchange": "publish-only scan + merge_wait over NVLink peer memory (rf_search_keys_device_scoped_fused), plans from the device-resident store table",
+                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                             "frac": alg / (ms * 1e-3) / 1e9 / (hbm_peak * world)}}
+    finally:
+        eng.close()
+
+
 def leg_ingest(torch, dev, hbm_peak, sample_parity: bool):
     """Ingest featurisation throughput: one 22.8 MB synthetic document through rf_ingest_text (host buffer)."""
     from rag_foundation_b200 import Engine
@@ -660,6 +722,12 @@ def run_b200(args) -> None:
     shard_rows = hi - lo
     eng.close()
     del searcher
+    cfg4_spmd = None
+    if world > 1 and not args.no_configs:
+        try:
+            cfg4_spmd = leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, 10_000, 10_000, not args.no_parity)
+        except Exception as exc:   # noqa: BLE001
+            cfg4_spmd = {"spmd_error": f"{type(exc).__name__}: {exc}"}
 
     # ---- N > 1: the host-facing legs run in ONE process (rank 0) that drives all N GPUs through the engine
     # group behind the adapter; the other ranks have released their engines and wait on the host
@@ -717,6 +785,8 @@ def run_b200(args) -> None:
                     configs["scaling_base"] = leg_scaling_base(torch, dev, hbm_peak, steps)
                 else:
                     configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp, devices=list(range(n_gpus)))
+                    if cfg4_spmd:
+                        configs["cfg4"].update(cfg4_spmd)
             except Exception as exc:   # noqa: BLE001  (a secondary leg must not lose the headline line)
                 configs["error"] = f"{type(exc).__name__}: {exc}"
     if world > 1:

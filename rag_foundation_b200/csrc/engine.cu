@@ -281,6 +281,16 @@ struct CopyPool {
             }
             while (job_live.load(std::memory_order_acquire) && stage_one()) {}
             helpers_in.fetch_sub(1);
+            // a worker that uploads document after document finds the helpers awake: spin briefly for the next job
+            const auto t0 = std::chrono::steady_clock::now();
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
+                bool again = false;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    again = stop || job_gen != seen;
+                }
+                if (again) break;
+            }
         }
     }
 };
