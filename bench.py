@@ -394,7 +394,17 @@ def leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, n_stores, per_store, 
     scopes = [[int(rng.integers(0, n_stores))] for _ in range(nq)]
     owned = (n_stores + world - 1 - rank) // world
     base = StoreShardedSearcher.id_base_for(rank, world)
-    eng = Engine(capacity_rows=owned * per_store, device=dev.index or 0, id_base=base)
+    eng, srch, err = None, None, ""
+    try:   # set-up can fail on one rank only (memory, symmetric-memory rendezvous): agree before any collective step
+        eng = Engine(capacity_rows=owned * per_store, device=dev.index or 0, id_base=base)
+    except Exception as exc:   # noqa: BLE001
+        err = f"{type(exc).__name__}: {exc}"
+    ok = torch.tensor([0 if err else 1], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not int(ok.item()):
+        if eng is not None:
+            eng.close()
+        return {"spmd_error": err or "another rank could not set up"}
     try:
         srch = FusedStoreShardedSearcher(eng, nq_cap=nq, k=K)
         for g in range(n_stores):
