@@ -317,9 +317,11 @@ __device__ __forceinline__ void block_merge(WarpTopK &top, MergeScratch<kWarps> 
 
 // Block top-k -> partial buffer; the last block of the query merges all partials and writes the
 // answer.  Called by every thread of the block.
+// `n_blocks`: blocks of the launch that take part for this query (gridDim.x, or 1 when the query has nothing
+// to scan here and only block 0 stays to write the empty answer).
 template <int kWarps>
 __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK &top, const int4 &qv, MergeScratch<kWarps> &ms,
-                                             int k, int warp, int lane) {
+                                             int k, int warp, int lane, uint32_t n_blocks) {
     constexpr int n_warps = kWarps;
     block_merge(top, ms, k, warp, lane);
     uint64_t *part = a.partial + (static_cast<size_t>(qi) * gridDim.x) * k;
@@ -329,7 +331,7 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         __syncwarp();
         if (lane == 0) {
             const uint32_t ticket = atomicAdd(a.tickets + qi, 1u);
-            ms.flag = (ticket == gridDim.x - 1) ? 1u : 0u;
+            ms.flag = (ticket == n_blocks - 1) ? 1u : 0u;
             stamp(a, 4);
         }
     }
@@ -338,7 +340,7 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
 
     // ---- last block of this query: two tournament levels over the gridDim.x partial lists
     __threadfence();
-    const int n_lists = static_cast<int>(gridDim.x);       // engine keeps this <= 1024
+    const int n_lists = static_cast<int>(n_blocks);        // engine keeps this <= 1024
     const int n_groups = (n_lists + 31) / 32;
     constexpr int l1_warps = MergeScratch<kWarps>::kL1Warps;
     const int total_keys = n_lists * k;
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
         offer_tile(top, first, key, floor_seen, g_floor, k, lane);
     }
     if (lane == 0) stamp_max(a, 3);
-    finish_query(a, qi, top, qv, ms, k, warp, lane);
+    finish_query(a, qi, top, qv, ms, k, warp, lane, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,6 +589,16 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
 
     const uint32_t total_tiles = bp.total_tiles;
     uint32_t *tile_ctr = a.tile_ctr + qi;
+    if (total_tiles == 0) {
+        // Nothing of this query's scope lives here (store-sharded batches: most queries on most ranks).  Block 0
+        // alone writes -- and, in a sharded launch, publishes -- the empty answer; the others are done.
+        if (blockIdx.x != 0) return;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        using Scratch0 = MergeScratch<kConsumers + 1>;
+        finish_query(a, qi, top, qv, *reinterpret_cast<Scratch0 *>(&sm.stage[0][0]), k, warp, lane, 1u);
+        return;
+    }
 
     if (warp == 0) {
         // ===== producer warp: lane s owns ring stage s and refills it as soon as it is released,
@@ -685,7 +697,7 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     using Scratch = MergeScratch<kConsumers + 1>;
     static_assert(sizeof(Scratch) <= sizeof(sm.stage), "ring too small to double as merge scratch");
     __syncthreads();
-    finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane);
+    finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane, gridDim.x);
 }
 
 // k-way merge of n_lists sorted top-k lists per query (after the all-gather of the sharded path,
