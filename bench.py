@@ -412,7 +412,7 @@ def leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, n_stores, per_store, 
         for g in range(rank, n_stores, world):
             eng.ingest_synthetic(srch.local_seg[g], 0, seed=SEED + 4, start_counter=g * per_store, n_rows=per_store)
         qd = torch.from_numpy(Q).to(dev)
-        local = srch.prepare(scopes)
+        local = srch.prepare_fused(scopes)
         out = torch.zeros((nq, K), dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev)
         torch.cuda.synchronize(dev)

@@ -211,16 +211,25 @@ typedef struct rf_peer_exchange {
     const uint64_t *keys_ptrs; /* HOST array [world] of device pointers */
     const uint64_t *flag_ptrs; /* HOST array [world] of device pointers */
     uint32_t *timeout_flag_dev;
+    /* rf_search_keys_device_scoped_fused only (zero / NULL elsewhere): the call carries just the queries this
+     * rank has rows for.  q_dev still holds the WHOLE batch of nq_total rows; local query j is batch query
+     * q_index[j]; owner_masks[i] has bit r set when rank r holds rows of batch query i's scope (it is what the
+     * merge waits for, so it must be the same on every rank).  NULL q_index = every query, in order;
+     * NULL owner_masks = every rank publishes every query. */
+    uint32_t nq_total;
+    const uint32_t *q_index;    /* HOST [nq] */
+    const uint8_t *owner_masks; /* HOST [nq_total] */
 } rf_peer_exchange;
 int rf_search_keys_device_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
                                 uint32_t n_segs, uint32_t k, const rf_peer_exchange *px,
                                 uint64_t *out_keys_dev, void *stream);
 
 /* The store-sharded form of the fused exchange (whole stores per rank, configs[4]): one scope per query as in
- * rf_search_keys_device_scoped, `px` as above with nq_cap >= nq.  Every rank runs every query over the part of
- * its scope it owns (mostly nothing); the scan kernel stores each query's k keys into every rank's gather
- * buffer and releases the flag, and a second small kernel behind it on the stream acquires the `world` flags
- * of each query and merges into out_keys_dev [nq, k] -- two launches, no collective, no host round trip. */
+ * rf_search_keys_device_scoped, `px` as above with nq_cap >= px->nq_total.  Each rank scans only the queries it
+ * has rows for (px->q_index); its scan kernel stores each such query's k keys into every rank's gather buffer
+ * and releases a flag there, and a second small kernel behind it on the stream acquires, per batch query, the
+ * flags of the ranks in its owner mask and merges their lists into out_keys_dev [nq_total, k] -- two launches,
+ * no collective, no host round trip, and no work at all for a query on a rank that holds none of its stores. */
 int rf_search_keys_device_scoped_fused(rf_engine *e, const int8_t *q_dev, uint32_t nq, const uint32_t *store_segs,
                                        const uint32_t *seg_off, uint32_t k, const rf_peer_exchange *px,
                                        uint64_t *out_keys_dev, void *stream);

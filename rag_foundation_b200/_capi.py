@@ -27,7 +27,7 @@ class rf_config(C.Structure):
 class rf_peer_exchange(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("nq_cap", C.c_uint32),
                 ("k", C.c_uint32), ("seq", C.c_uint32), ("keys_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p),
-                ("timeout_flag_dev", C.c_void_p)]
+                ("timeout_flag_dev", C.c_void_p), ("nq_total", C.c_uint32), ("q_index", C.c_void_p), ("owner_masks", C.c_void_p)]
 
 
 class rf_group_config(C.Structure):

@@ -2182,8 +2182,9 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
                                           const rf_peer_exchange *px) {
     if (!e || !q_dev || !seg_off || !out_keys_dev) return fail(RF_EINVAL, "null argument");
     if (k == 0 || k > RF_TOPK_MAX) return fail(RF_EINVAL, "k must be in [1, %u]", RF_TOPK_MAX);
-    if (nq == 0) return RF_OK;
     if (nq > 65535) return fail(RF_EINVAL, "at most 65535 queries per call");
+    const uint32_t nq_total = (px && px->nq_total) ? px->nq_total : nq;     // queries of the whole batch (rows of q_dev, rows of the result)
+    if (nq_total == 0) return RF_OK;
     RF_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // plans: from the device-resident store table when every scope fits a plan, else built here per query
@@ -2191,27 +2192,39 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
     bool use_table = false;
     uint32_t max_tiles = 0;
     int rc = RF_OK;
-    if (e->table_enabled) {
+    if (e->table_enabled && nq) {
         if ((rc = table_acquire(e, tbl_lock))) return rc;
         use_table = table_batch_ok(e, nq, store_segs, seg_off, &max_tiles);
         if (!use_table) tbl_lock.unlock();
     }
     PlanBlob b;
+    auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
     size_t off_off = 0, off_segs = 0;
     if (use_table) {
-        auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
         const size_t n_segs = seg_off[nq];
         off_segs = align((static_cast<size_t>(nq) + 1) * 4);
         b.bytes.resize(align(off_segs + std::max<size_t>(n_segs, 1) * 4));
         memcpy(b.bytes.data() + off_off, seg_off, (static_cast<size_t>(nq) + 1) * 4);
         if (n_segs) memcpy(b.bytes.data() + off_segs, store_segs, n_segs * 4);
         b.max_tiles = max_tiles;
-    } else if ((rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b))) {
+    } else if (nq && (rc = build_blob(e, nullptr, nq, store_segs, seg_off, false, b))) {
         return rc;
+    }
+    // the exchange's own tables ride behind the plans in the same upload
+    size_t off_qindex = 0, off_masks = 0;
+    if (px && px->q_index && nq) {
+        off_qindex = align(b.bytes.size());
+        b.bytes.resize(off_qindex + static_cast<size_t>(nq) * 4);
+        memcpy(b.bytes.data() + off_qindex, px->q_index, static_cast<size_t>(nq) * 4);
+    }
+    if (px && px->owner_masks) {
+        off_masks = align(std::max<size_t>(b.bytes.size(), 16));
+        b.bytes.resize(off_masks + nq_total);
+        memcpy(b.bytes.data() + off_masks, px->owner_masks, nq_total);
     }
     std::shared_ptr<StreamState> st = stream_state(e, stream);
     std::lock_guard<std::mutex> lk(st->mu);
-    const uint32_t X = pick_blocks(e, nq, b.max_tiles);
+    const uint32_t X = pick_blocks(e, std::max(nq, 1u), b.max_tiles);
     const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
     const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
     const size_t need_local = px ? static_cast<size_t>(nq) * k * 8 : 0;
@@ -2225,12 +2238,15 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
             RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
         }
     }
-    if (!st->h_blob_free) RF_CUDA(cudaEventCreateWithFlags(&st->h_blob_free, cudaEventDisableTiming));
-    else RF_CUDA(cudaEventSynchronize(st->h_blob_free));      // the previous call's upload has left the staging buffer
-    RF_CUDA(st->h_blob.reserve(b.bytes.size()));
-    memcpy(st->h_blob.p, b.bytes.data(), b.bytes.size());
-    RF_CUDA(cudaMemcpyAsync(st->blob.p, st->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
-    RF_CUDA(cudaEventRecord(st->h_blob_free, s));
+    if (!b.bytes.empty()) {
+        if (!st->h_blob_free) RF_CUDA(cudaEventCreateWithFlags(&st->h_blob_free, cudaEventDisableTiming));
+        else RF_CUDA(cudaEventSynchronize(st->h_blob_free));      // the previous call's upload has left the staging buffer
+        RF_CUDA(st->h_blob.reserve(b.bytes.size()));
+        memcpy(st->h_blob.p, b.bytes.data(), b.bytes.size());
+        RF_CUDA(cudaMemcpyAsync(st->blob.p, st->h_blob.p, b.bytes.size(), cudaMemcpyHostToDevice, s));
+        RF_CUDA(cudaEventRecord(st->h_blob_free, s));
+    }
+    const uint8_t *d_blob = static_cast<const uint8_t *>(st->blob.p);
     ScanArgs a{};
     if (use_table) {
         a.F = e->F;
@@ -2241,21 +2257,22 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
         a.k = k;
         a.debug_ts = e->debug_ts;
         a.dbg_flags = e->dbg_flags;
-        fill_table_args(e, a, static_cast<const uint8_t *>(st->blob.p), off_off, off_segs);
-    } else {
-        fill_args(e, a, static_cast<const uint8_t *>(st->blob.p), b, q_dev, k, false);
+        fill_table_args(e, a, d_blob, off_off, off_segs);
+    } else if (nq) {
+        fill_args(e, a, d_blob, b, q_dev, k, false);
     }
+    if (off_qindex) a.q_index = reinterpret_cast<const uint32_t *>(d_blob + off_qindex);
     a.partial = static_cast<uint64_t *>(st->partial.p);
-    set_sync_bufs(a, st->tickets, st->launches++);
+    if (nq) set_sync_bufs(a, st->tickets, st->launches++);
     a.out_keys = out_keys_dev;
     uint64_t *gather_local = nullptr;
     uint32_t *flags_local = nullptr;
     if (px) {
-        // Store-sharded exchange: a query's rows live on one rank (or a few), every rank runs every query, most
-        // of them over nothing.  A block that WAITED for its peers here would hold an SM slot the peers' own
-        // scans may need (hundreds of such blocks per launch), so the scan only publishes -- keys into every
-        // rank's gather buffer, then a release flag -- and a second, tiny kernel behind it acquires the flags
-        // and merges (one warp per query).
+        // Store-sharded exchange: a query's rows live on one rank (or a few).  A rank launches only the queries
+        // it has rows for.  A block that WAITED for its peers here would hold an SM slot the peers' own scans may
+        // need (hundreds of such blocks per launch), so the scan only publishes -- keys into every rank's
+        // gather buffer, then a release flag -- and a second, tiny kernel behind it acquires the flags of each
+        // query's owners and merges (one warp per query of the whole batch).
         const size_t slot = px->seq & 3u;
         const size_t keys_off = slot * px->world * px->nq_cap * static_cast<size_t>(k);
         const size_t flag_off = slot * px->world * static_cast<size_t>(px->nq_cap);
@@ -2274,13 +2291,17 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
         gather_local = a.px_keys[px->rank];
         flags_local = a.px_flags[px->rank];
     }
-    // the plans / scope lists were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
-    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
-    uint32_t launched = 1;
-    if (px && px->world > 1) {
-        RF_CUDA(rf::launch_merge_wait(gather_local, flags_local, px->world, px->nq_cap, nq, k, px->seq, out_keys_dev, px->timeout_flag_dev, s));
+    uint32_t launched = 0;
+    if (nq) {
+        // the plans / scope lists were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
         ++launched;
-    } else if (px) {
+    }
+    if (px && px->world > 1) {
+        RF_CUDA(rf::launch_merge_wait(gather_local, flags_local, off_masks ? d_blob + off_masks : nullptr, px->world, px->nq_cap, nq_total, k,
+                                      px->seq, out_keys_dev, px->timeout_flag_dev, s));
+        ++launched;
+    } else if (px && nq) {
         RF_CUDA(cudaMemcpyAsync(out_keys_dev, a.out_keys, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToDevice, s));
     }
     e->launches.fetch_add(launched, std::memory_order_relaxed);
@@ -2299,7 +2320,11 @@ int rf_search_keys_device_scoped_fused(rf_engine *e, const int8_t *q_dev, uint32
     if (!px || px->struct_size != sizeof(rf_peer_exchange)) return fail(RF_EINVAL, "bad rf_peer_exchange");
     if (px->world == 0 || px->world > 8 || px->rank >= px->world) return fail(RF_EINVAL, "world must be in [1, 8] and rank < world");
     if (!px->keys_ptrs || !px->flag_ptrs || !px->timeout_flag_dev) return fail(RF_EINVAL, "null exchange buffer");
-    if (nq > px->nq_cap || k != px->k || px->seq == 0) return fail(RF_EINVAL, "exchange buffers are sized for nq <= %u, k == %u, seq > 0", px->nq_cap, px->k);
+    const uint32_t total = px->nq_total ? px->nq_total : nq;
+    if (nq > total || total > px->nq_cap || k != px->k || px->seq == 0) return fail(RF_EINVAL, "exchange buffers are sized for nq_total <= %u, k == %u, seq > 0", px->nq_cap, px->k);
+    if (px->q_index)
+        for (uint32_t j = 0; j < nq; ++j)
+            if (px->q_index[j] >= total) return fail(RF_EINVAL, "q_index[%u] = %u is not a query of the batch (%u)", j, px->q_index[j], total);
     return search_keys_device_scoped_impl(e, q_dev, nq, store_segs, seg_off, k, out_keys_dev, stream, px);
 }
 

@@ -59,6 +59,7 @@ struct ScanArgs {
     const uint32_t *seg;        // [rows] store segment word (0xFFFFFFFF = tombstone)
     const int32_t *ff;          // [rows] sum of squares (read for the k winners only); may be null
     const int8_t *q;            // [nq, 256] query vectors (device)
+    const uint32_t *q_index;    // null, or [nq]: launch query qi reads row q_index[qi] of q (and publishes under that number)
     const ScanPlan *plans;      // [nq]
     const uint32_t *ext_lo;     // flat extents
     const uint32_t *ext_hi;
@@ -135,8 +136,9 @@ cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t n
 uint32_t scan_default_blocks_per_query(int sm_count, int variant);
 // Second half of the publish-only exchange: one warp per query acquires the `world` flags of its query in this
 // rank's buffer (bounded wait -> zeroed result + *timeout = 1) and merges the `world` lists into out [nq, k].
-cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k,
-                              uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s);
+// masks: null (wait for every rank) or [nq] owner bit masks (device)
+cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, const uint8_t *masks, uint32_t world, uint32_t nq_cap,
+                              uint32_t nq, uint32_t k, uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s);
 
 // ---- batched GEMM path (score_topk_gemm.cu) ----------------------------------------------------
 constexpr int kGemmListK = 10;      // top-k kept per (thread, query) in registers; searches with k <= 10 qualify

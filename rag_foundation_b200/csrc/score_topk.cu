@@ -421,21 +421,22 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         // (peer-mapped stores), one release store per peer publishes it; then lane r acquires rank
         // r's flag (the peers' scan kernels run concurrently on their own GPUs; the wait is
         // bounded) and the warp plays the tournament over the `world` lists in the local buffer.
+        const uint32_t gq = a.q_index ? a.q_index[qi] : static_cast<uint32_t>(qi);    // the query's number in the whole batch
         if (lane < k) {
-            const size_t slot = (static_cast<size_t>(a.px_rank) * a.px_nq_cap + qi) * k + lane;
+            const size_t slot = (static_cast<size_t>(a.px_rank) * a.px_nq_cap + gq) * k + lane;
             for (uint32_t p = 0; p < a.px_world; ++p) a.px_keys[p][slot] = key;
         }
         __threadfence_system();
         __syncwarp();
         if (lane < static_cast<int>(a.px_world)) {
-            uint32_t *flag = a.px_flags[lane] + static_cast<size_t>(a.px_rank) * a.px_nq_cap + qi;
+            uint32_t *flag = a.px_flags[lane] + static_cast<size_t>(a.px_rank) * a.px_nq_cap + gq;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.px_seq) : "memory");
         }
         if (a.px_publish_only) goto px_done;     // merge_wait_kernel (next in the stream) acquires and merges
         {
         bool arrived = true;
         if (lane < static_cast<int>(a.px_world)) {
-            const uint32_t *flag = a.px_flags[a.px_rank] + static_cast<size_t>(lane) * a.px_nq_cap + qi;
+            const uint32_t *flag = a.px_flags[a.px_rank] + static_cast<size_t>(lane) * a.px_nq_cap + gq;
             const long long t0 = clock64();
             uint32_t v;
             while (true) {
@@ -449,7 +450,7 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
         const uint64_t *gather = a.px_keys[a.px_rank];
         for (int i = lane; i < static_cast<int>(a.px_world) * k; i += 32) {
             const int r = i / k, j = i % k;
-            lists[i] = __ldcg(gather + (static_cast<size_t>(r) * a.px_nq_cap + qi) * k + j);   // peers wrote into L2
+            lists[i] = __ldcg(gather + (static_cast<size_t>(r) * a.px_nq_cap + gq) * k + j);   // peers wrote into L2
         }
         __syncwarp();
         const uint64_t merged = warp_tournament(lists, static_cast<int>(a.px_world), k, k, lane);
@@ -502,7 +503,8 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
     const int warp = threadIdx.x >> 5;
     const int k = static_cast<int>(a.k);
     if (threadIdx.x == 0) stamp(a, 0);
-    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16)
+    const uint32_t q_row = a.q_index ? a.q_index[qi] : static_cast<uint32_t>(qi);
+    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(q_row) * kDim + (lane & 15) * 16)
                         : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
     stage_plan(a, qi, bp);
     if (threadIdx.x == 0) stamp(a, 1);
@@ -578,7 +580,8 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
         mbar_fence_init();
     }
     if (threadIdx.x == 0) stamp(a, 0);
-    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(qi) * kDim + (lane & 15) * 16)
+    const uint32_t q_row = a.q_index ? a.q_index[qi] : static_cast<uint32_t>(qi);
+    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(q_row) * kDim + (lane & 15) * 16)
                         : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
     stage_plan(a, qi, sm.bp);  // ends with __syncthreads()
     if (threadIdx.x == 0) stamp(a, 1);
@@ -737,14 +740,16 @@ __global__ void __launch_bounds__(kMergeWarps * 32) merge_lists_kernel(const uin
 // Second half of the publish-only exchange (store-sharded batches): one warp per query.  Lane r acquires rank
 // r's flag for the query in this rank's buffer, then the warp plays the tournament over the `world` lists.
 __global__ void __launch_bounds__(128) merge_wait_kernel(const uint64_t *__restrict__ gather, const uint32_t *__restrict__ flags,
-                                                         uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k, uint32_t seq,
-                                                         uint64_t *__restrict__ out, uint32_t *__restrict__ timeout) {
+                                                         const uint8_t *__restrict__ masks, uint32_t world, uint32_t nq_cap, uint32_t nq,
+                                                         uint32_t k, uint32_t seq, uint64_t *__restrict__ out,
+                                                         uint32_t *__restrict__ timeout) {
     __shared__ uint64_t lists[4][8 * kListCap];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t qi = blockIdx.x * 4 + w;
     if (qi >= nq) return;
+    const uint32_t mask = masks ? masks[qi] : 0xFFu;      // ranks that hold rows of this query's scope
     bool arrived = true;
-    if (lane < static_cast<int>(world)) {
+    if (lane < static_cast<int>(world) && ((mask >> lane) & 1u)) {
         const uint32_t *flag = flags + static_cast<size_t>(lane) * nq_cap + qi;
         const long long t0 = clock64();
         uint32_t v;
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(128) merge_wait_kernel(const uint64_t *__restr
     const int kk = static_cast<int>(k);
     for (int i = lane; i < static_cast<int>(world) * kk; i += 32) {
         const int r = i / kk, j = i % kk;
-        lists[w][i] = __ldcg(gather + (static_cast<size_t>(r) * nq_cap + qi) * kk + j);
+        lists[w][i] = ((mask >> r) & 1u) ? __ldcg(gather + (static_cast<size_t>(r) * nq_cap + qi) * kk + j) : 0ull;
     }
     __syncwarp();
     const uint64_t merged = warp_tournament(lists[w], static_cast<int>(world), kk, kk, lane);
@@ -869,10 +874,10 @@ cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int3
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, uint32_t world, uint32_t nq_cap, uint32_t nq, uint32_t k,
-                              uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s) {
+cudaError_t launch_merge_wait(const uint64_t *gather, const uint32_t *flags, const uint8_t *masks, uint32_t world, uint32_t nq_cap,
+                              uint32_t nq, uint32_t k, uint32_t seq, uint64_t *out, uint32_t *timeout, cudaStream_t s) {
     if (world == 0 || world > 8 || k == 0 || k > RF_TOPK_MAX || nq == 0) return cudaErrorInvalidValue;
-    merge_wait_kernel<<<(nq + 3) / 4, 128, 0, s>>>(gather, flags, world, nq_cap, nq, k, seq, out, timeout);
+    merge_wait_kernel<<<(nq + 3) / 4, 128, 0, s>>>(gather, flags, masks, world, nq_cap, nq, k, seq, out, timeout);
     return cudaGetLastError();
 }
 

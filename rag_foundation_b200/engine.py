@@ -317,14 +317,18 @@ class Engine:
 
     def search_keys_device_scoped_fused(self, q_ptr: int, nq: int, scopes, k: int, out_keys_ptr: int, stream: int,
                                         rank: int, world: int, nq_cap: int, seq: int, keys_ptrs: np.ndarray, flag_ptrs: np.ndarray,
-                                        timeout_flag_ptr: int) -> None:
+                                        timeout_flag_ptr: int, nq_total: int = 0, q_index: Optional[np.ndarray] = None,
+                                        owner_masks: Optional[np.ndarray] = None) -> None:
         """Store-sharded batch with the exchange in the kernels (rf_search_keys_device_scoped_fused): one scope
-        per query (`scopes`: list of lists or a CSR tuple of THIS rank's segments, possibly empty per query)."""
+        per LAUNCHED query (`scopes`: list of lists or a CSR tuple of THIS rank's segments).  `q_index` (uint32 [nq])
+        names the batch queries this rank launches (the device query buffer holds all `nq_total`), `owner_masks`
+        (uint8 [nq_total]) the ranks each batch query's merge waits for."""
         segs, off = scopes if isinstance(scopes, tuple) else scopes_to_csr(scopes)
         if len(off) != nq + 1:
             raise ValueError("one scope per query")
         px = _capi.rf_peer_exchange(C.sizeof(_capi.rf_peer_exchange), int(rank), int(world), int(nq_cap), int(k), int(seq),
-                                    keys_ptrs.ctypes.data, flag_ptrs.ctypes.data, int(timeout_flag_ptr))
+                                    keys_ptrs.ctypes.data, flag_ptrs.ctypes.data, int(timeout_flag_ptr),
+                                    int(nq_total or 0), _ptr(q_index), _ptr(owner_masks))
         check(self._L.rf_search_keys_device_scoped_fused(self.handle, int(q_ptr), int(nq), _ptr(segs), _ptr(off), int(k), C.byref(px),
                                                          int(out_keys_ptr), int(stream) or None))
 

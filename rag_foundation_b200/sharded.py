@@ -235,18 +235,45 @@ class FusedStoreShardedSearcher(StoreShardedSearcher):
         torch.cuda.synchronize(dev)
         dist.barrier(pg)          # every rank has zeroed its flags before anyone publishes
 
+    def prepare_fused(self, scopes: Sequence[Sequence[int]]):
+        """Resolve a batch's scopes (global store numbers) once: the queries THIS rank has stores for and their local
+        segments (CSR), and for every query of the batch the ranks that own part of its scope (what its merge waits
+        for; identical on every rank)."""
+        import numpy as np
+        from .engine import scopes_to_csr
+        q_index, local, masks = [], [], np.zeros(len(scopes), np.uint8)
+        for i, sc in enumerate(scopes):
+            mine = []
+            for g in dict.fromkeys(sc):
+                if g < 0 or g >= len(self.by_name):
+                    continue
+                masks[i] |= 1 << self.owner(g)
+                if g in self.local_seg:
+                    mine.append(self.local_seg[g])
+            if mine:
+                q_index.append(i)
+                local.append(mine)
+        segs, off = scopes_to_csr(local) if local else (np.zeros(1, np.uint32), np.zeros(1, np.uint32))
+        return ("fused", segs, off, np.asarray(q_index, np.uint32), masks)
+
     def search_keys(self, q: torch.Tensor, scopes, k: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """q int8 [nq, 256] (the whole batch, replicated on every rank); scopes: global store numbers per query, or the
+        result of `prepare_fused` -> packed keys int64 [nq, k] on every rank."""
         k = k or self.k
+        prepared = scopes if (isinstance(scopes, tuple) and len(scopes) == 5 and scopes[0] == "fused") else None
         if q.shape[0] > self.nq_cap or k != self.k:
             return super().search_keys(q, scopes, k)
+        if prepared is None:
+            prepared = self.prepare_fused(scopes)
         assert q.is_cuda and q.dtype == torch.int8 and q.is_contiguous()
         if out is None:
             out = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
         self._seq += 1
-        local = scopes if isinstance(scopes, tuple) else self.prepare(scopes)
-        self.engine.search_keys_device_scoped_fused(q.data_ptr(), q.shape[0], local, k, out.data_ptr(),
+        _, segs, off, q_index, masks = prepared
+        self.engine.search_keys_device_scoped_fused(q.data_ptr(), int(q_index.size), (segs, off), k, out.data_ptr(),
                                                     torch.cuda.current_stream(q.device).cuda_stream, self.rank, self.world,
-                                                    self.nq_cap, self._seq, self._keys_ptrs, self._flag_ptrs, self._timeout.data_ptr())
+                                                    self.nq_cap, self._seq, self._keys_ptrs, self._flag_ptrs, self._timeout.data_ptr(),
+                                                    nq_total=q.shape[0], q_index=q_index, owner_masks=masks)
         return out
 
     def timed_out(self) -> bool:

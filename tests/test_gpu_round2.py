@@ -637,6 +637,19 @@ def test_store_sharded_fused_exchange_two_engines_one_process(co, zb):
         fp = np.asarray([t.data_ptr() for t in flag_buf], np.uint64)
         qd = torch.from_numpy(Q).cuda()
         outs = [torch.zeros((nq, k), dtype=torch.int64, device="cuda") for _ in range(world)]
+        # what each 'rank' launches: the queries it owns stores of, and for every query the ranks its merge waits for
+        masks = np.zeros(nq, np.uint8)
+        per_rank = []
+        for r in range(world):
+            q_index, local = [], []
+            for i, sc in enumerate(scopes):
+                mine = [g for g in sc if g % world == r]
+                if mine:
+                    masks[i] |= 1 << r
+                    q_index.append(i)
+                    local.append(mine)
+            per_rank.append((np.asarray(q_index, np.uint32), scopes_to_csr(local)))
+        assert int((masks == 3).sum()) > 5 and int((masks == 0).sum()) == 1
         # warm-up without an exchange so the per-stream scratch exists (see the chunk-sharded fused test)
         for r in range(world):
             engines[r].search_keys_device_scoped_fused(qd.data_ptr(), nq, csr, k, outs[r].data_ptr(), streams[r].cuda_stream,
@@ -650,8 +663,10 @@ def test_store_sharded_fused_exchange_two_engines_one_process(co, zb):
                 o.zero_()
             torch.cuda.synchronize()
             for r in range(world):
-                engines[r].search_keys_device_scoped_fused(qd.data_ptr(), nq, csr, k, outs[r].data_ptr(), streams[r].cuda_stream,
-                                                           r, world, nq_cap, seq, kp, fp, timeout[r].data_ptr())
+                q_index, local_csr = per_rank[r]
+                engines[r].search_keys_device_scoped_fused(qd.data_ptr(), int(q_index.size), local_csr, k, outs[r].data_ptr(), streams[r].cuda_stream,
+                                                           r, world, nq_cap, seq, kp, fp, timeout[r].data_ptr(),
+                                                           nq_total=nq, q_index=q_index, owner_masks=masks)
             torch.cuda.synchronize()
             assert not any(int(t.item()) for t in timeout)
             got = [o.cpu().numpy().view(np.uint64) for o in outs]
