@@ -80,8 +80,9 @@ def fnv1a32(data: bytes) -> int:
     return h
 
 
-def bucket(tok: bytes) -> int:
-    return fnv1a32(tok) & (D - 1)
+def bucket(tok: bytes, dim: int = D) -> int:
+    """SPEC.md step 3; `dim` is the row width (a power of two: 256 by default, 512 / 1024 for the wider variants)."""
+    return fnv1a32(tok) & (dim - 1)
 
 
 # ----------------------------------------------------------------------------- step 2: chunk
@@ -100,29 +101,29 @@ def chunk_windows(n_tokens: int) -> List[Tuple[int, int]]:
 
 
 # ----------------------------------------------------------------------------- steps 4-5: features
-def _row_from_buckets(buckets: Iterable[int]) -> np.ndarray:
-    tf = np.zeros(D, dtype=np.int64)
+def _row_from_buckets(buckets: Iterable[int], dim: int = D) -> np.ndarray:
+    tf = np.zeros(dim, dtype=np.int64)
     for b in buckets:
         tf[b] += 1
     return np.minimum(tf, 127).astype(np.int8)
 
 
-def featurize_doc(data: bytes):
-    """-> (F int8 [n,256], ff int32 [n], spans int64 [n,2] byte spans, n_tokens)."""
+def featurize_doc(data: bytes, dim: int = D):
+    """-> (F int8 [n,dim], ff int32 [n], spans int64 [n,2] byte spans, n_tokens)."""
     toks = tokenize(data)
     wins = chunk_windows(len(toks))
-    F = np.zeros((len(wins), D), dtype=np.int8)
+    F = np.zeros((len(wins), dim), dtype=np.int8)
     spans = np.zeros((len(wins), 2), dtype=np.int64)
     for w, (lo, hi) in enumerate(wins):
-        F[w] = _row_from_buckets(bucket(t) for _, _, t in toks[lo:hi])
+        F[w] = _row_from_buckets((bucket(t, dim) for _, _, t in toks[lo:hi]), dim)
         spans[w, 0] = toks[lo][0]
         spans[w, 1] = toks[hi - 1][1]
     ff = (F.astype(np.int32) ** 2).sum(axis=1).astype(np.int32)
     return F, ff, spans, len(toks)
 
 
-def query_vector(data: bytes) -> np.ndarray:
-    return _row_from_buckets(bucket(t) for _, _, t in tokenize(data))
+def query_vector(data: bytes, dim: int = D) -> np.ndarray:
+    return _row_from_buckets((bucket(t, dim) for _, _, t in tokenize(data)), dim)
 
 
 # ----------------------------------------------------------------------------- steps 6-8
@@ -201,10 +202,10 @@ def load_zipf_vocab() -> np.ndarray:
     return t
 
 
-def zipf_bucket_table(zipf_vocab: np.ndarray | None = None) -> np.ndarray:
-    """uint8[65536]: bucket of the decimal-ASCII token of zipf_vocab[r]."""
+def zipf_bucket_table(zipf_vocab: np.ndarray | None = None, dim: int = D) -> np.ndarray:
+    """uint16[65536]: bucket (< dim) of the decimal-ASCII token of zipf_vocab[r]."""
     zv = load_zipf_vocab() if zipf_vocab is None else zipf_vocab
-    per_vocab = np.array([bucket(str(v).encode()) for v in range(int(zv.max()) + 1)], dtype=np.uint8)
+    per_vocab = np.array([bucket(str(v).encode(), dim) for v in range(int(zv.max()) + 1)], dtype=np.uint16)
     return per_vocab[zv]
 
 
@@ -224,12 +225,12 @@ def mix64(seed, a, b):
     return x
 
 
-def synth_rows(seed: int, start: int, n: int, zb: np.ndarray | None = None) -> np.ndarray:
-    """int8 [n,256] rows `start .. start+n-1` of the synthetic corpus `seed`."""
-    zb = zipf_bucket_table() if zb is None else zb
+def synth_rows(seed: int, start: int, n: int, zb: np.ndarray | None = None, dim: int = D) -> np.ndarray:
+    """int8 [n,dim] rows `start .. start+n-1` of the synthetic corpus `seed` (zb: the bucket table for `dim`)."""
+    zb = zipf_bucket_table(dim=dim) if zb is None else zb
     c = np.arange(start, start + n, dtype=np.uint64)
     lens = 64 + (mix64(seed ^ 0xA5, c, 0) & np.uint64(63)).astype(np.int64)
-    tf = np.zeros((n, D), dtype=np.int32)
+    tf = np.zeros((n, dim), dtype=np.int32)
     rows = np.arange(n)
     for j in range(127):
         live = lens > j
@@ -240,10 +241,10 @@ def synth_rows(seed: int, start: int, n: int, zb: np.ndarray | None = None) -> n
     return np.minimum(tf, 127).astype(np.int8)
 
 
-def synth_query(seed: int, qi: int, zb: np.ndarray | None = None, n_tokens: int = 8) -> np.ndarray:
-    zb = zipf_bucket_table() if zb is None else zb
+def synth_query(seed: int, qi: int, zb: np.ndarray | None = None, n_tokens: int = 8, dim: int = D) -> np.ndarray:
+    zb = zipf_bucket_table(dim=dim) if zb is None else zb
     r = (mix64(seed ^ 0x51, qi, np.arange(n_tokens, dtype=np.uint64)) >> np.uint64(48)).astype(np.int64)
-    return _row_from_buckets(int(zb[x]) for x in r)
+    return _row_from_buckets((int(zb[x]) for x in r), dim)
 
 
 def synth_text(seed: int, n_tokens: int, zipf_vocab: np.ndarray | None = None) -> bytes:

@@ -22,7 +22,8 @@
 #include <immintrin.h>
 #endif
 
-#define RF1_D 256
+#define RF1_D 256          /* default row width; every function takes `dim` (a power of two, 128 .. RF1_D_MAX; SPEC.md step 3) */
+#define RF1_D_MAX 4096
 #define RF1_L 128
 #define RF1_S 112
 #define RF1_TOMBSTONE 0xFFFFFFFFu
@@ -47,7 +48,7 @@ static int is_stopword(const uint8_t *p, size_t len) {
 }
 
 /* Kept tokens: writes up to max_tokens (start, end, bucket) triples; returns the total count. */
-int64_t rf1_tokenize(const uint8_t *data, size_t n, int64_t *starts, int64_t *ends, uint8_t *buckets,
+int64_t rf1_tokenize(const uint8_t *data, size_t n, int dim, int64_t *starts, int64_t *ends, uint16_t *buckets,
                      int64_t max_tokens) {
     int64_t cnt = 0;
     size_t i = 0;
@@ -60,7 +61,7 @@ int64_t rf1_tokenize(const uint8_t *data, size_t n, int64_t *starts, int64_t *en
             if (cnt < max_tokens) {
                 if (starts) starts[cnt] = (int64_t)i;
                 if (ends) ends[cnt] = (int64_t)j;
-                if (buckets) buckets[cnt] = (uint8_t)(h & (RF1_D - 1));
+                if (buckets) buckets[cnt] = (uint16_t)(h & (uint32_t)(dim - 1));
             }
             ++cnt;
         }
@@ -75,12 +76,12 @@ int64_t rf1_n_chunks(int64_t n_tokens) {
     return 1 + (extra + RF1_S - 1) / RF1_S;
 }
 
-static void row_from_buckets(const uint8_t *b, int64_t n, int8_t *row, int32_t *ff) {
-    int32_t tf[RF1_D];
-    memset(tf, 0, sizeof tf);
+static void row_from_buckets(const uint16_t *b, int64_t n, int dim, int8_t *row, int32_t *ff) {
+    int32_t tf[RF1_D_MAX];
+    memset(tf, 0, sizeof(int32_t) * (size_t)dim);
     for (int64_t i = 0; i < n; ++i) tf[b[i]]++;
     int32_t acc = 0;
-    for (int d = 0; d < RF1_D; ++d) {
+    for (int d = 0; d < dim; ++d) {
         int32_t v = tf[d] > 127 ? 127 : tf[d];
         row[d] = (int8_t)v;
         acc += v * v;
@@ -90,21 +91,21 @@ static void row_from_buckets(const uint8_t *b, int64_t n, int8_t *row, int32_t *
 
 /* steps 1-4 for one document.  Returns n_chunks (may exceed max_chunks: then only the first
  * max_chunks rows are written), or -1 on allocation failure. */
-int64_t rf1_featurize_doc(const uint8_t *data, size_t n, int8_t *F, int32_t *ff, int64_t *spans,
+int64_t rf1_featurize_doc(const uint8_t *data, size_t n, int dim, int8_t *F, int32_t *ff, int64_t *spans,
                           int64_t max_chunks, int64_t *n_tokens_out) {
-    int64_t T = rf1_tokenize(data, n, NULL, NULL, NULL, 0);
+    int64_t T = rf1_tokenize(data, n, dim, NULL, NULL, NULL, 0);
     if (n_tokens_out) *n_tokens_out = T;
     int64_t nc = rf1_n_chunks(T);
     if (T == 0) return 0;
     int64_t *st = (int64_t *)malloc(sizeof(int64_t) * (size_t)T);
     int64_t *en = (int64_t *)malloc(sizeof(int64_t) * (size_t)T);
-    uint8_t *bk = (uint8_t *)malloc((size_t)T);
+    uint16_t *bk = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)T);
     if (!st || !en || !bk) { free(st); free(en); free(bk); return -1; }
-    rf1_tokenize(data, n, st, en, bk, T);
+    rf1_tokenize(data, n, dim, st, en, bk, T);
     for (int64_t w = 0; w < nc && w < max_chunks; ++w) {
         int64_t lo = (int64_t)RF1_S * w;
         int64_t hi = lo + RF1_L < T ? lo + RF1_L : T;
-        row_from_buckets(bk + lo, hi - lo, F + w * RF1_D, ff ? ff + w : NULL);
+        row_from_buckets(bk + lo, hi - lo, dim, F + w * (int64_t)dim, ff ? ff + w : NULL);
         if (spans) { spans[2 * w] = st[lo]; spans[2 * w + 1] = en[hi - 1]; }
     }
     free(st); free(en); free(bk);
@@ -112,26 +113,26 @@ int64_t rf1_featurize_doc(const uint8_t *data, size_t n, int8_t *F, int32_t *ff,
 }
 
 /* step 5 */
-void rf1_query_vector(const uint8_t *data, size_t n, int8_t *q) {
-    int64_t T = rf1_tokenize(data, n, NULL, NULL, NULL, 0);
-    uint8_t *bk = (uint8_t *)malloc((size_t)(T > 0 ? T : 1));
-    rf1_tokenize(data, n, NULL, NULL, bk, T);
-    row_from_buckets(bk, T, q, NULL);
+void rf1_query_vector(const uint8_t *data, size_t n, int dim, int8_t *q) {
+    int64_t T = rf1_tokenize(data, n, dim, NULL, NULL, NULL, 0);
+    uint16_t *bk = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(T > 0 ? T : 1));
+    rf1_tokenize(data, n, dim, NULL, NULL, bk, T);
+    row_from_buckets(bk, T, dim, q, NULL);
     free(bk);
 }
 
 /* ------------------------------------------------------------------ step 6: int8 dot */
-static int32_t dot256_generic(const int8_t *a, const int8_t *b) {
+static int32_t dot256_generic(const int8_t *a, const int8_t *b, int dim) {
     int32_t s = 0;
-    for (int d = 0; d < RF1_D; ++d) s += (int32_t)a[d] * (int32_t)b[d];
+    for (int d = 0; d < dim; ++d) s += (int32_t)a[d] * (int32_t)b[d];
     return s;
 }
 
 #if defined(__x86_64__)
 __attribute__((target("avx2")))
-static int32_t dot256_avx2(const int8_t *a, const int8_t *b) {
+static int32_t dot256_avx2(const int8_t *a, const int8_t *b, int dim) {
     __m256i acc = _mm256_setzero_si256();
-    for (int d = 0; d < RF1_D; d += 16) {
+    for (int d = 0; d < dim; d += 16) {
         __m256i x = _mm256_cvtepi8_epi16(_mm_loadu_si128((const __m128i *)(a + d)));
         __m256i y = _mm256_cvtepi8_epi16(_mm_loadu_si128((const __m128i *)(b + d)));
         acc = _mm256_add_epi32(acc, _mm256_madd_epi16(x, y));
@@ -144,16 +145,16 @@ static int32_t dot256_avx2(const int8_t *a, const int8_t *b) {
 
 /* Features are counts in [0,127], so the unsigned x signed VNNI form is exact. */
 __attribute__((target("avx512f,avx512bw,avx512vl,avx512vnni")))
-static int32_t dot256_vnni(const int8_t *a, const int8_t *b) {
+static int32_t dot256_vnni(const int8_t *a, const int8_t *b, int dim) {
     __m512i acc = _mm512_setzero_si512();
-    for (int d = 0; d < RF1_D; d += 64)
+    for (int d = 0; d < dim; d += 64)
         acc = _mm512_dpbusd_epi32(acc, _mm512_loadu_si512((const void *)(a + d)),
                                   _mm512_loadu_si512((const void *)(b + d)));
     return _mm512_reduce_add_epi32(acc);
 }
 #endif
 
-typedef int32_t (*dot_fn)(const int8_t *, const int8_t *);
+typedef int32_t (*dot_fn)(const int8_t *, const int8_t *, int);   /* dim: a multiple of 64 */
 static dot_fn pick_dot(void) {
 #if defined(__x86_64__)
     __builtin_cpu_init();
@@ -201,7 +202,7 @@ static int in_scope(uint32_t seg, const uint32_t *scope, int n_scope) {
 
 /* Largest k keys over rows [row_lo,row_hi) of F that are in scope; out_keys zero-padded.
  * Returns the number of valid results. threads <= 0: all OpenMP threads. */
-int rf1_score_topk_keys(const int8_t *F, const uint32_t *store_seg, int64_t row_lo, int64_t row_hi,
+int rf1_score_topk_keys(const int8_t *F, const uint32_t *store_seg, int dim, int64_t row_lo, int64_t row_hi,
                         const int8_t *q, const uint32_t *scope, int n_scope, int k, uint64_t id_base,
                         uint64_t *out_keys, int threads) {
     if (k <= 0 || k > 64) return -1;
@@ -224,7 +225,7 @@ int rf1_score_topk_keys(const int8_t *F, const uint32_t *store_seg, int64_t row_
         int64_t lo = row_lo + span * t / T, hi = row_lo + span * (t + 1) / T;
         for (int64_t r = lo; r < hi; ++r) {
             if (!in_scope(store_seg[r], scope, n_scope)) continue;
-            int32_t s = dot(F + r * RF1_D, q);
+            int32_t s = dot(F + r * (int64_t)dim, q, dim);
             topk_insert(top, k, pack_key(s, id_base + (uint64_t)r));
         }
     }
@@ -244,14 +245,14 @@ float rf1_cosine(int32_t s, int32_t qq, int32_t ff) {
 }
 
 /* steps 6-8 with unpacked outputs; ff may be NULL (then out_cos untouched). */
-int rf1_score_topk(const int8_t *F, const uint32_t *store_seg, const int32_t *ff, int64_t n_rows,
+int rf1_score_topk(const int8_t *F, const uint32_t *store_seg, const int32_t *ff, int dim, int64_t n_rows,
                    const int8_t *q, const uint32_t *scope, int n_scope, int k, uint64_t id_base,
                    uint64_t *out_ids, int32_t *out_scores, float *out_cos, int threads) {
     uint64_t keys[64];
-    int n = rf1_score_topk_keys(F, store_seg, 0, n_rows, q, scope, n_scope, k, id_base, keys, threads);
+    int n = rf1_score_topk_keys(F, store_seg, dim, 0, n_rows, q, scope, n_scope, k, id_base, keys, threads);
     if (n < 0) return n;
     int32_t qq = 0;
-    for (int d = 0; d < RF1_D; ++d) qq += (int32_t)q[d] * (int32_t)q[d];
+    for (int d = 0; d < dim; ++d) qq += (int32_t)q[d] * (int32_t)q[d];
     for (int i = 0; i < n; ++i) {
         out_ids[i] = (uint64_t)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFu));
         out_scores[i] = (int32_t)(keys[i] >> 32);
@@ -261,11 +262,11 @@ int rf1_score_topk(const int8_t *F, const uint32_t *store_seg, const int32_t *ff
 }
 
 /* nq queries one after another (each uses all threads): the CPU baseline for batched configs. */
-int rf1_score_topk_batch(const int8_t *F, const uint32_t *store_seg, int64_t n_rows, const int8_t *Q,
+int rf1_score_topk_batch(const int8_t *F, const uint32_t *store_seg, int dim, int64_t n_rows, const int8_t *Q,
                          int nq, const uint32_t *scope_flat, const int32_t *scope_off, int k,
                          uint64_t id_base, uint64_t *out_keys, int threads) {
     for (int i = 0; i < nq; ++i) {
-        int n = rf1_score_topk_keys(F, store_seg, 0, n_rows, Q + (size_t)i * RF1_D,
+        int n = rf1_score_topk_keys(F, store_seg, dim, 0, n_rows, Q + (size_t)i * (size_t)dim,
                                     scope_flat + scope_off[i], scope_off[i + 1] - scope_off[i], k,
                                     id_base, out_keys + (size_t)i * (size_t)k, threads);
         if (n < 0) return n;
@@ -288,21 +289,21 @@ int rf1_merge_topk(const uint64_t *keys, int64_t n, int k, uint64_t *out) {
 }
 
 /* ---- RF-1w (SPEC.md "IDF-weighted variant"): document frequencies, weights, weighted query ---- */
-int64_t rf1_bucket_df(const int8_t *F, const uint32_t *store_seg, int64_t n_rows, const uint32_t *scope, int n_scope,
-                      uint64_t *df /* [RF1_D] */) {
+int64_t rf1_bucket_df(const int8_t *F, const uint32_t *store_seg, int dim, int64_t n_rows, const uint32_t *scope, int n_scope,
+                      uint64_t *df /* [dim] */) {
     int64_t n = 0;
-    memset(df, 0, sizeof(uint64_t) * RF1_D);
+    memset(df, 0, sizeof(uint64_t) * (size_t)dim);
     for (int64_t r = 0; r < n_rows; ++r) {
         if (!in_scope(store_seg[r], scope, n_scope)) continue;
         ++n;
-        const int8_t *row = F + r * RF1_D;
-        for (int d = 0; d < RF1_D; ++d) df[d] += row[d] > 0;
+        const int8_t *row = F + r * (int64_t)dim;
+        for (int d = 0; d < dim; ++d) df[d] += row[d] > 0;
     }
     return n;
 }
 
-void rf1_idf_weights(const uint64_t *df, uint64_t n, uint8_t *w /* [RF1_D] */) {
-    for (int d = 0; d < RF1_D; ++d) {
+void rf1_idf_weights(const uint64_t *df, uint64_t n, int dim, uint8_t *w /* [dim] */) {
+    for (int d = 0; d < dim; ++d) {
         const uint64_t r = ((n + 1) * 256) / (df[d] + 1);
         int lg = 63;
         while (!(r >> lg)) --lg;
@@ -311,8 +312,8 @@ void rf1_idf_weights(const uint64_t *df, uint64_t n, uint8_t *w /* [RF1_D] */) {
     }
 }
 
-void rf1_weight_query(const int8_t *q, const uint8_t *w, int8_t *qw) {
-    for (int d = 0; d < RF1_D; ++d) {
+void rf1_weight_query(const int8_t *q, const uint8_t *w, int dim, int8_t *qw) {
+    for (int d = 0; d < dim; ++d) {
         const int v = (int)q[d] * (int)w[d];
         qw[d] = (int8_t)(v < 127 ? v : 127);
     }
@@ -330,8 +331,8 @@ static inline uint64_t mix64(uint64_t seed, uint64_t a, uint64_t b) {
 
 uint64_t rf1_mix64(uint64_t seed, uint64_t a, uint64_t b) { return mix64(seed, a, b); }
 
-/* zb: uint8[65536] bucket of the decimal-ASCII token of zipf_vocab[r] */
-void rf1_synth_rows(uint64_t seed, uint64_t start, int64_t n, const uint8_t *zb, int8_t *F, int32_t *ff,
+/* zb: uint16[65536] bucket (< dim) of the decimal-ASCII token of zipf_vocab[r] */
+void rf1_synth_rows(uint64_t seed, uint64_t start, int64_t n, const uint16_t *zb, int dim, int8_t *F, int32_t *ff,
                     int threads) {
     int nt = threads > 0 ? threads : rf1_max_threads();
     (void)nt;
@@ -341,15 +342,15 @@ void rf1_synth_rows(uint64_t seed, uint64_t start, int64_t n, const uint8_t *zb,
     for (int64_t i = 0; i < n; ++i) {
         uint64_t c = start + (uint64_t)i;
         int len = 64 + (int)(mix64(seed ^ 0xA5ull, c, 0) & 63);
-        uint8_t bk[128];
+        uint16_t bk[128];
         for (int j = 0; j < len; ++j) bk[j] = zb[mix64(seed, c, (uint64_t)j) >> 48];
-        row_from_buckets(bk, len, F + i * RF1_D, ff ? ff + i : NULL);
+        row_from_buckets(bk, len, dim, F + i * (int64_t)dim, ff ? ff + i : NULL);
     }
 }
 
-void rf1_synth_query(uint64_t seed, uint64_t qi, int n_tokens, const uint8_t *zb, int8_t *q) {
-    uint8_t bk[256];
+void rf1_synth_query(uint64_t seed, uint64_t qi, int n_tokens, const uint16_t *zb, int dim, int8_t *q) {
+    uint16_t bk[256];
     if (n_tokens > 256) n_tokens = 256;
     for (int j = 0; j < n_tokens; ++j) bk[j] = zb[mix64(seed ^ 0x51ull, qi, (uint64_t)j) >> 48];
-    row_from_buckets(bk, n_tokens, q, NULL);
+    row_from_buckets(bk, n_tokens, dim, q, NULL);
 }
