@@ -12,8 +12,10 @@
  * points are thread-safe except rf_engine_create/destroy.  There is NO CPU fallback: every compute
  * entry point launches sm_100a kernels and fails with RF_ECUDA/RF_ENODEVICE when it cannot.
  *
- * Arithmetic is the frozen RF-1 spec (oracle/SPEC.md): D = 256 int8 hashed term counts per chunk,
- * int32 dot-product scores, rank by (score desc, global chunk id asc), float32 cosine reported.
+ * Arithmetic is the frozen RF-1 spec (oracle/SPEC.md): D int8 hashed term counts per chunk (D = 256, or the
+ * wider 512 / 1024 of SURVEY.md 8f-4: fewer bucket collisions, D + 4 bytes streamed per chunk), int32
+ * dot-product scores, rank by (score desc, global chunk id asc), float32 cosine reported.  D is fixed per
+ * engine (rf_config.dim); wherever a comment below says RF_DIM for a buffer size, read "the engine's dim".
  */
 #ifndef RF_B200_H
 #define RF_B200_H
@@ -25,7 +27,8 @@
 extern "C" {
 #endif
 
-#define RF_DIM 256u           /* feature dimension (int8 per chunk row)               */
+#define RF_DIM 256u           /* default feature dimension (int8 per chunk row)       */
+#define RF_DIM_MAX 1024u      /* widest row an engine can be created with             */
 #define RF_TOPK_MAX 32u       /* largest k a search may ask for (reference default 10) */
 #define RF_SCOPE_MAX 16u      /* store segments per query scope (reference: <= 10 stores/user, config.py:127) */
 #define RF_TOMBSTONE 0xFFFFFFFFu
@@ -46,9 +49,9 @@ typedef struct rf_engine rf_engine;
 typedef struct rf_config {
     uint32_t struct_size;    /* sizeof(rf_config), for forward compatibility            */
     int32_t device;          /* CUDA ordinal                                            */
-    uint32_t dim;            /* must be RF_DIM                                          */
+    uint32_t dim;            /* 256 (RF_DIM), 512 or 1024; batched tensor-core scoring is built for 256 */
     uint32_t n_contexts;     /* concurrent searches (reference: 50 streams/process, routes/chat.py:40); 0 -> 8 */
-    uint64_t capacity_rows;  /* chunk rows reserved in HBM (260 B + 12 B sidecar each)  */
+    uint64_t capacity_rows;  /* chunk rows reserved in HBM (dim + 8 B each)             */
     uint64_t id_base;        /* global chunk id of row 0 (shard offset in sharded mode) */
 } rf_config;
 
@@ -294,6 +297,8 @@ typedef struct rf_group_config {
     uint32_t n_contexts;      /* concurrent searches per device; 0 -> 8 */
     uint32_t placement;       /* RF_PLACE_* */
     uint64_t capacity_rows;   /* rows reserved PER DEVICE */
+    uint32_t dim;             /* feature dimension of every engine; 0 -> RF_DIM */
+    uint32_t reserved;
 } rf_group_config;
 int rf_group_create(const rf_group_config *cfg, rf_group **out);
 int rf_group_destroy(rf_group *g);

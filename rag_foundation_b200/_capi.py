@@ -11,7 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librf_b200.so")
 
-RF_DIM = 256
+RF_DIM = 256          # default row width; engines can also be created with 512 or 1024 (RF_DIM_MAX)
+RF_DIM_MAX = 1024
 RF_TOPK_MAX = 32
 RF_SCOPE_MAX = 16
 RF_TOMBSTONE = 0xFFFFFFFF
@@ -32,7 +33,8 @@ class rf_peer_exchange(C.Structure):
 
 class rf_group_config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_devices", C.c_uint32), ("devices", C.c_void_p), ("id_bases", C.c_void_p),
-                ("n_contexts", C.c_uint32), ("placement", C.c_uint32), ("capacity_rows", C.c_uint64)]
+                ("n_contexts", C.c_uint32), ("placement", C.c_uint32), ("capacity_rows", C.c_uint64),
+                ("dim", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 RF_PLACE_STORE, RF_PLACE_SPREAD = 0, 1

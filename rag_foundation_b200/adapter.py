@@ -157,13 +157,14 @@ _registry_lock = threading.Lock()
 
 def get_registry() -> Registry:
     """Lazily create the process-global engine from env flags (kept beside, not inside, the
-    reference's Settings -- SURVEY.md §5): RAG_B200_CAPACITY_ROWS, RAG_B200_DEVICE, or RAG_B200_DEVICES=0,1,..
+    reference's Settings -- SURVEY.md §5): RAG_B200_CAPACITY_ROWS, RAG_B200_DIM, RAG_B200_DEVICE, or RAG_B200_DEVICES=0,1,..
     for an engine group over several GPUs."""
     global _registry
     with _registry_lock:
         if _registry is None:
             cap = int(os.environ.get("RAG_B200_CAPACITY_ROWS", str(4_000_000)))
             n_ctx = int(os.environ.get("RAG_B200_CONTEXTS", "16"))
+            dim = int(os.environ.get("RAG_B200_DIM", "256"))     # 256, 512 or 1024 features per chunk (SURVEY.md 8f-4)
             devices = os.environ.get("RAG_B200_DEVICES", "").strip()
             if devices:
                 # several GPUs behind ONE adapter: an engine per device in this process, stores placed by
@@ -172,10 +173,10 @@ def get_registry() -> Registry:
                 from .engine import EngineGroup
                 devs = [int(x) for x in devices.split(",") if x.strip() != ""]
                 _registry = Registry(EngineGroup(devs, capacity_rows=cap, n_contexts=n_ctx,
-                                                 placement=os.environ.get("RAG_B200_PLACEMENT", "store")))
+                                                 placement=os.environ.get("RAG_B200_PLACEMENT", "store"), dim=dim))
             else:
                 dev = int(os.environ.get("RAG_B200_DEVICE", "0"))
-                _registry = Registry(Engine(capacity_rows=cap, device=dev, n_contexts=n_ctx))
+                _registry = Registry(Engine(capacity_rows=cap, device=dev, n_contexts=n_ctx, dim=dim))
         return _registry
 
 

@@ -1,6 +1,6 @@
 // librf_b200.so -- engine and C-ABI (include/rf_b200.h).
 //
-// One engine owns one GPU's share of the chunk index: a feature arena F[capacity, 256] int8 in HBM
+// One engine owns one GPU's share of the chunk index: a feature arena F[capacity, dim] int8 in HBM (dim = 256, 512 or 1024)
 // with three sidecar arrays (store-segment word, sum of squares, nothing else is per-row), rows in
 // append order (row index + id_base = global chunk id).  Host-side it keeps, per store, the list of
 // row extents that hold the store's rows, so a store-scoped query scans only those rows; the
@@ -316,11 +316,13 @@ void copy_pool_destroy(CopyPool *p) {
 
 struct rf_engine {
     rf_config cfg{};
+    uint32_t dim = RF_DIM;           // features (= bytes) per row: 256, 512 or 1024
+    uint32_t tile_rows = 32;         // rows per scan tile: rf::scan_tile_rows(dim)
     int sm_count = 148;
     int8_t *F = nullptr;
     uint32_t *seg = nullptr;
     int32_t *ff = nullptr;
-    uint8_t *zipf_bucket = nullptr;  // device, 65536 B, built on first synthetic ingest
+    uint16_t *zipf_bucket = nullptr; // device, 65536 entries, built on first synthetic ingest
     uint64_t hbm_bytes = 0;
 
     std::shared_mutex meta_mu;       // stores / docs / n_rows
@@ -330,7 +332,7 @@ struct rf_engine {
     uint64_t n_rows = 0;             // published rows
     std::atomic<uint64_t> epoch{0};  // bumps whenever extents change
     std::atomic<uint64_t> tomb_gen{0};   // bumps whenever rows are tombstoned
-    std::mutex df_mu;                // RF-1w statistics cache: scope -> (generation, df[256] + n)
+    std::mutex df_mu;                // RF-1w statistics cache: scope -> (generation, df[dim] + n)
     std::map<std::vector<uint32_t>, std::pair<uint64_t, std::vector<uint64_t>>> df_cache;
 
     std::mutex ingest_mu;            // one ingest at a time (shared scratch + append cursor + free list)
@@ -459,7 +461,7 @@ int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store
                 lo.push_back(x.lo);
                 hi.push_back(x.hi);
                 tile0.push_back(tiles);
-                tiles += (x.hi - x.lo + rf::kScanTileRows - 1) / rf::kScanTileRows;
+                tiles += (x.hi - x.lo + e->tile_rows - 1) / e->tile_rows;
             }
             tile0.push_back(tiles);
             p.total_tiles = tiles;
@@ -469,13 +471,13 @@ int build_blob(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *store
     if (lo.empty()) { lo.push_back(0); hi.push_back(0); }
     auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
     b.off_q = 0;
-    b.off_plans = align(q ? static_cast<size_t>(nq) * RF_DIM : 0);
+    b.off_plans = align(q ? static_cast<size_t>(nq) * e->dim : 0);
     b.off_lo = align(b.off_plans + plans.size() * sizeof(ScanPlan));
     b.off_hi = align(b.off_lo + lo.size() * 4);
     b.off_tile0 = align(b.off_hi + hi.size() * 4);
     const size_t total = align(b.off_tile0 + tile0.size() * 4);
     b.bytes.assign(total, 0);
-    if (q) memcpy(b.bytes.data() + b.off_q, q, static_cast<size_t>(nq) * RF_DIM);
+    if (q) memcpy(b.bytes.data() + b.off_q, q, static_cast<size_t>(nq) * e->dim);
     memcpy(b.bytes.data() + b.off_plans, plans.data(), plans.size() * sizeof(ScanPlan));
     memcpy(b.bytes.data() + b.off_lo, lo.data(), lo.size() * 4);
     memcpy(b.bytes.data() + b.off_hi, hi.data(), hi.size() * 4);
@@ -515,7 +517,7 @@ int table_acquire(rf_engine *e, std::shared_lock<std::shared_mutex> &lk) {
                 for (const Extent &x : *src) {
                     lo.push_back(x.lo);
                     hi.push_back(x.hi);
-                    en.total_tiles += (x.hi - x.lo + rf::kScanTileRows - 1) / rf::kScanTileRows;
+                    en.total_tiles += (x.hi - x.lo + e->tile_rows - 1) / e->tile_rows;
                 }
                 en.n_ext = static_cast<uint32_t>(src->size());
                 t.h_next[sg] = en.n_ext;
@@ -699,12 +701,12 @@ int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q
         // [queries | scope offsets | scope stores] in one H2D copy
         auto align = [](size_t x) { return (x + 15) & ~static_cast<size_t>(15); };
         const size_t n_segs = tq->off[nq];
-        const size_t off_off = align(static_cast<size_t>(nq) * RF_DIM), off_segs = align(off_off + (static_cast<size_t>(nq) + 1) * 4);
+        const size_t off_off = align(static_cast<size_t>(nq) * e->dim), off_segs = align(off_off + (static_cast<size_t>(nq) + 1) * 4);
         const size_t total = align(off_segs + std::max<size_t>(n_segs, 1) * 4);
         RF_CUDA(c->h_in.reserve(total));
         RF_CUDA(c->d_in.reserve(total));
         uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
-        memcpy(h, q_host, static_cast<size_t>(nq) * RF_DIM);
+        memcpy(h, q_host, static_cast<size_t>(nq) * e->dim);
         memcpy(h + off_off, tq->off, (static_cast<size_t>(nq) + 1) * 4);
         if (n_segs) memcpy(h + off_segs, tq->segs, n_segs * 4);
         RF_CUDA(cudaMemcpyAsync(c->d_in.p, h, total, cudaMemcpyHostToDevice, c->stream));
@@ -722,7 +724,7 @@ int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q
         maybe_inline_plan(a, b, nq, shared);
     }
     if (inline_q) {
-        memcpy(a.q_inline, q_host, RF_DIM);
+        memcpy(a.q_inline, q_host, e->dim);
         a.q = nullptr;
     }
     if (!tq && !(inline_q && a.inline_plan)) {   // queries and/or plans travel as one H2D copy
@@ -766,10 +768,10 @@ int search_launch(rf_engine *e, SearchCtx *c, const PlanBlob &b, const int8_t *q
         a.done_seq = ++c->seq ? c->seq : ++c->seq;
         pd.flag_off = flag_off;
         pd.done_seq = a.done_seq;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, e->dim, c->stream, true));
     } else {
         a.done_flag = nullptr;
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, c->stream, true));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, e->dim, c->stream, true));
         RF_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(c->h_out.p) + L.off_ids, d_out + L.off_ids, L.total - L.off_ids,
                                 cudaMemcpyDeviceToHost, c->stream));
     }
@@ -812,7 +814,7 @@ int search_wait(rf_engine *e, SearchCtx *c, uint64_t *out_ids, int32_t *out_scor
     memcpy(out_scores, h + L.off_scores, n * 4);
     if (out_cos) memcpy(out_cos, h + L.off_cos, n * 4);
     if (out_counts) memcpy(out_counts, h + L.off_counts, static_cast<size_t>(pd.nq) * 4);
-    if (out_q && pd.has_q) memcpy(out_q, h + L.total, RF_DIM);
+    if (out_q && pd.has_q) memcpy(out_q, h + L.total, e->dim);
     if (e->profile) {
         e->prof_ns[2] += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - pd.t_launched).count();
         e->prof_ns[3] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t2).count();
@@ -916,7 +918,7 @@ uint32_t fnv1a32(const char *s, size_t n) {
 // the per-row tenant mask drops the foreign rows in between); large batches are compute-bound:
 // 1024 queries x 1 M rows take 0.248 ms.
 bool gemm_pays(const rf_engine *e, uint32_t nq, uint64_t rows, uint64_t span, uint32_t k, double extra_us = 0.0) {
-    if (!e->gemm_enabled || k > static_cast<uint32_t>(rf::kGemmListK) || span < 32768 || nq < 2) return false;
+    if (!e->gemm_enabled || e->dim != RF_DIM || k > static_cast<uint32_t>(rf::kGemmListK) || span < 32768 || nq < 2) return false;   // (the tensor-core kernels are built for K = 256)
     if (e->gemm_min_queries) return nq >= e->gemm_min_queries && rows * 2 >= span;
     const double scan_us = 6.0 + 3.65e-5 * nq * static_cast<double>(rows);
     const double gemm_us = 33.0 + extra_us + std::max(4.6e-5, 2.1e-7 * nq) * static_cast<double>(span);
@@ -1016,7 +1018,7 @@ const char *rf_last_error(void) { return g_err; }
 
 int rf_build_info(char *buf, size_t n) {
     if (!buf || !n) return RF_EINVAL;
-    snprintf(buf, n, "librf_b200 sm_100a cuda-runtime %d dim %u topk_max %u scope_max %u", CUDART_VERSION, RF_DIM,
+    snprintf(buf, n, "librf_b200 sm_100a cuda-runtime %d dim %u (also 512, 1024) topk_max %u scope_max %u", CUDART_VERSION, RF_DIM,
              RF_TOPK_MAX, RF_SCOPE_MAX);
     return RF_OK;
 }
@@ -1024,7 +1026,7 @@ int rf_build_info(char *buf, size_t n) {
 int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     if (!cfg || !out) return fail(RF_EINVAL, "null argument");
     if (cfg->struct_size != sizeof(rf_config)) return fail(RF_EINVAL, "rf_config.struct_size %u != %zu", cfg->struct_size, sizeof(rf_config));
-    if (cfg->dim != RF_DIM) return fail(RF_EINVAL, "dim must be %u", RF_DIM);
+    if (cfg->dim != 256 && cfg->dim != 512 && cfg->dim != 1024) return fail(RF_EINVAL, "dim must be 256, 512 or 1024");
     if (cfg->capacity_rows == 0 || cfg->id_base + cfg->capacity_rows > 0xFFFFFFFEull)
         return fail(RF_EINVAL, "id_base + capacity_rows must be in (0, 2^32 - 2]");
     int n_dev = 0;
@@ -1041,6 +1043,8 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     rf_engine *e = new (std::nothrow) rf_engine();
     if (!e) return fail(RF_ENOMEM, "host allocation failed");
     e->cfg = *cfg;
+    e->dim = cfg->dim;
+    e->tile_rows = rf::scan_tile_rows(cfg->dim);
     if (e->cfg.n_contexts == 0) e->cfg.n_contexts = 8;
     e->sm_count = prop.multiProcessorCount;
     if (const char *s = getenv("RF_SCAN_BLOCKS")) e->blocks_override = static_cast<uint32_t>(atoi(s));
@@ -1063,6 +1067,7 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
         }
         e->scan_variant = v;
     }
+    if (e->dim != RF_DIM) e->scan_variant = rf::kScanVariantTma6x12;   // wider rows: the default ring only
 
     const uint64_t cap = cfg->capacity_rows;
     cudaError_t ce;
@@ -1073,14 +1078,14 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
         if (cudaMalloc(&e->debug_ts, e->debug_cap * 8) != cudaSuccess) e->debug_ts = nullptr;
         else cudaMemset(e->debug_ts, 0, e->debug_cap * 8);
     }
-    if ((ce = cudaMalloc(&e->F, cap * RF_DIM)) != cudaSuccess || (ce = cudaMalloc(&e->seg, cap * 4)) != cudaSuccess ||
+    if ((ce = cudaMalloc(&e->F, cap * e->dim)) != cudaSuccess || (ce = cudaMalloc(&e->seg, cap * 4)) != cudaSuccess ||
         (ce = cudaMalloc(&e->ff, cap * 4)) != cudaSuccess) {
         const int rc = fail(RF_ENOMEM, "cudaMalloc of %llu rows failed: %s", (unsigned long long)cap, cudaGetErrorString(ce));
         cudaGetLastError();
         rf_engine_destroy(e);
         return rc;
     }
-    e->hbm_bytes = cap * (RF_DIM + 8);
+    e->hbm_bytes = cap * (e->dim + 8);
     // unwritten rows read as tombstones
     if ((ce = cudaMemset(e->seg, 0xFF, cap * 4)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -1347,7 +1352,7 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     const size_t max_tokens = n / 2 + 1;
     RF_CUDA(e->sc_text.reserve(n + 64));
     RF_CUDA(e->sc_state.reserve((static_cast<size_t>(n_blocks) + 1) * 8));
-    RF_CUDA(e->sc_bucket.reserve(max_tokens));
+    RF_CUDA(e->sc_bucket.reserve(max_tokens * 2));
     RF_CUDA(e->sc_end.reserve(max_tokens * 4));
     RF_CUDA(e->sc_cstart.reserve((max_tokens / 112 + 2) * 4));
     RF_CUDA(e->sc_ctl.reserve(rf::kCtlWords * 4));
@@ -1360,7 +1365,8 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     t.n_blocks = n_blocks;
     t.state = static_cast<uint64_t *>(e->sc_state.p);
     t.ctl = static_cast<uint32_t *>(e->sc_ctl.p);
-    t.tok_bucket = static_cast<uint8_t *>(e->sc_bucket.p);
+    t.tok_bucket = static_cast<uint16_t *>(e->sc_bucket.p);
+    t.dim_mask = e->dim - 1;
     t.tok_end = static_cast<uint32_t *>(e->sc_end.p);
     t.chunk_start = static_cast<uint32_t *>(e->sc_cstart.p);
     t.deferred = static_cast<uint32_t *>(e->sc_deferred.p);
@@ -1387,7 +1393,7 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
         int64_t *d_spans = static_cast<int64_t *>(e->sc_spans.p);
         // rows taken from the free list lie inside ranges a concurrent search may be scanning (masked):
         // features and norms first, the segment words that un-mask them only after those are complete
-        RF_CUDA(rf::launch_rows_from_tokens(t, n_tokens, nc, e->F + first * RF_DIM, e->ff + first, reused ? nullptr : e->seg + first,
+        RF_CUDA(rf::launch_rows_from_tokens(t, n_tokens, nc, e->F + first * e->dim, e->ff + first, reused ? nullptr : e->seg + first,
                                             store_seg, d_spans, s));
         ++launches;
         const uint32_t ns = spans ? std::min(nc, max_spans) : 0;
@@ -1446,9 +1452,9 @@ int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const 
     if ((rc = reserve_rows(e, n_rows, &first, &reused))) return rc;
     cudaStream_t s = e->ingest_stream;
     if (n_rows) {
-        RF_CUDA(cudaMemcpyAsync(e->F + first * RF_DIM, rows, n_rows * RF_DIM,
+        RF_CUDA(cudaMemcpyAsync(e->F + first * e->dim, rows, n_rows * e->dim,
                                 rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-        RF_CUDA(rf::launch_row_meta(e->F + first * RF_DIM, n_rows, e->ff + first, reused ? nullptr : e->seg + first, store_seg, s));
+        RF_CUDA(rf::launch_row_meta(e->F + first * e->dim, n_rows, e->dim, e->ff + first, reused ? nullptr : e->seg + first, store_seg, s));
         e->launches.fetch_add(1);
         RF_CUDA(cudaStreamSynchronize(s));
         if (reused) {   // see rf_ingest_text
@@ -1481,21 +1487,21 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
     RF_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = e->ingest_stream;
     if (!e->zipf_bucket) {  // bucket of the decimal-ASCII token of each table entry (table prep, 64 KB)
-        std::vector<uint8_t> zb(65536);
+        std::vector<uint16_t> zb(65536);
         char tmp[8];
         for (int r = 0; r < 65536; ++r) {
             const int len = snprintf(tmp, sizeof tmp, "%u", static_cast<unsigned>(zipf_vocab[r]));
-            zb[r] = static_cast<uint8_t>(fnv1a32(tmp, static_cast<size_t>(len)) & (RF_DIM - 1));
+            zb[r] = static_cast<uint16_t>(fnv1a32(tmp, static_cast<size_t>(len)) & (e->dim - 1));
         }
-        RF_CUDA(cudaMalloc(&e->zipf_bucket, 65536));
-        RF_CUDA(cudaMemcpy(e->zipf_bucket, zb.data(), 65536, cudaMemcpyHostToDevice));
+        RF_CUDA(cudaMalloc(&e->zipf_bucket, 65536 * 2));
+        RF_CUDA(cudaMemcpy(e->zipf_bucket, zb.data(), 65536 * 2, cudaMemcpyHostToDevice));
     }
     // the generator appends at the tail only (row content is tied to its counter; a measurement input)
     if (e->n_rows + n_rows > e->cfg.capacity_rows)
         return fail(RF_ECAPACITY, "arena full: %llu + %llu rows > capacity %llu", (unsigned long long)e->n_rows,
                     (unsigned long long)n_rows, (unsigned long long)e->cfg.capacity_rows);
     const uint64_t first = e->n_rows;
-    RF_CUDA(rf::launch_synth_rows(seed, start_counter, n_rows, e->zipf_bucket, e->F + first * RF_DIM, e->ff + first,
+    RF_CUDA(rf::launch_synth_rows(seed, start_counter, n_rows, e->zipf_bucket, e->dim, e->F + first * e->dim, e->ff + first,
                                   e->seg + first, first_seg, rows_per_store, s));
     e->launches.fetch_add(1);
     RF_CUDA(cudaStreamSynchronize(s));
@@ -1595,7 +1601,7 @@ int rf_snapshot_save(rf_engine *e, const char *path) {
     };
     SnapHeader h{};
     memcpy(h.magic, "RFB2SNP2", 8);
-    h.dim = RF_DIM;
+    h.dim = e->dim;
     h.version = 2;
     h.n_rows = e->n_rows;
     h.id_base = e->cfg.id_base;
@@ -1613,8 +1619,8 @@ int rf_snapshot_save(rf_engine *e, const char *path) {
     }
     w.put(e->free_ext.data(), e->free_ext.size() * sizeof(Extent));
     if (!w.ok) return abandon("write to");
-    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(e->n_rows * RF_DIM, 1)));
-    const struct { const void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
+    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(e->n_rows * e->dim, 1)));
+    const struct { const void *base; size_t elt; } arrays[3] = {{e->F, e->dim}, {e->seg, 4}, {e->ff, 4}};
     for (const auto &arr : arrays) {
         const size_t total = e->n_rows * arr.elt;
         for (size_t off = 0; off < total; off += buf.size()) {
@@ -1648,8 +1654,9 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
     SnapReader r;
     r.f = f;
     SnapHeader h{};
-    if (!r.get(&h, sizeof h) || memcmp(h.magic, "RFB2SNP2", 8) != 0 || h.dim != RF_DIM || h.version != 2)
+    if (!r.get(&h, sizeof h) || memcmp(h.magic, "RFB2SNP2", 8) != 0 || h.version != 2)
         return fail(RF_EINVAL, "%s is not an RF-1 snapshot (version 2)", path);
+    if (h.dim != e->dim) return fail(RF_EINVAL, "snapshot rows have %u features, the engine was created with dim %u", h.dim, e->dim);
     if (h.n_rows > e->cfg.capacity_rows) return fail(RF_ECAPACITY, "snapshot holds %llu rows, engine capacity is %llu", (unsigned long long)h.n_rows, (unsigned long long)e->cfg.capacity_rows);
     if (h.id_base != e->cfg.id_base) return fail(RF_EINVAL, "snapshot id_base %llu != engine id_base %llu", (unsigned long long)h.id_base, (unsigned long long)e->cfg.id_base);
     if (h.n_stores > (1ull << 32) || h.n_docs > (1ull << 40) || h.n_free > h.n_rows + 1) return fail(RF_EINVAL, "%s: implausible table sizes", path);
@@ -1687,8 +1694,8 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
         cudaMemset(e->seg, 0xFF, static_cast<size_t>(h.n_rows) * 4);
         return fail(RF_EINVAL, "%s is %s; nothing was loaded", path, what);
     };
-    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(h.n_rows * RF_DIM, 1)));
-    const struct { void *base; size_t elt; } arrays[3] = {{e->F, RF_DIM}, {e->seg, 4}, {e->ff, 4}};
+    std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(h.n_rows * e->dim, 1)));
+    const struct { void *base; size_t elt; } arrays[3] = {{e->F, e->dim}, {e->seg, 4}, {e->ff, 4}};
     for (const auto &arr : arrays) {
         const size_t total = h.n_rows * arr.elt;
         for (size_t off = 0; off < total; off += buf.size()) {
@@ -1720,7 +1727,7 @@ int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uin
         if (first_row + n > e->n_rows) return fail(RF_EINVAL, "rows %llu..%llu beyond n_rows %llu", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)e->n_rows);
     }
     RF_CUDA(cudaSetDevice(e->cfg.device));
-    if (rows) RF_CUDA(cudaMemcpy(rows, e->F + first_row * RF_DIM, n * RF_DIM, cudaMemcpyDeviceToHost));
+    if (rows) RF_CUDA(cudaMemcpy(rows, e->F + first_row * e->dim, n * e->dim, cudaMemcpyDeviceToHost));
     if (store_seg) RF_CUDA(cudaMemcpy(store_seg, e->seg + first_row, n * 4, cudaMemcpyDeviceToHost));
     if (ff) RF_CUDA(cudaMemcpy(ff, e->ff + first_row, n * 4, cudaMemcpyDeviceToHost));
     return RF_OK;
@@ -1760,7 +1767,7 @@ int rf_search_begin(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *
             CtxGuard g{e, c};
             RF_CUDA(cudaSetDevice(e->cfg.device));
             const OutLayout L(nq, k);
-            const size_t q_bytes = static_cast<size_t>(nq) * RF_DIM;
+            const size_t q_bytes = static_cast<size_t>(nq) * e->dim;
             RF_CUDA(c->h_in.reserve(q_bytes));
             RF_CUDA(c->d_in.reserve(q_bytes));
             RF_CUDA(c->d_out.reserve(L.total));
@@ -1771,7 +1778,7 @@ int rf_search_begin(rf_engine *e, const int8_t *q, uint32_t nq, const uint32_t *
             uint64_t *d_keys = reinterpret_cast<uint64_t *>(d_out + L.off_keys);
             int rc = search_keys_device_impl(e, static_cast<const int8_t *>(c->d_in.p), nq, store_segs + seg_off[0], n0, k, d_keys, c->stream, nullptr);
             if (rc) return rc;
-            RF_CUDA(rf::launch_unpack_keys(d_keys, static_cast<const int8_t *>(c->d_in.p), e->ff, static_cast<uint32_t>(e->cfg.id_base), nq, k,
+            RF_CUDA(rf::launch_unpack_keys(d_keys, static_cast<const int8_t *>(c->d_in.p), e->dim, e->ff, static_cast<uint32_t>(e->cfg.id_base), nq, k,
                                            reinterpret_cast<uint64_t *>(d_out + L.off_ids), reinterpret_cast<int32_t *>(d_out + L.off_scores),
                                            reinterpret_cast<float *>(d_out + L.off_cos), reinterpret_cast<uint32_t *>(d_out + L.off_counts), c->stream));
             e->launches.fetch_add(1, std::memory_order_relaxed);
@@ -1844,17 +1851,17 @@ int rf_featurize_query(rf_engine *e, const uint8_t *utf8, size_t n, int8_t *out_
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
     const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
-    RF_CUDA(c->h_in.reserve(n + RF_DIM));
-    RF_CUDA(c->d_in.reserve(text_pad + RF_DIM));
+    RF_CUDA(c->h_in.reserve(n + e->dim));
+    RF_CUDA(c->d_in.reserve(text_pad + e->dim));
     if (n) memcpy(c->h_in.p, utf8, n);
     uint8_t *d_text = static_cast<uint8_t *>(c->d_in.p);
     int8_t *d_q = reinterpret_cast<int8_t *>(d_text + text_pad);
     if (n) RF_CUDA(cudaMemcpyAsync(d_text, c->h_in.p, n, cudaMemcpyHostToDevice, c->stream));
-    RF_CUDA(rf::launch_featurize_query(d_text, static_cast<uint32_t>(n), nullptr, d_q, c->stream));
+    RF_CUDA(rf::launch_featurize_query(d_text, static_cast<uint32_t>(n), nullptr, d_q, e->dim, c->stream));
     e->launches.fetch_add(1);
-    RF_CUDA(cudaMemcpyAsync(c->h_in.p, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaMemcpyAsync(c->h_in.p, d_q, e->dim, cudaMemcpyDeviceToHost, c->stream));
     RF_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(out_q, c->h_in.p, RF_DIM);
+    memcpy(out_q, c->h_in.p, e->dim);
     return RF_OK;
 }
 
@@ -1898,22 +1905,22 @@ int rf_search_text_begin(rf_engine *e, const uint8_t *utf8, size_t n, const uint
     // weights, query text and the query vector share the context's input buffer: one H2D copy (the plan
     // of a single query rides in the kernel parameters)
     const size_t text_pad = (n + 255) & ~static_cast<size_t>(255);
-    const size_t w_pad = weights ? RF_DIM : 0;   // [weights | text | query vector]
-    const size_t need = w_pad + text_pad + RF_DIM;
+    const size_t w_pad = weights ? e->dim : 0;   // [weights | text | query vector]
+    const size_t need = w_pad + text_pad + e->dim;
     RF_CUDA(c->h_in.reserve(need));
     RF_CUDA(c->d_in.reserve(need));
     uint8_t *h = static_cast<uint8_t *>(c->h_in.p);
     uint8_t *d = static_cast<uint8_t *>(c->d_in.p);
-    if (weights) memcpy(h, weights, RF_DIM);
+    if (weights) memcpy(h, weights, e->dim);
     if (n) memcpy(h + w_pad, utf8, n);
     if (w_pad + n) RF_CUDA(cudaMemcpyAsync(d, h, w_pad + n, cudaMemcpyHostToDevice, c->stream));
     int8_t *d_q = reinterpret_cast<int8_t *>(d + w_pad + text_pad);
-    RF_CUDA(rf::launch_featurize_query(d + w_pad, static_cast<uint32_t>(n), weights ? d : nullptr, d_q, c->stream));
+    RF_CUDA(rf::launch_featurize_query(d + w_pad, static_cast<uint32_t>(n), weights ? d : nullptr, d_q, e->dim, c->stream));
     e->launches.fetch_add(1);
 
     const OutLayout L(1, k);
     const uint32_t X = pick_blocks(e, 1, b.max_tiles);
-    RF_CUDA(c->h_out.reserve(L.total + RF_DIM));
+    RF_CUDA(c->h_out.reserve(L.total + e->dim));
     RF_CUDA(c->d_out.reserve(L.total));
     RF_CUDA(c->d_partial.reserve(static_cast<size_t>(X) * k * 8));
     if (c->d_tickets.cap < kSyncBytesPerQuery + 8) {
@@ -1934,11 +1941,11 @@ int rf_search_text_begin(rf_engine *e, const uint8_t *utf8, size_t n, const uint
     a.out_counts = reinterpret_cast<uint32_t *>(d_out + L.off_counts);
     // the query vector comes from the kernel just before this one on the stream: a fully serialised launch
     // (an overlapped one may read d_q before featurize_query's writes are visible)
-    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, e->scan_variant, c->stream, false));
+    RF_CUDA(rf::launch_score_topk_scan(a, 1, X, e->scan_variant, e->dim, c->stream, false));
     e->launches.fetch_add(1);
     uint8_t *ho = static_cast<uint8_t *>(c->h_out.p);
     RF_CUDA(cudaMemcpyAsync(ho + L.off_ids, d_out + L.off_ids, L.total - L.off_ids, cudaMemcpyDeviceToHost, c->stream));
-    RF_CUDA(cudaMemcpyAsync(ho + L.total, d_q, RF_DIM, cudaMemcpyDeviceToHost, c->stream));
+    RF_CUDA(cudaMemcpyAsync(ho + L.total, d_q, e->dim, cudaMemcpyDeviceToHost, c->stream));
     c->pend = SearchCtx::Pending{};
     c->pend.nq = 1;
     c->pend.k = k;
@@ -1968,6 +1975,7 @@ static int fill_df_args(rf_engine *e, const uint32_t *store_segs, uint32_t n_seg
     a.F = e->F;
     a.seg = e->seg;
     a.n_scope = n_segs;
+    a.dim = e->dim;
     for (uint32_t j = 0; j < RF_SCOPE_MAX; ++j) a.scope[j] = j < n_segs ? store_segs[j] : RF_TOMBSTONE;
     std::vector<Extent> ext;
     {
@@ -2008,8 +2016,8 @@ int rf_scope_df(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint6
         std::lock_guard<std::mutex> lk(e->df_mu);
         auto it = e->df_cache.find(key);
         if (it != e->df_cache.end() && it->second.first == gen) {
-            memcpy(out_df, it->second.second.data(), RF_DIM * 8);
-            *out_n = it->second.second[RF_DIM];
+            memcpy(out_df, it->second.second.data(), e->dim * 8);
+            *out_n = it->second.second[e->dim];
             return RF_OK;
         }
     }
@@ -2017,7 +2025,7 @@ int rf_scope_df(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint6
     if (!c) return fail(RF_EBUSY, "no search context free after 5 s");
     CtxGuard g{e, c};
     RF_CUDA(cudaSetDevice(e->cfg.device));
-    const size_t bytes = (RF_DIM + 1) * 8;
+    const size_t bytes = (e->dim + 1) * 8;
     RF_CUDA(c->d_out.reserve(bytes));
     RF_CUDA(c->h_out.reserve(bytes));
     RF_CUDA(cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream));
@@ -2026,12 +2034,12 @@ int rf_scope_df(rf_engine *e, const uint32_t *store_segs, uint32_t n_segs, uint6
     RF_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     RF_CUDA(cudaStreamSynchronize(c->stream));
     const uint64_t *h = static_cast<const uint64_t *>(c->h_out.p);
-    memcpy(out_df, h, RF_DIM * 8);
-    *out_n = h[RF_DIM];
+    memcpy(out_df, h, e->dim * 8);
+    *out_n = h[e->dim];
     {
         std::lock_guard<std::mutex> lk(e->df_mu);
         if (e->df_cache.size() > 4096) e->df_cache.clear();
-        e->df_cache[key] = {gen, std::vector<uint64_t>(h, h + RF_DIM + 1)};
+        e->df_cache[key] = {gen, std::vector<uint64_t>(h, h + e->dim + 1)};
     }
     return RF_OK;
 }
@@ -2171,7 +2179,7 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
         }
         a.out_keys = static_cast<uint64_t *>(st->gemm_keys_a.p);
     }
-    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
+    RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, e->dim, s, st->overlap));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     e->searches.fetch_add(nq, std::memory_order_relaxed);
     return RF_OK;
@@ -2294,7 +2302,7 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
     uint32_t launched = 0;
     if (nq) {
         // the plans / scope lists were copied in just above (a copy, not a kernel): the overlap rule only concerns q_dev
-        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, s, st->overlap));
+        RF_CUDA(rf::launch_score_topk_scan(a, nq, X, e->scan_variant, e->dim, s, st->overlap));
         ++launched;
     }
     if (px && px->world > 1) {

@@ -10,7 +10,7 @@
 //             tokens precede them by a decoupled look-back, hash each token (FNV-1a 32) and emit
 //             (bucket, byte end [, byte start of a window's first token]) at its global token ordinal
 //   rows      one warp per chunk window [112 w, 112 w + 128): shared-memory histogram of the
-//             window's buckets -> one 256-byte int8 row, its sum of squares, store word, byte span
+//             window's buckets -> one dim-byte int8 row, its sum of squares, store word, byte span
 // A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
 // look-ahead, so stop-word removal needs no second compaction.
 #include <algorithm>
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_kernel(const TokenizeAr
                 a.deferred[2 * slot + 1] = static_cast<uint32_t>(start);
             }
         } else {
-            a.tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
+            a.tok_bucket[ord] = static_cast<uint16_t>(h & a.dim_mask);
             a.tok_end[ord] = static_cast<uint32_t>(p);
         }
         ++ord;
@@ -225,41 +225,48 @@ __global__ void __launch_bounds__(64) hash_deferred_kernel(const TokenizeArgs a,
         h *= 0x01000193u;
         ++p;
     }
-    a.tok_bucket[ord] = static_cast<uint8_t>(h & (kDim - 1));
+    a.tok_bucket[ord] = static_cast<uint16_t>(h & a.dim_mask);
     a.tok_end[ord] = static_cast<uint32_t>(p);
 }
 
 constexpr int kRowWarps = 8;
 
+// kM: 256-byte sub-rows per row (dim = 256 * kM); the warp's histogram has dim counters, a lane writes
+// 8 bytes of each sub-row
+template <int kM>
 __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
-    const uint8_t *__restrict__ tok_bucket, const uint32_t *__restrict__ chunk_start,
+    const uint16_t *__restrict__ tok_bucket, const uint32_t *__restrict__ chunk_start,
     const uint32_t *__restrict__ tok_end, uint32_t n_tokens, uint32_t n_chunks, int8_t *__restrict__ F,
     int32_t *__restrict__ ff, uint32_t *__restrict__ seg, uint32_t store_seg, int64_t *__restrict__ spans) {
-    __shared__ uint32_t hist[kRowWarps][kDim];
+    constexpr int kD = kSubDim * kM;
+    __shared__ uint32_t hist[kRowWarps][kD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *h = hist[warp];
     for (uint32_t w = blockIdx.x * kRowWarps + warp; w < n_chunks; w += gridDim.x * kRowWarps) {
 #pragma unroll
-        for (int j = 0; j < kDim / 32; ++j) h[lane + 32 * j] = 0;
+        for (int j = 0; j < kD / 32; ++j) h[lane + 32 * j] = 0;
         __syncwarp();
         const uint32_t lo = w * kChunkStride;
         const uint32_t hi = min(lo + kChunkTokens, n_tokens);
         for (uint32_t t = lo + lane; t < hi; t += 32) atomicAdd(&h[tok_bucket[t]], 1u);
         __syncwarp();
-        uint32_t packed[2];
         int sq = 0;
 #pragma unroll
-        for (int x = 0; x < 2; ++x) {
-            uint32_t v = 0;
+        for (int sub = 0; sub < kM; ++sub) {
+            uint32_t packed[2];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t t = min(h[lane * 8 + x * 4 + b], 127u);
-                v |= t << (8 * b);
-                sq += static_cast<int>(t * t);
+            for (int x = 0; x < 2; ++x) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t t = min(h[sub * kSubDim + lane * 8 + x * 4 + b], 127u);
+                    v |= t << (8 * b);
+                    sq += static_cast<int>(t * t);
+                }
+                packed[x] = v;
             }
-            packed[x] = v;
+            *reinterpret_cast<uint2 *>(F + (static_cast<size_t>(w) * kM + sub) * kSubBytes + lane * 8) = make_uint2(packed[0], packed[1]);
         }
-        *reinterpret_cast<uint2 *>(F + static_cast<size_t>(w) * kRowBytes + lane * 8) = make_uint2(packed[0], packed[1]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
         if (lane == 0) {
@@ -278,9 +285,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
 // histograms every kept token of the (<= 32 KB, routes/chat.py:48) query text.
 __global__ void __launch_bounds__(256) featurize_query_kernel(const uint8_t *__restrict__ text, uint32_t n,
                                                               const uint8_t *__restrict__ weights,
-                                                              int8_t *__restrict__ q_out) {
-    __shared__ uint32_t hist[kDim];
-    hist[threadIdx.x] = 0;
+                                                              int8_t *__restrict__ q_out, uint32_t dim) {
+    __shared__ uint32_t hist[kSubDim * kMaxSub];
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) hist[d] = 0;
     __syncthreads();
     auto at = [&](long long i) -> uint8_t { return (i >= 0 && i < static_cast<long long>(n)) ? lower_byte(text[i]) : 0; };
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -295,42 +302,59 @@ __global__ void __launch_bounds__(256) featurize_query_kernel(const uint8_t *__r
             h ^= cb;
             h *= 0x01000193u;
         }
-        atomicAdd(&hist[h & (kDim - 1)], 1u);
+        atomicAdd(&hist[h & (dim - 1)], 1u);
     }
     __syncthreads();
-    const uint32_t tf = min(hist[threadIdx.x], 127u);
-    q_out[threadIdx.x] = static_cast<int8_t>(weights ? min(tf * weights[threadIdx.x], 127u) : tf);
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        const uint32_t tf = min(hist[d], 127u);
+        q_out[d] = static_cast<int8_t>(weights ? min(tf * weights[d], 127u) : tf);
+    }
 }
 
-// RF-1w document frequencies (oracle/SPEC.md "IDF-weighted variant").  A warp takes four rows per
-// step; a lane owns eight adjacent buckets (one 8-byte load per row).  Features are counts in
-// [0, 127], so (x + 0x7F7F7F7F) has bit 7 of a byte set exactly when that byte is non-zero: the
-// per-byte flags accumulate packed, four buckets per register, and are spilled into 32-bit
-// counters every 252 rows.  HBM-bound: 260 B per row, read once.
+// RF-1w document frequencies (oracle/SPEC.md "IDF-weighted variant").  A warp takes four 256-byte
+// sub-rows per step (4 / kM rows); a lane owns eight adjacent buckets of each sub-row position (one
+// 8-byte load per sub-row).  Features are counts in [0, 127], so (x + 0x7F7F7F7F) has bit 7 of a byte set
+// exactly when that byte is non-zero: the per-byte flags accumulate packed, four buckets per register,
+// and are spilled into 32-bit counters every 252 rows.  HBM-bound: dim + 4 B per row, read once.
+template <int kM>
 __global__ void __launch_bounds__(256) bucket_df_kernel(const __grid_constant__ DfArgs a) {
-    __shared__ unsigned int acc[kDim + 1];
-    for (int i = threadIdx.x; i <= kDim; i += blockDim.x) acc[i] = 0;
+    constexpr int kD = kSubDim * kM;
+    constexpr int kRowsPerStep = 4 / kM;
+    __shared__ unsigned int acc[kD + 1];
+    for (int i = threadIdx.x; i <= kD; i += blockDim.x) acc[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t total = a.prefix[a.n_ext];
-    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t p0 = 0, p1 = 0, pending = 0, live = 0;
+    uint32_t cnt[kM][8];
+    uint32_t p0[kM], p1[kM];
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        p0[m] = p1[m] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt[m][j] = 0;
+    }
+    uint32_t pending = 0, live = 0;
     auto spill = [&]() {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cnt[j] += (p0 >> (8 * j)) & 0xFF;
-            cnt[4 + j] += (p1 >> (8 * j)) & 0xFF;
+        for (int m = 0; m < kM; ++m) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cnt[m][j] += (p0[m] >> (8 * j)) & 0xFF;
+                cnt[m][4 + j] += (p1[m] >> (8 * j)) & 0xFF;
+            }
+            p0[m] = p1[m] = 0;
         }
-        p0 = p1 = pending = 0;
+        pending = 0;
     };
     uint32_t e = 0;
-    for (uint64_t v0 = static_cast<uint64_t>(warp) * 4; v0 < total; v0 += static_cast<uint64_t>(warps_total) * 4) {
+    for (uint64_t v0 = static_cast<uint64_t>(warp) * kRowsPerStep; v0 < total; v0 += static_cast<uint64_t>(warps_total) * kRowsPerStep) {
         int2 x[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            x[j] = make_int2(0, 0);
+        for (int j = 0; j < kRowsPerStep; ++j) {
+#pragma unroll
+            for (int m = 0; m < kM; ++m) x[j * kM + m] = make_int2(0, 0);
             const uint64_t v = v0 + j;
             if (v >= total) continue;
             while (v >= a.prefix[e + 1]) ++e;
@@ -340,36 +364,43 @@ __global__ void __launch_bounds__(256) bucket_df_kernel(const __grid_constant__ 
             for (uint32_t t = 0; t < a.n_scope; ++t) ok |= (a.scope[t] == sg);
             if (!ok || sg == RF_TOMBSTONE) continue;
             ++live;
-            x[j] = __ldg(reinterpret_cast<const int2 *>(a.F + static_cast<size_t>(row) * kRowBytes) + lane);
+#pragma unroll
+            for (int m = 0; m < kM; ++m)
+                x[j * kM + m] = __ldg(reinterpret_cast<const int2 *>(a.F + (static_cast<size_t>(row) * kM + m) * kSubBytes) + lane);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            p0 += ((static_cast<uint32_t>(x[j].x) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
-            p1 += ((static_cast<uint32_t>(x[j].y) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+        for (int u = 0; u < 4; ++u) {
+            p0[u % kM] += ((static_cast<uint32_t>(x[u].x) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+            p1[u % kM] += ((static_cast<uint32_t>(x[u].y) + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
         }
-        pending += 4;
+        pending += kRowsPerStep;
         if (pending >= 252) spill();
     }
     spill();
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (cnt[j]) atomicAdd(&acc[lane * 8 + j], cnt[j]);
-    if (lane == 0 && live) atomicAdd(&acc[kDim], live);
+    for (int m = 0; m < kM; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (cnt[m][j]) atomicAdd(&acc[m * kSubDim + lane * 8 + j], cnt[m][j]);
+    if (lane == 0 && live) atomicAdd(&acc[kD], live);
     __syncthreads();
-    for (int i = threadIdx.x; i <= kDim; i += blockDim.x)
+    for (int i = threadIdx.x; i <= kD; i += blockDim.x)
         if (acc[i]) atomicAdd(a.out + i, static_cast<unsigned long long>(acc[i]));
 }
 
-__global__ void __launch_bounds__(256) row_meta_kernel(const int8_t *__restrict__ F, uint64_t n_rows,
+__global__ void __launch_bounds__(256) row_meta_kernel(const int8_t *__restrict__ F, uint64_t n_rows, uint32_t m_sub,
                                                        int32_t *__restrict__ ff, uint32_t *__restrict__ seg,
                                                        uint32_t store_seg) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
          r += warps_total) {
-        const int2 v = *reinterpret_cast<const int2 *>(F + r * kRowBytes + lane * 8);
-        int sq = __dp4a(v.x, v.x, 0);
-        sq = __dp4a(v.y, v.y, sq);
+        int sq = 0;
+        for (uint32_t m = 0; m < m_sub; ++m) {
+            const int2 v = *reinterpret_cast<const int2 *>(F + (r * m_sub + m) * kSubBytes + lane * 8);
+            sq = __dp4a(v.x, v.x, sq);
+            sq = __dp4a(v.y, v.y, sq);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
         if (lane == 0) {
@@ -393,12 +424,12 @@ cudaError_t launch_fill_u32(uint32_t *p, uint64_t n, uint32_t value, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
+cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, uint32_t dim, int32_t *ff, uint32_t *seg, uint32_t store_seg,
                             cudaStream_t s) {
     if (n_rows == 0) return cudaSuccess;
     uint64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148ull * 8ull) blocks = 148ull * 8ull;
-    row_meta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(F, n_rows, ff, seg, store_seg);
+    row_meta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(F, n_rows, dim / kSubDim, ff, seg, store_seg);
     return cudaGetLastError();
 }
 
@@ -419,22 +450,37 @@ cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, ui
     if (n_chunks == 0) return cudaSuccess;
     uint32_t blocks = (n_chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
-    rows_from_tokens_kernel<<<blocks, kRowWarps * 32, 0, s>>>(w.tok_bucket, w.chunk_start, w.tok_end, n_tokens, n_chunks, F, ff,
-                                                             seg, store_seg, spans_dev);
+    auto go = [&](auto kern) {
+        kern<<<blocks, kRowWarps * 32, 0, s>>>(w.tok_bucket, w.chunk_start, w.tok_end, n_tokens, n_chunks, F, ff, seg, store_seg, spans_dev);
+    };
+    switch (w.dim_mask + 1u) {
+        case 256: go(rows_from_tokens_kernel<1>); break;
+        case 512: go(rows_from_tokens_kernel<2>); break;
+        case 1024: go(rows_from_tokens_kernel<4>); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, cudaStream_t s) {
-    featurize_query_kernel<<<1, 256, 0, s>>>(text_dev, n_bytes, weights, q_out);
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, uint32_t dim,
+                                   cudaStream_t s) {
+    if (dim > kSubDim * kMaxSub || (dim & (dim - 1))) return cudaErrorInvalidValue;
+    featurize_query_kernel<<<1, 256, 0, s>>>(text_dev, n_bytes, weights, q_out, dim);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bucket_df(const DfArgs &a, int sm_count, cudaStream_t s) {
     const uint32_t total = a.prefix[a.n_ext];
     if (total == 0) return cudaSuccess;
-    const uint32_t want = (total + 8 * 4 * 16 - 1) / (8 * 4 * 16);   // >= 16 steps per warp before another block pays off
+    const uint32_t m = a.dim / kSubDim;
+    const uint32_t want = (total * m + 8 * 4 * 16 - 1) / (8 * 4 * 16);   // >= 16 steps per warp before another block pays off
     const uint32_t blocks = std::max(1u, std::min(want, static_cast<uint32_t>(sm_count) * 8u));
-    bucket_df_kernel<<<blocks, 256, 0, s>>>(a);
+    switch (m) {
+        case 1: bucket_df_kernel<1><<<blocks, 256, 0, s>>>(a); break;
+        case 2: bucket_df_kernel<2><<<blocks, 256, 0, s>>>(a); break;
+        case 4: bucket_df_kernel<4><<<blocks, 256, 0, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -125,6 +125,7 @@ struct rf_group {
     std::vector<int> devices;
     std::vector<uint64_t> id_base;
     uint32_t placement = RF_PLACE_STORE;
+    uint32_t dim = RF_DIM;
     uint64_t capacity_rows = 0;
 
     std::shared_mutex mu;                              // store table, row counts, document map
@@ -186,12 +187,13 @@ int rf_group_create(const rf_group_config *cfg, rf_group **out) {
     rf_group *g = new (std::nothrow) rf_group();
     if (!g) return gfail(RF_ENOMEM, "host allocation failed");
     g->placement = cfg->placement;
+    g->dim = cfg->dim ? cfg->dim : RF_DIM;
     g->capacity_rows = cfg->capacity_rows;
     for (uint32_t d = 0; d < G; ++d) {
         rf_config ec{};
         ec.struct_size = sizeof(rf_config);
         ec.device = cfg->devices[d];
-        ec.dim = RF_DIM;
+        ec.dim = cfg->dim ? cfg->dim : RF_DIM;
         ec.n_contexts = cfg->n_contexts;
         ec.capacity_rows = cfg->capacity_rows;
         ec.id_base = cfg->id_bases ? cfg->id_bases[d] : d * stride;
@@ -492,8 +494,9 @@ int rf_group_search(rf_group *g, const int8_t *q, uint32_t nq, const uint32_t *s
         const uint32_t n_here = static_cast<uint32_t>(w.qidx.size());
         const int8_t *qd = b.q;
         if (n_here != b.nq) {                       // compact this device's queries
-            w.qrows.resize(static_cast<size_t>(n_here) * RF_DIM);
-            for (uint32_t j = 0; j < n_here; ++j) memcpy(w.qrows.data() + static_cast<size_t>(j) * RF_DIM, b.q + static_cast<size_t>(w.qidx[j]) * RF_DIM, RF_DIM);
+            const size_t dim = b.g->dim;
+            w.qrows.resize(static_cast<size_t>(n_here) * dim);
+            for (uint32_t j = 0; j < n_here; ++j) memcpy(w.qrows.data() + static_cast<size_t>(j) * dim, b.q + static_cast<size_t>(w.qidx[j]) * dim, dim);
             qd = w.qrows.data();
         }
         if (w.segs.empty()) w.segs.push_back(0);
@@ -622,14 +625,14 @@ int rf_group_scope_df(rf_group *g, const uint32_t *stores, uint32_t n_stores, ui
     g_gerr[0] = 0;
     if (!g || (!stores && n_stores) || !out_df || !out_n) return gfail(RF_EINVAL, "null argument");
     // the corpus statistic of RF-1w is a sum over rows: add the devices' counts (each cached per scope)
-    memset(out_df, 0, RF_DIM * 8);
+    memset(out_df, 0, static_cast<size_t>(g->dim) * 8);
     *out_n = 0;
-    uint64_t df[RF_DIM];
+    uint64_t df[RF_DIM_MAX];
     for (rf_engine *e : g->eng) {
         uint64_t nn = 0;
         const int rc = rf_scope_df(e, stores, n_stores, df, &nn);
         if (rc) return rc;
-        for (uint32_t i = 0; i < RF_DIM; ++i) out_df[i] += df[i];
+        for (uint32_t i = 0; i < g->dim; ++i) out_df[i] += df[i];
         *out_n += nn;
     }
     return RF_OK;

@@ -10,9 +10,13 @@
 
 namespace rf {
 
-constexpr int kDim = 256;          // int8 features per chunk row
-constexpr int kRowBytes = 256;
-constexpr int kTileRows = 32;      // rows one warp scores per step (8 KB)
+// A chunk row is `dim` int8 features, dim = 256 * m (m = 1, 2, 4: rf_config.dim): m consecutive 256-byte
+// SUB-ROWS.  The streaming kernels are written over sub-rows (a warp step always covers 32 of them = 8 KB)
+// and are templated on m where the row boundary matters.
+constexpr int kSubDim = 256;       // int8 features per sub-row
+constexpr int kSubBytes = 256;
+constexpr int kTileSubRows = 32;   // sub-rows one warp scores per step (8 KB) = 32 / m rows
+constexpr int kMaxSub = 4;         // widest row: 1024 features
 constexpr uint32_t kTombstone = 0xFFFFFFFFu;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 

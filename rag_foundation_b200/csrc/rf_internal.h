@@ -31,7 +31,9 @@ inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes) {
     return e;
 }
 
-constexpr uint32_t kScanTileRows = 32;  // rows per warp step of the scan kernel (== rf::kTileRows)
+constexpr uint32_t kScanTileSubRows = 32;  // 256-byte sub-rows per warp step of the scan kernel (== rf::kTileSubRows)
+// rows per scan tile for rows of `dim` features (dim = 256 * m): 32 / m
+inline constexpr uint32_t scan_tile_rows(uint32_t dim) { return kScanTileSubRows * 256u / dim; }
 
 // One query's scan plan (device memory).  The rows to scan are the union of `n_ext` extents
 // [ext_lo, ext_hi); extents are a SUPERSET hint of the scoped stores' rows -- the per-row store
@@ -39,7 +41,7 @@ constexpr uint32_t kScanTileRows = 32;  // rows per warp step of the scan kernel
 struct ScanPlan {
     uint32_t ext_off;      // first extent of this query in the flat extent arrays
     uint32_t n_ext;
-    uint32_t total_tiles;  // sum over extents of ceil(rows / 32)
+    uint32_t total_tiles;  // sum over extents of ceil(rows / scan_tile_rows(dim))
     uint32_t n_scope;
     uint32_t scope[RF_SCOPE_MAX];
 };
@@ -55,10 +57,10 @@ struct StoreEntry {
 };
 
 struct ScanArgs {
-    const int8_t *F;            // [rows, 256] int8, row-major, 256-byte rows
+    const int8_t *F;            // [rows, dim] int8, row-major (dim = 256 * m: the kernel's template parameter)
     const uint32_t *seg;        // [rows] store segment word (0xFFFFFFFF = tombstone)
     const int32_t *ff;          // [rows] sum of squares (read for the k winners only); may be null
-    const int8_t *q;            // [nq, 256] query vectors (device)
+    const int8_t *q;            // [nq, dim] query vectors (device)
     const uint32_t *q_index;    // null, or [nq]: launch query qi reads row q_index[qi] of q (and publishes under that number)
     const ScanPlan *plans;      // [nq]
     const uint32_t *ext_lo;     // flat extents
@@ -103,7 +105,7 @@ struct ScanArgs {
     uint32_t *done_flag;           // mapped host word: set to done_seq after the results are visible to the host (or null)
     uint32_t *done_count;          // device word (zero between launches): queries of this launch finished so far
     uint32_t done_seq;
-    int8_t q_inline[256];          // the query vector itself when q == nullptr (nq == 1, host-side searches)
+    alignas(16) int8_t q_inline[1024];   // the query vector itself (dim bytes) when q == nullptr (nq == 1, host-side searches)
     uint32_t dbg_flags;            // diagnostics (RF_SCAN_DBG): 1 = no seg bulk copy, 2 = static round-robin tiles instead of stealing
     unsigned long long *debug_ts;  // diagnostics (RF_SCAN_DEBUG=1): [grid.x][8] globaltimer stamps, else null
 };
@@ -126,10 +128,11 @@ enum : int {                    // scan kernel variants (RF_SCAN_VARIANT env, de
 // griddepcontrol.wait -- the query vectors and the plan -- must then be complete before the PREVIOUS
 // kernel in the stream started: true for kernel parameters and for buffers written by a copy, not for a
 // query vector another kernel has just produced.
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s,
+// dim: 256, 512 or 1024 (wider rows run the default ring variant only)
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, uint32_t dim, cudaStream_t s,
                                    bool overlap);
-// packed keys [nq, k] -> ids / scores / cosines / counts (host-visible result layout); q: [nq, 256] device
-cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
+// packed keys [nq, k] -> ids / scores / cosines / counts (host-visible result layout); q: [nq, dim] device
+cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, uint32_t dim, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
                                uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s);
 cudaError_t launch_merge_topk(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k,
                               uint64_t *out_keys, cudaStream_t s);
@@ -175,7 +178,8 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
                                cudaStream_t s, uint64_t *floors = nullptr, uint32_t k_floor = 0);
 
-cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint8_t *zipf_bucket_dev,
+// zipf_bucket_dev: uint16[65536], bucket (< dim) of each table entry's token
+cudaError_t launch_synth_rows(uint64_t seed, uint64_t start_counter, uint64_t n_rows, const uint16_t *zipf_bucket_dev, uint32_t dim,
                               int8_t *F, int32_t *ff, uint32_t *seg, uint32_t first_seg, uint64_t rows_per_store,
                               cudaStream_t s);
 
@@ -193,7 +197,8 @@ struct TokenizeArgs {        // device scratch for one document
     uint32_t n_blocks;       // 4 KB blocks of the whole document
     uint64_t *state;         // [n_blocks] look-back status words (zeroed per document)
     uint32_t *ctl;           // [kCtlWords]
-    uint8_t *tok_bucket;     // [cap_tokens]
+    uint16_t *tok_bucket;    // [cap_tokens] bucket = hash & dim_mask
+    uint32_t dim_mask;       // dim - 1
     uint32_t *tok_end;       // [cap_tokens]
     uint32_t *chunk_start;   // [cap_tokens / 112 + 2] byte offset of the first token of each chunk window
     uint32_t *deferred;      // [2 * kMaxDeferred] (ordinal, start) of parked tokens
@@ -204,16 +209,17 @@ cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStre
 cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
                                     int32_t *ff, uint32_t *seg, uint32_t store_seg, int64_t *spans_dev,
                                     cudaStream_t s);
-// weights: [256] u8 device (RF-1w) or null (plain RF-1)
-cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, cudaStream_t s);
-// RF-1w statistics: out[d] += rows of the extents that are in scope and have F[row, d] > 0 (d < 256);
-// out[256] += rows in scope.  One streaming pass over the extents' rows.
+// weights: [dim] u8 device (RF-1w) or null (plain RF-1)
+cudaError_t launch_featurize_query(const uint8_t *text_dev, uint32_t n_bytes, const uint8_t *weights, int8_t *q_out, uint32_t dim,
+                                   cudaStream_t s);
+// RF-1w statistics: out[d] += rows of the extents that are in scope and have F[row, d] > 0 (d < dim);
+// out[dim] += rows in scope.  One streaming pass over the extents' rows.
 constexpr uint32_t kDfMaxExtents = 64;
 struct DfArgs {
     const int8_t *F;
     const uint32_t *seg;
-    unsigned long long *out;            // [257] device, accumulated into (caller zeroes)
-    uint32_t n_ext, n_scope;
+    unsigned long long *out;            // [dim + 1] device, accumulated into (caller zeroes)
+    uint32_t n_ext, n_scope, dim;
     uint32_t scope[RF_SCOPE_MAX];
     uint32_t lo[kDfMaxExtents];
     uint32_t prefix[kDfMaxExtents + 1]; // rows before extent i; prefix[n_ext] = total
@@ -222,7 +228,7 @@ cudaError_t launch_bucket_df(const DfArgs &a, int sm_count, cudaStream_t s);
 // p[0 .. n) = value (segment words of rows that were written while still masked)
 cudaError_t launch_fill_u32(uint32_t *p, uint64_t n, uint32_t value, cudaStream_t s);
 // ff[r] = sum of squares of row r, seg[r] = store_seg (seg may be null), for rows appended as raw features
-cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, int32_t *ff, uint32_t *seg, uint32_t store_seg,
+cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, uint32_t dim, int32_t *ff, uint32_t *seg, uint32_t store_seg,
                             cudaStream_t s);
 
 }  // namespace rf

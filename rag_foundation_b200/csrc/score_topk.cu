@@ -31,8 +31,19 @@ namespace rf {
 
 namespace {
 
-static_assert(kTileRows == static_cast<int>(kScanTileRows), "host and device disagree on the tile height");
-constexpr int kTileBytes = kTileRows * kRowBytes;  // 8192
+static_assert(kTileSubRows == static_cast<int>(kScanTileSubRows), "host and device disagree on the tile height");
+constexpr int kTileBytes = kTileSubRows * kSubBytes;  // 8192
+// Rows of dim = 256 * kM features (kM = 1, 2, 4) are kM consecutive 256-byte sub-rows; a tile is always 32
+// sub-rows = 32 / kM whole rows, so the streaming side (ring, bulk copies, shared loads, dp4a, butterfly)
+// is the same for every width.  What changes with kM: the lane's query slice(s), log2(kM) more shuffles
+// that add a row's sub-row scores, and only every kM-th lane of the lower half-warp offers a key.
+template <int kM>
+struct RowGeom {
+    static_assert(kM == 1 || kM == 2 || kM == 4, "rows are 256, 512 or 1024 features");
+    static constexpr int kD = kSubDim * kM;                 // features (= bytes) per row
+    static constexpr int kTileRows = kTileSubRows / kM;     // whole rows per tile
+    static constexpr int kQ = kM >= 2 ? kM / 2 : 1;         // 16-byte query slices a lane holds
+};
 constexpr int kChunkTiles = 8;                     // tiles claimed per atomic by a producer lane (tma variant)
 constexpr int kMaxExtSmem = 64;                    // extents staged in shared memory (engine caps plans at 64)
 
@@ -75,16 +86,56 @@ __device__ __forceinline__ int transpose_reduce16(int (&p)[16], int lane) {
     return keep + __shfl_xor_sync(kFull, send, 1);
 }
 
-__device__ __forceinline__ int score_tile(const int4 (&x)[16], const int4 &qv, int lane) {
+// Load i of a tile covers sub-rows 2i (lanes 0-15) and 2i + 1 (lanes 16-31), i.e. part (2i + (lane >> 4)) % kM
+// of a row: the lane multiplies it with slice i % kQ of its query registers (load_query below).
+// Returns, on every lane, the score of row row_in_tile<kM>(lane) (valid there on the lanes key_lane<kM>).
+template <int kM>
+__device__ __forceinline__ int score_tile(const int4 (&x)[16], const int4 (&qv)[RowGeom<kM>::kQ], int lane) {
+    constexpr int kQ = RowGeom<kM>::kQ;
     int p[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        int acc = __dp4a(x[i].x, qv.x, 0);
-        acc = __dp4a(x[i].y, qv.y, acc);
-        acc = __dp4a(x[i].z, qv.z, acc);
-        p[i] = __dp4a(x[i].w, qv.w, acc);
+        const int4 &w = qv[i % kQ];
+        int acc = __dp4a(x[i].x, w.x, 0);
+        acc = __dp4a(x[i].y, w.y, acc);
+        acc = __dp4a(x[i].z, w.z, acc);
+        p[i] = __dp4a(x[i].w, w.w, acc);
     }
-    return transpose_reduce16(p, lane);
+    int s = transpose_reduce16(p, lane);       // score of sub-row 2 * (lane & 15) + (lane >> 4)
+    if (kM >= 2) s += __shfl_xor_sync(kFull, s, 16);
+#pragma unroll
+    for (int o = 1; o < kM / 2; o <<= 1) s += __shfl_xor_sync(kFull, s, o);
+    return s;
+}
+template <int kM>
+__device__ __forceinline__ int row_in_tile(int lane) {
+    return kM == 1 ? 2 * (lane & 15) + (lane >> 4) : (lane & 15) / (kM / 2 > 0 ? kM / 2 : 1);
+}
+template <int kM>
+__device__ __forceinline__ bool key_lane(int lane) {
+    return kM == 1 ? true : (lane < 16 && ((lane & 15) % (kM / 2 > 0 ? kM / 2 : 1)) == 0);
+}
+// the lane's slice(s) of query vector q (RowGeom<kM>::kD bytes)
+template <int kM>
+__device__ __forceinline__ void load_query(const int8_t *q, int lane, int4 (&qv)[RowGeom<kM>::kQ]) {
+#pragma unroll
+    for (int j = 0; j < RowGeom<kM>::kQ; ++j) {
+        const int part = kM == 1 ? 0 : 2 * j + (lane >> 4);
+        qv[j] = *reinterpret_cast<const int4 *>(q + part * kSubBytes + (lane & 15) * 16);
+    }
+}
+// this lane's share of ||q||^2 (summed over the warp it covers every query byte once)
+template <int kM>
+__device__ __forceinline__ int query_sq_lane(const int4 (&qv)[RowGeom<kM>::kQ], int lane) {
+    int qq = 0;
+#pragma unroll
+    for (int j = 0; j < RowGeom<kM>::kQ; ++j) {
+        qq = __dp4a(qv[j].x, qv[j].x, qq);
+        qq = __dp4a(qv[j].y, qv[j].y, qq);
+        qq = __dp4a(qv[j].z, qv[j].z, qq);
+        qq = __dp4a(qv[j].w, qv[j].w, qq);
+    }
+    return (kM == 1 && lane >= 16) ? 0 : qq;
 }
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -113,6 +164,7 @@ struct BlockPlan {
 // Plan of query qi gathered from the device-resident store table: the extents of every store in the query's
 // scope, concatenated (stores own disjoint rows, so the order does not matter: tiles are located through the
 // prefix array).  Warp 0 does it; ends with __syncthreads().
+template <int kTileRows>
 __device__ __forceinline__ void stage_plan_from_table(const ScanArgs &a, int qi, BlockPlan &bp) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -160,9 +212,10 @@ __device__ __forceinline__ void stage_plan_from_table(const ScanArgs &a, int qi,
     __syncthreads();
 }
 
+template <int kTileRows>
 __device__ __forceinline__ void stage_plan(const ScanArgs &a, int qi, BlockPlan &bp) {
     if (a.st_tbl) {
-        stage_plan_from_table(a, qi, bp);
+        stage_plan_from_table<kTileRows>(a, qi, bp);
         return;
     }
     if (a.inline_plan) {
@@ -219,6 +272,7 @@ struct TileCursor {
         }
         e = lo;
     }
+    template <int kTileRows>
     __device__ __forceinline__ void locate(const BlockPlan &bp, uint32_t t, uint32_t &row0, uint32_t &row_end) {
         while (t >= bp.tile0[e + 1]) ++e;
         row0 = bp.lo[e] + (t - bp.tile0[e]) * kTileRows;
@@ -227,6 +281,7 @@ struct TileCursor {
 };
 
 // Random access (work-stealing order): binary search over the <= 64 extents.
+template <int kTileRows>
 __device__ __forceinline__ void locate_tile(const BlockPlan &bp, uint32_t t, uint32_t &row0, uint32_t &row_end) {
     uint32_t lo = 0, hi = bp.n_ext;
     while (hi - lo > 1) {
@@ -320,7 +375,7 @@ __device__ __forceinline__ void block_merge(WarpTopK &top, MergeScratch<kWarps> 
 // `n_blocks`: blocks of the launch that take part for this query (gridDim.x, or 1 when the query has nothing
 // to scan here and only block 0 stays to write the empty answer).
 template <int kWarps>
-__device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK &top, const int4 &qv, MergeScratch<kWarps> &ms,
+__device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK &top, int qq_lane, MergeScratch<kWarps> &ms,
                                              int k, int warp, int lane, uint32_t n_blocks) {
     constexpr int n_warps = kWarps;
     block_merge(top, ms, k, warp, lane);
@@ -386,12 +441,8 @@ __device__ __forceinline__ void finish_query(const ScanArgs &a, int qi, WarpTopK
     if (warp != 0) return;
     set_list(top, warp_tournament(ms.level2, n_groups, k, k, lane), k);
 
-    // ||q||^2 for the reported cosine (lanes 0..15 cover the 256 query bytes once)
-    int qq = __dp4a(qv.x, qv.x, 0);
-    qq = __dp4a(qv.y, qv.y, qq);
-    qq = __dp4a(qv.z, qv.z, qq);
-    qq = __dp4a(qv.w, qv.w, qq);
-    if (lane >= 16) qq = 0;
+    // ||q||^2 for the reported cosine (the lanes' shares cover the query bytes once: query_sq_lane)
+    int qq = qq_lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
 
@@ -503,10 +554,12 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
     const int warp = threadIdx.x >> 5;
     const int k = static_cast<int>(a.k);
     if (threadIdx.x == 0) stamp(a, 0);
+    constexpr int kTileRows = kTileSubRows;     // this variant exists for 256-feature rows only
+    constexpr int kRowBytes = kSubBytes;
     const uint32_t q_row = a.q_index ? a.q_index[qi] : static_cast<uint32_t>(qi);
-    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(q_row) * kDim + (lane & 15) * 16)
-                        : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
-    stage_plan(a, qi, bp);
+    int4 qv[1];
+    load_query<1>(a.q ? a.q + static_cast<size_t>(q_row) * kSubDim : a.q_inline, lane, qv);
+    stage_plan<kTileRows>(a, qi, bp);
     if (threadIdx.x == 0) stamp(a, 1);
     const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
     uint64_t *g_floor = a.floors + qi;
@@ -519,7 +572,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
 
     for (uint32_t t = bp.t_lo + warp; t < bp.t_hi; t += kLdgWarps) {
         uint32_t row0, row_end;
-        cur.locate(bp, t, row0, row_end);
+        cur.locate<kTileRows>(bp, t, row0, row_end);
         const int4 *src = reinterpret_cast<const int4 *>(a.F + static_cast<size_t>(row0) * kRowBytes) + lane;
         int4 x[16];
         uint32_t seg;
@@ -537,13 +590,13 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) score_topk_scan_ldg_kernel(
             seg = my_row < row_end ? __ldg(a.seg + my_row) : kTombstone;
         }
         const uint64_t floor_seen = __ldcg(g_floor);
-        const int score = score_tile(x, qv, lane);
+        const int score = score_tile<1>(x, qv, lane);
         const uint64_t key = in_scope(bp, seg) ? pack_key(score, a.id_base + my_row) : 0ull;
         if (first && threadIdx.x == 0) stamp(a, 2);
         offer_tile(top, first, key, floor_seen, g_floor, k, lane);
     }
     if (lane == 0) stamp_max(a, 3);
-    finish_query(a, qi, top, qv, ms, k, warp, lane, gridDim.x);
+    finish_query(a, qi, top, query_sq_lane<1>(qv, lane), ms, k, warp, lane, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,15 +607,18 @@ struct TmaSmem {
     alignas(128) uint8_t stage[kStages][kTileBytes];
     alignas(8) uint64_t full[kStages];
     alignas(8) uint64_t empty[kStages];
-    alignas(16) uint32_t st_seg[kStages][kTileRows];   // store-segment words of the tile (when bulk-copied)
+    alignas(16) uint32_t st_seg[kStages][kTileSubRows];   // store-segment words of the tile (when bulk-copied)
     uint32_t st_row0[kStages];   // tile held by each stage (written by its producer lane)
     uint32_t st_rows[kStages];   // rows | 0x100 if st_seg is valid; 0 = sentinel: no more tiles on this stage
     BlockPlan bp;
 };
 
-template <int kConsumers, int kStages>
+template <int kConsumers, int kStages, int kM>
 __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_kernel(const ScanArgs a) {
     static_assert(kStages % kConsumers == 0, "a stage is always drained by the same consumer warp");
+    using Geom = RowGeom<kM>;
+    constexpr int kTileRows = Geom::kTileRows;
+    constexpr int kRowBytes = Geom::kD;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     using Smem = TmaSmem<kConsumers, kStages>;
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -581,9 +637,10 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     }
     if (threadIdx.x == 0) stamp(a, 0);
     const uint32_t q_row = a.q_index ? a.q_index[qi] : static_cast<uint32_t>(qi);
-    const int4 qv = a.q ? *reinterpret_cast<const int4 *>(a.q + static_cast<size_t>(q_row) * kDim + (lane & 15) * 16)
-                        : *reinterpret_cast<const int4 *>(a.q_inline + (lane & 15) * 16);
-    stage_plan(a, qi, sm.bp);  // ends with __syncthreads()
+    int4 qv[Geom::kQ];
+    load_query<kM>(a.q ? a.q + static_cast<size_t>(q_row) * Geom::kD : a.q_inline, lane, qv);
+    const int qq_lane = query_sq_lane<kM>(qv, lane);
+    stage_plan<kTileRows>(a, qi, sm.bp);  // ends with __syncthreads()
     if (threadIdx.x == 0) stamp(a, 1);
     const BlockPlan &bp = sm.bp;
 
@@ -599,7 +656,7 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         using Scratch0 = MergeScratch<kConsumers + 1>;
-        finish_query(a, qi, top, qv, *reinterpret_cast<Scratch0 *>(&sm.stage[0][0]), k, warp, lane, 1u);
+        finish_query(a, qi, top, qq_lane, *reinterpret_cast<Scratch0 *>(&sm.stage[0][0]), k, warp, lane, 1u);
         return;
     }
 
@@ -637,16 +694,17 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
                     break;
                 }
                 uint32_t row0, row_end;
-                locate_tile(bp, next, row0, row_end);
+                locate_tile<kTileRows>(bp, next, row0, row_end);
                 ++next;
                 const uint32_t rows = min(static_cast<uint32_t>(kTileRows), row_end - row0);
-                // the 32 store-segment words ride along when their 128 bytes are 16-byte aligned
+                // the tile's store-segment words ride along when their bytes are 16-byte aligned
+                constexpr uint32_t kSegBytes = kTileRows * 4u;                      // 128 / 64 / 32: multiples of 16
                 const bool seg_copy = rows == kTileRows && (row0 & 3u) == 0u && !(a.dbg_flags & 1u);
                 sm.st_row0[lane] = row0;
                 sm.st_rows[lane] = rows | (seg_copy ? 0x100u : 0u);
-                mbar_arrive_expect_tx(&sm.full[lane], rows * kRowBytes + (seg_copy ? 128u : 0u));   // release: publishes st_*
+                mbar_arrive_expect_tx(&sm.full[lane], rows * kRowBytes + (seg_copy ? kSegBytes : 0u));   // release: publishes st_*
                 bulk_g2s(sm.stage[lane], a.F + static_cast<size_t>(row0) * kRowBytes, rows * kRowBytes, &sm.full[lane]);
-                if (seg_copy) bulk_g2s(sm.st_seg[lane], a.seg + row0, 128u, &sm.full[lane]);
+                if (seg_copy) bulk_g2s(sm.st_seg[lane], a.seg + row0, kSegBytes, &sm.full[lane]);
                 if (round == 0 && lane == 0) stamp(a, 7);
                 ++round;
             }
@@ -655,7 +713,8 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     } else {
         // ===== consumers: warp c drains stages c, c + kConsumers, ... in ring order =====
         const int cw = warp - 1;
-        const int my_row_in_tile = 2 * (lane & 15) + (lane >> 4);
+        const int my_row_in_tile = row_in_tile<kM>(lane);
+        const bool offers = key_lane<kM>(lane);        // wider rows: one lane per row carries the key
         uint64_t *g_floor = a.floors + qi;
         bool first = true;
         constexpr int kMine = kStages / kConsumers;    // stages per consumer warp
@@ -674,16 +733,18 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
             const uint32_t rows = rows_word & 0xFFu;
             const uint32_t row0 = sm.st_row0[s];
             const uint32_t my_row = row0 + my_row_in_tile;
-            uint32_t seg;
-            if (rows_word & 0x100u) seg = sm.st_seg[s][my_row_in_tile];
-            else seg = my_row_in_tile < static_cast<int>(rows) ? __ldg(a.seg + my_row) : kTombstone;
+            uint32_t seg = kTombstone;
+            if (offers) {
+                if (rows_word & 0x100u) seg = sm.st_seg[s][my_row_in_tile];
+                else seg = my_row_in_tile < static_cast<int>(rows) ? __ldg(a.seg + my_row) : kTombstone;
+            }
             const int4 *src = reinterpret_cast<const int4 *>(sm.stage[s]) + lane;
             int4 x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = src[j * 32];
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[s]);   // stage may be refilled while we reduce
-            const int score = score_tile(x, qv, lane);
+            const int score = score_tile<kM>(x, qv, lane);
             const uint64_t key = in_scope(bp, seg) ? pack_key(score, a.id_base + my_row) : 0ull;
             if (first && threadIdx.x == 32) stamp(a, 2);
             offer_tile(top, first, key, floor_seen, g_floor, k, lane);
@@ -700,7 +761,7 @@ __global__ void __launch_bounds__((kConsumers + 1) * 32, 1) score_topk_scan_tma_
     using Scratch = MergeScratch<kConsumers + 1>;
     static_assert(sizeof(Scratch) <= sizeof(sm.stage), "ring too small to double as merge scratch");
     __syncthreads();
-    finish_query(a, qi, top, qv, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane, gridDim.x);
+    finish_query(a, qi, top, qq_lane, *reinterpret_cast<Scratch *>(&sm.stage[0][0]), k, warp, lane, gridDim.x);
 }
 
 // k-way merge of n_lists sorted top-k lists per query (after the all-gather of the sharded path,
@@ -773,16 +834,19 @@ __global__ void __launch_bounds__(128) merge_wait_kernel(const uint64_t *__restr
 
 // Packed keys -> the result arrays a host caller gets (same arithmetic as finish_query: RF-1 step 8
 // for the cosine).  One warp per query.
-__global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__restrict__ keys, const int8_t *__restrict__ q,
+__global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__restrict__ keys, const int8_t *__restrict__ q, uint32_t dim,
                                                           const int32_t *__restrict__ ff, uint32_t id_base, uint32_t nq, uint32_t k,
                                                           uint64_t *__restrict__ out_ids, int32_t *__restrict__ out_scores,
                                                           float *__restrict__ out_cos, uint32_t *__restrict__ out_counts) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (qi >= nq) return;
-    const int2 qv = *reinterpret_cast<const int2 *>(q + static_cast<size_t>(qi) * kDim + lane * 8);
-    int qq = __dp4a(qv.x, qv.x, 0);
-    qq = __dp4a(qv.y, qv.y, qq);
+    int qq = 0;
+    for (uint32_t part = 0; part < dim; part += kSubDim) {
+        const int2 qv = *reinterpret_cast<const int2 *>(q + static_cast<size_t>(qi) * dim + part + lane * 8);
+        qq = __dp4a(qv.x, qv.x, qq);
+        qq = __dp4a(qv.y, qv.y, qq);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
     const uint64_t key = lane < static_cast<int>(k) ? keys[static_cast<size_t>(qi) * k + lane] : 0ull;
@@ -807,10 +871,10 @@ __global__ void __launch_bounds__(128) unpack_keys_kernel(const uint64_t *__rest
     if (lane == 0 && out_counts) out_counts[qi] = __popc(found);
 }
 
-template <int kConsumers, int kStages>
+template <int kConsumers, int kStages, int kM = 1>
 cudaError_t launch_tma(const ScanArgs &a, dim3 grid, cudaStream_t s, bool overlap) {
     using Smem = TmaSmem<kConsumers, kStages>;
-    auto kern = score_topk_scan_tma_kernel<kConsumers, kStages>;
+    auto kern = score_topk_scan_tma_kernel<kConsumers, kStages, kM>;
     if (cudaError_t e = ensure_dynamic_smem(kern, static_cast<int>(sizeof(Smem))); e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -835,9 +899,13 @@ uint32_t scan_default_blocks_per_query(int sm_count, int variant) {
     return static_cast<uint32_t>(sm_count) * (two ? 2u : 1u);
 }
 
-cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, cudaStream_t s,
+cudaError_t launch_score_topk_scan(const ScanArgs &a, uint32_t nq, uint32_t blocks_per_query, int variant, uint32_t dim, cudaStream_t s,
                                    bool overlap) {
     dim3 grid(blocks_per_query, nq, 1);
+    // wider rows: the default ring (6 consumers x 12 stages, two blocks per SM) only
+    if (dim == 512) return variant == kScanVariantTma6x12 ? launch_tma<6, 12, 2>(a, grid, s, overlap) : cudaErrorInvalidValue;
+    if (dim == 1024) return variant == kScanVariantTma6x12 ? launch_tma<6, 12, 4>(a, grid, s, overlap) : cudaErrorInvalidValue;
+    if (dim != 256) return cudaErrorInvalidValue;
     switch (variant) {
         case kScanVariantLdg: {
             if (cudaError_t e = ensure_dynamic_smem(score_topk_scan_ldg_kernel, static_cast<int>(sizeof(MergeScratch<kLdgWarps>)));
@@ -868,9 +936,9 @@ cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
+cudaError_t launch_unpack_keys(const uint64_t *keys, const int8_t *q, uint32_t dim, const int32_t *ff, uint32_t id_base, uint32_t nq, uint32_t k,
                                uint64_t *out_ids, int32_t *out_scores, float *out_cos, uint32_t *out_counts, cudaStream_t s) {
-    unpack_keys_kernel<<<(nq + 3) / 4, 128, 0, s>>>(keys, q, ff, id_base, nq, k, out_ids, out_scores, out_cos, out_counts);
+    unpack_keys_kernel<<<(nq + 3) / 4, 128, 0, s>>>(keys, q, dim, ff, id_base, nq, k, out_ids, out_scores, out_cos, out_counts);
     return cudaGetLastError();
 }
 

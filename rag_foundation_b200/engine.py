@@ -53,8 +53,8 @@ def _search_text(owner, call, text: bytes, scope: Sequence[int], k: int, ranges,
     text = bytes(text)
     if weights is not None:
         weights = np.ascontiguousarray(weights, dtype=np.uint8)
-        if weights.shape != (RF_DIM,):
-            raise ValueError(f"weights must be uint8 [{RF_DIM}]")
+        if weights.shape != (owner.dim,):
+            raise ValueError(f"weights must be uint8 [{owner.dim}]")
     rng = None
     if ranges is not None:
         rng = np.ascontiguousarray(np.asarray(list(ranges), dtype=np.uint64).reshape(-1, 2))
@@ -74,7 +74,7 @@ def _search_text(owner, call, text: bytes, scope: Sequence[int], k: int, ranges,
     sc = np.zeros(k, np.int32)
     cs = np.zeros(k, np.float32)
     cnt = C.c_uint32()
-    q = np.zeros(RF_DIM, np.int8)
+    q = np.zeros(owner.dim, np.int8)
     call(text, segs, len(scope), rng, weights, k, ids, sc, cs, cnt, q)
     m = int(cnt.value)
     return ids[:m], sc[:m], cs[:m], q
@@ -85,9 +85,10 @@ class Engine:
 
     RANGES_PER_CALL = 16   # row-range restrictions per launch (the kernel plan holds 64 extents)
 
-    def __init__(self, capacity_rows: int, device: int = 0, id_base: int = 0, n_contexts: int = 8):
+    def __init__(self, capacity_rows: int, device: int = 0, id_base: int = 0, n_contexts: int = 8, dim: int = RF_DIM):
         self._L = lib()
-        cfg = _capi.rf_config(C.sizeof(_capi.rf_config), int(device), RF_DIM, int(n_contexts), int(capacity_rows),
+        self.dim = int(dim)       # features per chunk row: 256 (default), 512 or 1024
+        cfg = _capi.rf_config(C.sizeof(_capi.rf_config), int(device), self.dim, int(n_contexts), int(capacity_rows),
                               int(id_base))
         h = C.c_void_p()
         check(self._L.rf_engine_create(C.byref(cfg), C.byref(h)))
@@ -173,7 +174,7 @@ class Engine:
         if on_device:
             check(self._L.rf_ingest_features(self.handle, int(seg), int(doc_id), int(rows), int(n_rows), 1, C.byref(first)))
         else:
-            rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, RF_DIM)
+            rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, self.dim)
             check(self._L.rf_ingest_features(self.handle, int(seg), int(doc_id), _ptr(rows), rows.shape[0], 0,
                                              C.byref(first)))
         return int(first.value)
@@ -197,7 +198,7 @@ class Engine:
         check(self._L.rf_snapshot_load(self.handle, os.fsencode(path)))
 
     def read_rows(self, first_row: int, n: int):
-        F = np.zeros((n, RF_DIM), np.int8)
+        F = np.zeros((n, self.dim), np.int8)
         seg = np.zeros(n, np.uint32)
         ff = np.zeros(n, np.int32)
         check(self._L.rf_rows_read(self.handle, int(first_row), int(n), _ptr(F), _ptr(seg), _ptr(ff)))
@@ -205,11 +206,11 @@ class Engine:
 
     # ------------------------------------------------------------------ query
     def search(self, q, scopes: Sequence[Sequence[int]], k: int = 10):
-        """q int8 [nq, 256] (host). -> ids uint64 [nq,k], scores int32, cos float32, counts uint32.
+        """q int8 [nq, dim] (host). -> ids uint64 [nq,k], scores int32, cos float32, counts uint32.
 
         `scopes` is one list of store segments per query, or -- for large batches, to skip the
         Python loop -- the CSR pair (segs uint32 [n], off uint32 [nq + 1]) the C-ABI takes."""
-        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, RF_DIM)
+        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, self.dim)
         nq = q.shape[0]
         if isinstance(scopes, tuple) and len(scopes) == 2 and isinstance(scopes[0], np.ndarray):
             segs = np.ascontiguousarray(scopes[0], dtype=np.uint32)
@@ -236,10 +237,10 @@ class Engine:
         return ids, sc, cs, cnt
 
     def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None, weights=None):
-        """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [256]   (m <= k results).
+        """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [dim]   (m <= k results).
 
         `ranges`: optional sorted, disjoint [(lo, hi), ...] global chunk id ranges to stay inside
-        (doc-level metadata filters).  `weights`: optional uint8 [256] RF-1w bucket weights
+        (doc-level metadata filters).  `weights`: optional uint8 [dim] RF-1w bucket weights
         (`idf_weights`); the returned q is then the weighted vector."""
         return _search_text(self, self._search_text_call, text, scope, k, ranges, weights)
 
@@ -250,28 +251,28 @@ class Engine:
 
     def featurize_query(self, text: bytes) -> np.ndarray:
         text = bytes(text)
-        q = np.zeros(RF_DIM, np.int8)
+        q = np.zeros(self.dim, np.int8)
         check(self._L.rf_featurize_query(self.handle, text or b"\0", len(text), _ptr(q)))
         return q
 
     # ---- RF-1w (IDF-weighted variant, oracle/SPEC.md) ------------------------------------------
     def scope_df(self, scope: Sequence[int]) -> Tuple[np.ndarray, int]:
-        """-> (df uint64 [256], n): per-bucket document frequencies over the scope's live rows."""
+        """-> (df uint64 [dim], n): per-bucket document frequencies over the scope's live rows."""
         segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
-        df = np.zeros(RF_DIM, np.uint64)
+        df = np.zeros(self.dim, np.uint64)
         n = C.c_uint64()
         check(self._L.rf_scope_df(self.handle, _ptr(segs), len(scope), _ptr(df), C.byref(n)))
         return df, int(n.value)
 
     def scope_df_device(self, scope: Sequence[int], df_ptr: int, stream: int = 0) -> None:
-        """Adds the scope's df[256] and row count into the 257 u64 at device pointer `df_ptr`."""
+        """Adds the scope's df[dim] and row count into the dim + 1 u64 at device pointer `df_ptr`."""
         segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
         check(self._L.rf_scope_df_device(self.handle, _ptr(segs), len(scope), df_ptr, stream))
 
     def idf_weights(self, df: np.ndarray, n: int) -> np.ndarray:
         df = np.ascontiguousarray(df, dtype=np.uint64)
-        w = np.zeros(RF_DIM, np.uint8)
-        check(self._L.rf_idf_weights(_ptr(df), int(n), RF_DIM, _ptr(w)))
+        w = np.zeros(self.dim, np.uint8)
+        check(self._L.rf_idf_weights(_ptr(df), int(n), self.dim, _ptr(w)))
         return w
 
     def scope_weights(self, scope: Sequence[int]) -> np.ndarray:
@@ -281,8 +282,8 @@ class Engine:
         q = np.ascontiguousarray(q, dtype=np.int8)
         w = np.ascontiguousarray(w, dtype=np.uint8)
         out = np.zeros_like(q)
-        for row_in, row_out in zip(q.reshape(-1, RF_DIM), out.reshape(-1, RF_DIM)):
-            check(self._L.rf_weight_query(_ptr(row_in), _ptr(w), RF_DIM, _ptr(row_out)))
+        for row_in, row_out in zip(q.reshape(-1, self.dim), out.reshape(-1, self.dim)):
+            check(self._L.rf_weight_query(_ptr(row_in), _ptr(w), self.dim, _ptr(row_out)))
         return out
 
     def search_keys_device(self, q_ptr: int, nq: int, scope: Sequence[int], k: int, out_keys_ptr: int,
@@ -373,7 +374,7 @@ class EngineGroup:
     RANGES_PER_CALL = Engine.RANGES_PER_CALL
 
     def __init__(self, devices: Sequence[int], capacity_rows: int, n_contexts: int = 8, placement: str = "store",
-                 id_bases: Optional[Sequence[int]] = None):
+                 id_bases: Optional[Sequence[int]] = None, dim: int = RF_DIM):
         self._L = lib()
         placements = {"store": _capi.RF_PLACE_STORE, "spread": _capi.RF_PLACE_SPREAD}
         if placement not in placements:
@@ -383,10 +384,11 @@ class EngineGroup:
         if bases is not None and bases.shape != devs.shape:
             raise ValueError("one id base per device")
         cfg = _capi.rf_group_config(C.sizeof(_capi.rf_group_config), int(devs.size), _ptr(devs), _ptr(bases), int(n_contexts),
-                                    placements[placement], int(capacity_rows))
+                                    placements[placement], int(capacity_rows), int(dim), 0)
         h = C.c_void_p()
         check(self._L.rf_group_create(C.byref(cfg), C.byref(h)), group=True)
         self._h = h
+        self.dim = int(dim)
         self.devices = [int(d) for d in devs]
         self.placement = placement
         self.capacity_rows = int(capacity_rows)
@@ -454,7 +456,7 @@ class EngineGroup:
         return int(first.value), n, spans[:n].copy()
 
     def ingest_features(self, store: int, doc_id: int, rows) -> int:
-        rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, RF_DIM)
+        rows = np.ascontiguousarray(rows, dtype=np.int8).reshape(-1, self.dim)
         first = C.c_uint64()
         check(self._L.rf_group_ingest_features(self.handle, int(store), int(doc_id), _ptr(rows), rows.shape[0], C.byref(first)), group=True)
         return int(first.value)
@@ -476,8 +478,8 @@ class EngineGroup:
 
     # ------------------------------------------------------------------ query
     def search(self, q, scopes, k: int = 10):
-        """As Engine.search: q int8 [nq, 256] (host), one list of stores per query or a CSR pair."""
-        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, RF_DIM)
+        """As Engine.search: q int8 [nq, dim] (host), one list of stores per query or a CSR pair."""
+        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, self.dim)
         nq = q.shape[0]
         if isinstance(scopes, tuple) and len(scopes) == 2 and isinstance(scopes[0], np.ndarray):
             segs = np.ascontiguousarray(scopes[0], dtype=np.uint32)
@@ -512,13 +514,13 @@ class EngineGroup:
 
     def featurize_query(self, text: bytes) -> np.ndarray:
         text = bytes(text)
-        q = np.zeros(RF_DIM, np.int8)
+        q = np.zeros(self.dim, np.int8)
         check(self._L.rf_featurize_query(self.engine_handle(0), text or b"\0", len(text), _ptr(q)))
         return q
 
     def scope_df(self, scope: Sequence[int]) -> Tuple[np.ndarray, int]:
         segs = np.asarray(list(scope) if len(scope) else [0], dtype=np.uint32)
-        df = np.zeros(RF_DIM, np.uint64)
+        df = np.zeros(self.dim, np.uint64)
         n = C.c_uint64()
         check(self._L.rf_group_scope_df(self.handle, _ptr(segs), len(scope), _ptr(df), C.byref(n)), group=True)
         return df, int(n.value)

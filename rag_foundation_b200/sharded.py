@@ -37,8 +37,8 @@ def unpack_keys_torch(keys: torch.Tensor):
 def allreduce_scope_weights(local_df: Callable[[Sequence[int]], torch.Tensor], weights_fn, scope: Sequence[int],
                             group: Optional[dist.ProcessGroup] = None):
     """RF-1w weights of a sharded corpus (oracle/SPEC.md): every rank counts its own shard
-    (`local_df(scope)` -> int64 [257]: df per bucket, then the live row count), ONE integer
-    all-reduce (sum) makes the statistic global, and `weights_fn(df, n)` turns it into the uint8 [256]
+    (`local_df(scope)` -> int64 [dim + 1]: df per bucket, then the live row count), ONE integer
+    all-reduce (sum) makes the statistic global, and `weights_fn(df, n)` turns it into the uint8 [dim]
     weights -- identical on every rank, so the merged ranking equals the single-engine one."""
     stat = local_df(scope)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -50,7 +50,7 @@ def allreduce_scope_weights(local_df: Callable[[Sequence[int]], torch.Tensor], w
 def engine_local_df(engine) -> Callable[[Sequence[int]], torch.Tensor]:
     def local_df(scope: Sequence[int]) -> torch.Tensor:
         dev = torch.device("cuda", torch.cuda.current_device())
-        stat = torch.zeros(257, dtype=torch.int64, device=dev)
+        stat = torch.zeros(int(getattr(engine, "dim", 256)) + 1, dtype=torch.int64, device=dev)
         engine.scope_df_device(scope, stat.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         return stat
     return local_df

@@ -96,7 +96,8 @@ def make_labelled_set(n_docs: int, n_questions: int, seed: int = 0, doc_tokens=(
 def model_dim_sweep(docs: dict, questions: list, dims=(256, 1024, 4096), top_k: int = 10) -> dict:
     """NOT the product path: a numpy model of RF-1 (tf) and RF-1w (idf) with D = 256 / 1024 / 4096
     hash buckets on the same labelled set, to show how much of the miss rate is bucket collisions
-    (the engine is compiled for D = 256; wider rows are the next variant).
+    (engines run D = 256, 512 or 1024 -- `--dim`; the model's row for the engine's width must equal
+    the GPU numbers exactly, tests/test_gpu_wide_rows.py).
     Documents here are space-separated lower-case words without stop-words, so tokenising is split()."""
     def fnv(tok: bytes) -> int:
         h = 0x811C9DC5
@@ -198,16 +199,18 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--top-k", type=int, default=10)
     ap.add_argument("--dim-sweep", action="store_true", help="also run the CPU what-if model at D = 256 / 1024 / 4096")
+    ap.add_argument("--dim", type=int, default=256, help="features per chunk row of the engine (256, 512, 1024)")
     args = ap.parse_args()
     from rag_foundation_b200 import Engine
     from rag_foundation_b200 import adapter as ad
     docs, questions = make_labelled_set(args.docs, args.questions, args.seed)
-    reg = ad.Registry(Engine(capacity_rows=max(4096, args.docs * 8)))
+    reg = ad.Registry(Engine(capacity_rows=max(4096, args.docs * 8), dim=args.dim))
     try:
         res = run_eval(lambda scoring: ad.B200Rag(registry=reg, top_k=args.top_k, scoring=scoring), docs, questions, args.top_k)
     finally:
         reg.engine.close()
     res["seed"] = args.seed
+    res["dim"] = args.dim
     if args.dim_sweep:
         res["cpu_model_citation_hit_rate_by_dim"] = model_dim_sweep(docs, questions, top_k=args.top_k)
     res["note"] = ("synthetic labelled set: Zipf(1.07) word streams; a question = 6 words of one 40-word window of its gold "
