@@ -43,7 +43,7 @@ SEED = 0
 K = 10
 N_DISTINCT_QUERIES = 64
 METRIC = "chunks scored/s, top-10 store-scoped retrieval (QPS alongside)"
-SCAN_KERNEL = "score_topk_scan_tma_kernel<6, 12>"
+SCAN_KERNEL = "score_topk_scan_tma_kernel<6, 12, 1>"    # as ncu prints it: <consumer warps, ring stages, 256-feature sub-rows per row>
 
 
 def host_threads() -> int:
@@ -143,7 +143,7 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def make_queries(n: int, seed: int = SEED) -> np.ndarray:
+def make_queries(n: int, seed: int = SEED, dim: int = 256) -> np.ndarray:
     """RF-1 synthetic queries (oracle/SPEC.md).  Generated with the product's own table so the
     bench never needs the oracle on the GPU arm: same mix64 / bucket rule, vectorised in numpy."""
     from rag_foundation_b200.engine import load_zipf_vocab
@@ -153,11 +153,11 @@ def make_queries(n: int, seed: int = SEED) -> np.ndarray:
         h = 0x811C9DC5
         for b in str(v).encode():
             h = ((h ^ b) * 0x01000193) & 0xFFFFFFFF
-        return h & 255
+        return h & (dim - 1)
 
     bucket_of = {}
     M = (1 << 64) - 1
-    out = np.zeros((n, 256), np.int8)
+    out = np.zeros((n, dim), np.int8)
     for i in range(n):
         for j in range(8):
             x = ((seed ^ 0x51) * 0x9E3779B97F4A7C15 + i * 0xBF58476D1CE4E5B9 + j * 0x94D049BB133111EB + 0x2545F4914F6CDD1D) & M
@@ -214,9 +214,10 @@ def cpu_oracle_leg(n_total: int, budget_s: float, queries: np.ndarray, seed: int
 def oracle_parity(n_rows: int, queries: np.ndarray, gpu_keys: np.ndarray, id_base: int = 0, start_counter: int = 0, seed: int = SEED):
     """GPU packed keys vs the C oracle over rows [start_counter, start_counter + n_rows) of the corpus."""
     from oracle import c_oracle as co, rf1
-    zb = rf1.zipf_bucket_table()
+    dim = queries.shape[1]
+    zb = rf1.zipf_bucket_table(dim=dim)
     threads = host_threads()
-    F = co.synth_rows(seed, start_counter, n_rows, zb, threads=threads)
+    F = co.synth_rows(seed, start_counter, n_rows, zb, threads=threads, dim=dim)
     seg = np.zeros(n_rows, np.uint32)
     bad = 0
     for i in range(len(queries)):
@@ -535,6 +536,44 @@ def leg_scaling_base(torch, dev, hbm_peak, steps: int):
                 "e2e_ms_per_query": e2e_ms, "e2e_value": CFG4_ROWS / (e2e_ms * 1e-3)}
 
 
+def leg_wide(torch, dev, hbm_peak, steps: int, sample_parity: bool, dim: int = 1024):
+    """Wider rows: the configs[1] workload with D = 1024 features per chunk -- 1 M chunks, one
+    query at a time, top-10 -- on the same scan kernel (template on the row width).  1028 algorithmic bytes per chunk."""
+    from rag_foundation_b200 import Engine
+    n = CFG2_ROWS
+    Qh = make_queries(8, seed=SEED + 6, dim=dim)
+    with Engine(capacity_rows=n, device=dev.index or 0, dim=dim) as e:
+        s = e.open_store("fileSearchStores/wide")
+        e.ingest_synthetic(s, 0, seed=SEED, start_counter=0, n_rows=n)
+        qd = torch.from_numpy(Qh).to(dev)
+        out = torch.zeros((8, K), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        torch.cuda.synchronize(dev)
+        e.set_stream_overlap(stream.cuda_stream, True)
+        i = [0]
+
+        def one():
+            j = i[0] % 8
+            i[0] += 1
+            e.search_keys_device(qd[j:j + 1].data_ptr(), 1, [s], K, out[j].data_ptr(), stream.cuda_stream)
+        ms = events_ms(torch, stream, one, reps=max(16, min(steps, 200)), warm=8)
+        torch.cuda.synchronize(dev)
+        bad = oracle_parity(n, Qh, out.cpu().numpy().view(np.uint64)) if sample_parity else None
+        for j in range(3):
+            e.search(Qh[j:j + 1], [[s]], k=K)
+        t0 = time.perf_counter()
+        for j in range(20):
+            e.search(Qh[j % 8:j % 8 + 1], [[s]], k=K)
+        e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+        bytes_per_launch = n * (dim + 4)
+        gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+        return {"workload": f"configs[1] with wider rows: 1M chunks x {dim} int8 features, 1 query at a time, top-10 on 1 B200", "dim": dim,
+                "kernel": "score_topk_scan_tma_kernel<6, 12, %d>" % (dim // 256), "ms_per_query": ms, "qps": 1e3 / ms, "chunks_per_s": n / (ms * 1e-3),
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "frac_of_8TBps": gbs / 8000.0},
+                "e2e_ms_per_query": e2e_ms, "api": "rf_search (host buffers)", "parity_mismatches": bad, "parity_checked": 8 if sample_parity else 0}
+
+
 # ---------------------------------------------------------------------------------------------- the B200 arm
 def run_b200(args) -> None:
     import torch
@@ -792,6 +831,7 @@ def run_b200(args) -> None:
                         configs["cfg2"] = leg_cfg2(torch, dev, e2, s2, hbm_peak, sp)
                     configs["ingest"] = leg_ingest(torch, dev, hbm_peak, sp)
                     configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp)
+                    configs["wide"] = leg_wide(torch, dev, hbm_peak, steps, sp)
                     configs["scaling_base"] = leg_scaling_base(torch, dev, hbm_peak, steps)
                 else:
                     configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp, devices=list(range(n_gpus)))
