@@ -824,15 +824,21 @@ def run_b200(args) -> None:
         if not args.no_configs:
             sp = not args.no_parity
             try:
+                legs = set(args.legs.split(","))
                 if n_gpus == 1:
-                    with Engine(capacity_rows=CFG2_ROWS, device=local_rank) as e2:
-                        s2 = e2.open_store("fileSearchStores/cfg2")
-                        e2.ingest_synthetic(s2, 0, seed=SEED, start_counter=0, n_rows=CFG2_ROWS)
-                        configs["cfg2"] = leg_cfg2(torch, dev, e2, s2, hbm_peak, sp)
-                    configs["ingest"] = leg_ingest(torch, dev, hbm_peak, sp)
-                    configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp)
-                    configs["wide"] = leg_wide(torch, dev, hbm_peak, steps, sp)
-                    configs["scaling_base"] = leg_scaling_base(torch, dev, hbm_peak, steps)
+                    if "cfg2" in legs:
+                        with Engine(capacity_rows=CFG2_ROWS, device=local_rank) as e2:
+                            s2 = e2.open_store("fileSearchStores/cfg2")
+                            e2.ingest_synthetic(s2, 0, seed=SEED, start_counter=0, n_rows=CFG2_ROWS)
+                            configs["cfg2"] = leg_cfg2(torch, dev, e2, s2, hbm_peak, sp)
+                    if "ingest" in legs:
+                        configs["ingest"] = leg_ingest(torch, dev, hbm_peak, sp)
+                    if "cfg4" in legs:
+                        configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp)
+                    if "wide" in legs:
+                        configs["wide"] = leg_wide(torch, dev, hbm_peak, steps, sp)
+                    if "scaling_base" in legs:
+                        configs["scaling_base"] = leg_scaling_base(torch, dev, hbm_peak, steps)
                 else:
                     configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp, devices=list(range(n_gpus)))
                     if cfg4_spmd:
@@ -887,6 +893,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[4] / ingest / scaling_base legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle checks (profiling runs)")
+    ap.add_argument("--legs", default="cfg2,ingest,cfg4,wide,scaling_base", help="which configs legs to run at N = 1 (comma list)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU top-k exchange")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -942,7 +942,10 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
     const uint32_t q_groups = (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);          // 512 queries per block or pair
     const uint32_t units = pair ? static_cast<uint32_t>(e->sm_count) / 2 : static_cast<uint32_t>(e->sm_count);
     const uint32_t slices_full = std::max(1u, units / q_groups);
-    uint32_t sample = std::min(rows / 4, e->gemm_sample) / tile_rows * tile_rows;
+    // rows of the floor pass: the pair kernel's is branch-free (running maxima, no lists) and takes a sample twice the
+    // single-CTA kernel's -- the main pass then meets half the candidates (RF_GEMM_SAMPLE sets the latter; measured at
+    // 1024 x 1 M: 64 Ki rows 0.219 ms, 128 Ki 0.208, 256 Ki 0.213 -- tools/cfg2_sample_sweep.sh)
+    uint32_t sample = std::min(rows / 4, pair ? e->gemm_sample * 2 : e->gemm_sample) / tile_rows * tile_rows;
     uint32_t n_a = std::max(1u, std::min(slices_full, sample / tile_rows));
     if (e->gemm_slices_a) n_a = std::max(1u, std::min(n_a, e->gemm_slices_a));
     const uint32_t n_b = std::max(1u, std::min(slices_full, (rows + tile_rows - 1) / tile_rows));
@@ -980,7 +983,8 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
     g.row_lo = lo;
     g.row_hi = lo + sample;
     RF_CUDA(launch(g, n_a));
-    RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s, floors, k));   // floors[q] = k-th best group maximum
+    if (pair) RF_CUDA(rf::launch_kth_largest(reinterpret_cast<const uint32_t *>(lists), rf::gemm_pair_floor_groups(n_a), nq, k, floors, s));
+    else RF_CUDA(rf::launch_merge_lists(lists, n_a * lps, nq, kl, kl, keys_a, s, floors, k));   // floors[q] = k-th best group maximum
     // pass B: every row (the sample included: pass A kept maxima, not chunks), floors from pass A
     g.floors = floors;
     g.group_max_mode = 0;

@@ -174,6 +174,10 @@ constexpr int kGemmPairLists = 1;   // the four column-block lists of a CTA are 
 size_t gemm_pair_lists_bytes(uint32_t n_slices, uint32_t nq);
 cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
                                         cudaStream_t s);
+// The pair kernel's floor pass (GemmArgs.group_max_mode = 1) writes gemm_pair_floor_groups(n_slices) group maxima per query
+// ([groups][nq] u32, in out_lists); launch_kth_largest turns them into floors[q] = (k-th largest) << 32.
+uint32_t gemm_pair_floor_groups(uint32_t n_slices);
+cudaError_t launch_kth_largest(const uint32_t *vals, uint32_t n_groups, uint32_t nq, uint32_t k, uint64_t *floors, cudaStream_t s);
 // keys: [n_lists, nq, k_in] sorted lists -> out [nq, k_out] (k_out <= k_in <= 32, n_lists <= 1024)
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,
                                cudaStream_t s, uint64_t *floors = nullptr, uint32_t k_floor = 0);

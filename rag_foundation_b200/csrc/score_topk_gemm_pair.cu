@@ -27,6 +27,13 @@
 // candidate path, the floor (group-maximum) pass and the list merge are those of score_topk_gemm.cu;
 // the four column-block lists of a query are merged in shared memory at the end, so a pair writes one
 // list per query and slice.
+// Floor pass (kFloorPass): no lists at all.  A thread keeps ONE running maximum per M-group over every column
+// it reads (its 64 columns of each tile of the slice) and writes it at the end: n_slices x 4 group maxima per
+// query, of disjoint chunk groups, whose k-th largest (kth_largest_kernel) is a valid lower bound of the
+// query's final k-th best score.  Branch-free (two LDTM + two maximum trees per accumulator), so this pass
+// runs at the tensor pipe's pace and can afford a sample four times the size the list-keeping version could:
+// the main pass then meets a quarter of the candidates, and the candidates are what slows it down (a
+// candidate costs its warp ~1000 cycles, and the next tile's MMAs wait for the slowest of the pair's 32 warps).
 #include <algorithm>
 #include <cstddef>
 
@@ -132,49 +139,65 @@ __device__ __forceinline__ void umma2_commit_both_a(uint32_t bar) {
                  : "memory");
 }
 
-// One 32-column group of one query's scores -> the query's list.  Same logic as score_topk_gemm.cu.
-__device__ __forceinline__ void take_group(const uint32_t (&v)[32], uint32_t okm, bool live, bool group_max_mode, uint32_t id0,
-                                           RegList &list, uint64_t &thr) {
-    if (group_max_mode) {
-        int gm = 0;
+// One 32-column group of one query's scores, in two steps: the step that needs the values can run while
+// the accumulator is still held, the step that touches the list after it has been handed back.
+//
+// group_candidate: the lane's single candidate key of the group (0 = none) -- in normal mode the one score
+// that reaches the query's threshold, in group-maximum mode (floor pass) the group's maximum.  Out-of-scope
+// columns are zeroed first (uniform branch: a tile that lies wholly inside the scope skips it), so the
+// maximum is itself a candidate's score and "exactly one score >= threshold" means that score is the
+// maximum.  `multi` (warp-uniform) reports that some lane has several candidates in this group: the caller
+// then runs take_group_multi on the same values (rare: two chunks of one 32-chunk group above a query's floor).
+__device__ __forceinline__ uint64_t group_candidate(uint32_t (&v)[32], uint32_t okm, bool live, bool group_max_mode, uint32_t id0,
+                                                    uint64_t thr, bool &multi) {
+    multi = false;
+    if (okm != kFull) {                                  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gm = max(gm, ((okm >> j) & 1u) ? static_cast<int>(v[j]) : 0);
-        const uint64_t key = pack_key(gm, id0);      // low word only makes groups distinct
-        if (live && okm != 0u && key > thr) {
-            list.insert(key);
-            const uint64_t kth = list.e[kGemmK - 1];
-            if (kth > thr) thr = kth;
-        }
-        return;
+        for (int j = 0; j < 32; ++j) v[j] = ((okm >> j) & 1u) ? v[j] : 0u;
     }
     const int mx = max32(v);
+    if (group_max_mode) return (live && okm != 0u) ? pack_key(mx, id0) : 0ull;      // low word only makes groups distinct
     const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
-    if (__any_sync(kFull, live && static_cast<uint32_t>(mx) >= thr_s)) {     // scores are in [0, 2^31): unsigned compare is exact
+    const bool hit = live && static_cast<uint32_t>(mx) >= thr_s;     // scores are in [0, 2^31): unsigned compare is exact
+    uint64_t key = 0ull;
+    if (__any_sync(kFull, hit)) {
         uint32_t cand = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
-        cand &= okm;
-        if (!live) cand = 0;
-        uint32_t uni = __reduce_or_sync(kFull, cand);
-        while (uni) {
-            const int j = __ffs(uni) - 1;
-            uni &= uni - 1;
-            const uint32_t sc = pick32(v, j);        // j is warp-uniform: a jump, not a TMEM reload
-            if ((cand >> j) & 1u) {
-                const uint64_t key = pack_key(static_cast<int32_t>(sc), id0 + j);
-                if (key > thr) {
-                    list.insert(key);
-                    const uint64_t kth = list.e[kGemmK - 1];
-                    if (kth > thr) thr = kth;
-                }
-            }
-        }
+        cand = hit ? (cand & okm) : 0u;
+        const int cnt = __popc(cand);
+        multi = __any_sync(kFull, cnt > 1);
+        if (cnt == 1) key = pack_key(mx, id0 + (__ffs(cand) - 1));
+    }
+    return key;
+}
+__device__ __forceinline__ void offer_key(uint64_t key, RegList &list, uint64_t &thr) {
+    if (key > thr) {
+        list.insert(key);
+        const uint64_t kth = list.e[kGemmK - 1];
+        if (kth > thr) thr = kth;
+    }
+}
+// several candidates per lane: every score that reaches the threshold, one warp-uniform column at a time
+__device__ __forceinline__ void take_group_multi(const uint32_t (&v)[32], uint32_t okm, bool live, uint32_t id0, RegList &list, uint64_t &thr) {
+    const uint32_t thr_s = static_cast<uint32_t>(thr >> 32);
+    uint32_t cand = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) cand |= (v[j] >= thr_s ? 1u : 0u) << j;
+    cand &= okm;
+    if (!live) cand = 0;
+    uint32_t uni = __reduce_or_sync(kFull, cand);
+    while (uni) {
+        const int j = __ffs(uni) - 1;
+        uni &= uni - 1;
+        const uint32_t sc = pick32(v, j);        // j is warp-uniform: a jump, not a TMEM reload
+        if ((cand >> j) & 1u) offer_key(pack_key(static_cast<int32_t>(sc), id0 + j), list, thr);
     }
 }
 
 // kDebug: in-kernel cycle counters (RF_SCAN_DEBUG=1, tools/gemm_timeline.py); the production instantiation
 // carries no clock reads in its loops (they cost 5 % of the batch time)
-template <bool kDebug>
+template <bool kDebug, bool kFloorPass>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t pair_smem_raw[];
@@ -279,6 +302,9 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                             }
                         }
                         umma2_commit_both_a(a_tmem_full + 8 * g);
+                        // timeline (debug build, first cluster): MMAs of (tile, group) issued
+                        if (kDebug && a.debug && blockIdx.x == 0 && blockIdx.y == 0 && t >= 16 && t < 24)
+                            a.debug[2048 + ((t - 16) * 2 + g) * 8 + 0] = clock64();
                     }
                     __syncwarp();
                 }
@@ -304,7 +330,8 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         uint64_t thr0 = (a.floors && live0) ? a.floors[q0] : 0ull;
         uint64_t thr1 = (a.floors && live1) ? a.floors[q0 + 256] : 0ull;
         const uint32_t leader_empty0 = map_to_cta_a(a_tmem_empty, 0), leader_empty1 = map_to_cta_a(a_tmem_empty + 8, 0);
-        const bool gmm = a.group_max_mode != 0;
+        constexpr bool gmm = false;                        // (the floor pass has its own branch below)
+        int run0 = 0, run1 = 0;                            // floor pass: running maxima of this thread's columns
         long long w_tfull = 0;
         const long long e_start = kDebug ? clock64() : 0;
         // The scope test runs once per tile and column half: keep the first four scope words in
@@ -350,21 +377,67 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 if (kDebug) w_tfull += clock64() - c0;
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((lq * 32u) << 16) + g * kPN + cb * 64;
+                const bool live = g ? live1 : live0;
+                RegList &list = g ? list1 : list0;
+                uint64_t &thr = g ? thr1 : thr0;
+                // timeline (debug build): accumulator seen ready / handed back / values done, first and last epilogue warp
+                const bool tl = kDebug && a.debug && blockIdx.x == 0 && blockIdx.y == 0 && t >= 16 && t < 24 && lane == 0 && (warp == 2 || warp == 17);
+                unsigned long long *tl_d = a.debug + 2048 + ((t - 16) * 2 + g) * 8 + (warp == 2 ? 1 : 4);
+                if (tl) tl_d[0] = clock64();
+                // The next tile's MMAs into this accumulator wait for the SLOWEST of the pair's 32 epilogue warps, and in
+                // nearly every tile some warp meets a candidate in its first 32 columns.  So while the accumulator is held
+                // only the candidate is FOUND (one key per lane); the list work (~1000 cycles for the warp) waits until the
+                // second read is in registers and the accumulator has been handed back.
                 uint32_t v[32];
                 tmem_ld32(taddr, v);
-                take_group(v, ok_mask[0], g ? live1 : live0, gmm, a.id_base + row0, g ? list1 : list0, g ? thr1 : thr0);
+                if (kFloorPass) {
+                    if (ok_mask[0] != kFull) {               // warp-uniform: a tile wholly inside the scope skips the masking
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ((ok_mask[0] >> j) & 1u) ? v[j] : 0u;
+                    }
+                    const int m0 = max32(v);
+                    tmem_ld32(taddr + 32, v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) remote_arrive(g ? leader_empty1 : leader_empty0);
+                    if (ok_mask[1] != kFull) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ((ok_mask[1] >> j) & 1u) ? v[j] : 0u;
+                    }
+                    const int m1 = max32(v);
+                    if (g) run1 = __vimax3_s32(run1, m0, m1);
+                    else run0 = __vimax3_s32(run0, m0, m1);
+                    continue;
+                }
+                bool multi;
+                uint64_t first_key = group_candidate(v, ok_mask[0], live, gmm, a.id_base + row0, thr, multi);
+                if (multi) {                                   // rare: list work while holding (it covers every lane's candidates)
+                    take_group_multi(v, ok_mask[0], live, a.id_base + row0, list, thr);
+                    first_key = 0ull;
+                }
                 tmem_ld32(taddr + 32, v);
-                // the accumulator's last read is in registers: hand it back before working on the values
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) remote_arrive(g ? leader_empty1 : leader_empty0);
-                take_group(v, ok_mask[1], g ? live1 : live0, gmm, a.id_base + row0 + 32, g ? list1 : list0, g ? thr1 : thr0);
+                if (tl) tl_d[1] = clock64();
+                offer_key(first_key, list, thr);
+                const uint64_t second_key = group_candidate(v, ok_mask[1], live, gmm, a.id_base + row0 + 32, thr, multi);
+                if (multi) take_group_multi(v, ok_mask[1], live, a.id_base + row0 + 32, list, thr);
+                else offer_key(second_key, list, thr);
+                if (tl) tl_d[2] = clock64();
             }
         }
         if (kDebug && a.debug && warp == 2 && lane == 0) {
             unsigned long long *d = a.debug + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
             d[4] = clock64() - e_start; d[5] = w_tfull; 
         }
+        if (kFloorPass) {
+            // one group maximum per (slice, column block, query): [n_slices * 4][nq] u32 in the list buffer
+            uint32_t *vals = reinterpret_cast<uint32_t *>(a.out_lists);
+            const size_t grp = static_cast<size_t>(slice) * kPColBlocks + cb;
+            if (live0) vals[grp * a.nq + q0] = static_cast<uint32_t>(run0);
+            if (live1) vals[grp * a.nq + q0 + 256] = static_cast<uint32_t>(run1);
+        } else {
         // ---- the four column-block lists of a query -> one list, through the (now idle) feature ring:
         // every tile's MMAs have retired (the last "accumulator ready" was awaited above), so neither
         // the tensor core nor the TMA unit touches the ring any more
@@ -404,14 +477,20 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 }
             }
         }
+        }   // !kFloorPass
     }
     if (n_tiles == 0 && warp >= 2 && warp < 2 + 4 * kPGroups) {
-        // a slice without tiles still owes its (empty) lists
+        // a slice without tiles still owes its (empty) lists / group maxima
         const uint32_t lq = warp & 3, g = static_cast<uint32_t>(warp - 2) >> 2;
         const uint32_t q = q_base + rank * 128 + lq * 32 + lane + 256 * g;
         if (q < a.nq) {
-            uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
-            for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
+            if (kFloorPass) {
+                uint32_t *vals = reinterpret_cast<uint32_t *>(a.out_lists);
+                for (int c = 0; c < kPColBlocks; ++c) vals[(static_cast<size_t>(slice) * kPColBlocks + c) * a.nq + q] = 0u;
+            } else {
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+                for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
+            }
         }
     }
     tc_fence_before();
@@ -420,7 +499,47 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// floors[q] = (k-th largest of vals[0 .. n_groups)[q]) << 32: the floor pass's group maxima -> one lower-bound key per
+// query (score word only).  One warp per query; the values sit in shared memory, k rounds of lane maximum ->
+// warp maximum -> the lowest lane holding it retires ONE instance (equal maxima of different groups count separately:
+// each names a different chunk).
+constexpr int kKthWarps = 4;
+__global__ void __launch_bounds__(kKthWarps * 32) kth_largest_kernel(const uint32_t *__restrict__ vals, uint32_t n_groups, uint32_t nq, uint32_t k,
+                                                                  uint64_t *__restrict__ floors) {
+    extern __shared__ uint32_t kth_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kKthWarps + w;
+    if (q >= nq) return;
+    uint32_t *mine = kth_smem + static_cast<size_t>(w) * n_groups;
+    for (uint32_t i = lane; i < n_groups; i += 32) mine[i] = vals[static_cast<size_t>(i) * nq + q];
+    __syncwarp();
+    uint32_t kth = 0;
+    for (uint32_t r = 0; r < k; ++r) {
+        uint32_t best = 0, at = 0;
+        for (uint32_t i = lane; i < n_groups; i += 32) {
+            const uint32_t x = mine[i];
+            if (x > best) { best = x; at = i; }
+        }
+        kth = __reduce_max_sync(kFull, best);
+        if (kth == 0u) break;                                        // fewer than k groups with a positive maximum
+        const uint32_t owners = __ballot_sync(kFull, best == kth);
+        if (lane == __ffs(owners) - 1) mine[at] = 0u;
+        __syncwarp();
+    }
+    if (lane == 0) floors[q] = static_cast<uint64_t>(kth) << 32;
+}
+
 }  // namespace
+
+cudaError_t launch_kth_largest(const uint32_t *vals, uint32_t n_groups, uint32_t nq, uint32_t k, uint64_t *floors, cudaStream_t s) {
+    if (n_groups == 0 || n_groups > 8192 || k == 0 || nq == 0) return cudaErrorInvalidValue;
+    const size_t smem = static_cast<size_t>(kKthWarps) * n_groups * 4;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = ensure_dynamic_smem(kth_largest_kernel, static_cast<int>(smem)); e != cudaSuccess) return e;
+    kth_largest_kernel<<<(nq + kKthWarps - 1) / kKthWarps, kKthWarps * 32, smem, s>>>(vals, n_groups, nq, k, floors);
+    return cudaGetLastError();
+}
+uint32_t gemm_pair_floor_groups(uint32_t n_slices) { return n_slices * kPColBlocks; }
 
 size_t gemm_pair_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * kGemmPairLists * nq * kGemmK * 8; }
 
@@ -430,14 +549,14 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
     if (!make_map(&map_q, q_dev, a.nq) || !make_map(&map_f, F, f_rows)) return cudaErrorNotSupported;
     const int smem = static_cast<int>(sizeof(PairSmem)) + 1024;
     dim3 grid(2 * n_slices, (a.nq + kPGroups * 256 - 1) / (kPGroups * 256), 1);   // x: CTA pairs (cluster dims 2 x 1 x 1)
-    if (a.debug) {
-        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel<true>, smem); e != cudaSuccess) return e;
-        score_topk_gemm_pair_kernel<true><<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
-    } else {
-        if (cudaError_t e = ensure_dynamic_smem(score_topk_gemm_pair_kernel<false>, smem); e != cudaSuccess) return e;
-        score_topk_gemm_pair_kernel<false><<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
-    }
-    return cudaGetLastError();
+    auto go = [&](auto kern) -> cudaError_t {
+        if (cudaError_t e = ensure_dynamic_smem(kern, smem); e != cudaSuccess) return e;
+        kern<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+        return cudaGetLastError();
+    };
+    // floor pass: group maxima only ([n_slices * 4][nq] u32 in out_lists) / main pass: one sorted list per (slice, query)
+    if (a.group_max_mode) return a.debug ? go(score_topk_gemm_pair_kernel<true, true>) : go(score_topk_gemm_pair_kernel<false, true>);
+    return a.debug ? go(score_topk_gemm_pair_kernel<true, false>) : go(score_topk_gemm_pair_kernel<false, false>);
 }
 
 }  // namespace rf
