@@ -263,7 +263,7 @@ def run_reference(args) -> None:
             "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference has no local retriever (gemini_rag.py:704-718); this arm is the frozen RF-1 CPU oracle"}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- other configs
@@ -877,12 +877,31 @@ def run_b200(args) -> None:
             line["cpu_baseline"] = cpu
         if configs:
             line["configs"] = configs
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under torchrun,
+    # for one) goes to stderr instead -- file descriptor 1 is pointed at 2 until emit() writes the line
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
