@@ -129,6 +129,20 @@ int rf_doc_tombstone(rf_engine *e, uint64_t doc_id);
 int rf_snapshot_save(rf_engine *e, const char *path);
 int rf_snapshot_load(rf_engine *e, const char *path);
 
+/* ---- one HBM index, several processes: the reference runs four API worker processes and one
+ * ingest worker (backend/Dockerfile:42, backend/app/worker.py:122-126), each calling get_rag_client()
+ * (gemini_rag.py:721-725).  ONE process (the engine daemon, rag_foundation_b200/server.py) owns the arena.
+ * rf_engine_export writes a description of it -- CUDA IPC handles of the row arrays, geometry, the store table
+ * with its extents -- into buf (call with buf = NULL to learn *len).  ANOTHER process on the same GPU maps the
+ * arena read-only with rf_engine_attach and runs every search entry point of this header on its own streams;
+ * the entry points that change the index fail there with RF_EINVAL (rf_store_open finds existing stores).
+ * Deletes by the owner are visible to readers at once (they mask rows of the shared arena); rows and stores
+ * added later become visible after rf_engine_refresh with a newer export of the same engine.
+ * rf_engine_destroy unmaps.  The owner must outlive its readers' searches. */
+int rf_engine_export(rf_engine *e, void *buf, size_t cap, size_t *len);
+int rf_engine_attach(const void *export_blob, size_t len, uint32_t n_contexts /* 0 -> 8 */, rf_engine **out);
+int rf_engine_refresh(rf_engine *e, const void *export_blob, size_t len);
+
 /* Copy rows [first, first+n) back to the host (tests / snapshots): any of the outputs may be NULL. */
 int rf_rows_read(rf_engine *e, uint64_t first_row, uint64_t n, int8_t *rows, uint32_t *store_seg,
                  int32_t *ff);

@@ -68,6 +68,9 @@ SIGNATURES = {
     "rf_doc_tombstone": (_i32, [_vp, _u64]),
     "rf_snapshot_save": (_i32, [_vp, C.c_char_p]),
     "rf_snapshot_load": (_i32, [_vp, C.c_char_p]),
+    "rf_engine_export": (_i32, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "rf_engine_attach": (_i32, [_vp, _sz, _u32, C.POINTER(_vp)]),
+    "rf_engine_refresh": (_i32, [_vp, _vp, _sz]),
     "rf_rows_read": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp]),
     "rf_search": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "rf_search_begin": (_i32, [_vp, _vp, _u32, _vp, _vp, _u32, C.POINTER(_vp)]),

@@ -390,8 +390,14 @@ class B200Rag:
         else:
             ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges,
                                                           weights=weights)
+        return self.describe_chunks(ids.tolist(), scores.tolist(), cos.tolist())
+
+    def describe_chunks(self, ids: Sequence[int], scores: Sequence[int], cos: Sequence[float]) -> List[dict]:
+        """Chunk ids (rank order) -> grounding contexts: document, chunk number, snippet.  Also what a process that ran
+        the search itself on the shared arena (server.RemoteB200Rag in attach mode) asks the daemon for."""
+        reg = self._reg
         out = []
-        for gid, sc, c in zip(ids.tolist(), scores.tolist(), cos.tolist()):
+        for gid, sc, c in zip(ids, scores, cos):
             hit = reg.chunk_to_doc(int(gid))
             if hit is None:
                 continue

@@ -316,6 +316,7 @@ void copy_pool_destroy(CopyPool *p) {
 
 struct rf_engine {
     rf_config cfg{};
+    bool reader = false;             // attached to another process's arena over CUDA IPC: searches only (rf_engine_attach)
     uint32_t dim = RF_DIM;           // features (= bytes) per row: 256, 512 or 1024
     uint32_t tile_rows = 32;         // rows per scan tile: rf::scan_tile_rows(dim)
     int sm_count = 148;
@@ -581,6 +582,20 @@ uint32_t pick_blocks(rf_engine *e, uint32_t nq, uint32_t max_tiles) {
     const uint32_t fill = (wave + nq - 1) / nq;  // at least one full wave over all queries
     x = std::max(x, fill);
     if (nq == 1) x = wave;                       // single query: exactly one resident wave
+    else if (nq < wave && max_tiles >= 8 && x <= 16) {
+        // A batch smaller than a wave (store-sharded batches leave a rank 1/G of the queries): blocks per query such
+        // that the launch is whole waves -- a last wave that is mostly empty cannot keep HBM busy on its own (128 queries x 3
+        // blocks = 1.3 waves ran 12 % slower than x 2).  Cost of a choice ~ waves x (tiles per block + ~12 tiles of
+        // block start-up and merge).
+        double best = 1e30;
+        uint32_t best_x = x;
+        for (uint32_t c = 1; c <= 32 && c <= max_tiles; ++c) {
+            const double waves = static_cast<double>((static_cast<uint64_t>(nq) * c + wave - 1) / wave);
+            const double cost = waves * (static_cast<double>(max_tiles) / c + 12.0);
+            if (cost < best - 1e-9) { best = cost; best_x = c; }
+        }
+        x = best_x;
+    }
     x = std::min(x, std::max(max_tiles, 1u));
     x = std::min(x, 1024u);                      // the final merge is two tournament levels of 32
     return std::max(x, 1u);
@@ -1142,9 +1157,15 @@ int rf_engine_destroy(rf_engine *e) {
     e->sc_stage.release(); e->sc_ctl_host.release();
     if (e->debug_ts) cudaFree(e->debug_ts);
     if (e->zipf_bucket) cudaFree(e->zipf_bucket);
-    if (e->F) cudaFree(e->F);
-    if (e->seg) cudaFree(e->seg);
-    if (e->ff) cudaFree(e->ff);
+    if (e->reader) {   // the arena belongs to another process: unmap it
+        if (e->F) cudaIpcCloseMemHandle(e->F);
+        if (e->seg) cudaIpcCloseMemHandle(e->seg);
+        if (e->ff) cudaIpcCloseMemHandle(e->ff);
+    } else {
+        if (e->F) cudaFree(e->F);
+        if (e->seg) cudaFree(e->seg);
+        if (e->ff) cudaFree(e->ff);
+    }
     delete e;
     return RF_OK;
 }
@@ -1178,6 +1199,7 @@ int rf_engine_stats(rf_engine *e, rf_stats *out) {
 
 int rf_store_open(rf_engine *e, const char *fs_name, uint32_t *store_seg) {
     if (!e || !fs_name || !store_seg) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return rf_store_lookup(e, fs_name, store_seg);   // a reader cannot create stores; an existing one is found
     std::unique_lock<std::shared_mutex> lk(e->meta_mu);
     auto it = e->store_by_name.find(fs_name);
     if (it != e->store_by_name.end()) { *store_seg = it->second; return RF_OK; }
@@ -1211,6 +1233,7 @@ static int tombstone_extents(rf_engine *e, const std::vector<Extent> &ext) {
 
 int rf_store_drop(rf_engine *e, uint32_t store_seg) {
     if (!e) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process drops stores");
     std::lock_guard<std::mutex> ing(e->ingest_mu);
     std::vector<Extent> ext;
     {
@@ -1228,6 +1251,7 @@ int rf_store_drop(rf_engine *e, uint32_t store_seg) {
 
 int rf_doc_tombstone(rf_engine *e, uint64_t doc_id) {
     if (!e) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process deletes documents");
     std::lock_guard<std::mutex> ing(e->ingest_mu);
     std::vector<Extent> ext;
     {
@@ -1345,6 +1369,7 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
 int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint8_t *utf8, size_t n, uint64_t *first_chunk,
                    uint32_t *n_chunks, int64_t *spans, uint32_t max_spans) {
     if (!e || (!utf8 && n)) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process ingests");
     if (n > 0xFFFFFFF0ull) return fail(RF_EINVAL, "document larger than 4 GiB");
     int rc = check_store(e, store_seg);
     if (rc) return rc;
@@ -1447,6 +1472,7 @@ int rf_host_free(void *p) {
 int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const int8_t *rows, uint64_t n_rows,
                        int rows_on_device, uint64_t *first_chunk) {
     if (!e || (!rows && n_rows)) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process ingests");
     int rc = check_store(e, store_seg);
     if (rc) return rc;
     std::lock_guard<std::mutex> ing(e->ingest_mu);
@@ -1482,6 +1508,7 @@ int rf_ingest_features(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const 
 int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_store, uint64_t seed, uint64_t start_counter,
                         uint64_t n_rows, const uint16_t *zipf_vocab, uint64_t *first_chunk) {
     if (!e || !zipf_vocab) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process ingests");
     const uint64_t n_stores = rows_per_store ? (n_rows + rows_per_store - 1) / rows_per_store : 1;
     {
         std::shared_lock<std::shared_mutex> lk(e->meta_mu);
@@ -1590,6 +1617,7 @@ bool extents_valid(const std::vector<Extent> &v, uint64_t n_rows) {
 
 int rf_snapshot_save(rf_engine *e, const char *path) {
     if (!e || !path) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process writes snapshots");
     std::lock_guard<std::mutex> ing(e->ingest_mu);          // no appends / tombstones while we copy
     std::shared_lock<std::shared_mutex> lk(e->meta_mu);
     RF_CUDA(cudaSetDevice(e->cfg.device));
@@ -1648,6 +1676,7 @@ int rf_snapshot_save(rf_engine *e, const char *path) {
 
 int rf_snapshot_load(rf_engine *e, const char *path) {
     if (!e || !path) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "read-only attachment: the owning process loads snapshots");
     std::lock_guard<std::mutex> ing(e->ingest_mu);
     std::unique_lock<std::shared_mutex> lk(e->meta_mu);
     if (e->n_rows || !e->stores.empty()) return fail(RF_EINVAL, "snapshots load into an empty engine");
@@ -1721,6 +1750,165 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
     for (const Extent &x : e->free_ext) e->free_rows += x.hi - x.lo;
     e->n_rows = h.n_rows;
     e->epoch.fetch_add(1);
+    return RF_OK;
+}
+
+// ---- one HBM index, several processes -----------------------------------------------------
+// The reference runs four API worker processes and one ingest worker (backend/Dockerfile:42, worker.py:122-126).
+// The daemon process owns the arena; rf_engine_export describes it -- CUDA IPC handles of the three row arrays
+// plus the store table -- and another process maps it read-only with rf_engine_attach and then launches its own
+// searches on its own streams.  Deletes are visible to readers at once (they mask rows in the shared arena);
+// new rows and stores after rf_engine_refresh with a newer export.
+namespace {
+struct IpcHeader {
+    char magic[8];                       // "RFB2IPC1"
+    uint32_t dim, device;
+    uint64_t capacity_rows, id_base, n_rows, epoch, n_stores;
+    cudaIpcMemHandle_t h_F, h_seg, h_ff;
+};
+struct BlobWriter {
+    uint8_t *p;
+    size_t cap, len = 0;
+    void put(const void *src, size_t n) {
+        if (p && len + n <= cap) memcpy(p + len, src, n);
+        len += n;
+    }
+};
+struct BlobReader {
+    const uint8_t *p;
+    size_t len, at = 0;
+    bool get(void *dst, size_t n) {
+        if (at + n > len) return false;
+        memcpy(dst, p + at, n);
+        at += n;
+        return true;
+    }
+};
+// store table of an export -> stores / names (validated against n_rows)
+int read_ipc_stores(BlobReader &r, const IpcHeader &h, std::vector<Store> &stores) {
+    if (h.n_stores > (1ull << 32)) return fail(RF_EINVAL, "export: implausible store count");
+    stores.resize(h.n_stores);
+    for (Store &st : stores) {
+        uint32_t len = 0, dropped = 0, n_ext = 0;
+        if (!r.get(&len, 4) || len > (1u << 20)) return fail(RF_EINVAL, "export is truncated or corrupt");
+        st.name.resize(len);
+        if (!r.get(&st.name[0], len) || !r.get(&dropped, 4) || !r.get(&n_ext, 4) || n_ext > h.n_rows + 1)
+            return fail(RF_EINVAL, "export is truncated or corrupt");
+        st.dropped = dropped != 0;
+        st.ext.resize(n_ext);
+        if (!r.get(st.ext.data(), n_ext * sizeof(Extent)) || !extents_valid(st.ext, h.n_rows)) return fail(RF_EINVAL, "export is truncated or corrupt");
+    }
+    return RF_OK;
+}
+}  // namespace
+
+int rf_engine_export(rf_engine *e, void *buf, size_t cap, size_t *len) {
+    if (!e || !len) return fail(RF_EINVAL, "null argument");
+    if (e->reader) return fail(RF_EINVAL, "a read-only attachment cannot be exported again: ask the owning process");
+    RF_CUDA(cudaSetDevice(e->cfg.device));
+    IpcHeader h{};
+    memcpy(h.magic, "RFB2IPC1", 8);
+    h.dim = e->dim;
+    h.device = static_cast<uint32_t>(e->cfg.device);
+    h.capacity_rows = e->cfg.capacity_rows;
+    h.id_base = e->cfg.id_base;
+    RF_CUDA(cudaIpcGetMemHandle(&h.h_F, e->F));
+    RF_CUDA(cudaIpcGetMemHandle(&h.h_seg, e->seg));
+    RF_CUDA(cudaIpcGetMemHandle(&h.h_ff, e->ff));
+    BlobWriter w{static_cast<uint8_t *>(buf), buf ? cap : 0};
+    std::shared_lock<std::shared_mutex> lk(e->meta_mu);     // rows below n_rows are complete: every ingest synchronises before it publishes
+    h.n_rows = e->n_rows;
+    h.epoch = e->epoch.load();
+    h.n_stores = e->stores.size();
+    w.put(&h, sizeof h);
+    for (const Store &st : e->stores) {
+        const uint32_t nlen = static_cast<uint32_t>(st.name.size()), dropped = st.dropped ? 1u : 0u, n_ext = static_cast<uint32_t>(st.ext.size());
+        w.put(&nlen, 4); w.put(st.name.data(), nlen); w.put(&dropped, 4); w.put(&n_ext, 4); w.put(st.ext.data(), n_ext * sizeof(Extent));
+    }
+    *len = w.len;
+    if (buf && w.len > cap) return fail(RF_ENOMEM, "export needs %zu bytes, the buffer holds %zu", w.len, cap);
+    return RF_OK;
+}
+
+int rf_engine_refresh(rf_engine *e, const void *blob, size_t len) {
+    if (!e || !blob) return fail(RF_EINVAL, "null argument");
+    if (!e->reader) return fail(RF_EINVAL, "only a read-only attachment is refreshed");
+    BlobReader r{static_cast<const uint8_t *>(blob), len};
+    IpcHeader h{};
+    if (!r.get(&h, sizeof h) || memcmp(h.magic, "RFB2IPC1", 8) != 0) return fail(RF_EINVAL, "not an engine export");
+    if (h.dim != e->dim || h.capacity_rows != e->cfg.capacity_rows || h.id_base != e->cfg.id_base || static_cast<int>(h.device) != e->cfg.device)
+        return fail(RF_EINVAL, "this export describes a different engine");
+    if (h.n_rows > h.capacity_rows) return fail(RF_EINVAL, "export is corrupt (rows beyond capacity)");
+    std::vector<Store> stores;
+    if (int rc = read_ipc_stores(r, h, stores)) return rc;
+    std::unique_lock<std::shared_mutex> lk(e->meta_mu);
+    e->stores.swap(stores);
+    e->store_by_name.clear();
+    for (uint32_t i = 0; i < e->stores.size(); ++i)
+        if (!e->stores[i].dropped) e->store_by_name.emplace(e->stores[i].name, i);
+    e->n_rows = h.n_rows;
+    e->epoch.fetch_add(1);          // the reader's own epoch: its store table and cached statistics follow
+    return RF_OK;
+}
+
+int rf_engine_attach(const void *blob, size_t len, uint32_t n_contexts, rf_engine **out) {
+    if (!blob || !out) return fail(RF_EINVAL, "null argument");
+    *out = nullptr;
+    BlobReader r{static_cast<const uint8_t *>(blob), len};
+    IpcHeader h{};
+    if (!r.get(&h, sizeof h) || memcmp(h.magic, "RFB2IPC1", 8) != 0) return fail(RF_EINVAL, "not an engine export");
+    if (h.dim != 256 && h.dim != 512 && h.dim != 1024) return fail(RF_EINVAL, "export is corrupt (dim)");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(RF_ENODEVICE, "no CUDA device visible");
+    }
+    if (static_cast<int>(h.device) >= n_dev) return fail(RF_EINVAL, "the exporting process's device %u is not visible here (%d devices)", h.device, n_dev);
+    cudaDeviceProp prop{};
+    RF_CUDA(cudaGetDeviceProperties(&prop, static_cast<int>(h.device)));
+    if (prop.major != 10) return fail(RF_ENODEVICE, "device %u is sm_%d%d; this library holds sm_100a code only", h.device, prop.major, prop.minor);
+    RF_CUDA(cudaSetDevice(static_cast<int>(h.device)));
+    rf_engine *e = new (std::nothrow) rf_engine();
+    if (!e) return fail(RF_ENOMEM, "host allocation failed");
+    e->reader = true;
+    e->cfg.struct_size = sizeof(rf_config);
+    e->cfg.device = static_cast<int>(h.device);
+    e->cfg.dim = h.dim;
+    e->cfg.n_contexts = n_contexts ? n_contexts : 8;
+    e->cfg.capacity_rows = h.capacity_rows;
+    e->cfg.id_base = h.id_base;
+    e->dim = h.dim;
+    e->tile_rows = rf::scan_tile_rows(h.dim);
+    e->sm_count = prop.multiProcessorCount;
+    if (const char *s = getenv("RF_GEMM")) e->gemm_enabled = atoi(s) != 0;
+    if (const char *s = getenv("RF_STORE_TABLE")) e->table_enabled = atoi(s) != 0;
+    cudaError_t ce;
+    void *pF = nullptr, *pS = nullptr, *pN = nullptr;
+    if ((ce = cudaIpcOpenMemHandle(&pF, h.h_F, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess ||
+        (ce = cudaIpcOpenMemHandle(&pS, h.h_seg, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess ||
+        (ce = cudaIpcOpenMemHandle(&pN, h.h_ff, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) {
+        e->F = static_cast<int8_t *>(pF); e->seg = static_cast<uint32_t *>(pS); e->ff = static_cast<int32_t *>(pN);
+        const int rc = fail(RF_ECUDA, "cudaIpcOpenMemHandle failed: %s (the arena must be opened from a process other than its owner)", cudaGetErrorString(ce));
+        cudaGetLastError();
+        rf_engine_destroy(e);
+        return rc;
+    }
+    e->F = static_cast<int8_t *>(pF); e->seg = static_cast<uint32_t *>(pS); e->ff = static_cast<int32_t *>(pN);
+    for (uint32_t i = 0; i < e->cfg.n_contexts; ++i) {
+        SearchCtx *c = new (std::nothrow) SearchCtx();
+        if (!c || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            rf_engine_destroy(e);
+            return fail(RF_ECUDA, "search context creation failed");
+        }
+        e->all_ctx.push_back(c);
+        e->free_ctx.push_back(c);
+    }
+    if (int rc = rf_engine_refresh(e, blob, len)) {
+        rf_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
     return RF_OK;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 import threading
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -196,6 +197,40 @@ class Engine:
     def load_snapshot(self, path: str) -> None:
         """Into a freshly created engine (same id_base, capacity >= the snapshot's rows)."""
         check(self._L.rf_snapshot_load(self.handle, os.fsencode(path)))
+
+    # ---- one index, several processes (CUDA IPC; rf_engine_export / attach / refresh) --------------
+    def export_state(self) -> bytes:
+        """Description of this engine's arena (IPC handles, geometry, store table) for Engine.attach in ANOTHER process."""
+        n = C.c_size_t()
+        check(self._L.rf_engine_export(self.handle, None, 0, C.byref(n)))
+        while True:
+            buf = C.create_string_buffer(int(n.value) + 4096)      # (stores may be added between the two calls)
+            rc = self._L.rf_engine_export(self.handle, buf, len(buf), C.byref(n))
+            if rc == _capi.RF_ENOMEM:
+                continue
+            check(rc)
+            return buf.raw[:int(n.value)]
+
+    @classmethod
+    def attach(cls, blob: bytes, n_contexts: int = 8) -> "Engine":
+        """A read-only engine over the arena another process exported: searches run here, on this process's own
+        streams; ingest / deletes / snapshots stay with the owner."""
+        self = cls.__new__(cls)
+        self._L = lib()
+        h = C.c_void_p()
+        check(self._L.rf_engine_attach(blob, len(blob), int(n_contexts), C.byref(h)))
+        self._h = h
+        dim, device, cap, id_base = struct.unpack_from("<IIQQ", blob, 8)
+        self.dim, self.device, self.capacity_rows, self.id_base = int(dim), int(device), int(cap), int(id_base)
+        self._zipf = None
+        self._lock = threading.Lock()
+        self._csr_cache = {}
+        self.attached = True
+        return self
+
+    def refresh(self, blob: bytes) -> None:
+        """Attached engines: take the owner's newer export (rows and stores added since)."""
+        check(self._L.rf_engine_refresh(self.handle, blob, len(blob)))
 
     def read_rows(self, first_row: int, n: int):
         F = np.zeros((n, self.dim), np.int8)

@@ -38,8 +38,9 @@ import msgpack
 from .adapter import B200Rag, Registry, UploadResult, build_final_response, contents_to_text, get_registry, stream_lead
 
 _ALLOWED = {"create_store", "delete_store", "upload_bytes", "op_status", "delete_document_from_store", "retrieve",
-            "list_stores", "stats", "save"}
-_IDEMPOTENT = {"op_status", "retrieve", "list_stores", "stats", "delete_store", "delete_document_from_store"}
+            "list_stores", "stats", "save", "export_index", "describe_chunks"}
+_IDEMPOTENT = {"op_status", "retrieve", "list_stores", "stats", "delete_store", "delete_document_from_store", "export_index",
+               "describe_chunks"}
 _MAX_FRAME = 64 << 20          # uploads are capped at 25 MB upstream (config.py:118)
 _NONCE = 32
 _NAME_RE = re.compile(r"^[A-Za-z0-9._-]{1,64}$")
@@ -112,6 +113,17 @@ class _Service:
 
     def stats(self) -> dict:
         return self.registry.engine.stats()
+
+    def export_index(self) -> bytes:
+        """CUDA IPC description of the arena (rf_engine_export): a client process on the same GPU maps it read-only and
+        launches its own searches (RemoteB200Rag in attach mode).  One engine only: a group's devices are searched here."""
+        eng = self.registry.engine
+        if not hasattr(eng, "export_state"):
+            raise NotImplementedError("the daemon serves an engine group: attach mode needs a single engine")
+        return eng.export_state()
+
+    def describe_chunks(self, ids, scores, cos) -> list:
+        return self.rag.describe_chunks([int(x) for x in ids], [int(x) for x in scores], [float(x) for x in cos])
 
     def save(self, name: str = "snapshot") -> str:
         """Snapshot into <RAG_B200_SNAPSHOT_DIR>/<name>; the client chooses a plain name, never a path."""
@@ -209,16 +221,61 @@ _EXC = {"TimeoutError": TimeoutError, "ValueError": ValueError, "FileNotFoundErr
         "PermissionError": PermissionError}
 
 
-class RemoteB200Rag:
-    """Client-side adapter: same protocol as B200Rag / GeminiRag, index behind the socket."""
+# attach mode: one read-only engine per (process, daemon socket), shared by the per-request adapter objects
+_attached_lock = threading.Lock()
+_attached: Dict[str, Dict[str, Any]] = {}
 
-    def __init__(self, socket_path: Optional[str] = None, top_k: int = 10):
+
+class RemoteB200Rag:
+    """Client-side adapter: same protocol as B200Rag / GeminiRag, index behind the socket.
+
+    Attach mode (`attach=True` or RAG_B200_ATTACH=1; the daemon and this process on the same GPU): the process maps
+    the daemon's arena read-only over CUDA IPC (Engine.attach) and runs the search itself, on its own streams --
+    the four API workers of the reference deployment (backend/Dockerfile:42) then scan concurrently instead of
+    queueing on the daemon; only the small "which document is chunk N" question still goes over the socket.  The
+    mapping is refreshed from the daemon every RAG_B200_ATTACH_REFRESH_MS (default 200) and whenever a store name
+    is unknown; deletes need no refresh (they mask rows in the shared arena)."""
+
+    def __init__(self, socket_path: Optional[str] = None, top_k: int = 10, attach: Optional[bool] = None, scoring: Optional[str] = None):
         self.socket_path = socket_path or os.environ["RAG_B200_SOCKET"]
         self._key = _authkey()
         self.is_mock = True
         self.is_b200 = True
         self.top_k = top_k
+        self.attach = (os.environ.get("RAG_B200_ATTACH", "0") == "1") if attach is None else bool(attach)
+        self.scoring = (scoring or os.environ.get("RAG_B200_SCORING", "tf")).lower()
+        self._refresh_s = float(os.environ.get("RAG_B200_ATTACH_REFRESH_MS", "200")) / 1e3
         self._local = threading.local()
+
+    def _attached_engine(self, force_refresh: bool = False):
+        import time
+        from .engine import Engine
+        with _attached_lock:
+            slot = _attached.get(self.socket_path)
+            now = time.monotonic()
+            if slot is None:
+                slot = {"engine": Engine.attach(bytes(self._call("export_index"))), "at": now}
+                _attached[self.socket_path] = slot
+            elif force_refresh or now - slot["at"] > self._refresh_s:
+                slot["engine"].refresh(bytes(self._call("export_index")))
+                slot["at"] = now
+            return slot["engine"]
+
+    def _retrieve_attached(self, text: str, store_names: Sequence[str], k: int) -> List[dict]:
+        eng = self._attached_engine()
+        names = list(dict.fromkeys(store_names))
+        segs = [eng.lookup_store(s) for s in names]
+        if any(x is None for x in segs):                    # a store made after the last refresh?
+            eng = self._attached_engine(force_refresh=True)
+            segs = [eng.lookup_store(s) for s in names]
+        segs = [x for x in segs if x is not None]
+        if not segs:
+            return []
+        weights = eng.scope_weights(segs) if self.scoring == "idf" else None
+        ids, scores, cos, _q = eng.search_text(text.encode("utf-8"), segs, k, weights=weights)
+        if len(ids) == 0:
+            return []
+        return self._call("describe_chunks", ids.tolist(), scores.tolist(), cos.tolist())
 
     def _connect(self) -> socket.socket:
         s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
@@ -289,6 +346,8 @@ class RemoteB200Rag:
         self._call("delete_document_from_store", store_name, document_id, filename, file_id)
 
     def retrieve(self, text: str, store_names: Sequence[str], k: Optional[int] = None, metadata_filter=None) -> List[dict]:
+        if self.attach and not metadata_filter:             # (a metadata filter needs the daemon's document table)
+            return self._retrieve_attached(text, store_names, k or self.top_k)
         return self._call("retrieve", text, list(store_names), k or self.top_k, metadata_filter)
 
     def ask(self, *, contents: Any, store_names: Sequence[str], metadata_filter: Optional[Any], model: str,

@@ -222,6 +222,79 @@ def test_daemon_process_ingest_process_query_process(tmp_path, golden_dir):
             daemon.wait(30)
 
 
+@pytest.mark.timeout(300)
+def test_api_process_attaches_to_the_daemons_arena_over_cuda_ipc(tmp_path, golden_dir):
+    """SURVEY 8f-1, second half: an API process maps the daemon's HBM arena read-only (rf_engine_export ->
+    rf_engine_attach over CUDA IPC) and runs the searches ITSELF; only the chunk -> document question goes over the
+    socket.  Its answers equal the daemon's own; a store created later is found after a refresh; a delete by the
+    daemon is visible at once; the attachment refuses to change the index."""
+    import subprocess
+    import sys
+    import textwrap
+    import time
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = json.load(open(os.path.join(golden_dir, "rf1_golden.json")))
+    wire = json.load(open(os.path.join(golden_dir, "config1_wire.json")))
+    sock = str(tmp_path / "rag.sock")
+    env = dict(os.environ, RAG_B200_SOCKET=sock, RAG_B200_AUTHKEY="cuda-ipc-attach-secret-0123456789", RAG_B200_CAPACITY_ROWS="8192",
+               PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    doc = tmp_path / "sample-report.md"
+    doc.write_bytes(g["sample_report"]["text"].encode("utf-8"))
+    doc2 = tmp_path / "long.txt"
+    doc2.write_bytes(g["long_doc"]["text"].encode("utf-8"))
+    code = f"import sys; sys.path.insert(0, {root!r})\nfrom rag_foundation_b200.server import serve; serve()"
+    daemon = subprocess.Popen([sys.executable, "-c", code], env=env, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock):
+                break
+            assert daemon.poll() is None, "daemon died: " + daemon.stderr.read()[-2000:]
+            time.sleep(0.1)
+        api = textwrap.dedent(f"""
+            import json, os
+            from rag_foundation_b200.server import RemoteB200Rag
+            rpc = RemoteB200Rag(attach=False)
+            att = RemoteB200Rag(attach=True)
+            store = rpc.create_store("demo")
+            rpc.upload_file(store, {str(doc)!r}, display_name="sample-report.md")
+            q = {wire["demo_query"]!r}
+            out = {{}}
+            out["same_1"] = att.retrieve(q, [store]) == rpc.retrieve(q, [store]) and len(att.retrieve(q, [store])) >= 1
+            eng = att._attached_engine()
+            out["attached"] = bool(getattr(eng, "attached", False))
+            searches_before = rpc._call("stats")["searches"]
+            for _ in range(5):
+                att.retrieve(q, [store])
+            out["daemon_searches_during_attached_queries"] = rpc._call("stats")["searches"] - searches_before
+            # a second store and document appear AFTER the attachment was made: found through a refresh
+            store2 = rpc.create_store("later")
+            up = rpc.upload_file(store2, {str(doc2)!r}, display_name="long.txt")
+            out["same_2"] = att.retrieve("w5 w17 w30", [store2]) == rpc.retrieve("w5 w17 w30", [store2]) and len(rpc.retrieve("w5 w17 w30", [store2])) >= 1
+            out["same_both"] = att.retrieve("w5 demo flow", [store, store2]) == rpc.retrieve("w5 demo flow", [store, store2])
+            # idf scoring runs its statistics kernel in this process too
+            out["same_idf"] = RemoteB200Rag(attach=True, scoring="idf").retrieve("w5 w17 w30", [store2]) != [] 
+            # a delete by the daemon masks rows in the shared arena: no refresh needed
+            rpc.delete_document_from_store(store2, 0, file_id=up.file_id)
+            out["after_delete"] = att.retrieve("w5 w17 w30", [store2])
+            # the attachment is read-only
+            try:
+                eng.ingest_text(eng.lookup_store(store), 99, b"not allowed here")
+                out["read_only"] = False
+            except RuntimeError as exc:
+                out["read_only"] = "read-only" in str(exc)
+            print(json.dumps(out))
+        """)
+        r = _run_client(api, env)
+        assert r["same_1"] and r["attached"] and r["same_2"] and r["same_both"] and r["same_idf"], r
+        assert r["daemon_searches_during_attached_queries"] == 0, r       # the scans ran in the client process
+        assert r["after_delete"] == [] and r["read_only"] is True, r
+    finally:
+        if daemon.poll() is None:
+            daemon.kill()
+            daemon.wait(30)
+
+
 def test_idf_scoring_through_the_adapter_and_quality_eval(tmp_path):
     """RAG_B200_SCORING=idf (RF-1w): citations rank as the oracle's weighted ranking says, the plain
     adapter on the same registry is unchanged, and the reference-style citation grading runs end to end."""
