@@ -390,18 +390,25 @@ class B200Rag:
         else:
             ids, scores, cos, _q = reg.engine.search_text(text.encode("utf-8"), segs, k or self.top_k, ranges=ranges,
                                                           weights=weights)
-        return self.describe_chunks(ids.tolist(), scores.tolist(), cos.tolist())
+        return self.describe_chunks(ids.tolist(), scores.tolist(), cos.tolist(), store_names)
 
-    def describe_chunks(self, ids: Sequence[int], scores: Sequence[int], cos: Sequence[float]) -> List[dict]:
+    def describe_chunks(self, ids: Sequence[int], scores: Sequence[int], cos: Sequence[float],
+                        store_names: Optional[Sequence[str]] = None) -> List[dict]:
         """Chunk ids (rank order) -> grounding contexts: document, chunk number, snippet.  Also what a process that ran
-        the search itself on the shared arena (server.RemoteB200Rag in attach mode) asks the daemon for."""
+        the search itself on the shared arena (server.RemoteB200Rag in attach mode) asks the daemon for.
+        `store_names`: the request's scope.  Chunk ids are reused after deletes, so between the GPU's tenant test and this
+        lookup an id can have passed to a document of ANOTHER store (delete + ingest racing one search): such a hit is
+        dropped here -- the last line of the tenant mask (security/tenant.py:28-47 decides the scope)."""
         reg = self._reg
+        allowed = None if store_names is None else set(store_names)
         out = []
         for gid, sc, c in zip(ids, scores, cos):
             hit = reg.chunk_to_doc(int(gid))
             if hit is None:
                 continue
             doc, chunk_no = hit
+            if allowed is not None and doc.store_name not in allowed:
+                continue
             b0, b1 = int(doc.spans[chunk_no, 0]), int(doc.spans[chunk_no, 1])
             snippet = doc.data[b0:min(b1, b0 + SNIPPET_MAX_BYTES)].decode("utf-8", "replace")
             out.append({"uri": f"chunk://{doc.store_name}/{doc.doc_id}/{chunk_no}#{gid}", "title": doc.display_name,

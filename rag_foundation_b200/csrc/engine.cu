@@ -992,6 +992,7 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
     g.out_lists = lists;
     g.lists_per_slice = pair ? 0u : rf::gemm_lists_per_slice(nq);
     g.debug = nullptr;
+    if (const char *dm = getenv("RF_GEMM_DBG")) g.dbg_mode = static_cast<uint32_t>(atoi(dm));
     // pass A: group maxima over a sample -> per-query floors (a lower bound of the k-th best score)
     g.floors = nullptr;
     g.group_max_mode = 1;
@@ -2425,7 +2426,9 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
     std::shared_ptr<StreamState> st = stream_state(e, stream);
     std::lock_guard<std::mutex> lk(st->mu);
     const uint32_t X = pick_blocks(e, std::max(nq, 1u), b.max_tiles);
-    const size_t need_partial = static_cast<size_t>(nq) * X * k * 8;
+    // sized for the whole batch and a few blocks per query whatever this call's share is: a rank's share of a batch varies
+    // from call to call, and growing the scratch frees the old one (a device-wide synchronisation, mid-exchange)
+    const size_t need_partial = static_cast<size_t>(std::max(nq, nq_total)) * std::max(X, 4u) * k * 8;
     const size_t need_sync = static_cast<size_t>(nq) * kSyncBytesPerQuery + 8;
     const size_t need_local = px ? static_cast<size_t>(nq) * k * 8 : 0;
     if (b.bytes.size() > st->blob.cap || need_partial > st->partial.cap || need_sync > st->tickets.cap || need_local > st->gemm_keys_a.cap) {

@@ -160,6 +160,9 @@ struct GemmArgs {
     uint32_t lists_per_slice;   // = gemm_lists_per_slice(nq)
     uint32_t group_max_mode;    // 1: floor-finding pass -- keep the top-k of per-32-chunk group maxima, not of chunks
     unsigned long long *debug;  // diagnostics: [block][8] cycle counters, or null
+    uint32_t dbg_mode;          // diagnostics (RF_GEMM_DBG, debug instantiation of the pair kernel only; results are WRONG): the epilogue
+                                // 1 = hands accumulators straight back (tensor-pipe pace alone), 2 = reads them but looks at nothing,
+                                // 3 = + the maximum trees, 4 = + the threshold vote
 };
 // accumulator replicas per M-tile when a block holds fewer than four M-tiles (1 -> 4, 2 -> 2, else 1)
 __host__ __device__ inline uint32_t gemm_replicas(uint32_t m_tiles) { return m_tiles == 1 ? 4u : m_tiles == 2 ? 2u : 1u; }

@@ -122,8 +122,9 @@ class _Service:
             raise NotImplementedError("the daemon serves an engine group: attach mode needs a single engine")
         return eng.export_state()
 
-    def describe_chunks(self, ids, scores, cos) -> list:
-        return self.rag.describe_chunks([int(x) for x in ids], [int(x) for x in scores], [float(x) for x in cos])
+    def describe_chunks(self, ids, scores, cos, store_names=None) -> list:
+        return self.rag.describe_chunks([int(x) for x in ids], [int(x) for x in scores], [float(x) for x in cos],
+                                        None if store_names is None else [str(s) for s in store_names])
 
     def save(self, name: str = "snapshot") -> str:
         """Snapshot into <RAG_B200_SNAPSHOT_DIR>/<name>; the client chooses a plain name, never a path."""
@@ -275,7 +276,7 @@ class RemoteB200Rag:
         ids, scores, cos, _q = eng.search_text(text.encode("utf-8"), segs, k, weights=weights)
         if len(ids) == 0:
             return []
-        return self._call("describe_chunks", ids.tolist(), scores.tolist(), cos.tolist())
+        return self._call("describe_chunks", ids.tolist(), scores.tolist(), cos.tolist(), names)
 
     def _connect(self) -> socket.socket:
         s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)

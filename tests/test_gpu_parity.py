@@ -486,7 +486,7 @@ def test_gemm_path_parity(co, zb, n_rows, nq, k):
         seg = np.full(n_rows, s, np.uint32)
         Q = np.stack([co.synth_query(21, i, zb) for i in range(nq)])
         keys = _device_batch(e, Q, [s], k)
-        assert e.stats()["kernel_launches"] - launches0 == 4, "the batched search should have taken the GEMM path"
+        assert e.stats()["kernel_launches"] - launches0 in (4, 5), "the batched search should have taken the GEMM path"   # (pair kernel: + the tile-purity pass)
         step = max(1, nq // 48)
         for i in list(range(0, nq, step)) + [nq - 1]:
             want = co.score_topk_keys(F, seg, Q[i], [s], k=k, id_base=7)
