@@ -350,7 +350,10 @@ def test_ingest_text_edge_cases(co):
              b" ".join(b"w%d" % i for i in range(128)), b" ".join(b"w%d" % i for i in range(129)),
              b" ".join(b"w%d" % i for i in range(144)), b" ".join(b"w%d" % i for i in range(145)),
              b"A" + b" " * 4095 + b"the" + b" " * 4093 + b"an bc",       # tokens straddling 4 KB block edges
-             b"q" * 4095 + b" " + b"r" * 4097 + b" the", b"ab" * 2047 + b"the" + b" x"]
+             b"q" * 4095 + b" " + b"r" * 4097 + b" the", b"ab" * 2047 + b"the" + b" x",
+             # ... and the 16 KB edges of a tokeniser block / the 4 KB rounds inside it
+             b"A" + b" " * 16383 + b"the" + b" " * 16381 + b"an bc", b"w " * 8191 + b"the" + b" x y", b"q" * 16383 + b" " + b"r" * 16385 + b" the",
+             (b"tok " * 4096)[:16383] + b"the an a tail", b" " * 16380 + b"edge" + b"word more" + b" " * 4090 + b"lastthe"]
     with _engine(8192) as e:
         s = e.open_store("fileSearchStores/a")
         nxt = 0
