@@ -519,6 +519,259 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     if (warp == kPProducerWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// ---- 1024-feature rows (K = 1024): the same pair kernel with the K dimension streamed -----------------------------
+// A row is four 256-byte K-slabs.  A CTA keeps its 128 queries of ONE M-group resident with all of K (128 KB), so a pair
+// owns 256 queries; a chunk tile's B operand arrives as four ring stages (one K-slab of this CTA's 128 rows each, 32 KB,
+// three stages), the tile's 4 x 8 MMAs accumulate into one 256-column accumulator and the two accumulators alternate by
+// TILE.  Per tile the epilogue has one accumulator to drain per 4096 cycles of MMA time, so it is never the limit here;
+// with 256 queries per pair the pass is HBM-bound instead (256 KB of features per pair and tile): a batch of up to 256
+// queries costs one streaming pass over the scope, larger batches one pass per 256 queries that mostly hits L2 (the query
+// groups of a slice run side by side).
+constexpr int kWSlabs = 4;
+constexpr int kWStages = 3;
+struct WideSmem {
+    alignas(1024) uint8_t q[kWSlabs][2][kTileKBlock];      // 128 KB: this CTA's 128 queries, every K-slab
+    alignas(1024) uint8_t b[kWStages][2][kTileKBlock];     // 96 KB: K-slabs of this CTA's half of the chunk tiles
+    alignas(8) uint64_t q_full;                            // leader's copy in use
+    uint64_t full[kWStages];                               // leader's copy in use
+    uint64_t empty[kWStages];                              // own copy (multicast commit)
+    uint64_t tmem_full[2];                                 // own copy (multicast commit)
+    uint64_t tmem_empty[2];                                // leader's copy in use (2 x 16 warp arrivals)
+    uint32_t tmem_base;
+};
+
+template <bool kFloorPass>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
+score_topk_gemm_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t pair_smem_raw[];
+    WideSmem &sm = *reinterpret_cast<WideSmem *>((reinterpret_cast<uintptr_t>(pair_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t slice = blockIdx.x >> 1, n_slices = gridDim.x >> 1, qgroup = blockIdx.y;
+    const uint32_t total_tiles = (a.row_hi - a.row_lo + kPN - 1) / kPN;
+    const uint32_t t_lo = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * slice / n_slices);
+    const uint32_t t_hi = static_cast<uint32_t>(static_cast<uint64_t>(total_tiles) * (slice + 1) / n_slices);
+    const uint32_t n_tiles = t_hi - t_lo;
+    const uint32_t q_base = qgroup * 256;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.q_full, 2);
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&sm.full[s], 2); mbar_init(&sm.empty[s], 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&sm.tmem_full[g], 1); mbar_init(&sm.tmem_empty[g], 2 * kPEpiWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kPProducerWarp) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    uint32_t sm_a;
+    {
+        const uint32_t raw_a = smem_u32(pair_smem_raw);
+        const uint32_t aligned = (raw_a + 1023u) & ~1023u;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sm_a) : "r"(aligned));
+    }
+    const uint32_t a_q_full = sm_a + static_cast<uint32_t>(offsetof(WideSmem, q_full));
+    const uint32_t a_full = sm_a + static_cast<uint32_t>(offsetof(WideSmem, full));
+    const uint32_t a_empty = sm_a + static_cast<uint32_t>(offsetof(WideSmem, empty));
+    const uint32_t a_tmem_full = sm_a + static_cast<uint32_t>(offsetof(WideSmem, tmem_full));
+    const uint32_t a_tmem_empty = sm_a + static_cast<uint32_t>(offsetof(WideSmem, tmem_empty));
+
+    if (warp == kPProducerWarp) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0 && n_tiles) {
+            const uint32_t leader_q_full = map_to_cta_a(a_q_full, 0);
+            remote_arrive_expect_tx(leader_q_full, kWSlabs * 2 * kTileKBlock);
+            for (int sl = 0; sl < kWSlabs; ++sl)
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_2d_pair(sm.q[sl][kb], &map_q, sl * 256 + kb * kKBlockBytes, static_cast<int>(q_base + rank * 128), leader_q_full);
+            for (uint32_t i = 0; i < n_tiles * kWSlabs; ++i) {            // i: (tile, K-slab) in issue order
+                const uint32_t t = i / kWSlabs, sl = i % kWSlabs, s = i % kWStages;
+                if (i >= kWStages) mbar_wait_a(a_empty + 8 * s, ((i / kWStages) - 1) & 1);
+                const uint32_t row0 = a.row_lo + (t_lo + t) * kPN + rank * 128;
+                const uint32_t leader_full = map_to_cta_a(a_full + 8 * s, 0);
+                remote_arrive_expect_tx(leader_full, 2 * kTileKBlock);
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_2d_pair(sm.b[s][kb], &map_f, static_cast<int>(sl * 256 + kb * kKBlockBytes), static_cast<int>(row0), leader_full);
+            }
+        }
+        __syncwarp();
+    } else if (warp == kPMmaWarp) {
+        // ===== MMA issuer (leader CTA) =====
+        if (rank == 0 && n_tiles) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kPN >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+            constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);        // SBO = 1024 B, version 1, SWIZZLE_128B
+            const uint32_t q_lo0 = ((smem_u32(&sm.q[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(&sm.b[0][0][0]) & 0x3FFFFu) >> 4) | (1u << 16);
+            constexpr uint32_t kKBlockStep = kTileKBlock >> 4;
+            mbar_wait_a(a_q_full, 0);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t acc = t & 1u;
+                if (t >= 2) mbar_wait_a(a_tmem_empty + 8 * acc, ((t >> 1) - 1) & 1);    // both CTAs' epilogues drained this accumulator
+                for (uint32_t sl = 0; sl < kWSlabs; ++sl) {
+                    const uint32_t i = t * kWSlabs + sl, s = i % kWStages;
+                    mbar_wait_a(a_full + 8 * s, (i / kWStages) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t q_lo = q_lo0 + sl * 2 * kKBlockStep, b_lo = b_lo0 + s * 2 * kKBlockStep;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (q_lo + kb * kKBlockStep + 2u * k);
+                                const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + kb * kKBlockStep + 2u * k);
+                                if (sl | kb | k) umma2_i8<true>(tmem + acc * kPN, da, db, idesc);
+                                else umma2_i8<false>(tmem + acc * kPN, da, db, idesc);
+                            }
+                        }
+                        umma2_commit_both_a(a_empty + 8 * s);              // the K-slab's stage is free once these MMAs retire
+                        if (sl == kWSlabs - 1) umma2_commit_both_a(a_tmem_full + 8 * acc);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+    } else if (n_tiles) {
+        // ===== epilogue (both CTAs): warp -> lane quarter lq, column block cb; thread -> one query =====
+        const uint32_t lq = warp & 3;
+        const uint32_t cb = static_cast<uint32_t>(warp) >> 2;
+        const uint32_t n_scope = a.n_scope;
+        const uint32_t q0 = q_base + rank * 128 + lq * 32 + lane;
+        const bool live = q0 < a.nq;
+        RegList list;
+        list.clear();
+        uint64_t thr = (a.floors && live) ? a.floors[q0] : 0ull;
+        int run = 0;
+        const uint32_t leader_empty[2] = {map_to_cta_a(a_tmem_empty, 0), map_to_cta_a(a_tmem_empty + 8, 0)};
+        const uint32_t sc0 = a.scope[0], sc1 = a.scope[1], sc2 = a.scope[2], sc3 = a.scope[3];
+        const uint32_t row_hi = a.row_hi;
+        const uint32_t *__restrict__ seg_words = a.seg;
+        auto in_scope = [&](uint32_t sg) {
+            bool ok = (sg == sc0) | (sg == sc1) | (sg == sc2) | (sg == sc3);
+            if (n_scope > 4)
+                for (uint32_t x = 4; x < n_scope; ++x) ok |= (sg == a.scope[x]);
+            return ok && sg != kTombstone;
+        };
+        uint32_t seg_next[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t row = a.row_lo + t_lo * kPN + cb * 64 + h * 32 + lane;
+            seg_next[h] = row < row_hi ? __ldg(seg_words + row) : kTombstone;
+        }
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t row0 = a.row_lo + (t_lo + t) * kPN + cb * 64;
+            uint32_t ok_mask[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t row = row0 + h * 32 + lane;
+                ok_mask[h] = __ballot_sync(kFull, row < row_hi && in_scope(seg_next[h]));
+            }
+            if (t + 1 < n_tiles) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t row = row0 + kPN + h * 32 + lane;
+                    seg_next[h] = row < row_hi ? __ldg(seg_words + row) : kTombstone;
+                }
+            }
+            const uint32_t acc = t & 1u;
+            mbar_wait_a(a_tmem_full + 8 * acc, (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((lq * 32u) << 16) + acc * kPN + cb * 64;
+            uint32_t v[32];
+            tmem_ld32(taddr, v);
+            if (kFloorPass) {
+                if (ok_mask[0] != kFull) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((ok_mask[0] >> j) & 1u) ? v[j] : 0u;
+                }
+                const int m0 = max32(v);
+                tmem_ld32(taddr + 32, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) remote_arrive(leader_empty[acc]);
+                if (ok_mask[1] != kFull) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((ok_mask[1] >> j) & 1u) ? v[j] : 0u;
+                }
+                run = __vimax3_s32(run, m0, max32(v));
+                continue;
+            }
+            bool multi;
+            uint64_t first_key = group_candidate(v, ok_mask[0], live, false, a.id_base + row0, thr, multi);
+            if (multi) {
+                take_group_multi(v, ok_mask[0], live, a.id_base + row0, list, thr);
+                first_key = 0ull;
+            }
+            tmem_ld32(taddr + 32, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) remote_arrive(leader_empty[acc]);
+            offer_key(first_key, list, thr);
+            const uint64_t second_key = group_candidate(v, ok_mask[1], live, false, a.id_base + row0 + 32, thr, multi);
+            if (multi) take_group_multi(v, ok_mask[1], live, a.id_base + row0 + 32, list, thr);
+            else offer_key(second_key, list, thr);
+        }
+        if (kFloorPass) {
+            uint32_t *vals = reinterpret_cast<uint32_t *>(a.out_lists);
+            if (live) vals[(static_cast<size_t>(slice) * kPColBlocks + cb) * a.nq + q0] = static_cast<uint32_t>(run);
+        } else {
+            // the four column-block lists of a query -> one list, through the (now idle) feature ring
+            uint64_t *stage = reinterpret_cast<uint64_t *>(&sm.b[0][0][0]);       // [cb][128 rows][k]: 40 KB of the 96 KB ring
+            const uint32_t row_in_cta = lq * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < kGemmK; ++i) stage[(cb * 128 + row_in_cta) * kGemmK + i] = list.e[i];
+            asm volatile("bar.sync 1, %0;" ::"n"(kPEpiWarps * 32) : "memory");
+            if (cb == 0 && live) {
+                const uint64_t *src = stage + static_cast<size_t>(row_in_cta) * kGemmK;
+                uint32_t pos[kPColBlocks];
+                uint64_t head[kPColBlocks];
+#pragma unroll
+                for (int c = 0; c < kPColBlocks; ++c) { pos[c] = 0; head[c] = src[static_cast<size_t>(c) * 128 * kGemmK]; }
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q0) * kGemmK;
+#pragma unroll
+                for (int i = 0; i < kGemmK; ++i) {
+                    uint64_t best = head[0];
+                    int bc = 0;
+#pragma unroll
+                    for (int c = 1; c < kPColBlocks; ++c)
+                        if (head[c] > best) { best = head[c]; bc = c; }
+                    dst[i] = best;
+#pragma unroll
+                    for (int c = 0; c < kPColBlocks; ++c)
+                        if (c == bc) {
+                            ++pos[c];
+                            head[c] = pos[c] < static_cast<uint32_t>(kGemmK) ? src[static_cast<size_t>(c) * 128 * kGemmK + pos[c]] : 0ull;
+                        }
+                }
+            }
+        }
+    }
+    if (n_tiles == 0 && warp < 4) {
+        // a slice without tiles still owes its (empty) list / group maxima
+        const uint32_t q = q_base + rank * 128 + (warp & 3) * 32 + lane;
+        if (q < a.nq) {
+            if (kFloorPass) {
+                uint32_t *vals = reinterpret_cast<uint32_t *>(a.out_lists);
+                for (int c = 0; c < kPColBlocks; ++c) vals[(static_cast<size_t>(slice) * kPColBlocks + c) * a.nq + q] = 0u;
+            } else {
+                uint64_t *dst = a.out_lists + (static_cast<size_t>(slice) * a.nq + q) * kGemmK;
+                for (int i = 0; i < kGemmK; ++i) dst[i] = 0ull;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kPProducerWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 // floors[q] = (k-th largest of vals[0 .. n_groups)[q]) << 32: the floor pass's group maxima -> one lower-bound key per
 // query (score word only).  One warp per query; the values sit in shared memory, k rounds of lane maximum ->
 // warp maximum -> the lowest lane holding it retires ONE instance (equal maxima of different groups count separately:
@@ -577,6 +830,33 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
     // floor pass: group maxima only ([n_slices * 4][nq] u32 in out_lists) / main pass: one sorted list per (slice, query)
     if (a.group_max_mode) return a.debug ? go(score_topk_gemm_pair_kernel<true, true>) : go(score_topk_gemm_pair_kernel<false, true>);
     return a.debug ? go(score_topk_gemm_pair_kernel<true, false>) : go(score_topk_gemm_pair_kernel<false, false>);
+}
+
+// 1024-feature rows: [rows, 1024] int8 -> boxes of 128 rows x 128 bytes, 128-byte swizzle
+static bool make_map_wide(CUtensorMap *map, const void *base, uint64_t rows) {
+    gemm::EncodeTiledFn enc = gemm::encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {1024, rows};
+    cuuint64_t strides[1] = {1024};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t gemm_wide_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * nq * gemm::kGemmK * 8; }
+
+cudaError_t launch_score_topk_gemm_wide(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices, cudaStream_t s) {
+    CUtensorMap map_q, map_f;
+    if (!make_map_wide(&map_q, q_dev, a.nq) || !make_map_wide(&map_f, F, f_rows)) return cudaErrorNotSupported;
+    const int smem = static_cast<int>(sizeof(WideSmem)) + 1024;
+    dim3 grid(2 * n_slices, (a.nq + 255) / 256, 1);
+    auto go = [&](auto kern) -> cudaError_t {
+        if (cudaError_t e = ensure_dynamic_smem(kern, smem); e != cudaSuccess) return e;
+        kern<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
+        return cudaGetLastError();
+    };
+    return a.group_max_mode ? go(score_topk_gemm_wide_kernel<true>) : go(score_topk_gemm_wide_kernel<false>);
 }
 
 }  // namespace rf

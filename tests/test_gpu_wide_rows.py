@@ -138,7 +138,7 @@ def test_store_mask_tombstones_and_batches(co, zbs, dim):
             ids, sc, cs, cnt = e.search(np.stack([q] * len(scopes)), scopes, k=10)     # per-query scopes (store table)
             for i, scope in enumerate(scopes):
                 _check(co, (ids[i], sc[i], cs[i], cnt[i]), F, seg, q, scope, 10, 0, ff)
-        # a same-scope batch (shared plan; wider rows have no tensor-core route: nq scans in one launch)
+        # a same-scope batch (shared plan: nq scans in one launch, or the K = 1024 tensor-core kernel when it pays)
         Q = np.stack([co.synth_query(9, 10 + i, zb, dim=dim) for i in range(70)])
         ids, sc, cs, cnt = e.search(Q, [stores] * 70, k=10)
         for i in range(0, 70, 9):
@@ -246,6 +246,70 @@ def test_group_of_two_engines_equals_single_engine(co, zbs, dim):
         ids, sc, cs, q = g.search_text(b"17 4242 9", [gs], 10)
         wq = co.query_vector(b"17 4242 9", dim)
         assert (q == wq).all()
+
+
+def _device_batch(e, Q, scope, k):
+    import torch
+    qd = torch.from_numpy(np.ascontiguousarray(Q)).cuda()
+    out = torch.zeros((Q.shape[0], k), dtype=torch.int64, device="cuda")
+    e.search_keys_device(qd.data_ptr(), Q.shape[0], scope, k, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("n_rows,nq,k", [(100_001, 300, 10), (65_536, 128, 10), (200_000, 1024, 10), (150_000, 513, 3), (70_000, 17, 1)])
+def test_wide_gemm_path_parity(co, zbs, n_rows, nq, k):
+    """D = 1024 batches on the tensor cores (K = 1024 pair kernel: K streamed in four slabs, accumulators alternating by
+    tile) == oracle: ragged query groups, a ragged last chunk tile, k < 10."""
+    dim = 1024
+    zb = zbs[dim]
+    with _engine(n_rows + 200, dim, id_base=7) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=21, start_counter=0, n_rows=n_rows)
+        l0 = e.stats()["kernel_launches"]
+        F = co.synth_rows(21, 0, n_rows, zb, dim=dim)
+        seg = np.full(n_rows, s, np.uint32)
+        Q = np.stack([co.synth_query(21, i, zb, dim=dim) for i in range(nq)])
+        keys = _device_batch(e, Q, [s], k)
+        assert e.stats()["kernel_launches"] - l0 == 4, "the batch should have taken the tensor-core path (floor pass, k-th largest, main pass, merge)"
+        for i in range(0, nq, max(1, nq // 40)):
+            assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], [s], k=k, id_base=7).tolist(), i
+        # the same batch through the host entry point
+        ids, sc, cs, cnt = e.search(Q, [[s]] * nq, k=k)
+        got = (sc.astype(np.int64).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - ids)
+        assert (got == keys).all()
+
+
+def test_wide_gemm_masks_saturation_and_heavy_queries(co, zbs):
+    """K = 1024 kernel under the tenant mask (two stores interleaved in the scored range, tombstones), with saturated
+    features (127) and queries that hit every K-slab."""
+    dim = 1024
+    zb = zbs[dim]
+    rng = np.random.default_rng(11)
+    with _engine(90_000, dim) as e:
+        a = e.open_store("fileSearchStores/a"); b = e.open_store("fileSearchStores/b")
+        parts, segs, start = [], [], 0
+        for d in range(8):
+            n = 9000 + 113 * d
+            rows = co.synth_rows(33, start, n, zb, dim=dim)
+            if d == 2:
+                rows[::7, ::5] = 127                      # saturated features in every K-slab
+            st = a if d % 3 else b
+            e.ingest_features(st, d + 1, rows)
+            parts.append(rows); segs.append(np.full(n, st, np.uint32)); start += n
+        e.tombstone_doc(5)
+        segs[4][:] = 0xFFFFFFFF
+        F = np.concatenate(parts); seg = np.concatenate(segs)
+        Q = np.stack([co.synth_query(33, i, zb, dim=dim) for i in range(40)])
+        Q[3] = rng.integers(0, 4, dim).astype(np.int8)    # dense query: every feature position counts
+        Q[4] = 127
+        Q[5] = 0
+        for scope in ([a], [a, b]):
+            keys = _device_batch(e, Q, scope, 10)
+            for i in range(0, 40, 3):
+                assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], scope, k=10).tolist(), (scope, i)
+            for i in (3, 4, 5):
+                assert keys[i].tolist() == co.score_topk_keys(F, seg, Q[i], scope, k=10).tolist(), (scope, i)
 
 
 def test_one_million_wide_chunks_parity(co, zbs):
