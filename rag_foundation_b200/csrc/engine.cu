@@ -969,7 +969,8 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
     // rows of the floor pass: the pair kernel's is branch-free (running maxima, no lists) and takes a sample twice the
     // single-CTA kernel's -- the main pass then meets half the candidates (RF_GEMM_SAMPLE sets the latter; measured at
     // 1024 x 1 M: 64 Ki rows 0.219 ms, 128 Ki 0.208, 256 Ki 0.213 -- tools/cfg2_sample_sweep.sh)
-    uint32_t sample = std::min(rows / 4, pair ? e->gemm_sample * 2 : e->gemm_sample) / tile_rows * tile_rows;
+    // (the K = 1024 kernel's epilogue idles most of the time: candidates are cheap there, a 32 Ki-row sample is enough)
+    uint32_t sample = std::min(rows / 4, wide ? e->gemm_sample / 2 : pair ? e->gemm_sample * 2 : e->gemm_sample) / tile_rows * tile_rows;
     uint32_t n_a = std::max(1u, std::min(slices_full, sample / tile_rows));
     if (e->gemm_slices_a) n_a = std::max(1u, std::min(n_a, e->gemm_slices_a));
     const uint32_t n_b = std::max(1u, std::min(slices_full, (rows + tile_rows - 1) / tile_rows));

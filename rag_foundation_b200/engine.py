@@ -81,6 +81,28 @@ def _search_text(owner, call, text: bytes, scope: Sequence[int], k: int, ranges,
     return ids[:m], sc[:m], cs[:m], q
 
 
+class PendingSearch:
+    """A search in flight (Engine.search_begin).  `result()` must be called exactly once."""
+
+    def __init__(self, engine, handle, nq: int, k: int):
+        self._e, self._p, self._nq, self._k = engine, handle, nq, k
+
+    def result(self):
+        """-> ids uint64 [nq,k], scores int32, cos float32, counts uint32 (as Engine.search)."""
+        e, p = self._e, self._p
+        if p is None:
+            raise RuntimeError("result() was already taken")
+        self._p = None
+        ids = np.empty((self._nq, self._k), np.uint64)
+        sc = np.empty((self._nq, self._k), np.int32)
+        cs = np.empty((self._nq, self._k), np.float32)
+        cnt = np.empty(self._nq, np.uint32)
+        rc = e._L.rf_search_end(e._h, p, _ptr(ids), _ptr(sc), _ptr(cs), _ptr(cnt), None)
+        if rc:
+            check(rc)
+        return ids, sc, cs, cnt
+
+
 class Engine:
     """One GPU's share of the chunk index (feature arena in HBM + store extents)."""
 
@@ -270,6 +292,32 @@ class Engine:
         if rc:
             check(rc)
         return ids, sc, cs, cnt
+
+    def search_begin(self, q, scopes: Sequence[Sequence[int]], k: int = 10) -> "PendingSearch":
+        """First half of `search` (rf_search_begin): validates, takes a search context and enqueues the work, returns at
+        once.  `.result()` (rf_search_end) blocks until the answer is in host memory.  A serving loop keeps a few of
+        these in flight per thread -- each on its own context and stream -- so one query's host work and result
+        delivery overlap the next query's scan."""
+        q = np.ascontiguousarray(q, dtype=np.int8).reshape(-1, self.dim)
+        nq = q.shape[0]
+        if isinstance(scopes, tuple) and len(scopes) == 2 and isinstance(scopes[0], np.ndarray):
+            segs = np.ascontiguousarray(scopes[0], dtype=np.uint32)
+            off = np.ascontiguousarray(scopes[1], dtype=np.uint32)
+        else:
+            if len(scopes) != nq:
+                raise ValueError("one scope per query")
+            key = tuple(tuple(s) for s in scopes) if nq <= 4 else None
+            csr = self._csr_cache.get(key) if key is not None else None
+            if csr is None:
+                csr = scopes_to_csr(scopes)
+                if key is not None and len(self._csr_cache) < 1024:
+                    self._csr_cache[key] = csr
+            segs, off = csr
+        p = C.c_void_p()
+        rc = self._L.rf_search_begin(self._h, _ptr(q), nq, _ptr(segs), _ptr(off), k, C.byref(p))
+        if rc:
+            check(rc)
+        return PendingSearch(self, p, nq, k)
 
     def search_text(self, text: bytes, scope: Sequence[int], k: int = 10, ranges=None, weights=None):
         """-> ids uint64 [m], scores int32 [m], cos float32 [m], q int8 [dim]   (m <= k results).
