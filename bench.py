@@ -884,23 +884,9 @@ def run_b200(args) -> None:
                 for i in range(e2e_steps):
                     qi = i % N_DISTINCT_QUERIES
                     grp.search(Qh[qi:qi + 1], [[gs]], k=k)
-                e2e_seq_s = time.perf_counter() - t0
-                # two callers (the chat route serves up to 50 streams per process, routes/chat.py:40): two searches in flight,
-                # each query still travels from a host buffer to every GPU and its merged result comes back
-                half = e2e_steps // 2
-
-                def _pair_client(tid):
-                    for i in range(half):
-                        qi = (tid * 31 + i) % N_DISTINCT_QUERIES
-                        grp.search(Qh[qi:qi + 1], [[gs]], k=k)
-                pts = [threading.Thread(target=_pair_client, args=(t,)) for t in range(2)]
-                t0 = time.perf_counter()
-                [t.start() for t in pts]
-                [t.join() for t in pts]
-                e2e_s = (time.perf_counter() - t0) * e2e_steps / max(1, 2 * half)
+                e2e_s = time.perf_counter() - t0
                 h2d, d2h = n_gpus * (256 + 80 + 48), n_gpus * (k * 16 + 4)
-                api = (f"rf_group_search: one process, {n_gpus} engines (what B200Rag.retrieve calls with RAG_B200_DEVICES), host buffers, host-merged "
-                       "top-k; two host threads = two searches in flight; sequential_ms_per_query = one caller, nothing in flight")
+                api = f"rf_group_search: one process, {n_gpus} engines (what B200Rag.retrieve calls with RAG_B200_DEVICES), host buffers, host-merged top-k; one caller, nothing in flight (4 callers: qps_4_host_threads)"
                 n_thr, per_thr = 4, max(25, e2e_steps // 8)
 
                 def _gclient(tid):
@@ -992,6 +978,10 @@ def emit(line: dict) -> None:
 def main() -> None:
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under torchrun,
     # for one) goes to stderr instead -- file descriptor 1 is pointed at 2 until emit() writes the line
+    # watchdog: a hung run (a peer that never arrives, a wedged driver call) dumps every thread's stack to stderr and exits
+    # instead of sitting on the GPU box until the caller's limit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
