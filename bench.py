@@ -624,7 +624,8 @@ def leg_wide(torch, dev, hbm_peak, steps: int, sample_parity: bool, dim: int = 1
         return {"batched": batched, "workload": f"configs[1] with wider rows: 1M chunks x {dim} int8 features, 1 query at a time, top-10 on 1 B200", "dim": dim,
                 "kernel": "score_topk_scan_tma_kernel<6, 12, %d>" % (dim // 256), "ms_per_query": ms, "qps": 1e3 / ms, "chunks_per_s": n / (ms * 1e-3),
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "frac_of_8TBps": gbs / 8000.0},
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "frac_of_8TBps": gbs / 8000.0,
+                             "traffic": load_traffic("wide1024") if dim == 1024 else None},
                 "e2e_ms_per_query": e2e_ms, "api": "rf_search (host buffers)", "parity_mismatches": bad, "parity_checked": 8 if sample_parity else 0}
 
 
