@@ -64,6 +64,9 @@ typedef struct rf_stats {
     uint64_t searches;        /* queries answered                             */
     uint64_t kernel_launches; /* kernels launched by this engine since create */
     uint64_t free_rows;       /* rows below n_rows given back by deletes, waiting to be reused */
+    uint64_t ingest_bytes;    /* text bytes featurised by rf_ingest_text                       */
+    uint64_t ingest_kernel_ns;/* device time from the first tokeniser launch to the end of the rows kernel
+                                 (CUDA events on the ingest stream), summed over those documents */
 } rf_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

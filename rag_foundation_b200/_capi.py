@@ -44,7 +44,8 @@ RF_GROUP_MAX = 8
 class rf_stats(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("capacity_rows", C.c_uint64), ("n_stores", C.c_uint64),
                 ("n_docs", C.c_uint64), ("hbm_bytes", C.c_uint64), ("searches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("free_rows", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("free_rows", C.c_uint64), ("ingest_bytes", C.c_uint64),
+                ("ingest_kernel_ns", C.c_uint64)]
 
 
 # name -> (restype, argtypes); the test-suite checks every one of these is exported

@@ -349,7 +349,8 @@ struct rf_engine {
     uint32_t stage_threads = 1;      // (on the measured hosts aggregate memcpy bandwidth stops scaling at two threads)
     PinnedBuf sc_ctl_host;           // control words read back per document
     struct CopyPool *copy_pool = nullptr;   // helper threads that fill the staging ring (created on the first large document)
-    std::atomic<uint64_t> ingest_bytes{0}, ingest_ns{0};
+    std::atomic<uint64_t> ingest_bytes{0}, ingest_ns{0}, ingest_kernel_ns{0};
+    cudaEvent_t ingest_ev[4] = {};   // ingest stream: before the first / after the last tokeniser launch, before / after the rows kernel
 
     std::mutex ctx_mu;
     std::condition_variable ctx_cv;
@@ -1162,6 +1163,8 @@ int rf_engine_destroy(rf_engine *e) {
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ingest_idle) cudaEventDestroy(e->ingest_idle);
+    for (cudaEvent_t ev : e->ingest_ev)
+        if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->copy_ev)
         if (ev) cudaEventDestroy(ev);
     copy_pool_destroy(e->copy_pool);
@@ -1207,6 +1210,8 @@ int rf_engine_stats(rf_engine *e, rf_stats *out) {
     out->searches = e->searches.load();
     out->kernel_launches = e->launches.load();
     out->free_rows = e->free_rows;   // (read without ingest_mu: a statistic)
+    out->ingest_bytes = e->ingest_bytes.load();
+    out->ingest_kernel_ns = e->ingest_kernel_ns.load();
     return RF_OK;
 }
 
@@ -1300,7 +1305,8 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
         // already in HBM: one device copy into the padded, aligned scratch, one launch
         RF_CUDA(cudaMemcpyAsync(d_text, utf8, n, cudaMemcpyDeviceToDevice, s));
         t.avail_end = n;
-        RF_CUDA(rf::launch_tokenize(t, n_blocks, s));
+        RF_CUDA(cudaEventRecord(e->ingest_ev[0], s));
+        RF_CUDA(rf::launch_tokenize(t, 0, n_blocks, s));
         e->launches.fetch_add(1);
         return RF_OK;
     }
@@ -1314,7 +1320,8 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
         }
         RF_CUDA(cudaMemcpyAsync(d_text, src, n, cudaMemcpyHostToDevice, s));
         t.avail_end = n;
-        RF_CUDA(rf::launch_tokenize(t, n_blocks, s));
+        RF_CUDA(cudaEventRecord(e->ingest_ev[0], s));
+        RF_CUDA(rf::launch_tokenize(t, 0, n_blocks, s));
         e->launches.fetch_add(1);
         return RF_OK;
     }
@@ -1362,9 +1369,10 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
             if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, e->copy_ev[g % 16], 0);
             ++g;
             if (ce == cudaSuccess && w_off + off > 0) {
+                if (blocks_done == 0) ce = cudaEventRecord(e->ingest_ev[0], s);   // (pipelined: the span to ingest_ev[1] includes waiting for copies)
                 t.avail_end = w_off + off + len;
                 const uint32_t upto = blocks_upto(w_off + off);        // blocks that START before this chunk
-                ce = rf::launch_tokenize(t, upto - blocks_done, s);
+                if (ce == cudaSuccess) ce = rf::launch_tokenize(t, blocks_done, upto - blocks_done, s);
                 blocks_done = upto;
                 ++launches;
             }
@@ -1374,7 +1382,8 @@ static int copy_and_tokenize(rf_engine *e, const uint8_t *utf8, size_t n, rf::To
     }
     if (rc) return rc;
     t.avail_end = n;
-    RF_CUDA(rf::launch_tokenize(t, n_blocks - blocks_done, s));
+    if (blocks_done == 0) RF_CUDA(cudaEventRecord(e->ingest_ev[0], s));
+    RF_CUDA(rf::launch_tokenize(t, blocks_done, n_blocks - blocks_done, s));
     e->launches.fetch_add(launches + 1);
     return RF_OK;
 }
@@ -1414,7 +1423,10 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     t.deferred = static_cast<uint32_t *>(e->sc_deferred.p);
     RF_CUDA(cudaMemsetAsync(t.ctl, 0, rf::kCtlWords * 4, s));
     if (n_blocks) RF_CUDA(cudaMemsetAsync(t.state, 0, static_cast<size_t>(n_blocks) * 8, s));
+    for (cudaEvent_t &ev : e->ingest_ev)
+        if (!ev) RF_CUDA(cudaEventCreate(&ev));
     if ((rc = copy_and_tokenize(e, utf8, n, t))) return rc;
+    if (n) RF_CUDA(cudaEventRecord(e->ingest_ev[1], s));
     volatile uint32_t *h_ctl = static_cast<volatile uint32_t *>(e->sc_ctl_host.p);
     RF_CUDA(cudaMemcpyAsync(e->sc_ctl_host.p, t.ctl, rf::kCtlWords * 4, cudaMemcpyDeviceToHost, s));
     RF_CUDA(cudaStreamSynchronize(s));
@@ -1435,12 +1447,19 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
         int64_t *d_spans = static_cast<int64_t *>(e->sc_spans.p);
         // rows taken from the free list lie inside ranges a concurrent search may be scanning (masked):
         // features and norms first, the segment words that un-mask them only after those are complete
+        RF_CUDA(cudaEventRecord(e->ingest_ev[2], s));
         RF_CUDA(rf::launch_rows_from_tokens(t, n_tokens, nc, e->F + first * e->dim, e->ff + first, reused ? nullptr : e->seg + first,
                                             store_seg, d_spans, s));
+        RF_CUDA(cudaEventRecord(e->ingest_ev[3], s));
         ++launches;
         const uint32_t ns = spans ? std::min(nc, max_spans) : 0;
         if (ns) RF_CUDA(cudaMemcpyAsync(spans, d_spans, static_cast<size_t>(ns) * 16, cudaMemcpyDeviceToHost, s));
         RF_CUDA(cudaStreamSynchronize(s));
+        float ms_tok = 0.0f, ms_rows = 0.0f;
+        if (cudaEventElapsedTime(&ms_tok, e->ingest_ev[0], e->ingest_ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms_rows, e->ingest_ev[2], e->ingest_ev[3]) == cudaSuccess)
+            e->ingest_kernel_ns.fetch_add(static_cast<uint64_t>((static_cast<double>(ms_tok) + ms_rows) * 1e6), std::memory_order_relaxed);
+        else cudaGetLastError();
         if (reused) {
             RF_CUDA(rf::launch_fill_u32(e->seg + first, nc, store_seg, s));
             ++launches;

@@ -14,6 +14,9 @@
 // A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
 // look-ahead, so stop-word removal needs no second compaction.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <string>
 
 #include "rf_device.cuh"
 #include "rf_internal.h"
@@ -104,7 +107,9 @@ __device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_raw) {
     return flags;
 }
 
-// ---- single-pass tokeniser --------------------------------------------------------------------------------
+// ---- single-pass tokeniser, look-back variant (RF_TOKENIZE_VARIANT=lookback; kept for A/B comparison) -----
+// Measured: with ~1200 blocks in flight a block walks back over most of them, 32 per L2 round trip, so a
+// block lives ~29 us and a 22.8 MB document takes 136 us -- tokenize_span_kernel below replaces it.
 // One block per 4 KB of text: stage + lower-case it, flag the kept-token starts, and place the block's
 // tokens at their GLOBAL ordinals in the same pass -- the exclusive token count of everything before the
 // block comes from a decoupled look-back over a per-block status array (aggregate published as soon as
@@ -126,7 +131,7 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kFeatThreads) tokenize_kernel(const TokenizeArgs a) {
+__global__ void __launch_bounds__(kFeatThreads) tokenize_lookback_kernel(const TokenizeArgs a) {
     __shared__ __align__(16) uint8_t s_raw[kStageBytes];
     __shared__ uint32_t s_warp[kFeatThreads / 32];
     __shared__ uint32_t s_block, s_ex;
@@ -209,6 +214,239 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_kernel(const TokenizeAr
             a.tok_end[ord] = static_cast<uint32_t>(p);
         }
         ++ord;
+    }
+}
+
+// ---- single-pass tokeniser, span variant (default) ------------------------------------------------------------
+// One wave of CTAs covers the launch's text: CTA c (numbered by a ticket, so the CTAs before it have always
+// started) keeps a CONTIGUOUS span of up to 20 KB in shared memory.  The work is organised around the
+// instruction count per byte, which is what bounds this kernel (the look-back variant executes ~4.9 warp
+// instructions per text byte):
+//   stage   16 bytes per thread and step: lower-cased with packed arithmetic, and the "token byte" /
+//           "letter" predicates of the 16 bytes computed 4 bytes per operation and kept as two 16-bit masks
+//           per 16-byte unit
+//   flag    kept-token starts from the masks alone (start = token bit whose predecessor is clear; lengths
+//           1-3 from shifted masks); only short tokens that begin with a letter look at their bytes for
+//           a / an / the
+//   count   the CTA publishes its token count tagged with the launch number and sums the counts of the CTAs
+//           before it, every thread taking a share of those words: one or two L2 round trips however many
+//           CTAs are in flight
+//   hash    a thread walks the 20 byte positions of its unit (16 + 4 look-ahead) unrolled out of registers:
+//           starts reset the FNV-1a state, token bytes advance it, and "a kept token ends here"
+//           (= (T + S) & ~T: adding the start bits to the token-byte mask carries through each kept run) emits
+//           (bucket, byte end) with predicated stores; a token that runs further is finished from the masks
+// Tokens before this launch's bytes: ctl[kCtlTokens], read before the count is published and advanced by the
+// launch's last CTA after it has seen every other count.  The text may still be arriving: bytes are valid up to
+// `avail_end`; a token that runs past it (only possible for a token longer than a whole copy chunk) is parked
+// and finished by hash_deferred_kernel.
+constexpr int kSpanMaxIt = (static_cast<int>(kSpanMaxBytes) / 16 + kFeatThreads - 1) / kFeatThreads;   // steps of 4 KB
+constexpr int kSpanRows = kSpanMaxIt * (kFeatThreads / 32);                                               // warp rows per CTA
+static_assert(kSpanRows <= 64, "warp 0 scans the row totals two per lane");
+
+// Shared-memory layout of a CTA with span bytes of text (span a multiple of 16; U = span / 16 units):
+//   [0, 16)            the byte before the span in [15]
+//   [16, 16 + span+16) lowered text, one look-ahead unit included
+//   s_tok  u16[U + 3]  token-byte mask of unit u at [1 + u] (bit j = byte j); [0] bit 15 = the byte before the span
+//   s_aux  u16[U]      letter mask of the unit, replaced by its kept-start mask
+__host__ __device__ constexpr uint32_t span_tok_offset(uint32_t span) { return 16u + span + 16u; }
+__host__ __device__ constexpr uint32_t span_aux_offset(uint32_t span) { return span_tok_offset(span) + (span / 16u + 4u) * 2u; }
+__host__ __device__ constexpr uint32_t span_smem_bytes(uint32_t span) { return span_aux_offset(span) + (span / 16u) * 2u + 8u; }
+
+// token-byte / letter predicates of four lowered bytes -> 4 bits each (bit i = byte i)
+__device__ __forceinline__ uint32_t tok_bits4(uint32_t x, uint32_t &letter_bits) {
+    const uint32_t lo7 = x & 0x7F7F7F7Fu;
+    const uint32_t ascii = ~x & 0x80808080u;
+    const uint32_t letter = (lo7 + 0x1F1F1F1Fu) & ~(lo7 + 0x05050505u) & ascii;   // 'a' .. 'z'
+    const uint32_t digit = (lo7 + 0x50505050u) & ~(lo7 + 0x46464646u) & ascii;    // '0' .. '9'
+    // bits 7 / 15 / 23 / 31 -> 0 / 1 / 2 / 3: the four partial products that land on bits 21-24 are the only ones there
+    letter_bits = (((letter >> 7) * 0x00204081u) >> 21) & 0xFu;
+    return ((((letter | digit) >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+__global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const TokenizeArgs a) {
+    extern __shared__ __align__(16) uint8_t span_smem[];
+    __shared__ uint32_t s_row[64];                    // tokens per warp row (step, warp), then their exclusive prefix
+    __shared__ uint32_t s_red[kFeatThreads / 32];
+    __shared__ uint32_t s_cta, s_base, s_total, s_ex;
+    if (threadIdx.x == 0) {
+        s_base = __ldcg(a.ctl + kCtlTokens);          // read before this CTA publishes anything: see above
+        s_cta = atomicAdd(a.ctl + kCtlTicket, 1u) - a.ticket_base;
+    }
+    __syncthreads();
+    const uint32_t cta = s_cta;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t span_lo = a.byte_lo + static_cast<size_t>(cta) * a.span;
+    const size_t span_hi = span_lo < a.byte_hi ? (span_lo + a.span < a.byte_hi ? span_lo + a.span : a.byte_hi) : span_lo;
+    const uint32_t n_units = static_cast<uint32_t>((span_hi - span_lo + 15) / 16);
+    uint8_t *s_txt = span_smem + 16;                  // s_txt[i] = lowered text[span_lo + i]
+    uint16_t *s_tok = reinterpret_cast<uint16_t *>(span_smem + span_tok_offset(a.span));
+    uint16_t *s_aux = reinterpret_cast<uint16_t *>(span_smem + span_aux_offset(a.span));
+
+    // ---- stage: n_units + 1 units (the last one is look-ahead), bytes past the document read as separators
+    for (uint32_t u = threadIdx.x; u <= n_units; u += kFeatThreads) {
+        const size_t at = span_lo + static_cast<size_t>(u) * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (at < a.n) {
+            v = *reinterpret_cast<const uint4 *>(a.text + at);        // the text buffer is padded by 64 bytes
+            if (at + 16 > a.n) {
+                const uint32_t keep = static_cast<uint32_t>(a.n - at);   // 1 .. 15
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int valid = static_cast<int>(keep) - 4 * i;
+                    w[i] = valid >= 4 ? w[i] : valid <= 0 ? 0u : (w[i] & ((1u << (8 * valid)) - 1u));
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            v = make_uint4(lower4(v.x), lower4(v.y), lower4(v.z), lower4(v.w));
+        }
+        *reinterpret_cast<uint4 *>(s_txt + u * 16) = v;
+        uint32_t l0, l1, l2, l3;
+        const uint32_t t0 = tok_bits4(v.x, l0), t1 = tok_bits4(v.y, l1), t2 = tok_bits4(v.z, l2), t3 = tok_bits4(v.w, l3);
+        s_tok[1 + u] = static_cast<uint16_t>(t0 | (t1 << 4) | (t2 << 8) | (t3 << 12));
+        if (u < n_units) s_aux[u] = static_cast<uint16_t>(l0 | (l1 << 4) | (l2 << 8) | (l3 << 12));
+    }
+    if (threadIdx.x == 0) {
+        const uint8_t before = span_lo > 0 ? lower_byte(a.text[span_lo - 1]) : 0;
+        s_txt[-1] = before;
+        s_tok[0] = token_byte(before) ? 0x8000u : 0u;
+        s_tok[n_units + 2] = 0;                        // read (and discarded) by the last unit's 4-bit look-ahead of its look-ahead
+    }
+    if (threadIdx.x < 64) s_row[threadIdx.x] = 0;
+    __syncthreads();
+
+    // ---- flag the kept-token starts + count
+    const uint32_t n_it = (n_units + kFeatThreads - 1) / kFeatThreads;
+    for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t u = it * kFeatThreads + threadIdx.x;
+        uint32_t S = 0;
+        if (u < n_units) {
+            const uint32_t tp = s_tok[u], tc = s_tok[u + 1], tn = s_tok[u + 2];
+            const uint32_t T = tc | ((tn & 0xFu) << 16);             // bit j = byte j of the unit is a token byte, j < 20
+            S = T & ~((T << 1) | (tp >> 15)) & 0xFFFFu;              // ... and the byte before it is not: a token starts
+            const uint32_t n1 = ~(T >> 1), n2 = ~(T >> 2), n3 = ~(T >> 3);
+            const uint32_t L1 = S & n1, L2 = S & ~n1 & n2, L3 = S & ~n1 & ~n2 & n3;   // tokens of 1 / 2 / 3 bytes
+            uint32_t cand = (L1 | L2 | L3) & s_aux[u];               // short and starting with a letter: a / an / the?
+            while (cand) {
+                const int j = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint8_t *c = s_txt + u * 16 + j;
+                const bool stop = ((L1 >> j) & 1u)   ? c[0] == 'a'
+                                  : ((L2 >> j) & 1u) ? (c[0] == 'a' && c[1] == 'n')
+                                                     : (c[0] == 't' && c[1] == 'h' && c[2] == 'e');
+                if (stop) S &= ~(1u << j);
+            }
+            s_aux[u] = static_cast<uint16_t>(S);
+        }
+        const uint32_t row_total = __reduce_add_sync(kFull, __popc(S));
+        if (lane == 0) s_row[it * (kFeatThreads / 32) + warp] = row_total;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t ta = s_row[lane], tb = s_row[lane + 32];
+        uint32_t ia = ta, ib = tb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t xa = __shfl_up_sync(kFull, ia, o), xb = __shfl_up_sync(kFull, ib, o);
+            if (lane >= o) { ia += xa; ib += xb; }
+        }
+        const uint32_t total_a = __shfl_sync(kFull, ia, 31), total = total_a + __shfl_sync(kFull, ib, 31);
+        s_row[lane] = ia - ta;
+        s_row[lane + 32] = total_a + ib - tb;
+        if (lane == 0) {
+            s_total = total;
+            st_release_u64(a.state + cta, (static_cast<uint64_t>(a.seq) << 32) | total);
+        }
+    }
+    // ---- tokens of the CTAs before this one (they have all started: ticket order)
+    uint32_t before = 0;
+    for (uint32_t j = threadIdx.x; j < cta; j += kFeatThreads) {
+        uint64_t v;
+        do { v = ld_acquire_u64(a.state + j); } while (static_cast<uint32_t>(v >> 32) != a.seq);
+        before += static_cast<uint32_t>(v);
+    }
+    before = __reduce_add_sync(kFull, before);
+    if (lane == 0) s_red[warp] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ex = 0;
+#pragma unroll
+        for (int w = 0; w < kFeatThreads / 32; ++w) ex += s_red[w];
+        s_ex = ex;
+        if (cta + 1 == gridDim.x) a.ctl[kCtlTokens] = s_base + ex + s_total;   // every other CTA has read the old value
+    }
+    __syncthreads();
+    const uint32_t ord_base = s_base + s_ex;
+
+    // ---- hash + emit
+    const uint32_t staged = (n_units + 1) * 16;       // bytes of s_txt (and bits of s_tok) that hold text
+    const size_t avail_left = a.avail_end - span_lo;  // launches only cover blocks that start below avail_end
+    const uint32_t avail_rel = avail_left > 0xFFFFFFF0ull ? 0xFFFFFFF0u : static_cast<uint32_t>(avail_left);
+    const uint32_t lo32 = static_cast<uint32_t>(span_lo);             // documents are < 4 GiB
+    for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t u = it * kFeatThreads + threadIdx.x;
+        const uint32_t S = u < n_units ? s_aux[u] : 0u;
+        const uint32_t c = __popc(S);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (S == 0) continue;                          // (no shuffles below)
+        uint32_t ord = ord_base + s_row[it * (kFeatThreads / 32) + warp] + inc - c;
+        uint32_t r = ord % kChunkStride;               // ord % 112, kept incrementally
+        const uint32_t T = s_tok[u + 1] | ((s_tok[u + 2] & 0xFu) << 16);
+        const uint32_t E = (T + S) & ~T;               // bit j: a kept token ends in front of byte j (bit 20: it runs on)
+        const uint4 v = *reinterpret_cast<const uint4 *>(s_txt + u * 16);
+        const uint32_t words[5] = {v.x, v.y, v.z, v.w, *reinterpret_cast<const uint32_t *>(s_txt + u * 16 + 16)};
+        const uint32_t pos0 = u * 16;                  // relative to span_lo
+        uint32_t h = 0x811C9DC5u;
+        auto emit = [&](uint32_t end_rel) {
+            a.tok_bucket[ord] = static_cast<uint16_t>(h & a.dim_mask);
+            a.tok_end[ord] = lo32 + end_rel;
+            ++ord;
+            r = r == kChunkStride - 1 ? 0u : r + 1u;
+        };
+#pragma unroll
+        for (int j = 0; j < 20; ++j) {
+            const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (j > 0 && ((E >> j) & 1u)) emit(pos0 + j);
+            if (j < 16 && ((S >> j) & 1u)) {
+                h = 0x811C9DC5u;
+                if (r == 0) a.chunk_start[ord / kChunkStride] = lo32 + pos0 + j;
+            }
+            if ((T >> j) & 1u) h = (h ^ b) * 0x01000193u;
+        }
+        if ((E >> 20) & 1u) {
+            // the unit's last kept token runs past the look-ahead: finish it from the staged masks / bytes,
+            // and past those (a token longer than the rest of the span) from L2
+            uint32_t p = pos0 + 20;
+            bool ended = false;
+            while (p < staged) {
+                if (!((s_tok[1 + (p >> 4)] >> (p & 15u)) & 1u)) { ended = true; break; }
+                h = (h ^ s_txt[p]) * 0x01000193u;
+                ++p;
+            }
+            if (!ended) {
+                while (p < avail_rel) {
+                    const uint8_t cb = lower_byte(a.text[span_lo + p]);
+                    if (!token_byte(cb)) break;
+                    h = (h ^ cb) * 0x01000193u;
+                    ++p;
+                }
+            }
+            if (!ended && p >= avail_rel && a.avail_end < a.n) {
+                // ran out of copied bytes mid-token: finish it later (hash_deferred_kernel)
+                const uint32_t slot = atomicAdd(a.ctl + kCtlDeferred, 1u);
+                if (slot < kMaxDeferred) {
+                    a.deferred[2 * slot] = ord;
+                    a.deferred[2 * slot + 1] = lo32 + pos0 + (31 - __clz(S));   // its start: the unit's last kept start
+                }
+            } else {
+                emit(p);
+            }
+        }
     }
 }
 
@@ -433,10 +671,59 @@ cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, uint32_t dim, int3
     return cudaGetLastError();
 }
 
-cudaError_t launch_tokenize(const TokenizeArgs &a, uint32_t n_blocks_here, cudaStream_t s) {
+namespace {
+// CTAs of tokenize_span_kernel one wave can hold (all devices of a process are the same part)
+int span_wave_ctas() {
+    static std::atomic<int> cached{0};
+    int v = cached.load(std::memory_order_acquire);
+    if (v) return v;
+    int dev = 0, sms = 0, per_sm = 0;
+    const uint32_t smem = span_smem_bytes(kSpanMaxBytes);
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaFuncSetAttribute(tokenize_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tokenize_span_kernel, kFeatThreads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    v = sms * per_sm;
+    cached.store(v, std::memory_order_release);
+    return v;
+}
+bool use_lookback_variant() {
+    static const bool v = [] {
+        const char *e = std::getenv("RF_TOKENIZE_VARIANT");
+        return e && std::string(e) == "lookback";
+    }();
+    return v;
+}
+}  // namespace
+
+cudaError_t launch_tokenize(TokenizeArgs &t, uint32_t blk_first, uint32_t n_blocks_here, cudaStream_t s) {
     if (n_blocks_here == 0) return cudaSuccess;
-    tokenize_kernel<<<n_blocks_here, kFeatThreads, 0, s>>>(a);
-    return cudaGetLastError();
+    if (use_lookback_variant()) {   // block numbers come from the ticket: launches cover the blocks in order
+        tokenize_lookback_kernel<<<n_blocks_here, kFeatThreads, 0, s>>>(t);
+        return cudaGetLastError();
+    }
+    const int wave = span_wave_ctas();
+    if (wave <= 0) return cudaErrorInvalidDeviceFunction;
+    size_t lo = static_cast<size_t>(blk_first) * kFeatBlockBytes;
+    const size_t hi = std::min(t.n, (static_cast<size_t>(blk_first) + n_blocks_here) * kFeatBlockBytes);
+    while (lo < hi) {
+        const size_t len = std::min(hi - lo, static_cast<size_t>(wave) * kSpanMaxBytes);
+        // at least 4 KB per CTA; otherwise the wave shares the bytes evenly (16-byte granules)
+        uint32_t ctas = static_cast<uint32_t>(std::min<size_t>(static_cast<size_t>(wave), (len + kFeatBlockBytes - 1) / kFeatBlockBytes));
+        const uint32_t span = static_cast<uint32_t>(((len + ctas - 1) / ctas + 15) / 16 * 16);
+        ctas = static_cast<uint32_t>((len + span - 1) / span);
+        t.byte_lo = lo;
+        t.byte_hi = lo + len;
+        t.span = span;
+        t.seq += 1;
+        tokenize_span_kernel<<<ctas, kFeatThreads, span_smem_bytes(span), s>>>(t);
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+        t.ticket_base += ctas;
+        lo += len;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStream_t s) {

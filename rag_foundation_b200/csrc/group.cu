@@ -274,6 +274,8 @@ int rf_group_stats(rf_group *g, rf_stats *total, rf_stats *per_device) {
         total->searches += st.searches;
         total->kernel_launches += st.kernel_launches;
         total->free_rows += st.free_rows;
+        total->ingest_bytes += st.ingest_bytes;
+        total->ingest_kernel_ns += st.ingest_kernel_ns;
     }
     std::shared_lock<std::shared_mutex> lk(g->mu);
     for (uint8_t dr : g->dropped) total->n_stores += dr ? 0 : 1;

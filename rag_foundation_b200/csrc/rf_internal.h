@@ -202,21 +202,28 @@ void stage_copy(void *dst, const void *src, size_t n);
 constexpr uint32_t kFeatBlockBytes = 4096;
 constexpr uint32_t kMaxDeferred = 64;    // tokens longer than a whole copy chunk, finished after the last copy
 enum : uint32_t { kCtlTicket = 0, kCtlTokens = 1, kCtlDeferred = 2, kCtlWords = 4 };   // control words (zeroed per document)
+constexpr uint32_t kSpanMaxBytes = 20u << 10;   // text bytes one tokeniser CTA keeps in shared memory (8 CTAs per SM: 24 MB per wave)
 struct TokenizeArgs {        // device scratch for one document
     const uint8_t *text;     // [>= n + 64] padded device copy of the document, 16-byte aligned
     size_t n;                // document bytes
     size_t avail_end;        // bytes [0, avail_end) have arrived (== n for the last / only launch)
     uint32_t n_blocks;       // 4 KB blocks of the whole document
-    uint64_t *state;         // [n_blocks] look-back status words (zeroed per document)
+    uint64_t *state;         // [n_blocks] per-CTA token counts, tagged with the launch number (zeroed per document)
     uint32_t *ctl;           // [kCtlWords]
     uint16_t *tok_bucket;    // [cap_tokens] bucket = hash & dim_mask
     uint32_t dim_mask;       // dim - 1
     uint32_t *tok_end;       // [cap_tokens]
     uint32_t *chunk_start;   // [cap_tokens / 112 + 2] byte offset of the first token of each chunk window
     uint32_t *deferred;      // [2 * kMaxDeferred] (ordinal, start) of parked tokens
+    // one launch (filled in by launch_tokenize): CTA c of the launch takes bytes [byte_lo + c * span, + span) below byte_hi
+    size_t byte_lo, byte_hi;
+    uint32_t span;           // bytes per CTA, a multiple of 16, <= kSpanMaxBytes
+    uint32_t seq;            // launch number within the document, from 1 (tags the state words)
+    uint32_t ticket_base;    // CTAs launched for this document before this launch
 };
-// the next n_blocks_here blocks of the document (block numbers come from the ticket in ctl)
-cudaError_t launch_tokenize(const TokenizeArgs &a, uint32_t n_blocks_here, cudaStream_t s);
+// Tokenise the document's 4 KB blocks [blk_first, blk_first + n_blocks_here): as many launches as the range needs
+// (one, unless it is longer than a full wave of CTAs can hold in shared memory).  Updates t.seq / t.ticket_base.
+cudaError_t launch_tokenize(TokenizeArgs &t, uint32_t blk_first, uint32_t n_blocks_here, cudaStream_t s);
 cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStream_t s);
 cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,
                                     int32_t *ff, uint32_t *seg, uint32_t store_seg, int64_t *spans_dev,

@@ -30,7 +30,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_struct_layout_matches_header():
     assert C.sizeof(_capi.rf_config) == 32
-    assert C.sizeof(_capi.rf_stats) == 64
+    assert C.sizeof(_capi.rf_stats) == 80
 
 
 def test_library_holds_sm100a_code_only():

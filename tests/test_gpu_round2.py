@@ -517,6 +517,36 @@ def test_pipelined_ingest_sources_and_chunk_boundaries(co):
         assert not errs, errs[:1]
 
 
+@pytest.mark.timeout(600)
+def test_ingest_spans_and_waves_of_the_tokeniser(co):
+    """The tokeniser gives every CTA of a launch one contiguous span of the text (4 KB ... 22 KB, a multiple of 16
+    bytes) and sums the token counts of the CTAs before it; a range longer than one wave of CTAs can hold takes
+    several launches that hand the running token count on.  Device-resident documents take ONE range: sizes
+    around the points where the span stops being 4 KB (wave x 4 KB), where it reaches 22 KB (one full wave) and
+    beyond (two launches), with tokens / stop words straddling span edges by construction (running text)."""
+    import torch
+    rng = np.random.default_rng(23)
+    words = [b"alpha", b"the", b"Beta9", b"a", b"an", b"gamma", b"x", b"\xc3\xa9t\xc3\xa9", b"Zeta_zeta", b"0042", b"The", b"theory"]
+
+    def running_text(n):
+        idx = rng.integers(0, len(words), n // 3 + 8)
+        return b" ".join(words[int(i)] for i in idx)[:n]
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    wave = sms * 8
+    sizes = [wave * 4096 - 1, wave * 4096 + 16, wave * 4096 + 4097, 3 * wave * 4096 // 2 + 5,
+             wave * 22 * 1024, wave * 22 * 1024 + 1, wave * 22 * 1024 + 70_001]
+    base = running_text(max(sizes))
+    with _engine(120_000) as e:
+        s = e.open_store("fileSearchStores/spans")
+        dd = torch.frombuffer(bytearray(base), dtype=torch.uint8).cuda()
+        torch.cuda.synchronize()
+        for i, n in enumerate(sizes):
+            first, nc = _check_ingest(e, s, i + 1, base[:n], co, ptr=dd.data_ptr())
+            assert nc > 0
+            e.tombstone_doc(i + 1)     # the rows go back to the free list: the next document reuses them
+
+
 # ------------------------------------------------------------------ store table + store-sharded fused exchange
 def test_store_table_batches_equal_host_built_plans(co, zb):
     """Batches of differently-scoped queries read their plans from the device-resident store table: same answers
