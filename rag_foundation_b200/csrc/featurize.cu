@@ -218,39 +218,47 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_lookback_kernel(const T
 }
 
 // ---- single-pass tokeniser, span variant (default) ------------------------------------------------------------
-// One wave of CTAs covers the launch's text: CTA c (numbered by a ticket, so the CTAs before it have always
-// started) keeps a CONTIGUOUS span of up to 20 KB in shared memory.  The work is organised around the
-// instruction count per byte, which is what bounds this kernel (the look-back variant executes ~4.9 warp
-// instructions per text byte):
+// CTA c of a launch (numbered by a ticket, so the CTAs before it have always started) keeps a CONTIGUOUS span
+// of the text (8 KB by default, at most 12 KB) in shared memory and produces its tokens there before it needs
+// to know how many tokens precede it.  The kernel is shaped by two measurements of the look-back variant:
+// ~4.9 warp instructions per text byte, and two scattered 2 / 4-byte global stores per token.
 //   stage   16 bytes per thread and step: lower-cased with packed arithmetic, and the "token byte" /
 //           "letter" predicates of the 16 bytes computed 4 bytes per operation and kept as two 16-bit masks
 //           per 16-byte unit
 //   flag    kept-token starts from the masks alone (start = token bit whose predecessor is clear; lengths
 //           1-3 from shifted masks); only short tokens that begin with a letter look at their bytes for
-//           a / an / the
-//   count   the CTA publishes its token count tagged with the launch number and sums the counts of the CTAs
-//           before it, every thread taking a share of those words: one or two L2 round trips however many
-//           CTAs are in flight
+//           a / an / the.  The CTA's token count is published at once, tagged with the launch number
 //   hash    a thread walks the 20 byte positions of its unit (16 + 4 look-ahead) unrolled out of registers:
 //           starts reset the FNV-1a state, token bytes advance it, and "a kept token ends here"
-//           (= (T + S) & ~T: adding the start bits to the token-byte mask carries through each kept run) emits
-//           (bucket, byte end) with predicated stores; a token that runs further is finished from the masks
+//           (= (T + S) & ~T: adding the start bits to the token-byte mask carries through each kept run) puts
+//           (bucket, byte end) at the token's CTA-local index in shared memory with predicated stores; a token
+//           that runs further is finished from the masks
+//   place   only now the counts of the CTAs before this one are summed (every thread takes a share of those
+//           words; by now they have long been published), and the token records leave in coalesced stores at
+//           their global ordinals; the byte start of every 112th token (a chunk window opens there) is found
+//           again from the kept-start masks
 // Tokens before this launch's bytes: ctl[kCtlTokens], read before the count is published and advanced by the
 // launch's last CTA after it has seen every other count.  The text may still be arriving: bytes are valid up to
 // `avail_end`; a token that runs past it (only possible for a token longer than a whole copy chunk) is parked
 // and finished by hash_deferred_kernel.
+constexpr uint32_t kSpanDefaultBytes = 8u << 10;
 constexpr int kSpanMaxIt = (static_cast<int>(kSpanMaxBytes) / 16 + kFeatThreads - 1) / kFeatThreads;   // steps of 4 KB
 constexpr int kSpanRows = kSpanMaxIt * (kFeatThreads / 32);                                               // warp rows per CTA
 static_assert(kSpanRows <= 64, "warp 0 scans the row totals two per lane");
+static_assert(kSpanMaxBytes + 64 < 0xFFFFu, "token ends inside the staged span fit 16 bits");
 
 // Shared-memory layout of a CTA with span bytes of text (span a multiple of 16; U = span / 16 units):
 //   [0, 16)            the byte before the span in [15]
 //   [16, 16 + span+16) lowered text, one look-ahead unit included
-//   s_tok  u16[U + 3]  token-byte mask of unit u at [1 + u] (bit j = byte j); [0] bit 15 = the byte before the span
-//   s_aux  u16[U]      letter mask of the unit, replaced by its kept-start mask
+//   s_tok  u16[U + 4]  token-byte mask of unit u at [1 + u] (bit j = byte j); [0] bit 15 = the byte before the span
+//   s_aux  u16[U + 4]  letter mask of the unit, replaced by its kept-start mask
+//   s_bkt  u16[span/2] bucket of the CTA's i-th kept token (a kept token takes >= 2 bytes of text)
+//   s_end  u16[span/2] its byte end relative to the span (0xFFFF: it runs far past the span, see s_long_end)
 __host__ __device__ constexpr uint32_t span_tok_offset(uint32_t span) { return 16u + span + 16u; }
 __host__ __device__ constexpr uint32_t span_aux_offset(uint32_t span) { return span_tok_offset(span) + (span / 16u + 4u) * 2u; }
-__host__ __device__ constexpr uint32_t span_smem_bytes(uint32_t span) { return span_aux_offset(span) + (span / 16u) * 2u + 8u; }
+__host__ __device__ constexpr uint32_t span_bkt_offset(uint32_t span) { return span_aux_offset(span) + (span / 16u + 4u) * 2u; }
+__host__ __device__ constexpr uint32_t span_end_offset(uint32_t span) { return span_bkt_offset(span) + span + 16u; }
+__host__ __device__ constexpr uint32_t span_smem_bytes(uint32_t span) { return span_end_offset(span) + span + 16u; }
 
 // token-byte / letter predicates of four lowered bytes -> 4 bits each (bit i = byte i)
 __device__ __forceinline__ uint32_t tok_bits4(uint32_t x, uint32_t &letter_bits) {
@@ -267,10 +275,11 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     extern __shared__ __align__(16) uint8_t span_smem[];
     __shared__ uint32_t s_row[64];                    // tokens per warp row (step, warp), then their exclusive prefix
     __shared__ uint32_t s_red[kFeatThreads / 32];
-    __shared__ uint32_t s_cta, s_base, s_total, s_ex;
+    __shared__ uint32_t s_cta, s_base, s_total, s_ex, s_long_end, s_def_li, s_def_start;
     if (threadIdx.x == 0) {
         s_base = __ldcg(a.ctl + kCtlTokens);          // read before this CTA publishes anything: see above
         s_cta = atomicAdd(a.ctl + kCtlTicket, 1u) - a.ticket_base;
+        s_def_li = 0xFFFFFFFFu;
     }
     __syncthreads();
     const uint32_t cta = s_cta;
@@ -281,6 +290,8 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     uint8_t *s_txt = span_smem + 16;                  // s_txt[i] = lowered text[span_lo + i]
     uint16_t *s_tok = reinterpret_cast<uint16_t *>(span_smem + span_tok_offset(a.span));
     uint16_t *s_aux = reinterpret_cast<uint16_t *>(span_smem + span_aux_offset(a.span));
+    uint16_t *s_bkt = reinterpret_cast<uint16_t *>(span_smem + span_bkt_offset(a.span));
+    uint16_t *s_end = reinterpret_cast<uint16_t *>(span_smem + span_end_offset(a.span));
 
     // ---- stage: n_units + 1 units (the last one is look-ahead), bytes past the document read as separators
     for (uint32_t u = threadIdx.x; u <= n_units; u += kFeatThreads) {
@@ -304,13 +315,12 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
         uint32_t l0, l1, l2, l3;
         const uint32_t t0 = tok_bits4(v.x, l0), t1 = tok_bits4(v.y, l1), t2 = tok_bits4(v.z, l2), t3 = tok_bits4(v.w, l3);
         s_tok[1 + u] = static_cast<uint16_t>(t0 | (t1 << 4) | (t2 << 8) | (t3 << 12));
-        if (u < n_units) s_aux[u] = static_cast<uint16_t>(l0 | (l1 << 4) | (l2 << 8) | (l3 << 12));
+        s_aux[u] = static_cast<uint16_t>(l0 | (l1 << 4) | (l2 << 8) | (l3 << 12));
     }
     if (threadIdx.x == 0) {
         const uint8_t before = span_lo > 0 ? lower_byte(a.text[span_lo - 1]) : 0;
         s_txt[-1] = before;
         s_tok[0] = token_byte(before) ? 0x8000u : 0u;
-        s_tok[n_units + 2] = 0;                        // read (and discarded) by the last unit's 4-bit look-ahead of its look-ahead
     }
     if (threadIdx.x < 64) s_row[threadIdx.x] = 0;
     __syncthreads();
@@ -358,31 +368,15 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
             st_release_u64(a.state + cta, (static_cast<uint64_t>(a.seq) << 32) | total);
         }
     }
-    // ---- tokens of the CTAs before this one (they have all started: ticket order)
-    uint32_t before = 0;
-    for (uint32_t j = threadIdx.x; j < cta; j += kFeatThreads) {
-        uint64_t v;
-        do { v = ld_acquire_u64(a.state + j); } while (static_cast<uint32_t>(v >> 32) != a.seq);
-        before += static_cast<uint32_t>(v);
-    }
-    before = __reduce_add_sync(kFull, before);
-    if (lane == 0) s_red[warp] = before;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ex = 0;
-#pragma unroll
-        for (int w = 0; w < kFeatThreads / 32; ++w) ex += s_red[w];
-        s_ex = ex;
-        if (cta + 1 == gridDim.x) a.ctl[kCtlTokens] = s_base + ex + s_total;   // every other CTA has read the old value
-    }
-    __syncthreads();
-    const uint32_t ord_base = s_base + s_ex;
 
-    // ---- hash + emit
+    // ---- hash: token records at their CTA-local index
     const uint32_t staged = (n_units + 1) * 16;       // bytes of s_txt (and bits of s_tok) that hold text
     const size_t avail_left = a.avail_end - span_lo;  // launches only cover blocks that start below avail_end
     const uint32_t avail_rel = avail_left > 0xFFFFFFF0ull ? 0xFFFFFFF0u : static_cast<uint32_t>(avail_left);
-    const uint32_t lo32 = static_cast<uint32_t>(span_lo);             // documents are < 4 GiB
+    const uint32_t dim_mask = a.dim_mask;
+    const uint32_t bkt_s = static_cast<uint32_t>(__cvta_generic_to_shared(s_bkt));
+    const uint32_t end_s = static_cast<uint32_t>(__cvta_generic_to_shared(s_end));
     for (uint32_t it = 0; it < n_it; ++it) {
         const uint32_t u = it * kFeatThreads + threadIdx.x;
         const uint32_t S = u < n_units ? s_aux[u] : 0u;
@@ -394,29 +388,28 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
             if (lane >= o) inc += t;
         }
         if (S == 0) continue;                          // (no shuffles below)
-        uint32_t ord = ord_base + s_row[it * (kFeatThreads / 32) + warp] + inc - c;
-        uint32_t r = ord % kChunkStride;               // ord % 112, kept incrementally
+        uint32_t li = s_row[it * (kFeatThreads / 32) + warp] + inc - c;   // CTA-local index of the unit's first kept token
+        const uint32_t pos0 = u * 16;                  // relative to span_lo
         const uint32_t T = s_tok[u + 1] | ((s_tok[u + 2] & 0xFu) << 16);
         const uint32_t E = (T + S) & ~T;               // bit j: a kept token ends in front of byte j (bit 20: it runs on)
         const uint4 v = *reinterpret_cast<const uint4 *>(s_txt + u * 16);
         const uint32_t words[5] = {v.x, v.y, v.z, v.w, *reinterpret_cast<const uint32_t *>(s_txt + u * 16 + 16)};
-        const uint32_t pos0 = u * 16;                  // relative to span_lo
         uint32_t h = 0x811C9DC5u;
-        auto emit = [&](uint32_t end_rel) {
-            a.tok_bucket[ord] = static_cast<uint16_t>(h & a.dim_mask);
-            a.tok_end[ord] = lo32 + end_rel;
-            ++ord;
-            r = r == kChunkStride - 1 ? 0u : r + 1u;
-        };
 #pragma unroll
         for (int j = 0; j < 20; ++j) {
             const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (j > 0 && ((E >> j) & 1u)) emit(pos0 + j);
-            if (j < 16 && ((S >> j) & 1u)) {
-                h = 0x811C9DC5u;
-                if (r == 0) a.chunk_start[ord / kChunkStride] = lo32 + pos0 + j;
+            if (j > 0) {
+                // predicated stores: nearly every step has SOME lane at a token end, a branch would only add reconvergence
+                const uint32_t e = (E >> j) & 1u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u16 [%1], %2;\n\t@p st.shared.u16 [%3], %4;\n\t}"
+                    ::"r"(e), "r"(bkt_s + 2u * li), "h"(static_cast<uint16_t>(h & dim_mask)), "r"(end_s + 2u * li),
+                      "h"(static_cast<uint16_t>(pos0 + j))
+                    : "memory");
+                li += e;
             }
-            if ((T >> j) & 1u) h = (h ^ b) * 0x01000193u;
+            if (j < 16) h = ((S >> j) & 1u) ? 0x811C9DC5u : h;
+            h = ((T >> j) & 1u) ? (h ^ b) * 0x01000193u : h;
         }
         if ((E >> 20) & 1u) {
             // the unit's last kept token runs past the look-ahead: finish it from the staged masks / bytes,
@@ -436,16 +429,59 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
                     ++p;
                 }
             }
+            s_bkt[li] = static_cast<uint16_t>(h & dim_mask);
+            s_end[li] = static_cast<uint16_t>(p < 0xFFFFu ? p : 0xFFFFu);
+            if (p >= 0xFFFFu) s_long_end = p;         // at most one token of a span can run this far past it
             if (!ended && p >= avail_rel && a.avail_end < a.n) {
-                // ran out of copied bytes mid-token: finish it later (hash_deferred_kernel)
-                const uint32_t slot = atomicAdd(a.ctl + kCtlDeferred, 1u);
-                if (slot < kMaxDeferred) {
-                    a.deferred[2 * slot] = ord;
-                    a.deferred[2 * slot + 1] = lo32 + pos0 + (31 - __clz(S));   // its start: the unit's last kept start
-                }
-            } else {
-                emit(p);
+                // ran out of copied bytes mid-token (at most one token of a launch does): hash_deferred_kernel
+                // finishes it -- parked below, once its ordinal is known
+                s_def_li = li;
+                s_def_start = pos0 + (31 - __clz(S));  // its start: the unit's last kept start
             }
+        }
+    }
+
+    // ---- tokens of the CTAs before this one (they have all started: ticket order)
+    uint32_t before = 0;
+    for (uint32_t j = threadIdx.x; j < cta; j += kFeatThreads) {
+        uint64_t v;
+        while (static_cast<uint32_t>((v = ld_acquire_u64(a.state + j)) >> 32) != a.seq) __nanosleep(200);
+        before += static_cast<uint32_t>(v);
+    }
+    before = __reduce_add_sync(kFull, before);
+    if (lane == 0) s_red[warp] = before;
+    __syncthreads();                                   // (also: every token record is in shared memory)
+    if (threadIdx.x == 0) {
+        uint32_t ex = 0;
+#pragma unroll
+        for (int w = 0; w < kFeatThreads / 32; ++w) ex += s_red[w];
+        s_ex = ex;
+        if (cta + 1 == gridDim.x) a.ctl[kCtlTokens] = s_base + ex + s_total;   // every other CTA has read the old value
+    }
+    __syncthreads();
+    const uint32_t ord_base = s_base + s_ex, total = s_total;
+    const uint32_t lo32 = static_cast<uint32_t>(span_lo);             // documents are < 4 GiB
+
+    // ---- place: coalesced records, chunk-window starts, the parked token
+    for (uint32_t i = threadIdx.x; i < total; i += kFeatThreads) {
+        const uint32_t e = s_end[i];
+        a.tok_bucket[ord_base + i] = s_bkt[i];
+        a.tok_end[ord_base + i] = lo32 + (e == 0xFFFFu ? s_long_end : e);
+    }
+    for (uint32_t k = (ord_base + kChunkStride - 1) / kChunkStride + threadIdx.x; k * kChunkStride < ord_base + total; k += kFeatThreads) {
+        // token k * 112 opens a chunk window: its start is the first kept start at or behind the end of the token before it
+        const uint32_t i = k * kChunkStride - ord_base;
+        const uint32_t from = i ? s_end[i - 1] : 0u;
+        uint32_t u = from >> 4;
+        uint32_t m = s_aux[u] & ~((1u << (from & 15u)) - 1u);
+        while (m == 0) m = s_aux[++u];
+        a.chunk_start[k] = lo32 + u * 16 + (__ffs(m) - 1);
+    }
+    if (threadIdx.x == 0 && s_def_li != 0xFFFFFFFFu) {
+        const uint32_t slot = atomicAdd(a.ctl + kCtlDeferred, 1u);
+        if (slot < kMaxDeferred) {
+            a.deferred[2 * slot] = ord_base + s_def_li;
+            a.deferred[2 * slot + 1] = lo32 + s_def_start;
         }
     }
 }
@@ -672,23 +708,6 @@ cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, uint32_t dim, int3
 }
 
 namespace {
-// CTAs of tokenize_span_kernel one wave can hold (all devices of a process are the same part)
-int span_wave_ctas() {
-    static std::atomic<int> cached{0};
-    int v = cached.load(std::memory_order_acquire);
-    if (v) return v;
-    int dev = 0, sms = 0, per_sm = 0;
-    const uint32_t smem = span_smem_bytes(kSpanMaxBytes);
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        cudaFuncSetAttribute(tokenize_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tokenize_span_kernel, kFeatThreads, smem) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        return 0;
-    }
-    v = sms * per_sm;
-    cached.store(v, std::memory_order_release);
-    return v;
-}
 bool use_lookback_variant() {
     static const bool v = [] {
         const char *e = std::getenv("RF_TOKENIZE_VARIANT");
@@ -704,14 +723,21 @@ cudaError_t launch_tokenize(TokenizeArgs &t, uint32_t blk_first, uint32_t n_bloc
         tokenize_lookback_kernel<<<n_blocks_here, kFeatThreads, 0, s>>>(t);
         return cudaGetLastError();
     }
-    const int wave = span_wave_ctas();
-    if (wave <= 0) return cudaErrorInvalidDeviceFunction;
+    // bytes per CTA: small spans keep several generations of CTAs in flight per SM, so one CTA's latencies (ticket,
+    // first loads, the counts before it) are covered by its neighbours' hashing (RF_TOKENIZE_SPAN_KB: measurement knob)
+    static const uint32_t span_target = [] {
+        const char *e = std::getenv("RF_TOKENIZE_SPAN_KB");
+        const long kb = e ? std::atol(e) : 0;
+        return kb >= 4 && kb * 1024 <= static_cast<long>(kSpanMaxBytes) ? static_cast<uint32_t>(kb) * 1024u : kSpanDefaultBytes;
+    }();
+    static_assert(span_smem_bytes(kSpanMaxBytes) <= 48u * 1024u, "the span kernel launches without a shared-memory opt-in");
     size_t lo = static_cast<size_t>(blk_first) * kFeatBlockBytes;
     const size_t hi = std::min(t.n, (static_cast<size_t>(blk_first) + n_blocks_here) * kFeatBlockBytes);
     while (lo < hi) {
-        const size_t len = std::min(hi - lo, static_cast<size_t>(wave) * kSpanMaxBytes);
-        // at least 4 KB per CTA; otherwise the wave shares the bytes evenly (16-byte granules)
-        uint32_t ctas = static_cast<uint32_t>(std::min<size_t>(static_cast<size_t>(wave), (len + kFeatBlockBytes - 1) / kFeatBlockBytes));
+        // a CTA reads one count word per CTA before it: longer ranges take several launches (the running token
+        // count travels in ctl[kCtlTokens])
+        const size_t len = std::min(hi - lo, static_cast<size_t>(kSpanMaxCtas) * span_target);
+        uint32_t ctas = static_cast<uint32_t>((len + span_target - 1) / span_target);
         const uint32_t span = static_cast<uint32_t>(((len + ctas - 1) / ctas + 15) / 16 * 16);
         ctas = static_cast<uint32_t>((len + span - 1) / span);
         t.byte_lo = lo;

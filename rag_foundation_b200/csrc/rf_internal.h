@@ -202,7 +202,8 @@ void stage_copy(void *dst, const void *src, size_t n);
 constexpr uint32_t kFeatBlockBytes = 4096;
 constexpr uint32_t kMaxDeferred = 64;    // tokens longer than a whole copy chunk, finished after the last copy
 enum : uint32_t { kCtlTicket = 0, kCtlTokens = 1, kCtlDeferred = 2, kCtlWords = 4 };   // control words (zeroed per document)
-constexpr uint32_t kSpanMaxBytes = 20u << 10;   // text bytes one tokeniser CTA keeps in shared memory (8 CTAs per SM: 24 MB per wave)
+constexpr uint32_t kSpanMaxBytes = 12u << 10;   // most text bytes one tokeniser CTA keeps in shared memory (with its masks and token records: < 48 KB)
+constexpr uint32_t kSpanMaxCtas = 4096;         // CTAs per tokeniser launch
 struct TokenizeArgs {        // device scratch for one document
     const uint8_t *text;     // [>= n + 64] padded device copy of the document, 16-byte aligned
     size_t n;                // document bytes
@@ -222,7 +223,7 @@ struct TokenizeArgs {        // device scratch for one document
     uint32_t ticket_base;    // CTAs launched for this document before this launch
 };
 // Tokenise the document's 4 KB blocks [blk_first, blk_first + n_blocks_here): as many launches as the range needs
-// (one, unless it is longer than a full wave of CTAs can hold in shared memory).  Updates t.seq / t.ticket_base.
+// (one, unless the range is longer than kSpanMaxCtas spans).  Updates t.seq / t.ticket_base.
 cudaError_t launch_tokenize(TokenizeArgs &t, uint32_t blk_first, uint32_t n_blocks_here, cudaStream_t s);
 cudaError_t launch_hash_deferred(const TokenizeArgs &a, uint32_t count, cudaStream_t s);
 cudaError_t launch_rows_from_tokens(const TokenizeArgs &w, uint32_t n_tokens, uint32_t n_chunks, int8_t *F,

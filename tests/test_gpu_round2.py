@@ -518,12 +518,14 @@ def test_pipelined_ingest_sources_and_chunk_boundaries(co):
 
 
 @pytest.mark.timeout(600)
-def test_ingest_spans_and_waves_of_the_tokeniser(co):
-    """The tokeniser gives every CTA of a launch one contiguous span of the text (4 KB ... 22 KB, a multiple of 16
-    bytes) and sums the token counts of the CTAs before it; a range longer than one wave of CTAs can hold takes
-    several launches that hand the running token count on.  Device-resident documents take ONE range: sizes
-    around the points where the span stops being 4 KB (wave x 4 KB), where it reaches 22 KB (one full wave) and
-    beyond (two launches), with tokens / stop words straddling span edges by construction (running text)."""
+def test_ingest_spans_and_launches_of_the_tokeniser(co):
+    """The tokeniser gives every CTA of a launch one contiguous span of the text (up to 8 KB, a multiple of 16
+    bytes), keeps the span's token records in shared memory and places them once it has summed the token counts of
+    the CTAs before it; a range longer than 4096 spans takes several launches that hand the running token count
+    on.  Device-resident documents take ONE range: sizes around one span, a few spans, and the 32 MB where the
+    second launch begins, with tokens / stop words straddling span edges by construction (running text), the
+    densest token stream there is ("a b c ...": the record buffers are sized for it) and one token that runs
+    from the first span to the last."""
     import torch
     rng = np.random.default_rng(23)
     words = [b"alpha", b"the", b"Beta9", b"a", b"an", b"gamma", b"x", b"\xc3\xa9t\xc3\xa9", b"Zeta_zeta", b"0042", b"The", b"theory"]
@@ -532,19 +534,25 @@ def test_ingest_spans_and_waves_of_the_tokeniser(co):
         idx = rng.integers(0, len(words), n // 3 + 8)
         return b" ".join(words[int(i)] for i in idx)[:n]
 
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    wave = sms * 8
-    sizes = [wave * 4096 - 1, wave * 4096 + 16, wave * 4096 + 4097, 3 * wave * 4096 // 2 + 5,
-             wave * 22 * 1024, wave * 22 * 1024 + 1, wave * 22 * 1024 + 70_001]
+    per_launch = 4096 * 8192
+    sizes = [8191, 8192, 8192 + 16, 3 * 8192 + 4097, (1 << 20) + 13, per_launch - 1, per_launch, per_launch + 1, per_launch + 70_001]
     base = running_text(max(sizes))
+    dense = b" ".join(bytes([98 + i % 24]) for i in range(40_000))                  # b c d ... : one kept token per 2 bytes
+    giant = b"lead in " + b"q" * 100_000 + b" tail words follow " + running_text(5_000)
     with _engine(120_000) as e:
         s = e.open_store("fileSearchStores/spans")
         dd = torch.frombuffer(bytearray(base), dtype=torch.uint8).cuda()
         torch.cuda.synchronize()
-        for i, n in enumerate(sizes):
-            first, nc = _check_ingest(e, s, i + 1, base[:n], co, ptr=dd.data_ptr())
+        doc = 1
+        for n in sizes:
+            first, nc = _check_ingest(e, s, doc, base[:n], co, ptr=dd.data_ptr())
             assert nc > 0
-            e.tombstone_doc(i + 1)     # the rows go back to the free list: the next document reuses them
+            e.tombstone_doc(doc)      # the rows go back to the free list: the next document reuses them
+            doc += 1
+        for data in (dense, giant):
+            for off in (0, 1, 7):
+                _check_ingest(e, s, doc, data[off:], co)
+                doc += 1
 
 
 # ------------------------------------------------------------------ store table + store-sharded fused exchange
