@@ -6,17 +6,15 @@
 // scripts/benchmark/metrics.py:6,13-19 at byte level.
 //
 // Byte/integer work, bound by the H2D copy of the text (PCIe), which the engine overlaps with it:
-//   tokenise  ONE pass per copied chunk of text: 4 KB blocks flag their kept-token starts, learn how many
-//             tokens precede them by a decoupled look-back, hash each token (FNV-1a 32) and emit
-//             (bucket, byte end [, byte start of a window's first token]) at its global token ordinal
-//   rows      one warp per chunk window [112 w, 112 w + 128): shared-memory histogram of the
-//             window's buckets -> one dim-byte int8 row, its sum of squares, store word, byte span
-// A token is "kept" when it is not one of a / an / the, decided at its first byte with a 3-byte
-// look-ahead, so stop-word removal needs no second compaction.
+//   tokenise  ONE pass per copied chunk of text: a CTA stages a contiguous span (<= 8 KB) in shared memory,
+//             derives token-byte / kept-start masks with packed arithmetic, hashes each token (FNV-1a 32) into
+//             shared-memory records, and places (bucket, byte end [, byte start of a window's first token]) at
+//             the global token ordinals once it has summed the token counts of the CTAs before it
+//   rows      one warp per chunk window [112 w, 112 w + 128): shared-memory byte histogram of the window's
+//             buckets = the dim-byte int8 row itself; its sum of squares, store word, byte span
+// A token is "kept" when it is not one of a / an / the.
 #include <algorithm>
-#include <atomic>
 #include <cstdlib>
-#include <string>
 
 #include "rf_device.cuh"
 #include "rf_internal.h"
@@ -26,7 +24,6 @@ namespace rf {
 namespace {
 
 constexpr int kFeatThreads = 256;
-constexpr int kBytesPerThread = kFeatBlockBytes / kFeatThreads;  // 16
 constexpr int kChunkTokens = 128;
 constexpr int kChunkStride = 112;
 
@@ -46,13 +43,6 @@ __device__ __forceinline__ bool kept_start(const uint8_t *s) {
     return !stop;
 }
 
-// Stage one 4 KB block of lowered text (+1 byte before, +4 after; zero = separator outside).
-// Shared copy of a 4 KB text block, lower-cased: s_txt[1 + i] = text[base + i]; s_txt[0] is the byte before the
-// block and s_txt[4097 .. 4100] the four after it (0 outside the document).  s_txt + 1 is 16-byte aligned:
-// the block is exactly one 16-byte global load and one 16-byte shared store per thread.
-constexpr int kStageBytes = 16 + static_cast<int>(kFeatBlockBytes) + 16;
-__device__ __forceinline__ uint8_t *stage_origin(uint8_t *s_raw) { return s_raw + 15; }
-
 // four packed ASCII bytes -> lower case (bytes >= 0x80 are left alone)
 __device__ __forceinline__ uint32_t lower4(uint32_t x) {
     const uint32_t lo7 = x & 0x7F7F7F7Fu;
@@ -61,66 +51,6 @@ __device__ __forceinline__ uint32_t lower4(uint32_t x) {
     const uint32_t upper = ge_A & ~ge_bracket & ~x & 0x80808080u;
     return x | (upper >> 2);                            // + 0x20
 }
-
-__device__ __forceinline__ void stage_block(const uint8_t *__restrict__ text, size_t n, size_t base, uint8_t *s_raw) {
-    static_assert(kFeatBlockBytes == kFeatThreads * 16, "one 16-byte load per thread");
-    const size_t at = base + static_cast<size_t>(threadIdx.x) * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (at < n) {
-        v = *reinterpret_cast<const uint4 *>(text + at);       // the text buffer is padded by 64 bytes
-        if (at + 16 > n) {                                      // last bytes of the document: clear what lies beyond it
-            const uint32_t keep = static_cast<uint32_t>(n - at);        // 1 .. 15
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int valid = static_cast<int>(keep) - 4 * i;       // bytes of this word inside the document
-                w[i] = valid >= 4 ? w[i] : valid <= 0 ? 0u : (w[i] & ((1u << (8 * valid)) - 1u));
-            }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        v = make_uint4(lower4(v.x), lower4(v.y), lower4(v.z), lower4(v.w));
-    }
-    *reinterpret_cast<uint4 *>(s_raw + 16 + threadIdx.x * 16) = v;
-    uint8_t *s_txt = stage_origin(s_raw);
-    if (threadIdx.x == 0) s_txt[0] = base > 0 ? lower_byte(text[base - 1]) : 0;
-    if (threadIdx.x >= 1 && threadIdx.x <= 4) {
-        const size_t g = base + kFeatBlockBytes + (threadIdx.x - 1);
-        s_txt[1 + kFeatBlockBytes + (threadIdx.x - 1)] = g < n ? lower_byte(text[g]) : 0;
-    }
-    __syncthreads();
-}
-
-// bit j <=> a kept token starts at the thread's byte j: the 16 bytes come back as one 16-byte shared load,
-// the byte before and the four after as two more, and the rule runs on registers
-__device__ __forceinline__ uint32_t thread_flags(const uint8_t *s_raw) {
-    const uint8_t *mine = s_raw + 16 + threadIdx.x * 16;
-    const uint4 v = *reinterpret_cast<const uint4 *>(mine);
-    const uint32_t next = *reinterpret_cast<const uint32_t *>(mine + 16);
-    uint8_t w[21];
-    w[0] = mine[-1];
-    const uint32_t words[5] = {v.x, v.y, v.z, v.w, next};
-#pragma unroll
-    for (int i = 0; i < 20; ++i) w[1 + i] = static_cast<uint8_t>(words[i >> 2] >> (8 * (i & 3)));
-    uint32_t flags = 0;
-#pragma unroll
-    for (int j = 0; j < kBytesPerThread; ++j) flags |= (kept_start(w + 1 + j) ? 1u : 0u) << j;
-    return flags;
-}
-
-// ---- single-pass tokeniser, look-back variant (RF_TOKENIZE_VARIANT=lookback; kept for A/B comparison) -----
-// Measured: with ~1200 blocks in flight a block walks back over most of them, 32 per L2 round trip, so a
-// block lives ~29 us and a 22.8 MB document takes 136 us -- tokenize_span_kernel below replaces it.
-// One block per 4 KB of text: stage + lower-case it, flag the kept-token starts, and place the block's
-// tokens at their GLOBAL ordinals in the same pass -- the exclusive token count of everything before the
-// block comes from a decoupled look-back over a per-block status array (aggregate published as soon as
-// the block has counted, inclusive prefix once it has looked back), so the text is read once and there is
-// no separate count / scan pass.  Blocks take their number from a ticket, so a block's predecessors have
-// always started.  The text may still be arriving: a launch covers the blocks of one copied chunk and
-// bytes are valid up to `avail_end`; a token that runs past it (only possible for a token longer than a
-// whole chunk) is parked in a short list and hashed by hash_deferred_kernel once every byte is there.
-// Per kept token: bucket (1 B) and end offset (4 B) at its ordinal; the start offset only for the tokens
-// that open a chunk window (ordinal % 112 == 0).
-constexpr uint64_t kStAggregate = 1ull << 32, kStInclusive = 2ull << 32;
 
 __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
     uint64_t v;
@@ -131,97 +61,12 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kFeatThreads) tokenize_lookback_kernel(const TokenizeArgs a) {
-    __shared__ __align__(16) uint8_t s_raw[kStageBytes];
-    __shared__ uint32_t s_warp[kFeatThreads / 32];
-    __shared__ uint32_t s_block, s_ex;
-    if (threadIdx.x == 0) s_block = atomicAdd(a.ctl + kCtlTicket, 1u);
-    __syncthreads();
-    const uint32_t B = s_block;
-    const size_t base = static_cast<size_t>(B) * kFeatBlockBytes;
-    stage_block(a.text, a.n, base, s_raw);
-    const uint8_t *s_txt = stage_origin(s_raw);
-    const uint32_t flags = thread_flags(s_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t c = __popc(flags);
-    uint32_t inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t warp_off = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kFeatThreads / 32; ++w) {
-        if (w < warp) warp_off += s_warp[w];
-        total += s_warp[w];
-    }
-    if (warp == 0) {
-        // ---- decoupled look-back (warp 0): 32 predecessors per step, nearest first
-        if (lane == 0) st_release_u64(a.state + B, (B == 0 ? kStInclusive : kStAggregate) | total);
-        uint32_t ex = 0;
-        for (int64_t j = static_cast<int64_t>(B) - 1; j >= 0; j -= 32) {
-            const int64_t idx = j - lane;
-            uint64_t v = kStInclusive;                        // before the first block: an inclusive prefix of 0
-            if (idx >= 0) {
-                do { v = ld_acquire_u64(a.state + idx); } while ((v >> 32) == 0);
-            }
-            const unsigned incl = __ballot_sync(kFull, (v >> 32) == 2);
-            const int stop = incl ? __ffs(incl) - 1 : 31;    // nearest predecessor that already knows its prefix
-            uint32_t part = lane <= stop ? static_cast<uint32_t>(v) : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-            ex += part;
-            if (incl) break;
-        }
-        if (lane == 0) {
-            if (B) st_release_u64(a.state + B, kStInclusive | (ex + total));
-            s_ex = ex;
-            if (B + 1 == a.n_blocks) a.ctl[kCtlTokens] = ex + total;
-        }
-    }
-    __syncthreads();
-    uint32_t ord = s_ex + warp_off + inc - c;
-
-    uint32_t f = flags;
-    while (f) {
-        const int j = __ffs(f) - 1;
-        f &= f - 1;
-        const size_t start = base + static_cast<size_t>(threadIdx.x) * kBytesPerThread + j;
-        uint32_t h = 0x811C9DC5u;
-        size_t p = start;
-        // tokens are short; bytes past this block come from L2 (the copy just streamed them in)
-        while (p < a.avail_end) {
-            const uint8_t cb = (p - base) < static_cast<size_t>(kFeatBlockBytes) + 4 ? s_txt[p - base + 1]
-                                                                                    : lower_byte(a.text[p]);
-            if (!token_byte(cb)) break;
-            h ^= cb;
-            h *= 0x01000193u;
-            ++p;
-        }
-        if (ord % kChunkStride == 0) a.chunk_start[ord / kChunkStride] = static_cast<uint32_t>(start);
-        if (p == a.avail_end && a.avail_end < a.n) {
-            // ran out of copied bytes mid-token: finish it later (hash_deferred_kernel)
-            const uint32_t slot = atomicAdd(a.ctl + kCtlDeferred, 1u);
-            if (slot < kMaxDeferred) {
-                a.deferred[2 * slot] = ord;
-                a.deferred[2 * slot + 1] = static_cast<uint32_t>(start);
-            }
-        } else {
-            a.tok_bucket[ord] = static_cast<uint16_t>(h & a.dim_mask);
-            a.tok_end[ord] = static_cast<uint32_t>(p);
-        }
-        ++ord;
-    }
-}
-
-// ---- single-pass tokeniser, span variant (default) ------------------------------------------------------------
+// ---- single-pass tokeniser ----------------------------------------------------------------------------------
 // CTA c of a launch (numbered by a ticket, so the CTAs before it have always started) keeps a CONTIGUOUS span
 // of the text (8 KB by default, at most 12 KB) in shared memory and produces its tokens there before it needs
-// to know how many tokens precede it.  The kernel is shaped by two measurements of the look-back variant:
-// ~4.9 warp instructions per text byte, and two scattered 2 / 4-byte global stores per token.
+// to know how many tokens precede it.  The kernel is shaped by two measurements of its predecessor (one 4 KB block
+// per CTA, decoupled look-back, one thread hashing each token byte by byte: 136 us per 22.8 MB): ~4.9 warp
+// instructions per text byte, and two scattered 2 / 4-byte global stores per token.
 //   stage   16 bytes per thread and step: lower-cased with packed arithmetic, and the "token byte" /
 //           "letter" predicates of the 16 bytes computed 4 bytes per operation and kept as two 16-bit masks
 //           per 16-byte unit
@@ -505,41 +350,44 @@ __global__ void __launch_bounds__(64) hash_deferred_kernel(const TokenizeArgs a,
 
 constexpr int kRowWarps = 8;
 
-// kM: 256-byte sub-rows per row (dim = 256 * kM); the warp's histogram has dim counters, a lane writes
-// 8 bytes of each sub-row
+// kM: 256-byte sub-rows per row (dim = 256 * kM).  A window holds at most 128 tokens, so a bucket's count fits
+// a byte: the warp's histogram IS the row -- dim byte counters bumped four to a 32-bit word (shared atomicAdd of
+// 1 << 8 * (bucket & 3); 128 in one byte cannot carry), read back 8 bytes per lane and sub-row without bank
+// conflicts, clamped to 127 (only a count of exactly 128 is above it) and stored as they are.
 template <int kM>
 __global__ void __launch_bounds__(kRowWarps * 32) rows_from_tokens_kernel(
     const uint16_t *__restrict__ tok_bucket, const uint32_t *__restrict__ chunk_start,
     const uint32_t *__restrict__ tok_end, uint32_t n_tokens, uint32_t n_chunks, int8_t *__restrict__ F,
     int32_t *__restrict__ ff, uint32_t *__restrict__ seg, uint32_t store_seg, int64_t *__restrict__ spans) {
     constexpr int kD = kSubDim * kM;
-    __shared__ uint32_t hist[kRowWarps][kD];
+    static_assert(kChunkTokens <= 128, "a byte counter holds a window's largest count");
+    __shared__ __align__(8) uint32_t hist[kRowWarps][kD / 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *h = hist[warp];
     for (uint32_t w = blockIdx.x * kRowWarps + warp; w < n_chunks; w += gridDim.x * kRowWarps) {
 #pragma unroll
-        for (int j = 0; j < kD / 32; ++j) h[lane + 32 * j] = 0;
+        for (int sub = 0; sub < kM; ++sub) *reinterpret_cast<uint2 *>(h + sub * (kSubDim / 4) + lane * 2) = make_uint2(0u, 0u);
         __syncwarp();
         const uint32_t lo = w * kChunkStride;
         const uint32_t hi = min(lo + kChunkTokens, n_tokens);
-        for (uint32_t t = lo + lane; t < hi; t += 32) atomicAdd(&h[tok_bucket[t]], 1u);
+#pragma unroll
+        for (int j = 0; j < kChunkTokens / 32; ++j) {
+            const uint32_t t = lo + j * 32 + lane;
+            if (t < hi) {
+                const uint32_t b = tok_bucket[t];
+                atomicAdd(&h[b >> 2], 1u << (8 * (b & 3u)));
+            }
+        }
         __syncwarp();
         int sq = 0;
 #pragma unroll
         for (int sub = 0; sub < kM; ++sub) {
-            uint32_t packed[2];
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t t = min(h[sub * kSubDim + lane * 8 + x * 4 + b], 127u);
-                    v |= t << (8 * b);
-                    sq += static_cast<int>(t * t);
-                }
-                packed[x] = v;
-            }
-            *reinterpret_cast<uint2 *>(F + (static_cast<size_t>(w) * kM + sub) * kSubBytes + lane * 8) = make_uint2(packed[0], packed[1]);
+            uint2 v = *reinterpret_cast<const uint2 *>(h + sub * (kSubDim / 4) + lane * 2);
+            v.x -= (v.x >> 7) & 0x01010101u;          // 128 -> 127
+            v.y -= (v.y >> 7) & 0x01010101u;
+            sq = __dp4a(static_cast<int>(v.x), static_cast<int>(v.x), sq);
+            sq = __dp4a(static_cast<int>(v.y), static_cast<int>(v.y), sq);
+            *reinterpret_cast<uint2 *>(F + (static_cast<size_t>(w) * kM + sub) * kSubBytes + lane * 8) = v;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
@@ -707,22 +555,8 @@ cudaError_t launch_row_meta(const int8_t *F, uint64_t n_rows, uint32_t dim, int3
     return cudaGetLastError();
 }
 
-namespace {
-bool use_lookback_variant() {
-    static const bool v = [] {
-        const char *e = std::getenv("RF_TOKENIZE_VARIANT");
-        return e && std::string(e) == "lookback";
-    }();
-    return v;
-}
-}  // namespace
-
 cudaError_t launch_tokenize(TokenizeArgs &t, uint32_t blk_first, uint32_t n_blocks_here, cudaStream_t s) {
     if (n_blocks_here == 0) return cudaSuccess;
-    if (use_lookback_variant()) {   // block numbers come from the ticket: launches cover the blocks in order
-        tokenize_lookback_kernel<<<n_blocks_here, kFeatThreads, 0, s>>>(t);
-        return cudaGetLastError();
-    }
     // bytes per CTA: small spans keep several generations of CTAs in flight per SM, so one CTA's latencies (ticket,
     // first loads, the counts before it) are covered by its neighbours' hashing (RF_TOKENIZE_SPAN_KB: measurement knob)
     static const uint32_t span_target = [] {

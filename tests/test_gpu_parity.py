@@ -353,7 +353,9 @@ def test_ingest_text_edge_cases(co):
              b"q" * 4095 + b" " + b"r" * 4097 + b" the", b"ab" * 2047 + b"the" + b" x",
              # ... and the 16 KB edges of a tokeniser block / the 4 KB rounds inside it
              b"A" + b" " * 16383 + b"the" + b" " * 16381 + b"an bc", b"w " * 8191 + b"the" + b" x y", b"q" * 16383 + b" " + b"r" * 16385 + b" the",
-             (b"tok " * 4096)[:16383] + b"the an a tail", b" " * 16380 + b"edge" + b"word more" + b" " * 4090 + b"lastthe"]
+             (b"tok " * 4096)[:16383] + b"the an a tail", b" " * 16380 + b"edge" + b"word more" + b" " * 4090 + b"lastthe",
+             # every token of a window in ONE bucket (count 128 saturates to 127), and in two buckets of the same 4-byte word
+             b"zq " * 400, b"zq " * 127 + b"other " + b"zq " * 300, b" ".join(b"w%d" % (i % 4) for i in range(1000))]
     with _engine(8192) as e:
         s = e.open_store("fileSearchStores/a")
         nxt = 0

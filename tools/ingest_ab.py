@@ -1,6 +1,6 @@
-"""A/B of the tokeniser variants on one resident document (RF_TOKENIZE_VARIANT is read once per process, so run
-this script once per variant): device time of the featurise kernels (CUDA events inside the engine) and the
-call's wall time.  Usage: python tools/ingest_ab.py [bytes]"""
+"""Device time of the featurise kernels (CUDA events inside the engine) and the call's wall time for one
+device-resident document; RF_TOKENIZE_SPAN_KB sets the bytes per tokeniser CTA.
+Usage: python tools/ingest_ab.py [bytes]"""
 import json
 import os
 import sys
@@ -32,7 +32,7 @@ def main():
         wall = (time.perf_counter() - t0) / reps
         kern = (e.stats()["ingest_kernel_ns"] - k0) / reps
         same = bool(c == nc and (e.read_rows(f - e.id_base, c)[0] == F0).all())
-        print(json.dumps({"variant": os.environ.get("RF_TOKENIZE_VARIANT", "span"), "bytes": len(data), "chunks": nc,
+        print(json.dumps({"bytes": len(data), "chunks": nc,
                           "kernel_us": kern / 1e3, "wall_us": wall * 1e6, "rows_repeatable": same,
                           "rows_sum": int(F0.astype(np.int64).sum())}))
 
