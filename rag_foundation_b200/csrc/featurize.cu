@@ -52,9 +52,11 @@ __device__ __forceinline__ uint32_t lower4(uint32_t x) {
     return x | (upper >> 2);                            // + 0x20
 }
 
-__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
+// A count word carries its own tag (launch number) and nothing else is read on its strength, so polling it needs
+// no acquire: a relaxed L2 load (ld.acquire.gpu costs an L1 invalidation, CCTL.IVALL, per poll).
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     uint32_t before = 0;
     for (uint32_t j = threadIdx.x; j < cta; j += kFeatThreads) {
         uint64_t v;
-        while (static_cast<uint32_t>((v = ld_acquire_u64(a.state + j)) >> 32) != a.seq) __nanosleep(200);
+        while (static_cast<uint32_t>((v = ld_relaxed_u64(a.state + j)) >> 32) != a.seq) __nanosleep(200);
         before += static_cast<uint32_t>(v);
     }
     before = __reduce_add_sync(kFull, before);
