@@ -460,7 +460,7 @@ def _check_ingest(e, seg, doc_id, data, co, ptr=None):
 @pytest.mark.timeout(600)
 def test_pipelined_ingest_sources_and_chunk_boundaries(co):
     """Documents larger than one 2 MB copy chunk go through the staging ring (helper threads + chunk-by-chunk
-    DMA + one tokeniser launch per chunk with a decoupled look-back across all of them): rows, norms and spans
+    DMA + one tokeniser launch per chunk, the running token count handed from launch to launch): rows, norms and spans
     equal the oracle for pageable, pinned (rf_host_alloc) and device-resident sources; tokens that straddle a
     chunk boundary, stop words at the boundary, and tokens LONGER than a whole chunk (hashed after the last
     copy) included."""
