@@ -687,14 +687,44 @@ def run_b200(args) -> None:
     # the query batch is resident and complete before the first search: back-to-back scans may overlap
     torch.cuda.synchronize(dev)
     eng.set_stream_overlap(stream.cuda_stream, True)
+    # N = 1: the device-resident searches alternate between TWO caller streams (what a server with several requests
+    # in flight does; `e2e` below does the same through rf_search_begin / rf_search_end).  A stream's searches still
+    # follow each other under programmatic dependent launch; the other stream's blocks are already queued on the
+    # device and take an SM the moment one of this query's blocks retires, so no SM waits for the slowest block of
+    # the query before it.  --streams 1 is the single-stream schedule (reported beside it either way).
+    streams = [stream]
+    if n_gpus == 1:
+        for _ in range(max(1, args.streams) - 1):
+            s2 = torch.cuda.Stream(dev)
+            eng.set_stream_overlap(s2.cuda_stream, True)
+            streams.append(s2)
 
-    def step(i: int):
+    def step(i: int, n_streams: int = 0):
         qi = i % N_DISTINCT_QUERIES
         q = Qd[qi:qi + 1]
         if n_gpus == 1:
-            eng.search_keys_device(q.data_ptr(), 1, [seg], k, out_keys[qi].data_ptr(), stream.cuda_stream)
+            st = streams[i % (n_streams or len(streams))]
+            eng.search_keys_device(q.data_ptr(), 1, [seg], k, out_keys[qi].data_ptr(), st.cuda_stream)
         else:
             searcher.search_keys(q, [seg], k, out=out_keys[qi:qi + 1])
+
+    def timed_region(n: int, n_streams: int = 0) -> float:
+        """ms for steps 0 .. n-1: CUDA events on the first stream, which the other streams start behind and which
+        joins them again before the closing event."""
+        use = streams[:(n_streams or len(streams))]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(use[0])
+        for o in use[1:]:
+            o.wait_event(e0)
+        for i in range(n):
+            step(i, len(use))
+        for o in use[1:]:
+            j = torch.cuda.Event()
+            j.record(o)
+            use[0].wait_event(j)
+        e1.record(use[0])
+        e1.synchronize()
+        return e0.elapsed_time(e1)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -756,26 +786,30 @@ def run_b200(args) -> None:
             step(i)
         sync_all()
         launches0 = eng.stats()["kernel_launches"]
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for i in range(steps):
-            step(i)
-        ev1.record(stream)
+        ms = timed_region(steps)
         sync_all()
-        ms = ev0.elapsed_time(ev1)
         launches = eng.stats()["kernel_launches"] - launches0
 
-        # ---- scan kernel alone (the dominant kernel), same stream, CUDA events
+        # ---- scan kernel alone (the dominant kernel): the same launches without the exchange, CUDA events on the
+        # launching stream(s); at N = 1 also the single-stream schedule
         kq = min(steps, 512)
-        ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scratch = torch.zeros((1, k), dtype=torch.int64, device=dev)
-        ek0.record(stream)
-        for i in range(kq):
-            qi = i % N_DISTINCT_QUERIES
-            eng.search_keys_device(Qd[qi:qi + 1].data_ptr(), 1, [seg], k, scratch.data_ptr(), stream.cuda_stream)
-        ek1.record(stream)
-        sync_all()
-        kernel_ms = ek0.elapsed_time(ek1) / kq
+        single_stream_ms = None
+        if n_gpus == 1:
+            kernel_ms = timed_region(kq) / kq
+            sync_all()
+            if len(streams) > 1:
+                single_stream_ms = timed_region(kq, 1) / kq
+                sync_all()
+        else:
+            ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ek0.record(stream)
+            for i in range(kq):
+                qi = i % N_DISTINCT_QUERIES
+                eng.search_keys_device(Qd[qi:qi + 1].data_ptr(), 1, [seg], k, scratch.data_ptr(), stream.cuda_stream)
+            ek1.record(stream)
+            sync_all()
+            kernel_ms = ek0.elapsed_time(ek1) / kq
 
         # ---- isolated launches (a lone caller's latency: no overlap with a neighbouring query)
         lat_us = []
@@ -942,10 +976,20 @@ def run_b200(args) -> None:
             "vs_baseline": None, "dtype": "s8 x s8 -> s32", "data": "synthetic",
             "config": make_config(n_gpus, n_total, custom=bool(args.chunks)),
             "exchange": exchange, "qps": steps / (ms * 1e-3),
+            **({"schedule": f"unbatched single-query searches (one scan-kernel launch each), alternating between {len(streams)} caller streams, "
+                            "so two searches are in flight on the GPU; roofline.single_stream and e2e.sequential_ms_per_query are the one-stream / one-caller figures"}
+               if n_gpus == 1 and len(streams) > 1 else {}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": load_traffic(traffic_key), "traffic_source": "ncu --set full capture of this kernel at this shard size (profiles/roofline_traffic.json)",
                          "kernel": SCAN_KERNEL, "kernel_ms": kernel_ms,
-                         "kernel_ms_note": "local scan + fused top-k per GPU, back-to-back launches, max over ranks" + ("" if n_gpus == 1 else " (the exchange is in ms_per_step, not here)"),
+                         "kernel_ms_note": (f"timed region / launches, launches alternating between {len(streams)} caller streams (each stream's searches under programmatic "
+                                            "dependent launch): the aggregate rate of the kernel with two queries in flight; one launch alone takes "
+                                            "isolated_launch_latency_us" if n_gpus == 1 and len(streams) > 1 else
+                                            "local scan + fused top-k per GPU, back-to-back launches on one stream, max over ranks" + ("" if n_gpus == 1 else " (the exchange is in ms_per_step, not here)")),
+                         **({"single_stream": {"kernel_ms": single_stream_ms, "achieved": shard_rows * BYTES_PER_CHUNK / (single_stream_ms * 1e-3) / 1e9,
+                                               "frac": shard_rows * BYTES_PER_CHUNK / (single_stream_ms * 1e-3) / 1e9 / hbm_peak,
+                                               "note": "the same launches back to back on ONE stream (programmatic dependent launch only)"}}
+                            if single_stream_ms else {}),
                          "algorithmic_bytes_per_launch": shard_rows * BYTES_PER_CHUNK, "peak_source": peak_src,
                          "frac_of_8TBps": achieved / 8000.0},
             "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
@@ -1000,6 +1044,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[4] / ingest / scaling_base legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle checks (profiling runs)")
+    ap.add_argument("--streams", type=int, default=2, help="caller streams the N = 1 device-resident searches alternate between")
     ap.add_argument("--legs", default="cfg2,ingest,cfg4,wide,scaling_base", help="which configs legs to run at N = 1 (comma list)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU top-k exchange")
     args = ap.parse_args()
