@@ -567,7 +567,8 @@ def leg_scaling_base(torch, dev, hbm_peak, steps: int):
         gbs = CFG4_ROWS * BYTES_PER_CHUNK / (ms * 1e-3) / 1e9
         return {"workload": "configs[3] corpus (100M chunks) on ONE B200: same-corpus origin of the 2/4/8-GPU lines", "n_gpus": 1,
                 "ms_per_step": ms, "value": CFG4_ROWS / (ms * 1e-3), "unit": "chunks/s",
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak},
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "traffic": load_traffic(f"shard_{CFG4_ROWS}")},
                 "e2e_ms_per_query": e2e_ms, "e2e_value": CFG4_ROWS / (e2e_ms * 1e-3)}
 
 
@@ -980,7 +981,7 @@ def run_b200(args) -> None:
                             "so two searches are in flight on the GPU; roofline.single_stream and e2e.sequential_ms_per_query are the one-stream / one-caller figures"}
                if n_gpus == 1 and len(streams) > 1 else {}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": load_traffic(traffic_key), "traffic_source": "ncu --set full capture of this kernel at this shard size (profiles/roofline_traffic.json)",
+                         "traffic": load_traffic(traffic_key), "traffic_source": "ncu capture of this kernel at this shard size (profiles/roofline_traffic.json, ncu_traffic_r02c.txt)",
                          "kernel": SCAN_KERNEL, "kernel_ms": kernel_ms,
                          "kernel_ms_note": (f"timed region / launches, launches alternating between {len(streams)} caller streams (each stream's searches under programmatic "
                                             "dependent launch): the aggregate rate of the kernel with two queries in flight; one launch alone takes "
