@@ -49,7 +49,7 @@ typedef struct rf_engine rf_engine;
 typedef struct rf_config {
     uint32_t struct_size;    /* sizeof(rf_config), for forward compatibility            */
     int32_t device;          /* CUDA ordinal                                            */
-    uint32_t dim;            /* 256 (RF_DIM), 512 or 1024; batched tensor-core scoring is built for 256 */
+    uint32_t dim;            /* 256 (RF_DIM), 512 or 1024; batches take the tensor cores at every width */
     uint32_t n_contexts;     /* concurrent searches (reference: 50 streams/process, routes/chat.py:40); 0 -> 8 */
     uint64_t capacity_rows;  /* chunk rows reserved in HBM (dim + 8 B each)             */
     uint64_t id_base;        /* global chunk id of row 0 (shard offset in sharded mode) */

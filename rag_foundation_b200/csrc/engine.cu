@@ -935,15 +935,15 @@ uint32_t fnv1a32(const char *s, size_t n) {
 // 1024 queries x 1 M rows take 0.248 ms.
 bool gemm_pays(const rf_engine *e, uint32_t nq, uint64_t rows, uint64_t span, uint32_t k, double extra_us = 0.0) {
     if (!e->gemm_enabled || k > static_cast<uint32_t>(rf::kGemmListK) || span < 32768 || nq < 2) return false;
-    if (e->gemm_min_queries) return nq >= e->gemm_min_queries && rows * 2 >= span && (e->dim == RF_DIM || e->dim == 1024);
-    if (e->dim == 1024) {
-        // K = 1024 pair kernel: 256 queries per pair keep it HBM-bound -- one streaming pass over the span per 256 queries
-        // (~1.6e-4 us per row and pass), against one 1028-byte-per-row scan per query
-        const double scan_us = 6.0 + 1.46e-4 * nq * static_cast<double>(rows);
-        const double gemm_us = 45.0 + extra_us + 1.6e-4 * static_cast<double>(span) * ((nq + 255) / 256);
+    if (e->gemm_min_queries) return nq >= e->gemm_min_queries && rows * 2 >= span;
+    if (e->dim != RF_DIM) {
+        // K = 512 / 1024 pair kernel: 256 queries per pair keep it HBM-bound -- one streaming pass over the span per 256
+        // queries (~1.6e-4 us per 1024-byte row and pass), against one (dim + 4)-byte-per-row scan per query
+        const double w = static_cast<double>(e->dim) / 1024.0;
+        const double scan_us = 6.0 + 1.46e-4 * w * nq * static_cast<double>(rows);
+        const double gemm_us = 45.0 + extra_us + 1.6e-4 * w * static_cast<double>(span) * ((nq + 255) / 256);
         return scan_us > gemm_us;
     }
-    if (e->dim != RF_DIM) return false;          // (no tensor-core kernel for 512-feature rows)
     const double scan_us = 6.0 + 3.65e-5 * nq * static_cast<double>(rows);
     const double gemm_us = 33.0 + extra_us + std::max(4.6e-5, 2.1e-7 * nq) * static_cast<double>(span);
     return scan_us > gemm_us;
@@ -961,7 +961,7 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
     const uint32_t rows = hi - lo;
     // More than 256 queries: CTA pairs (tcgen05 cta_group::2, 256-row tiles, full tensor-pipe rate);
     // smaller batches stay on the single-CTA kernel, whose spare accumulators take alternate tiles.
-    const bool wide = e->dim == 1024;               // K = 1024: the pair kernel with the K dimension streamed, 256 queries per pair
+    const bool wide = e->dim != RF_DIM;             // K = 512 / 1024: the pair kernel with the K dimension streamed, 256 queries per pair
     const bool pair = wide || (e->gemm_pair && nq > 256 && e->sm_count >= 2);
     const uint32_t tile_rows = pair ? rf::kGemmPairTileRows : rf::kGemmTileRows;
     const uint32_t q_groups = wide ? (nq + 255) / 256 : (nq + rf::kGemmMT * 128 - 1) / (rf::kGemmMT * 128);   // 512 queries per block or pair
@@ -988,7 +988,7 @@ int search_gemm(rf_engine *e, StreamState *dp, const int8_t *q_dev, uint32_t nq,
         RF_CUDA(dp->gemm_floors.reserve(static_cast<size_t>(nq) * 8));
     }
     auto launch = [&](const rf::GemmArgs &g, uint32_t n_slices) {
-        return wide ? rf::launch_score_topk_gemm_wide(g, q_dev, e->F, e->cfg.capacity_rows, n_slices, s)
+        return wide ? rf::launch_score_topk_gemm_wide(g, q_dev, e->F, e->cfg.capacity_rows, e->dim, n_slices, s)
                : pair ? rf::launch_score_topk_gemm_pair(g, q_dev, e->F, e->cfg.capacity_rows, n_slices, s)
                       : rf::launch_score_topk_gemm(g, q_dev, e->F, e->cfg.capacity_rows, n_slices, s);
     };

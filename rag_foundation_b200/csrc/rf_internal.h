@@ -184,7 +184,7 @@ cudaError_t launch_kth_largest(const uint32_t *vals, uint32_t n_groups, uint32_t
 // 1024-feature rows (K = 1024): the pair kernel with the K dimension streamed; 256 queries per pair, one list per (slice, query);
 // floor pass and k-th largest as the pair kernel's
 size_t gemm_wide_lists_bytes(uint32_t n_slices, uint32_t nq);
-cudaError_t launch_score_topk_gemm_wide(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices,
+cudaError_t launch_score_topk_gemm_wide(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t dim, uint32_t n_slices,
                                         cudaStream_t s);
 // keys: [n_lists, nq, k_in] sorted lists -> out [nq, k_out] (k_out <= k_in <= 32, n_lists <= 1024)
 cudaError_t launch_merge_lists(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k_in, uint32_t k_out, uint64_t *out,

@@ -519,18 +519,19 @@ score_topk_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     if (warp == kPProducerWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-// ---- 1024-feature rows (K = 1024): the same pair kernel with the K dimension streamed -----------------------------
-// A row is four 256-byte K-slabs.  A CTA keeps its 128 queries of ONE M-group resident with all of K (128 KB), so a pair
-// owns 256 queries; a chunk tile's B operand arrives as four ring stages (one K-slab of this CTA's 128 rows each, 32 KB,
-// three stages), the tile's 4 x 8 MMAs accumulate into one 256-column accumulator and the two accumulators alternate by
-// TILE.  Per tile the epilogue has one accumulator to drain per 4096 cycles of MMA time, so it is never the limit here;
-// with 256 queries per pair the pass is HBM-bound instead (256 KB of features per pair and tile): a batch of up to 256
-// queries costs one streaming pass over the scope, larger batches one pass per 256 queries that mostly hits L2 (the query
-// groups of a slice run side by side).
-constexpr int kWSlabs = 4;
+// ---- wider rows (K = 512, 1024): the same pair kernel with the K dimension streamed ------------------------------------
+// A row is kSlabs 256-byte K-slabs (2 or 4).  A CTA keeps its 128 queries of ONE M-group resident with all of K (64 / 128
+// KB), so a pair owns 256 queries; a chunk tile's B operand arrives as kSlabs ring stages (one K-slab of this CTA's 128
+// rows each, 32 KB, three stages), the tile's kSlabs x 8 MMAs accumulate into one 256-column accumulator and the two
+// accumulators alternate by TILE.  Per tile the epilogue has one accumulator to drain per 2048 / 4096 cycles of MMA time, so
+// it is never the limit here; with 256 queries per pair the pass is HBM-bound instead (128 / 256 KB of features per pair and
+// tile): a batch of up to 256 queries costs one streaming pass over the scope, larger batches one pass per 256 queries
+// that mostly hits L2 (the query groups of a slice run side by side).
+constexpr int kWMaxSlabs = 4;
 constexpr int kWStages = 3;
-struct WideSmem {
-    alignas(1024) uint8_t q[kWSlabs][2][kTileKBlock];      // 128 KB: this CTA's 128 queries, every K-slab
+template <int kSlabs>
+struct WideSmemT {
+    alignas(1024) uint8_t q[kSlabs][2][kTileKBlock];       // 64 / 128 KB: this CTA's 128 queries, every K-slab
     alignas(1024) uint8_t b[kWStages][2][kTileKBlock];     // 96 KB: K-slabs of this CTA's half of the chunk tiles
     alignas(8) uint64_t q_full;                            // leader's copy in use
     uint64_t full[kWStages];                               // leader's copy in use
@@ -540,9 +541,11 @@ struct WideSmem {
     uint32_t tmem_base;
 };
 
-template <bool kFloorPass>
+template <bool kFloorPass, int kWSlabs>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 score_topk_gemm_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_f, const GemmArgs a) {
+    static_assert(kWSlabs == 2 || kWSlabs == 4, "rows of 512 or 1024 features");
+    using WideSmem = WideSmemT<kWSlabs>;
     extern __shared__ __align__(1024) uint8_t pair_smem_raw[];
     WideSmem &sm = *reinterpret_cast<WideSmem *>((reinterpret_cast<uintptr_t>(pair_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -832,12 +835,12 @@ cudaError_t launch_score_topk_gemm_pair(const GemmArgs &a, const int8_t *q_dev, 
     return a.debug ? go(score_topk_gemm_pair_kernel<true, false>) : go(score_topk_gemm_pair_kernel<false, false>);
 }
 
-// 1024-feature rows: [rows, 1024] int8 -> boxes of 128 rows x 128 bytes, 128-byte swizzle
-static bool make_map_wide(CUtensorMap *map, const void *base, uint64_t rows) {
+// wider rows: [rows, dim] int8 -> boxes of 128 rows x 128 bytes, 128-byte swizzle
+static bool make_map_wide(CUtensorMap *map, const void *base, uint64_t rows, uint32_t dim) {
     gemm::EncodeTiledFn enc = gemm::encode_fn();
     if (!enc) return false;
-    cuuint64_t dims[2] = {1024, rows};
-    cuuint64_t strides[1] = {1024};
+    cuuint64_t dims[2] = {dim, rows};
+    cuuint64_t strides[1] = {dim};
     cuuint32_t box[2] = {128, 128};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -846,17 +849,23 @@ static bool make_map_wide(CUtensorMap *map, const void *base, uint64_t rows) {
 
 size_t gemm_wide_lists_bytes(uint32_t n_slices, uint32_t nq) { return static_cast<size_t>(n_slices) * nq * gemm::kGemmK * 8; }
 
-cudaError_t launch_score_topk_gemm_wide(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t n_slices, cudaStream_t s) {
+cudaError_t launch_score_topk_gemm_wide(const GemmArgs &a, const int8_t *q_dev, const int8_t *F, uint64_t f_rows, uint32_t dim, uint32_t n_slices,
+                                        cudaStream_t s) {
+    if (dim != 512 && dim != 1024) return cudaErrorInvalidValue;
     CUtensorMap map_q, map_f;
-    if (!make_map_wide(&map_q, q_dev, a.nq) || !make_map_wide(&map_f, F, f_rows)) return cudaErrorNotSupported;
-    const int smem = static_cast<int>(sizeof(WideSmem)) + 1024;
+    if (!make_map_wide(&map_q, q_dev, a.nq, dim) || !make_map_wide(&map_f, F, f_rows, dim)) return cudaErrorNotSupported;
     dim3 grid(2 * n_slices, (a.nq + 255) / 256, 1);
-    auto go = [&](auto kern) -> cudaError_t {
+    auto go = [&](auto kern, int smem) -> cudaError_t {
         if (cudaError_t e = ensure_dynamic_smem(kern, smem); e != cudaSuccess) return e;
         kern<<<grid, kPThreads, smem, s>>>(map_q, map_f, a);
         return cudaGetLastError();
     };
-    return a.group_max_mode ? go(score_topk_gemm_wide_kernel<true>) : go(score_topk_gemm_wide_kernel<false>);
+    if (dim == 512) {
+        const int smem = static_cast<int>(sizeof(WideSmemT<2>)) + 1024;
+        return a.group_max_mode ? go(score_topk_gemm_wide_kernel<true, 2>, smem) : go(score_topk_gemm_wide_kernel<false, 2>, smem);
+    }
+    const int smem = static_cast<int>(sizeof(WideSmemT<4>)) + 1024;
+    return a.group_max_mode ? go(score_topk_gemm_wide_kernel<true, 4>, smem) : go(score_topk_gemm_wide_kernel<false, 4>, smem);
 }
 
 }  // namespace rf

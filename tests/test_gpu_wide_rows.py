@@ -257,11 +257,11 @@ def _device_batch(e, Q, scope, k):
     return out.cpu().numpy().view(np.uint64)
 
 
+@pytest.mark.parametrize("dim", [512, 1024])
 @pytest.mark.parametrize("n_rows,nq,k", [(100_001, 300, 10), (65_536, 128, 10), (200_000, 1024, 10), (150_000, 513, 3), (70_000, 17, 1)])
-def test_wide_gemm_path_parity(co, zbs, n_rows, nq, k):
-    """D = 1024 batches on the tensor cores (K = 1024 pair kernel: K streamed in four slabs, accumulators alternating by
-    tile) == oracle: ragged query groups, a ragged last chunk tile, k < 10."""
-    dim = 1024
+def test_wide_gemm_path_parity(co, zbs, n_rows, nq, k, dim):
+    """D = 512 / 1024 batches on the tensor cores (streamed-K pair kernel: K in two / four slabs, accumulators alternating
+    by tile) == oracle: ragged query groups, a ragged last chunk tile, k < 10."""
     zb = zbs[dim]
     with _engine(n_rows + 200, dim, id_base=7) as e:
         s = e.open_store("fileSearchStores/a")
@@ -280,10 +280,10 @@ def test_wide_gemm_path_parity(co, zbs, n_rows, nq, k):
         assert (got == keys).all()
 
 
-def test_wide_gemm_masks_saturation_and_heavy_queries(co, zbs):
-    """K = 1024 kernel under the tenant mask (two stores interleaved in the scored range, tombstones), with saturated
+@pytest.mark.parametrize("dim", [512, 1024])
+def test_wide_gemm_masks_saturation_and_heavy_queries(co, zbs, dim):
+    """Streamed-K kernel under the tenant mask (two stores interleaved in the scored range, tombstones), with saturated
     features (127) and queries that hit every K-slab."""
-    dim = 1024
     zb = zbs[dim]
     rng = np.random.default_rng(11)
     with _engine(90_000, dim) as e:
