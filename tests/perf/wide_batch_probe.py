@@ -1,12 +1,12 @@
 """1024 queries x 1 M chunks at D = 512 through the streamed-K tensor-core kernel: ms per batch (CUDA events), sampled
-parity against the C oracle.  Usage: python tools/wide512_probe.py [dim]"""
+parity against the C oracle.  Usage: python tests/perf/wide_batch_probe.py [dim]"""
 import json
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
