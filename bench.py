@@ -573,8 +573,9 @@ def leg_scaling_base(torch, dev, hbm_peak, steps: int):
 
 
 def leg_wide(torch, dev, hbm_peak, steps: int, sample_parity: bool, dim: int = 1024):
-    """Wider rows: the configs[1] workload with D = 1024 features per chunk -- 1 M chunks, one
-    query at a time, top-10 -- on the same scan kernel (template on the row width).  1028 algorithmic bytes per chunk."""
+    """Wider rows: the configs[1] workload with D = 512 / 1024 features per chunk -- 1 M chunks, one
+    query at a time, top-10 -- on the same scan kernel (template on the row width), D + 4 algorithmic bytes per chunk;
+    and the configs[2] batch at that width on the streamed-K tensor-core kernel."""
     from rag_foundation_b200 import Engine
     n = CFG2_ROWS
     Qh = make_queries(8, seed=SEED + 6, dim=dim)
@@ -603,7 +604,7 @@ def leg_wide(torch, dev, hbm_peak, steps: int, sample_parity: bool, dim: int = 1
         e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
         bytes_per_launch = n * (dim + 4)
         gbs = bytes_per_launch / (ms * 1e-3) / 1e9
-        # the batched form (configs[2] at this width): 1024 queries on the K = 1024 tensor-core kernel
+        # the batched form (configs[2] at this width): 1024 queries on the streamed-K tensor-core kernel
         nqb = 1024
         Qb = make_queries(nqb, seed=SEED + 7, dim=dim)
         qbd = torch.from_numpy(Qb).to(dev)
@@ -618,10 +619,10 @@ def leg_wide(torch, dev, hbm_peak, steps: int, sample_parity: bool, dim: int = 1
         peak_ops, _ = probe_int8_peak(dev.index or 0)
         ops_b = 2.0 * nqb * n * dim
         batched = {"workload": f"configs[2] with wider rows: 1M chunks x {dim} features, batched 1024 queries, top-10 on 1 B200",
-                   "kernel": "score_topk_gemm_wide_kernel (tcgen05.mma.cta_group::2.kind::i8, K = 1024 streamed in four slabs) + floor pass + kth_largest + merge_lists",
+                   "kernel": f"score_topk_gemm_wide_kernel (tcgen05.mma.cta_group::2.kind::i8, K = {dim} streamed in {dim // 256} slabs) + floor pass + kth_largest + merge_lists",
                    "ms_per_batch": ms_b, "qps": nqb / (ms_b * 1e-3), "launches_per_batch": launches_b,
                    "roofline": {"bound": "hbm (256 queries per CTA pair: one pass over the features per 256 queries, mostly from L2 after the first)",
-                                "achieved": (nqb // 256) * n * dim / (ms_b * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s of feature reads (4 passes x 1.02 GB; L2 serves part)",
+                                "achieved": (nqb // 256) * n * dim / (ms_b * 1e-3) / 1e9, "peak": hbm_peak, "unit": f"GB/s of feature reads (4 passes x {n * dim / 1e9:.2f} GB; L2 serves part)",
                                 "frac": (nqb // 256) * n * dim / (ms_b * 1e-3) / 1e9 / hbm_peak,
                                 "tensor_TOPs": ops_b / (ms_b * 1e-3) / 1e12, "tensor_frac": ops_b / (ms_b * 1e-3) / peak_ops},
                    "parity_mismatches": bad_b, "parity_checked": len(Qb[::64]) if sample_parity else 0}
@@ -955,6 +956,7 @@ def run_b200(args) -> None:
                         configs["cfg4"] = leg_cfg4(torch, dev, hbm_peak, 10_000, 10_000, sp)
                     if "wide" in legs:
                         configs["wide"] = leg_wide(torch, dev, hbm_peak, steps, sp)
+                        configs["wide512"] = leg_wide(torch, dev, hbm_peak, steps, sp, dim=512)
                     if "scaling_base" in legs:
                         configs["scaling_base"] = leg_scaling_base(torch, dev, hbm_peak, steps)
                 else:
