@@ -91,7 +91,7 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
 constexpr uint32_t kSpanDefaultBytes = 8u << 10;
 constexpr int kSpanMaxIt = (static_cast<int>(kSpanMaxBytes) / 16 + kFeatThreads - 1) / kFeatThreads;   // steps of 4 KB
 constexpr int kSpanRows = kSpanMaxIt * (kFeatThreads / 32);                                               // warp rows per CTA
-static_assert(kSpanRows <= 64, "warp 0 scans the row totals two per lane");
+static_assert(kSpanRows <= 32, "a warp scans the row totals one per lane");
 static_assert(kSpanMaxBytes + 64 < 0xFFFFu, "token ends inside the staged span fit 16 bits");
 
 // Shared-memory layout of a CTA with span bytes of text (span a multiple of 16; U = span / 16 units):
@@ -120,9 +120,9 @@ __device__ __forceinline__ uint32_t tok_bits4(uint32_t x, uint32_t &letter_bits)
 
 __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const TokenizeArgs a) {
     extern __shared__ __align__(16) uint8_t span_smem[];
-    __shared__ uint32_t s_row[64];                    // tokens per warp row (step, warp), then their exclusive prefix
+    __shared__ uint32_t s_row[32];                    // tokens per warp row (step, warp)
     __shared__ uint32_t s_red[kFeatThreads / 32];
-    __shared__ uint32_t s_cta, s_base, s_total, s_ex, s_long_end, s_def_li, s_def_start;
+    __shared__ uint32_t s_cta, s_base, s_long_end, s_def_li, s_def_start;
     if (threadIdx.x == 0) {
         s_base = __ldcg(a.ctl + kCtlTokens);          // read before this CTA publishes anything: see above
         s_cta = atomicAdd(a.ctl + kCtlTicket, 1u) - a.ticket_base;
@@ -140,11 +140,12 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     uint16_t *s_bkt = reinterpret_cast<uint16_t *>(span_smem + span_bkt_offset(a.span));
     uint16_t *s_end = reinterpret_cast<uint16_t *>(span_smem + span_end_offset(a.span));
 
-    // ---- stage: n_units + 1 units (the last one is look-ahead), bytes past the document read as separators
-    for (uint32_t u = threadIdx.x; u <= n_units; u += kFeatThreads) {
+    // ---- stage: n_units + 1 units (the last one is look-ahead), bytes past the document read as separators;
+    // a thread's next unit is loaded before the current one is worked on
+    auto load_unit = [&](uint32_t u) {
         const size_t at = span_lo + static_cast<size_t>(u) * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (at < a.n) {
+        if (u <= n_units && at < a.n) {
             v = *reinterpret_cast<const uint4 *>(a.text + at);        // the text buffer is padded by 64 bytes
             if (at + 16 > a.n) {
                 const uint32_t keep = static_cast<uint32_t>(a.n - at);   // 1 .. 15
@@ -156,8 +157,14 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
                 }
                 v = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            v = make_uint4(lower4(v.x), lower4(v.y), lower4(v.z), lower4(v.w));
         }
+        return v;
+    };
+    uint4 nxt = load_unit(threadIdx.x);
+    for (uint32_t u = threadIdx.x; u <= n_units; u += kFeatThreads) {
+        uint4 v = nxt;
+        nxt = load_unit(u + kFeatThreads);
+        v = make_uint4(lower4(v.x), lower4(v.y), lower4(v.z), lower4(v.w));      // (zero bytes stay zero)
         *reinterpret_cast<uint4 *>(s_txt + u * 16) = v;
         uint32_t l0, l1, l2, l3;
         const uint32_t t0 = tok_bits4(v.x, l0), t1 = tok_bits4(v.y, l1), t2 = tok_bits4(v.z, l2), t3 = tok_bits4(v.w, l3);
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
         s_txt[-1] = before;
         s_tok[0] = token_byte(before) ? 0x8000u : 0u;
     }
-    if (threadIdx.x < 64) s_row[threadIdx.x] = 0;
+    if (threadIdx.x < 32) s_row[threadIdx.x] = 0;
     __syncthreads();
 
     // ---- flag the kept-token starts + count
@@ -199,23 +206,20 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
         if (lane == 0) s_row[it * (kFeatThreads / 32) + warp] = row_total;
     }
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t ta = s_row[lane], tb = s_row[lane + 32];
-        uint32_t ia = ta, ib = tb;
+    // exclusive prefix of the (<= 24) row totals: every warp scans them itself -- no second barrier, no broadcast
+    uint32_t row_ex, total;
+    {
+        const uint32_t tr = s_row[lane];
+        uint32_t inc_r = tr;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t xa = __shfl_up_sync(kFull, ia, o), xb = __shfl_up_sync(kFull, ib, o);
-            if (lane >= o) { ia += xa; ib += xb; }
+            const uint32_t x = __shfl_up_sync(kFull, inc_r, o);
+            if (lane >= o) inc_r += x;
         }
-        const uint32_t total_a = __shfl_sync(kFull, ia, 31), total = total_a + __shfl_sync(kFull, ib, 31);
-        s_row[lane] = ia - ta;
-        s_row[lane + 32] = total_a + ib - tb;
-        if (lane == 0) {
-            s_total = total;
-            st_release_u64(a.state + cta, (static_cast<uint64_t>(a.seq) << 32) | total);
-        }
+        row_ex = inc_r - tr;
+        total = __shfl_sync(kFull, inc_r, 31);
     }
-    __syncthreads();
+    if (threadIdx.x == 0) st_release_u64(a.state + cta, (static_cast<uint64_t>(a.seq) << 32) | total);
 
     // ---- hash: token records at their CTA-local index
     const uint32_t staged = (n_units + 1) * 16;       // bytes of s_txt (and bits of s_tok) that hold text
@@ -234,11 +238,13 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
             const uint32_t t = __shfl_up_sync(kFull, inc, o);
             if (lane >= o) inc += t;
         }
+        const uint32_t row_off = __shfl_sync(kFull, row_ex, static_cast<int>(it * (kFeatThreads / 32) + warp));
         if (S == 0) continue;                          // (no shuffles below)
-        uint32_t li = s_row[it * (kFeatThreads / 32) + warp] + inc - c;   // CTA-local index of the unit's first kept token
+        uint32_t li = row_off + inc - c;               // CTA-local index of the unit's first kept token
         const uint32_t pos0 = u * 16;                  // relative to span_lo
         const uint32_t T = s_tok[u + 1] | ((s_tok[u + 2] & 0xFu) << 16);
         const uint32_t E = (T + S) & ~T;               // bit j: a kept token ends in front of byte j (bit 20: it runs on)
+        const uint32_t Kb = T & ~(T + S);              // bit j: byte j belongs to a kept token that starts in this unit
         const uint4 v = *reinterpret_cast<const uint4 *>(s_txt + u * 16);
         const uint32_t words[5] = {v.x, v.y, v.z, v.w, *reinterpret_cast<const uint32_t *>(s_txt + u * 16 + 16)};
         uint32_t h = 0x811C9DC5u;
@@ -254,9 +260,9 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
                       "h"(static_cast<uint16_t>(pos0 + j))
                     : "memory");
                 li += e;
+                h = e ? 0x811C9DC5u : h;               // the next kept token starts from the offset basis
             }
-            if (j < 16) h = ((S >> j) & 1u) ? 0x811C9DC5u : h;
-            h = ((T >> j) & 1u) ? (h ^ b) * 0x01000193u : h;
+            h = ((Kb >> j) & 1u) ? (h ^ b) * 0x01000193u : h;
         }
         if ((E >> 20) & 1u) {
             // the unit's last kept token runs past the look-ahead: finish it from the staged masks / bytes,
@@ -298,15 +304,11 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     before = __reduce_add_sync(kFull, before);
     if (lane == 0) s_red[warp] = before;
     __syncthreads();                                   // (also: every token record is in shared memory)
-    if (threadIdx.x == 0) {
-        uint32_t ex = 0;
+    uint32_t ex = 0;
 #pragma unroll
-        for (int w = 0; w < kFeatThreads / 32; ++w) ex += s_red[w];
-        s_ex = ex;
-        if (cta + 1 == gridDim.x) a.ctl[kCtlTokens] = s_base + ex + s_total;   // every other CTA has read the old value
-    }
-    __syncthreads();
-    const uint32_t ord_base = s_base + s_ex, total = s_total;
+    for (int w = 0; w < kFeatThreads / 32; ++w) ex += s_red[w];
+    if (threadIdx.x == 0 && cta + 1 == gridDim.x) a.ctl[kCtlTokens] = s_base + ex + total;   // every other CTA has read the old value
+    const uint32_t ord_base = s_base + ex;
     const uint32_t lo32 = static_cast<uint32_t>(span_lo);             // documents are < 4 GiB
 
     // ---- place: coalesced records, chunk-window starts, the parked token
