@@ -446,6 +446,42 @@ def leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, n_stores, per_store, 
         timed_out = srch.timed_out()
         again = out.cpu().numpy().view(np.uint64)
         alg = nq * per_store * BYTES_PER_CHUNK
+        # The same batches with TWO in flight per rank (alternating caller streams, as a server that keeps receiving
+        # batches would): a batch's plan upload, scan start-up and exchange wait overlap its neighbour's scan.  Every rank
+        # alternates identically, so a gather slot (4 per rank, indexed by the call number) is still free when it comes round.
+        two = {}
+        try:
+            s2 = torch.cuda.Stream(dev)
+            eng.set_stream_overlap(s2.cuda_stream, True)
+            pair_streams, outs = [stream, s2], [out, torch.zeros_like(out)]
+
+            def call(i):
+                with torch.cuda.stream(pair_streams[i & 1]):
+                    srch.search_keys(qd, local, K, out=outs[i & 1])
+            for i in range(4):
+                call(i)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            reps2 = 20
+            e0.record(stream)
+            s2.wait_event(e0)
+            for i in range(reps2):
+                call(i)
+            j = torch.cuda.Event()
+            j.record(s2)
+            stream.wait_event(j)
+            e1.record(stream)
+            e1.synchronize()
+            t2 = torch.tensor([e0.elapsed_time(e1) / reps2], dtype=torch.float64, device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            ms2 = float(t2.item())
+            same2 = bool((outs[1].cpu().numpy().view(np.uint64) == keys).all() and (outs[0].cpu().numpy().view(np.uint64) == keys).all())
+            two = {"spmd_two_in_flight": {"ms_per_batch": ms2, "qps": nq / (ms2 * 1e-3), "equals_sequential": same2 and not srch.timed_out(),
+                                          "roofline": {"bound": "hbm", "achieved": alg / (ms2 * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                                                       "frac": alg / (ms2 * 1e-3) / 1e9 / (hbm_peak * world)}}}
+        except Exception as exc:   # noqa: BLE001
+            two = {"spmd_two_in_flight": {"error": f"{type(exc).__name__}: {exc}"}}
         # weak-scaling point: a batch of 1024 x world queries (the per-GPU work of the single-GPU batch): what is left of
         # the fixed per-batch costs (plan upload, two launches, the exchange) once a rank has 0.4 ms of scanning again
         weak = {}
@@ -478,7 +514,7 @@ def leg_cfg4_spmd(torch, dist, dev, rank, world, hbm_peak, n_stores, per_store, 
                                   "timed_out": srch_w.timed_out()}}
         except Exception as exc:   # noqa: BLE001
             weak = {"spmd_weak": {"error": f"{type(exc).__name__}: {exc}"}}
-        return {**weak, "spmd_ms_per_batch": ms, "spmd_qps": nq / (ms * 1e-3), "spmd_parity_mismatches": bad, "spmd_stable": bool((again == keys).all()) and not timed_out,
+        return {**weak, **two, "spmd_ms_per_batch": ms, "spmd_qps": nq / (ms * 1e-3), "spmd_parity_mismatches": bad, "spmd_stable": bool((again == keys).all()) and not timed_out,
                 "spmd_exchange": "publish-only scan + merge_wait over NVLink peer memory (rf_search_keys_device_scoped_fused), plans from the device-resident store table",
                 "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
                              "frac": alg / (ms * 1e-3) / 1e9 / (hbm_peak * world)}}

@@ -2372,7 +2372,7 @@ static int search_keys_device_impl(rf_engine *e, const int8_t *q_dev, uint32_t n
         RF_CUDA(st->partial.reserve(need_partial));
         if (need_sync > st->tickets.cap) {
             RF_CUDA(st->tickets.reserve(need_sync));
-            RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
+            RF_CUDA(cudaMemsetAsync(st->tickets.p, 0, st->tickets.cap, s));   // on the caller's stream: the legacy default stream does not order with a non-blocking one
         }
     }
     ScanArgs a{};
@@ -2469,7 +2469,7 @@ static int search_keys_device_scoped_impl(rf_engine *e, const int8_t *q_dev, uin
         RF_CUDA(st->gemm_keys_a.reserve(need_local));
         if (need_sync > st->tickets.cap) {
             RF_CUDA(st->tickets.reserve(need_sync));
-            RF_CUDA(cudaMemset(st->tickets.p, 0, st->tickets.cap));
+            RF_CUDA(cudaMemsetAsync(st->tickets.p, 0, st->tickets.cap, s));   // on the caller's stream: the legacy default stream does not order with a non-blocking one
         }
     }
     if (!b.bytes.empty()) {

@@ -441,6 +441,39 @@ def test_many_scopes_hold_no_device_state(co, zb):
         assert out.cpu().numpy().view(np.uint64)[0].tolist() == want.tolist()
 
 
+def test_first_search_on_a_fresh_non_blocking_stream(co, zb):
+    """A caller stream's scratch (tickets, floors, tile counters) is zeroed on THAT stream.  It used to be zeroed with
+    cudaMemset -- the legacy default stream, which does not order with a non-blocking stream: while the default stream
+    was busy the zeroing landed in the middle of the new stream's searches and left their block tickets off by a few
+    for good (found with two store-sharded batches in flight per rank)."""
+    import torch
+    n, k = 1_000_000, 10
+    with _engine(n) as e:
+        s = e.open_store("fileSearchStores/a")
+        e.ingest_synthetic(s, 0, seed=3, start_counter=0, n_rows=n)
+        Q = np.stack([co.synth_query(3, i, zb) for i in range(16)])
+        qd = torch.from_numpy(Q).cuda()
+        want = torch.zeros((16, k), dtype=torch.int64, device="cuda")
+        for i in range(16):
+            e.search_keys_device(qd[i:i + 1].data_ptr(), 1, [s], k, want[i].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(4e-3 * 1.9e9))               # ~4 ms of work on the default stream
+        fresh = torch.cuda.Stream()
+        got = torch.zeros((256, k), dtype=torch.int64, device="cuda")
+        for i in range(256):                               # ~11 ms of searches: the default stream wakes up half-way
+            e.search_keys_device(qd[i % 16:i % 16 + 1].data_ptr(), 1, [s], k, got[i].data_ptr(), fresh.cuda_stream)
+        # ... and a store-scoped batch, whose scratch is set up by the other entry point, on another fresh stream
+        torch.cuda._sleep(int(4e-3 * 1.9e9))
+        fresh2 = torch.cuda.Stream()
+        gotb = torch.zeros((40, 16, k), dtype=torch.int64, device="cuda")
+        csr = (np.full(16, s, np.uint32), np.arange(17, dtype=np.uint32))
+        for i in range(40):
+            e.search_keys_device_scoped(qd.data_ptr(), 16, csr, k, gotb[i].data_ptr(), fresh2.cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(16, 16, k), want.expand(16, 16, k))
+        assert torch.equal(gotb, want.expand(40, 16, k))
+
+
 # ------------------------------------------------------------------ staged, chunk-pipelined ingest
 def _check_ingest(e, seg, doc_id, data, co, ptr=None):
     if ptr is None:
