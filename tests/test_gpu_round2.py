@@ -443,9 +443,12 @@ def test_many_scopes_hold_no_device_state(co, zb):
 
 def test_first_search_on_a_fresh_non_blocking_stream(co, zb):
     """A caller stream's scratch (tickets, floors, tile counters) is zeroed on THAT stream.  It used to be zeroed with
-    cudaMemset -- the legacy default stream, which does not order with a non-blocking stream: while the default stream
-    was busy the zeroing landed in the middle of the new stream's searches and left their block tickets off by a few
-    for good (found with two store-sharded batches in flight per rank)."""
+    cudaMemset -- the legacy default stream, which does not order with a non-blocking stream: with two store-sharded
+    batches in flight per rank the zeroing landed inside the new stream's first batch (queries never answered, one block
+    ticket left off for good; `tools/two_in_flight_check.py` under torchrun on 2 GPUs reproduces it with the old library
+    and is clean with this one).  This single-GPU test walks the same path -- first searches on fresh non-blocking
+    streams while the default stream is busy, through both device-resident entry points -- but the race window is too
+    narrow here for it to fail reliably on the old code."""
     import torch
     n, k = 1_000_000, 10
     with _engine(n) as e:
@@ -456,17 +459,17 @@ def test_first_search_on_a_fresh_non_blocking_stream(co, zb):
         want = torch.zeros((16, k), dtype=torch.int64, device="cuda")
         for i in range(16):
             e.search_keys_device(qd[i:i + 1].data_ptr(), 1, [s], k, want[i].data_ptr(), torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
+        got = torch.zeros((256, k), dtype=torch.int64, device="cuda")
+        gotb = torch.zeros((40, 16, k), dtype=torch.int64, device="cuda")
+        csr = (np.full(16, s, np.uint32), np.arange(17, dtype=np.uint32))
+        torch.cuda.synchronize()                           # (the result buffers are zeroed before the default stream gets busy)
         torch.cuda._sleep(int(4e-3 * 1.9e9))               # ~4 ms of work on the default stream
         fresh = torch.cuda.Stream()
-        got = torch.zeros((256, k), dtype=torch.int64, device="cuda")
         for i in range(256):                               # ~11 ms of searches: the default stream wakes up half-way
             e.search_keys_device(qd[i % 16:i % 16 + 1].data_ptr(), 1, [s], k, got[i].data_ptr(), fresh.cuda_stream)
         # ... and a store-scoped batch, whose scratch is set up by the other entry point, on another fresh stream
         torch.cuda._sleep(int(4e-3 * 1.9e9))
         fresh2 = torch.cuda.Stream()
-        gotb = torch.zeros((40, 16, k), dtype=torch.int64, device="cuda")
-        csr = (np.full(16, s, np.uint32), np.arange(17, dtype=np.uint32))
         for i in range(40):
             e.search_keys_device_scoped(qd.data_ptr(), 16, csr, k, gotb[i].data_ptr(), fresh2.cuda_stream)
         torch.cuda.synchronize()
