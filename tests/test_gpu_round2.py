@@ -745,6 +745,29 @@ def test_store_sharded_fused_exchange_two_engines_one_process(co, zb):
             assert not any(int(t.item()) for t in timeout)
             got = [o.cpu().numpy().view(np.uint64) for o in outs]
             assert (got[0] == got[1]).all()
+        # two batches in flight per 'rank' (each rank alternates between two caller streams, both ranks identically, nothing
+        # synchronises in between): a gather slot -- four per rank, indexed by the call number -- is free again when it comes
+        # round, and every call returns the answer above
+        streams_b = [torch.cuda.Stream() for _ in range(world)]
+        for r in range(world):                                     # the second streams' scratch, set up outside an exchange
+            engines[r].search_keys_device_scoped_fused(qd.data_ptr(), nq, csr, k, outs[r].data_ptr(), streams_b[r].cuda_stream,
+                                                       0, 1, nq_cap, 1, kp[r:r + 1], fp[r:r + 1], timeout[r].data_ptr())
+        torch.cuda.synchronize()
+        n_calls = 10
+        outs2 = [[torch.zeros((nq, k), dtype=torch.int64, device="cuda") for _ in range(n_calls)] for _ in range(world)]
+        torch.cuda.synchronize()
+        for c in range(n_calls):
+            for r in range(world):
+                q_index, local_csr = per_rank[r]
+                st = (streams[r], streams_b[r])[c & 1]
+                engines[r].search_keys_device_scoped_fused(qd.data_ptr(), int(q_index.size), local_csr, k, outs2[r][c].data_ptr(), st.cuda_stream,
+                                                           r, world, nq_cap, 7 + c, kp, fp, timeout[r].data_ptr(),
+                                                           nq_total=nq, q_index=q_index, owner_masks=masks)
+        torch.cuda.synchronize()
+        assert not any(int(t.item()) for t in timeout)
+        for r in range(world):
+            for c in range(n_calls):
+                assert (outs2[r][c].cpu().numpy().view(np.uint64) == got[0]).all(), (r, c)
         for i in range(nq):
             m = np.isin(seg, np.asarray(scopes[i], np.uint32))
             sc = F[m].astype(np.int32) @ Q[i].astype(np.int32)
