@@ -75,11 +75,11 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
 //   flag    kept-token starts from the masks alone (start = token bit whose predecessor is clear; lengths
 //           1-3 from shifted masks); only short tokens that begin with a letter look at their bytes for
 //           a / an / the.  The CTA's token count is published at once, tagged with the launch number
-//   hash    a thread walks the 20 byte positions of its unit (16 + 4 look-ahead) unrolled out of registers:
-//           starts reset the FNV-1a state, token bytes advance it, and "a kept token ends here"
-//           (= (T + S) & ~T: adding the start bits to the token-byte mask carries through each kept run) puts
-//           (bucket, byte end) at the token's CTA-local index in shared memory with predicated stores; a token
-//           that runs further is finished from the masks
+//   hash    a thread walks the 20 byte positions of its unit (16 + 4 look-ahead) unrolled out of registers.
+//           Adding the start bits S to the token-byte mask T carries through each kept run: T & ~(T + S) are the
+//           bytes of the unit's kept tokens (they advance the FNV-1a state), (T + S) & ~T marks where a kept
+//           token ends -- there (bucket, byte end) go to the token's CTA-local index in shared memory with
+//           predicated stores and the state starts over; a token that runs further is finished from the masks
 //   place   only now the counts of the CTAs before this one are summed (every thread takes a share of those
 //           words; by now they have long been published), and the token records leave in coalesced stores at
 //           their global ordinals; the byte start of every 112th token (a chunk window opens there) is found
