@@ -844,7 +844,7 @@ def run_b200(args) -> None:
 
     steps, warmup = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
-    e2e_steps = max(10, min(steps, 2000))
+    e2e_steps = max(200 if n_gpus == 1 else 10, min(steps, 2000))   # e2e.steps says how many; N = 1: at least 200 (8 ms)
     e2e_s, e2e_conc_qps, h2d, d2h, api = None, None, 0, 0, ""
     e2e_seq_s = None
     with sampler:
@@ -858,7 +858,7 @@ def run_b200(args) -> None:
 
         # ---- scan kernel alone (the dominant kernel): the same launches without the exchange, CUDA events on the
         # launching stream(s); at N = 1 also the single-stream schedule
-        kq = min(steps, 512)
+        kq = 512 if n_gpus == 1 else min(steps, 512)       # (N = 1: a region long enough that its two ends do not show: 21 ms)
         scratch = torch.zeros((1, k), dtype=torch.int64, device=dev)
         single_stream_ms = None
         if n_gpus == 1:
@@ -1048,7 +1048,7 @@ def run_b200(args) -> None:
                if n_gpus == 1 and len(streams) > 1 else {}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": load_traffic(traffic_key), "traffic_source": "ncu capture of this kernel at this shard size (profiles/roofline_traffic.json, ncu_traffic_r02c.txt)",
-                         "kernel": SCAN_KERNEL, "kernel_ms": kernel_ms,
+                         "kernel": SCAN_KERNEL, "kernel_ms": kernel_ms, "kernel_launches_timed": kq,
                          "kernel_ms_note": (f"timed region / launches, launches alternating between {len(streams)} caller streams (each stream's searches under programmatic "
                                             "dependent launch): the aggregate rate of the kernel with two queries in flight; one launch alone takes "
                                             "isolated_launch_latency_us" if n_gpus == 1 and len(streams) > 1 else
