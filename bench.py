@@ -765,14 +765,18 @@ def run_b200(args) -> None:
             eng.set_stream_overlap(s2.cuda_stream, True)
             streams.append(s2)
 
+    # (addresses and stream handles looked up once: inside the timed region a step is the C-ABI call and nothing else)
+    q_ptrs = [Qd[qi:qi + 1].data_ptr() for qi in range(N_DISTINCT_QUERIES)]
+    out_ptrs = [out_keys[qi].data_ptr() for qi in range(N_DISTINCT_QUERIES)]
+    stream_handles = [st.cuda_stream for st in streams]
+    scope = [seg]
+
     def step(i: int, n_streams: int = 0):
         qi = i % N_DISTINCT_QUERIES
-        q = Qd[qi:qi + 1]
         if n_gpus == 1:
-            st = streams[i % (n_streams or len(streams))]
-            eng.search_keys_device(q.data_ptr(), 1, [seg], k, out_keys[qi].data_ptr(), st.cuda_stream)
+            eng.search_keys_device(q_ptrs[qi], 1, scope, k, out_ptrs[qi], stream_handles[i % (n_streams or len(streams))])
         else:
-            searcher.search_keys(q, [seg], k, out=out_keys[qi:qi + 1])
+            searcher.search_keys(Qd[qi:qi + 1], scope, k, out=out_keys[qi:qi + 1])
 
     def timed_region(n: int, n_streams: int = 0) -> float:
         """ms for steps 0 .. n-1: CUDA events on the first stream, which the other streams start behind and which
