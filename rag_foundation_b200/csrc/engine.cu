@@ -1431,6 +1431,7 @@ int rf_ingest_text(rf_engine *e, uint32_t store_seg, uint64_t doc_id, const uint
     RF_CUDA(cudaMemcpyAsync(e->sc_ctl_host.p, t.ctl, rf::kCtlWords * 4, cudaMemcpyDeviceToHost, s));
     RF_CUDA(cudaStreamSynchronize(s));
     const uint32_t n_tokens = h_ctl[rf::kCtlTokens], n_deferred = h_ctl[rf::kCtlDeferred];
+    if (h_ctl[rf::kCtlStalled]) return fail(RF_ECUDA, "internal: the tokeniser's token-count exchange timed out");
     int launches = 0;
     if (n_deferred) {   // tokens longer than a whole copy chunk: hash them now that every byte is here
         if (n_deferred > rf::kMaxDeferred) return fail(RF_EINVAL, "internal: %u parked tokens (max %u)", n_deferred, rf::kMaxDeferred);

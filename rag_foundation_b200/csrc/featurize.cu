@@ -298,7 +298,15 @@ __global__ void __launch_bounds__(kFeatThreads) tokenize_span_kernel(const Token
     uint32_t before = 0;
     for (uint32_t j = threadIdx.x; j < cta; j += kFeatThreads) {
         uint64_t v;
-        while (static_cast<uint32_t>((v = ld_relaxed_u64(a.state + j)) >> 32) != a.seq) __nanosleep(200);
+        const long long t0 = clock64();
+        while (static_cast<uint32_t>((v = ld_relaxed_u64(a.state + j)) >> 32) != a.seq) {
+            __nanosleep(200);
+            if (clock64() - t0 > (4ll << 30)) {       // ~2 s: fail loudly (the host reports it), never hang
+                atomicExch(a.ctl + kCtlStalled, 1u);
+                v = 0;
+                break;
+            }
+        }
         before += static_cast<uint32_t>(v);
     }
     before = __reduce_add_sync(kFull, before);

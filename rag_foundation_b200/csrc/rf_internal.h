@@ -201,7 +201,7 @@ void stage_copy(void *dst, const void *src, size_t n);
 // featurisation (featurize.cu)
 constexpr uint32_t kFeatBlockBytes = 4096;
 constexpr uint32_t kMaxDeferred = 64;    // tokens longer than a whole copy chunk, finished after the last copy
-enum : uint32_t { kCtlTicket = 0, kCtlTokens = 1, kCtlDeferred = 2, kCtlWords = 4 };   // control words (zeroed per document)
+enum : uint32_t { kCtlTicket = 0, kCtlTokens = 1, kCtlDeferred = 2, kCtlStalled = 3, kCtlWords = 4 };   // control words (zeroed per document)
 constexpr uint32_t kSpanMaxBytes = 12u << 10;   // most text bytes one tokeniser CTA keeps in shared memory (with its masks and token records: < 48 KB)
 constexpr uint32_t kSpanMaxCtas = 4096;         // CTAs per tokeniser launch
 struct TokenizeArgs {        // device scratch for one document
