@@ -536,6 +536,9 @@ int table_acquire(rf_engine *e, std::shared_lock<std::shared_mutex> &lk) {
         RF_CUDA(cudaMemcpy(t.entries.p, ent.data(), ent.size() * sizeof(rf::StoreEntry), cudaMemcpyHostToDevice));
         RF_CUDA(cudaMemcpy(t.lo.p, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
         RF_CUDA(cudaMemcpy(t.hi.p, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+        // (a copy from pageable memory may return once the bytes are staged: the searches that read the table run on
+        // non-blocking streams, which do not order with the legacy default stream the DMA is on)
+        RF_CUDA(cudaDeviceSynchronize());
         t.n_stores = static_cast<uint32_t>(t.h_next.size());
         t.epoch = now;
     }
@@ -1122,7 +1125,9 @@ int rf_engine_create(const rf_config *cfg, rf_engine **out) {
     // unwritten rows read as tombstones
     if ((ce = cudaMemset(e->seg, 0xFF, cap * 4)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (ce = cudaEventCreateWithFlags(&e->ingest_idle, cudaEventDisableTiming)) != cudaSuccess) {
+        (ce = cudaEventCreateWithFlags(&e->ingest_idle, cudaEventDisableTiming)) != cudaSuccess ||
+        (ce = cudaDeviceSynchronize()) != cudaSuccess) {   // the fill ran on the legacy default stream, which the engine's
+                                                            // (non-blocking) streams and the callers' do not order with
         const int rc = fail(RF_ECUDA, "engine init failed: %s", cudaGetErrorString(ce));
         rf_engine_destroy(e);
         return rc;
@@ -1559,6 +1564,7 @@ int rf_ingest_synthetic(rf_engine *e, uint32_t first_seg, uint64_t rows_per_stor
         }
         RF_CUDA(cudaMalloc(&e->zipf_bucket, 65536 * 2));
         RF_CUDA(cudaMemcpy(e->zipf_bucket, zb.data(), 65536 * 2, cudaMemcpyHostToDevice));
+        RF_CUDA(cudaDeviceSynchronize());       // (staged copy: on the device before the generator reads it on the ingest stream)
     }
     // the generator appends at the tail only (row content is tied to its counter; a measurement input)
     if (e->n_rows + n_rows > e->cfg.capacity_rows)
@@ -1758,6 +1764,7 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
     // and a failed load masks whatever it wrote.
     auto unwind = [&](const char *what) {
         cudaMemset(e->seg, 0xFF, static_cast<size_t>(h.n_rows) * 4);
+        cudaDeviceSynchronize();
         return fail(RF_EINVAL, "%s is %s; nothing was loaded", path, what);
     };
     std::vector<uint8_t> buf(std::min<size_t>(kSnapChunk, std::max<size_t>(h.n_rows * e->dim, 1)));
@@ -1773,6 +1780,7 @@ int rf_snapshot_load(rf_engine *e, const char *path) {
     SnapTrailer t{};
     if (fread(&t, 1, sizeof t, f) != sizeof t || memcmp(t.magic, "RFB2END2", 8) != 0) return unwind("truncated (no trailer)");
     if (t.checksum != r.hs.h) return unwind("corrupt (checksum mismatch)");
+    RF_CUDA(cudaDeviceSynchronize());           // the staged copies are on the device before any search can see the rows
     e->stores.swap(stores);
     e->store_by_name.clear();
     for (uint32_t i = 0; i < e->stores.size(); ++i)
